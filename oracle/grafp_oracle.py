@@ -1,0 +1,377 @@
+"""CPU oracle for the GraFP GraphEncoder hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``grafp_b200/`` may import this file;
+only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` use it, and there only as the checker
+or as the timed CPU reference - never as the product path.
+
+It is a functional restatement (plain fp32 PyTorch ops on whatever device the
+inputs live on, normally the CPU) of the reference algorithm; each function
+cites the reference file:line it follows (paths relative to the upstream
+chymaera96/GraFP checkout).  The model-level functions are driven by a
+``state_dict`` with the reference's own key names, so the same weights can be
+loaded into the reference, the oracle and the B200 path.
+
+Parity pin: the reference's own unit tests hold no numeric golden vectors for
+this path.  The oracle is therefore pinned against the
+reference *itself*: ``tests/golden/make_golden.py`` imports the upstream modules
+from /root/reference (CPU), runs them on seeded inputs and stores the outputs in
+``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` replays the oracle on the
+stored inputs and demands bit-identical results (same torch build) for the
+graph/aggregation ops and <= 1e-6 relative error for the whole encoder.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+# --------------------------------------------------------------------------
+# k-NN graph (reference: encoder/gcn_lib/torch_edge.py)
+# --------------------------------------------------------------------------
+
+
+def l2_normalize_channels(x: Tensor) -> Tensor:
+    """``F.normalize(x, p=2.0, dim=1)`` as used at torch_edge.py:274-275,281.
+
+    x: (B, C, N, 1).  Every node vector is divided by max(||v||_2, 1e-12).
+    """
+    norm = torch.linalg.vector_norm(x, ord=2, dim=1, keepdim=True)
+    return x / norm.clamp_min(1e-12).expand_as(x)
+
+
+def sq_distance_matrix(x_rows: Tensor, y_rows: Optional[Tensor] = None) -> Tensor:
+    """Squared distances in the reference's association order.
+
+    torch_edge.py:15-18 (x only) and :46-53 (x against y):
+    ``D = |x|^2 + (-2 * x y^T) + |y|^2^T`` evaluated left to right.
+    x_rows: (B, N, C), y_rows: (B, M, C) -> (B, N, M).
+    """
+    if y_rows is None:
+        y_rows = x_rows
+    inner = -2 * torch.matmul(x_rows, y_rows.transpose(2, 1))
+    x_sq = torch.sum(torch.mul(x_rows, x_rows), dim=-1, keepdim=True)
+    y_sq = torch.sum(torch.mul(y_rows, y_rows), dim=-1, keepdim=True)
+    return x_sq + inner + y_sq.transpose(2, 1)
+
+
+def knn_edge_index(x: Tensor, K: int, y: Optional[Tensor] = None,
+                   relative_pos: Optional[Tensor] = None) -> Tensor:
+    """Top-K nearest key nodes per query node, sorted by ascending distance.
+
+    dense_knn_matrix (torch_edge.py:70-103) and xy_dense_knn_matrix (:144-164).
+    x: (B, C, N, 1) queries, y: (B, C, M, 1) keys (defaults to x),
+    relative_pos: (1, N, M) bias added to the distances (:97-99, :160-162).
+    Returns (2, B, N, K) int64: [0] neighbour ids, [1] centre ids (:102-103).
+    The reference's row chunking for N > 10000 (:82-94) only bounds memory and
+    does not change the result, so it is not restated.
+    """
+    with torch.no_grad():
+        xr = x.detach().transpose(2, 1).squeeze(-1)
+        yr = None if y is None else y.detach().transpose(2, 1).squeeze(-1)
+        B, N, _ = xr.shape
+        dist = sq_distance_matrix(xr, yr)
+        if relative_pos is not None:
+            dist = dist + relative_pos
+        nn_idx = torch.topk(-dist, k=K).indices
+        centre = torch.arange(N, device=x.device).view(1, N, 1).expand(B, N, K)
+    return torch.stack((nn_idx, centre), dim=0)
+
+
+def dilate_edge_index(edge_index: Tensor, dilation: int) -> Tensor:
+    """Deterministic branch of DenseDilated.forward (torch_edge.py:252,254)."""
+    return edge_index[:, :, :, ::dilation]
+
+
+def dilated_knn_graph(x: Tensor, k: int, dilation: int = 1, y: Optional[Tensor] = None,
+                      relative_pos: Optional[Tensor] = None) -> Tensor:
+    """DenseDilatedKnnGraph.forward with stochastic=False (torch_edge.py:270-284)."""
+    xn = l2_normalize_channels(x)
+    yn = None if y is None else l2_normalize_channels(y)
+    full = knn_edge_index(xn, k * dilation, yn, relative_pos)
+    return dilate_edge_index(full, dilation)
+
+
+# --------------------------------------------------------------------------
+# gather + aggregation (reference: torch_nn.py, torch_vertex.py)
+# --------------------------------------------------------------------------
+
+
+def gather_neighbors(x: Tensor, idx: Tensor) -> Tensor:
+    """batched_index_select (torch_nn.py:79-98).
+
+    x: (B, C, M, 1), idx: (B, N, k) -> (B, C, N, k) with
+    out[b, c, n, j] = x[b, c, idx[b, n, j]].
+    """
+    B, C, M = x.shape[:3]
+    _, N, k = idx.shape
+    flat = (idx + torch.arange(B, device=idx.device).view(B, 1, 1) * M).reshape(-1)
+    rows = x.transpose(2, 1).reshape(B * M, C)[flat]
+    return rows.view(B, N, k, C).permute(0, 3, 1, 2).contiguous()
+
+
+def max_relative_features(x: Tensor, edge_index: Tensor, y: Optional[Tensor] = None) -> Tensor:
+    """The aggregation half of MRConv2d.forward (torch_vertex.py:19-32).
+
+    Returns (B, 2C, N, 1) with channels interleaved [x_0, m_0, x_1, m_1, ...]
+    where m_c = max_j (x_j[c] - x_i[c]).
+    """
+    x_i = gather_neighbors(x, edge_index[1])
+    x_j = gather_neighbors(x if y is None else y, edge_index[0])
+    m = torch.max(x_j - x_i, dim=-1, keepdim=True).values
+    B, C, N, _ = x.shape
+    return torch.cat([x.unsqueeze(2), m.unsqueeze(2)], dim=2).reshape(B, 2 * C, N, 1)
+
+
+def edge_features(x: Tensor, edge_index: Tensor, y: Optional[Tensor] = None) -> Tensor:
+    """Input of the EdgeConv2d MLP (torch_vertex.py:45-51): cat[x_i, x_j - x_i] on dim 1."""
+    x_i = gather_neighbors(x, edge_index[1])
+    x_j = gather_neighbors(x if y is None else y, edge_index[0])
+    return torch.cat([x_i, x_j - x_i], dim=1)
+
+
+# --------------------------------------------------------------------------
+# parameterised layers, driven by a reference-keyed state_dict
+# --------------------------------------------------------------------------
+
+Params = Dict[str, Tensor]
+
+
+def _sub(prefix: str, name: str) -> str:
+    """Join state_dict key parts; an empty prefix addresses a bare sub-module."""
+    return f"{prefix}.{name}" if prefix else name
+
+
+def _bn(p: Params, prefix: str, x: Tensor, training: bool) -> Tensor:
+    """nn.BatchNorm2d (eps 1e-5, momentum 0.1); updates running stats in place."""
+    rm, rv = p[prefix + ".running_mean"], p[prefix + ".running_var"]
+    out = F.batch_norm(x, rm, rv, p[prefix + ".weight"], p[prefix + ".bias"],
+                       training=training, momentum=0.1, eps=1e-5)
+    key = prefix + ".num_batches_tracked"
+    if training and key in p:
+        p[key] += 1
+    return out
+
+
+def _act(name: str, x: Tensor) -> Tensor:
+    """act_layer (torch_nn.py:9-25); only the parameter-free activations."""
+    name = name.lower()
+    if name == "relu":
+        return F.relu(x)
+    if name == "leakyrelu":
+        return F.leaky_relu(x, 0.2)
+    if name == "gelu":
+        return F.gelu(x)
+    if name == "hswish":
+        return F.hardswish(x)
+    raise NotImplementedError(name)
+
+
+def basic_conv(p: Params, prefix: str, x: Tensor, training: bool, act: str = "relu",
+               norm: Optional[str] = "batch") -> Tensor:
+    """BasicConv with a single layer (torch_nn.py:52-64): grouped(4) 1x1 conv, BN, act."""
+    x = F.conv2d(x, p[prefix + ".0.weight"], p.get(prefix + ".0.bias"), groups=4)
+    nxt = 1
+    if norm is not None and norm.lower() != "none":
+        x = _bn(p, f"{prefix}.{nxt}", x, training)
+        nxt += 1
+    if act is not None and act.lower() != "none":
+        x = _act(act, x)
+    return x
+
+
+def mr_conv(p: Params, prefix: str, x: Tensor, edge_index: Tensor, y: Optional[Tensor],
+            training: bool, act: str = "relu", norm: Optional[str] = "batch") -> Tensor:
+    """MRConv2d.forward (torch_vertex.py:19-34)."""
+    return basic_conv(p, prefix + ".nn", max_relative_features(x, edge_index, y), training, act, norm)
+
+
+def edge_conv(p: Params, prefix: str, x: Tensor, edge_index: Tensor, y: Optional[Tensor],
+              training: bool, act: str = "relu", norm: Optional[str] = "batch") -> Tensor:
+    """EdgeConv2d.forward (torch_vertex.py:45-52)."""
+    h = basic_conv(p, prefix + ".nn", edge_features(x, edge_index, y), training, act, norm)
+    return torch.max(h, dim=-1, keepdim=True).values
+
+
+def sage_conv(p: Params, prefix: str, x: Tensor, edge_index: Tensor, y: Optional[Tensor],
+              training: bool, act: str = "relu", norm: Optional[str] = "batch") -> Tensor:
+    """GraphSAGE.forward (torch_vertex.py:64-70)."""
+    x_j = gather_neighbors(x if y is None else y, edge_index[0])
+    x_j = torch.max(basic_conv(p, prefix + ".nn1", x_j, training, act, norm), dim=-1, keepdim=True).values
+    return basic_conv(p, prefix + ".nn2", torch.cat([x, x_j], dim=1), training, act, norm)
+
+
+def gin_conv(p: Params, prefix: str, x: Tensor, edge_index: Tensor, y: Optional[Tensor],
+             training: bool, act: str = "relu", norm: Optional[str] = "batch") -> Tensor:
+    """GINConv2d.forward (torch_vertex.py:83-89)."""
+    x_j = gather_neighbors(x if y is None else y, edge_index[0])
+    x_j = torch.sum(x_j, dim=-1, keepdim=True)
+    return basic_conv(p, prefix + ".nn", (1 + p[prefix + ".eps"]) * x + x_j, training, act, norm)
+
+
+_GCONVS = {"mr": mr_conv, "edge": edge_conv, "sage": sage_conv, "gin": gin_conv}
+
+
+def dy_graph_conv(p: Params, prefix: str, x: Tensor, training: bool, k: int, dilation: int = 1,
+                  conv: str = "mr", act: str = "relu", norm: Optional[str] = "batch", r: int = 1,
+                  relative_pos: Optional[Tensor] = None) -> Tensor:
+    """DyGraphConv2d.forward (torch_vertex.py:126-139)."""
+    B, C, H, W = x.shape
+    y = None
+    if r > 1:
+        y = F.avg_pool2d(x, r, r).reshape(B, C, -1, 1)
+    x = x.reshape(B, C, -1, 1)
+    edge_index = dilated_knn_graph(x, k, dilation, y, relative_pos)
+    out = _GCONVS[conv](p, _sub(prefix, "gconv"), x, edge_index, y, training, act, norm)
+    return out.reshape(B, -1, H, W)
+
+
+def grapher(p: Params, prefix: str, x: Tensor, training: bool, k: int, dilation: int = 1,
+            conv: str = "mr", act: str = "relu", norm: Optional[str] = "batch", r: int = 1) -> Tensor:
+    """Grapher.forward (torch_vertex.py:183-194); relative_pos is always None (:190)."""
+    h = F.conv2d(x, p[_sub(prefix, "fc1.0.weight")], p[_sub(prefix, "fc1.0.bias")])
+    h = _bn(p, _sub(prefix, "fc1.1"), h, training)
+    h = dy_graph_conv(p, _sub(prefix, "graph_conv"), h, training, k, dilation, conv, act, norm, r)
+    h = F.conv2d(h, p[_sub(prefix, "fc2.0.weight")], p[_sub(prefix, "fc2.0.bias")])
+    h = _bn(p, _sub(prefix, "fc2.1"), h, training)
+    return h + x  # drop_path is Identity for every block (graph_encoder.py:135,148)
+
+
+def ffn(p: Params, prefix: str, x: Tensor, training: bool, act: str = "relu") -> Tensor:
+    """FFN.forward (graph_encoder.py:60-67)."""
+    h = _bn(p, prefix + ".fc1.1", F.conv2d(x, p[prefix + ".fc1.0.weight"]), training)
+    h = _act(act, h)
+    h = _bn(p, prefix + ".fc2.1", F.conv2d(h, p[prefix + ".fc2.0.weight"]), training)
+    return h + x
+
+
+def graph_encoder(p: Params, x: Tensor, training: bool, k: int = 3, blocks=(2, 2, 6, 2),
+                  prefix: str = "") -> Tensor:
+    """GraphEncoder.forward (graph_encoder.py:167-191) for the shipped layout.
+
+    x: (B, C_in, N) -> (B, 1024).  Backbone order follows graph_encoder.py:137-150:
+    a Downsample before every stage but the first, then ``blocks[i]`` Seq(Grapher, FFN).
+    The block counter in the reference never advances (:138,147), so every Grapher
+    has the same k and dilation 1.
+    """
+    h = x.unsqueeze(-1)
+    h = F.conv2d(h, p[prefix + "stem.0.weight"])
+    h = F.leaky_relu(_bn(p, prefix + "stem.1", h, training), 0.2)
+    pos = 0
+    for stage, reps in enumerate(blocks):
+        if stage > 0:
+            pre = f"{prefix}backbone.{pos}.conv"
+            h = F.conv2d(h, p[pre + ".0.weight"], p[pre + ".0.bias"], stride=2, padding=1)
+            h = _bn(p, pre + ".1", h, training)
+            pos += 1
+        for _ in range(reps):
+            h = grapher(p, f"{prefix}backbone.{pos}.0", h, training, k)
+            h = ffn(p, f"{prefix}backbone.{pos}.1", h, training)
+            pos += 1
+    h = F.conv2d(h, p[prefix + "proj.weight"], p[prefix + "proj.bias"])
+    return torch.mean(h, dim=2).squeeze(-1).squeeze(-1)
+
+
+# --------------------------------------------------------------------------
+# callers either side of the path (needed to state the benchmark workloads)
+# --------------------------------------------------------------------------
+
+
+def peak_extractor(p: Params, spec: Tensor, stride: int = 2, prefix: str = "peak_extractor.") -> Tensor:
+    """GPUPeakExtractorv2.forward (peak_extractor.py:56-82): (B, F, T) -> (B, n_filters, F*T/stride)."""
+    B, n_f, n_t = spec.shape
+    lo = torch.amin(spec, dim=(1, 2), keepdim=True)
+    hi = torch.amax(spec, dim=(1, 2), keepdim=True)
+    s = (spec - lo) / (hi - lo)
+    t_ramp = torch.linspace(0, 1, steps=n_t, device=spec.device).view(1, 1, n_t).expand(B, n_f, n_t)
+    f_ramp = torch.linspace(0, 1, steps=n_f, device=spec.device).view(1, n_f, 1).expand(B, n_f, n_t)
+    stack = torch.stack((t_ramp, f_ramp, s), dim=1)
+    w = p[prefix + "convs.0.weight"]
+    feat = F.relu(F.conv2d(stack, w, p[prefix + "convs.0.bias"], stride=(stride, 1),
+                           padding=(w.shape[2] // 2, w.shape[3] // 2)))
+    return feat.reshape(B, feat.shape[1], -1)
+
+
+def simclr_forward(p: Params, spec_i: Tensor, spec_j: Tensor, training: bool, k: int = 3):
+    """SimCLR.forward for arch 'grafp' (simclr/simclr.py:29-47): the two views run one after the other."""
+    outs = []
+    for spec in (spec_i, spec_j):
+        h = graph_encoder(p, peak_extractor(p, spec), training, k, prefix="encoder.")
+        z = F.linear(h, p["projector.0.weight"], p["projector.0.bias"])
+        z = F.linear(F.elu(z), p["projector.2.weight"], p["projector.2.bias"])
+        outs.append((h, F.normalize(z, p=2)))
+    return outs[0][0], outs[1][0], outs[0][1], outs[1][1]
+
+
+def ntxent_loss(z_i: Tensor, z_j: Tensor, tau: float) -> Tensor:
+    """ntxent_loss (simclr/ntxent.py:17-29).
+
+    Rows are interleaved (i0, j0, i1, j1, ...) (:18); for every row the loss is
+    -log_softmax over all other rows evaluated at its partner (:22-25), averaged
+    over the 2B rows (:28).  Restated without the per-row Python loop.
+    """
+    n2 = 2 * z_i.shape[0]
+    z = torch.stack((z_i, z_j), dim=1).view(n2, z_i.shape[1])
+    a = torch.matmul(z, z.T) / tau
+    a = a.masked_fill(torch.eye(n2, dtype=torch.bool, device=a.device), float("-inf"))
+    partner = torch.arange(n2, device=a.device) ^ 1
+    logp = F.log_softmax(a, dim=1)
+    return -logp[torch.arange(n2, device=a.device), partner].sum() / n2
+
+
+def top1_retrieval(db: Tensor, queries: Tensor) -> Tensor:
+    """Exact L2 top-1 (what faiss IndexFlatL2 returns, eval.py:54-60) on row vectors."""
+    d = (queries * queries).sum(1, keepdim=True) - 2 * queries @ db.T + (db * db).sum(1)[None]
+    return torch.argmin(d, dim=1)
+
+
+# --------------------------------------------------------------------------
+# helpers for tests
+# --------------------------------------------------------------------------
+
+
+def knn_mismatch_report(x: Tensor, ours: Tensor, K: int, y: Optional[Tensor] = None,
+                        relative_pos: Optional[Tensor] = None, ordered: bool = True,
+                        dilation: int = 1) -> dict:
+    """Compare neighbour ids against the oracle and classify every difference.
+
+    ``x`` / ``y`` are the *un-normalised* (B, C, N, 1) inputs; ``ours`` is (B, N, k)
+    holding ranks 0, d, 2d, ... of the top-K list.  A differing entry is a
+    "tie" when the oracle's own fp32 distance of our neighbour and of the oracle's
+    neighbour at that rank differ by no more than ``tie_tol`` (documented
+    equal-distance ties, SURVEY.md section 7 hard part 2); anything else is a
+    "hard" mismatch.  Distances are re-evaluated in fp64 for the hard/tie split so the
+    verdict does not depend on either side's rounding.
+    """
+    xn = l2_normalize_channels(x)
+    yn = xn if y is None else l2_normalize_channels(y)
+    xr = xn.transpose(2, 1).squeeze(-1)
+    yr = yn.transpose(2, 1).squeeze(-1)
+    dist = sq_distance_matrix(xr, yr if y is not None else None)
+    d64 = sq_distance_matrix(xr.double(), yr.double())
+    if relative_pos is not None:
+        dist = dist + relative_pos
+        d64 = d64 + relative_pos.double()
+    ref = torch.topk(-dist, k=K).indices[..., ::dilation]
+    ours = ours.to(ref.device).long()
+    if not ordered:
+        ref = ref.sort(dim=-1).values
+        ours = ours.sort(dim=-1).values
+    diff = ref != ours
+    n_diff = int(diff.sum())
+    gap = (torch.gather(d64, 2, ours) - torch.gather(d64, 2, ref)).abs()
+    # fp32 evaluation noise of one distance: ~ sqrt(C) * 2^-24 * |terms| with terms <= 4
+    tie_tol = 4.0 * math.sqrt(x.shape[1]) * 2.0 ** -23
+    hard = diff & (gap > tie_tol)
+    return {
+        "entries": diff.numel(),
+        "mismatch": n_diff,
+        "hard": int(hard.sum()),
+        "max_gap": float(gap[diff].max()) if n_diff else 0.0,
+        "tie_tol": tie_tol,
+        "rows_differing": int(diff.any(-1).sum()),
+    }
