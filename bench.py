@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark: segments/s of a GraphEncoder forward+backward NT-Xent training step.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+
+Workload (BASELINE.json configs[1]): SimCLR(GraphEncoder(k=3)) on synthetic log-mel segments,
+batch 512 pairs per GPU (= 1024 segments per step), fp32, Adam.  One step = zero_grad, both
+views forward, NT-Xent, backward, optimizer step.  Prints ONE JSON line (see DESIGN.md, section
+"Measurement", for every key).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "segments/sec GraphEncoder fwd+bwd"
+UNIT = "segments/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=512, help="pairs per GPU per step (2 segments each)")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="pairs per step of the CPU reference sample")
+    ap.add_argument("--knn-algo", choices=["auto", "simt", "tc"], default="auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle's restatement of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_reference_steps(pairs, steps, warmup, seed=1234):
+    """Time `steps` SimCLR training steps of the reference algorithm on the CPU (all host threads)."""
+    from grafp_b200 import synth
+    from grafp_b200.encoder.graph_encoder import GraphEncoder
+    from grafp_b200.simclr.simclr import SimCLR
+    from oracle import grafp_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = dict(synth.DEFAULT_CFG)
+    torch.manual_seed(0)
+    shapes_model = SimCLR(cfg, GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3))  # parameter container only
+    params = {k: v.detach().clone() for k, v in shapes_model.state_dict().items() if not k.endswith("relative_pos")}
+    trainable = [n for n, p in shapes_model.named_parameters() if p.requires_grad]
+    for n in trainable:
+        params[n].requires_grad_(True)
+    opt = torch.optim.Adam([params[n] for n in trainable], lr=cfg["lr"])
+    s_i, s_j = synth.synth_spec(pairs, seed)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        _, _, z_i, z_j = O.simclr_forward(params, s_i, s_j, True, k=3)
+        loss = O.ntxent_loss(z_i, z_j, cfg["tau"])
+        loss.backward()
+        opt.step()
+        loss.item()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": 2 * pairs * steps / total, "seconds": total, "cores": cores, "pairs": pairs, "steps": steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_steps(args.cpu_batch, args.steps, args.warmup)
+    sample = (f"{args.steps} steps x {args.cpu_batch} pairs ({2 * args.cpu_batch} segments/step) of the same SimCLR step, "
+              f"oracle port of the reference on {r['cores']} host threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "configs[1]: GraphEncoder fwd+bwd NT-Xent training step, batch 512 pairs/GPU, fp32",
+            "pairs_per_gpu": args.batch, "segments_per_step": 2 * args.batch * world, "k": 3, "nodes": 1024,
+            "encoder": "GraphEncoder size t (12 Grapher+FFN blocks)", "optimizer": "Adam",
+            "parallelism": f"dp{world}", "conv_math": "PyTorch default (cuDNN conv TF32 allowed, matmul fp32)",
+            "l2": "no explicit flush: one step touches ~70 GB of activations, far above the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def algorithmic_work(name, m):
+    """Algorithmic bytes / flops of one C-ABI call, fp32 (e = 4) or bf16 (e = 2)."""
+    e = 4 if m.get("dtype", 0) == 0 else 2
+    B, N, C = m["B"], m["N"], m["C"]
+    if name == "knn_fwd":
+        M, K = m["M"], m["K"]
+        return {"flops": 2.0 * B * N * M * C, "bytes": B * (N * C * e + (M * C * e if M != N else 0) + N * K * 12)}
+    k = m["k"]
+    idx_b = 8 if m.get("i64") else 4
+    if name == "mr_aggregate_fwd":
+        return {"bytes": B * (N * C * e + N * k * idx_b + 2 * N * C * e + (N * C if m.get("argmax") else 0))}
+    if name == "mr_aggregate_bwd":
+        return {"bytes": B * (2 * N * C * e + N * C + N * k * idx_b + N * C * e)}
+    return {"bytes": 0}
+
+
+def run_ours(args):
+    from grafp_b200 import _native, ops, synth
+    from grafp_b200.encoder.graph_encoder import GraphEncoder
+    from grafp_b200.simclr.simclr import SimCLR
+    from grafp_b200.simclr.ntxent import ntxent_loss
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    _native.load()
+
+    cfg = dict(synth.DEFAULT_CFG)
+    cfg["bsz_train"] = args.batch
+    torch.manual_seed(0)
+    model = SimCLR(cfg, GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3)).to(dev).train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=True,
+                                                        gradient_as_bucket_view=True)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"])
+    algo = {"auto": _native.KNN_AUTO, "simt": _native.KNN_SIMT, "tc": _native.KNN_TC}[args.knn_algo]
+    if algo != _native.KNN_AUTO:
+        _orig = ops.knn_graph
+        ops.knn_graph = lambda *a, **kw: _orig(*a, **{**kw, "algo": algo})
+
+    s_i, s_j = synth.synth_spec(args.batch, 1234 + rank)
+    host_i, host_j = s_i.pin_memory(), s_j.pin_memory()
+    dev_i, dev_j = host_i.to(dev), host_j.to(dev)
+    h2d_bytes = host_i.numel() * 4 + host_j.numel() * 4
+
+    def loss_fn(z_i, z_j):
+        if world == 1:
+            return ntxent_loss(z_i, z_j, cfg)
+        # global-batch negatives like the reference's DataParallel gather (train.py:69-71): all_gather the
+        # embeddings, keep the local rows differentiable; the sum over ranks of the local losses' gradients
+        # equals the gradient of the global loss, DDP's mean-reduction is undone by scaling with `world`.
+        import torch.distributed.nn.functional as dfn
+        zi_all = torch.cat(dfn.all_gather(z_i), 0)
+        zj_all = torch.cat(dfn.all_gather(z_j), 0)
+        return ntxent_loss(zi_all, zj_all, cfg)
+
+    def step(x_i, x_j):
+        opt.zero_grad(set_to_none=True)
+        _, _, z_i, z_j = net(x_i, x_j)
+        loss = loss_fn(z_i, z_j)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(dev_i, dev_j)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM (the `value`) ----
+    timer = ops.KernelTimer(timing=True)
+    ops.set_timer(timer)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(dev_i, dev_j)
+    e1.record()
+    barrier()
+    ms_resident = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    ops.set_timer(None)
+    ksum = timer.summary()
+
+    # ---- timed region 2: end to end through the public API with host buffers (the `e2e`) ----
+    losses = []
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        x_i = host_i.to(dev, non_blocking=True)
+        x_j = host_j.to(dev, non_blocking=True)
+        losses.append(float(step(x_i, x_j)))  # .item(): device -> host read of the step's result
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    t = torch.tensor([ms_resident, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_resident, ms_e2e = float(t[0]), float(t[1])
+    segs = 2 * args.batch * world * args.steps
+    value = segs / (ms_resident / 1e3)
+    e2e_value = segs / (ms_e2e / 1e3)
+
+    if rank == 0:
+        pk = peaks()
+        kernels = {}
+        for name, rec in ksum.items():
+            work = {"bytes": 0.0, "flops": 0.0}
+            for key, sh in rec["by_shape"].items():
+                w = algorithmic_work(name, dict(key))
+                work["bytes"] += w.get("bytes", 0.0) * sh["calls"]
+                work["flops"] += w.get("flops", 0.0) * sh["calls"]
+            sec = rec["ms_total"] / 1e3
+            kernels[name] = {"calls": rec["calls"], "ms_total": rec["ms_total"],
+                             "share_of_step": rec["ms_total"] / ms_resident,
+                             "gbs": work["bytes"] / sec / 1e9 if sec > 0 else None,
+                             "tflops": work["flops"] / sec / 1e12 if sec > 0 and work["flops"] else None,
+                             "_bytes": work["bytes"], "_flops": work["flops"]}
+        roofline = None
+        if kernels:
+            top = max(kernels, key=lambda n: kernels[n]["ms_total"])
+            kt = kernels[top]
+            if top == "knn_fwd":
+                tc = ops.knn_last_algo() == "tcgen05"
+                peak = pk["bf16_tflops_sustained"] / 2.0  # dense TF32 is half the bf16 rate
+                roofline = {"kernel": f"knn_fwd ({ops.knn_last_algo()}; normalise + Gram/top-k launches)",
+                            "bound": "tensor", "achieved": kt["tflops"], "peak": peak, "unit": "TFLOP/s",
+                            "frac": kt["tflops"] / peak, "traffic": None,
+                            "peak_source": f"{pk['source']} bf16 sustained / 2 (TF32)",
+                            "note": "algorithmic 2*N*M*C flops; the 3xTF32 split issues 3x that" if tc else
+                                    "CUDA-core fp32 path, reported against the tensor peak"}
+            else:
+                peak = pk["hbm_gbs"]
+                roofline = {"kernel": top, "bound": "hbm", "achieved": kt["gbs"], "peak": peak, "unit": "GB/s",
+                            "frac": kt["gbs"] / peak, "traffic": None, "peak_source": pk["source"]}
+        for kt in kernels.values():
+            kt.pop("_bytes"); kt.pop("_flops")
+
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_steps(args.cpu_batch, 3, 1)
+            cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                            "sample": f"3 steps x {args.cpu_batch} pairs of the same SimCLR training step (oracle port "
+                                      f"of the reference algorithm), {r['seconds']:.1f} s on {r['cores']} host threads"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": timer.launches, "knn_algo": ops.knn_last_algo(),
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "loss_last": losses[-1] if losses else None, "pairs_per_s": value / 2,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

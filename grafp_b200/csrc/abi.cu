@@ -1,0 +1,257 @@
+// extern "C" entry points of libgrafp_b200.so: argument validation + dispatch.
+#include <mutex>
+#include <string>
+
+#include "knn.cuh"
+
+namespace grafp {
+
+namespace {
+thread_local std::string g_error;
+thread_local const char* g_knn_algo = "none";
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+}
+void clear_error() { g_error.clear(); }
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return GRAFP_OK;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// Every entry point refuses to run anywhere but on an sm_100 device with device pointers.
+static int require_device(const char* fn) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("%s: no CUDA device available (%s); this library has no CPU path", fn, cudaGetErrorString(e));
+    cudaGetLastError();
+    return GRAFP_ENODEVICE;
+  }
+  static int major[64] = {0};
+  if (dev >= 0 && dev < 64 && major[dev] == 0) {
+    int m = 0;
+    cudaDeviceGetAttribute(&m, cudaDevAttrComputeCapabilityMajor, dev);
+    major[dev] = m;
+  }
+  if (dev >= 0 && dev < 64 && major[dev] != 10) {
+    set_error("%s: device %d has compute capability %d.x; libgrafp_b200 is built for sm_100a only", fn, dev, major[dev]);
+    return GRAFP_ENODEVICE;
+  }
+  return GRAFP_OK;
+}
+
+static int require_device_ptr(const char* fn, const char* name, const void* p) {
+  cudaPointerAttributes a;
+  const cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess || (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged)) {
+    cudaGetLastError();
+    set_error("%s: %s is not a device pointer (there is no CPU path)", fn, name);
+    return GRAFP_EINVAL;
+  }
+  return GRAFP_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace grafp
+
+using namespace grafp;
+
+#define COMMON_SHAPE_CHECKS(fn)                                                                                 \
+  clear_error();                                                                                                \
+  GRAFP_REQUIRE(B > 0 && N > 0 && M > 0 && C > 0 && k > 0, GRAFP_EINVAL, fn ": B, N, M, C, k must be positive"); \
+  GRAFP_REQUIRE(dtype == GRAFP_F32 || dtype == GRAFP_BF16, GRAFP_EUNSUPPORTED, fn ": dtype %d not supported", dtype); \
+  GRAFP_REQUIRE(k <= 255, GRAFP_EUNSUPPORTED, fn ": k = %d exceeds the uint8 argmax range", k);                 \
+  { int rc_ = require_device(fn); if (rc_ != GRAFP_OK) return rc_; }
+
+extern "C" {
+
+int grafp_abi_version(void) { return GRAFP_ABI_VERSION; }
+const char* grafp_last_error(void) { return g_error.c_str(); }
+const char* grafp_knn_last_algo(void) { return g_knn_algo; }
+
+size_t grafp_knn_workspace_bytes(int B, int N, int M, int C, int K, int dtype) {
+  (void)K; (void)dtype;
+  if (B <= 0 || N <= 0 || M <= 0 || C <= 0) return 0;
+  const size_t qx = align_up((size_t)B * N * C * sizeof(float), 1024);
+  const size_t qy = align_up((size_t)B * M * C * sizeof(float), 1024);
+  const size_t sx = align_up((size_t)B * N * sizeof(float), 1024);
+  const size_t sy = align_up((size_t)B * M * sizeof(float), 1024);
+  return 2 * (qx + qy) + sx + sy + 1024;  // hi+lo (or x_hat) for queries and keys, squared norms, base alignment
+}
+
+int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn_idx, int32_t* nn_idx32, int B, int N,
+                  int M, int C, int k, int dilation, int emit_all, int normalize, int dtype, int algo, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  COMMON_SHAPE_CHECKS("grafp_knn_fwd");
+  GRAFP_REQUIRE(x && nn_idx && workspace, GRAFP_EINVAL, "grafp_knn_fwd: x, nn_idx and workspace must be non-null");
+  GRAFP_REQUIRE(dilation > 0, GRAFP_EINVAL, "grafp_knn_fwd: dilation must be positive");
+  GRAFP_REQUIRE(y != nullptr || M == N, GRAFP_EINVAL, "grafp_knn_fwd: M (%d) must equal N (%d) when y is null", M, N);
+  GRAFP_REQUIRE(B <= 65535, GRAFP_EUNSUPPORTED, "grafp_knn_fwd: B = %d exceeds 65535", B);
+  const long long K = (long long)k * dilation;
+  GRAFP_REQUIRE(K <= M, GRAFP_EINVAL, "grafp_knn_fwd: k*dilation = %lld exceeds the number of key nodes %d", K, M);
+  GRAFP_REQUIRE(K <= GRAFP_KNN_MAX_K, GRAFP_EUNSUPPORTED, "grafp_knn_fwd: k*dilation = %lld exceeds %d", K, GRAFP_KNN_MAX_K);
+  GRAFP_REQUIRE(algo >= GRAFP_KNN_AUTO && algo <= GRAFP_KNN_TC, GRAFP_EINVAL, "grafp_knn_fwd: unknown algo %d", algo);
+  GRAFP_REQUIRE(workspace_bytes >= grafp_knn_workspace_bytes(B, N, M, C, (int)K, dtype), GRAFP_EWORKSPACE,
+                "grafp_knn_fwd: workspace of %zu bytes is smaller than grafp_knn_workspace_bytes()", workspace_bytes);
+  { int rc = require_device_ptr("grafp_knn_fwd", "x", x); if (rc) return rc; }
+  { int rc = require_device_ptr("grafp_knn_fwd", "nn_idx", nn_idx); if (rc) return rc; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+  const bool tc_ok = knn_tc_supported(N, M, C, (int)K, dtype);
+  if (algo == GRAFP_KNN_TC && !tc_ok) {
+    set_error("grafp_knn_fwd: the tcgen05 path does not support N=%d M=%d C=%d K=%lld dtype=%d", N, M, C, K, dtype);
+    return GRAFP_EUNSUPPORTED;
+  }
+  const bool use_tc = (algo == GRAFP_KNN_TC) || (algo == GRAFP_KNN_AUTO && tc_ok);
+
+  // carve the workspace
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
+  const size_t qx = align_up((size_t)B * N * C * sizeof(float), 1024);
+  const size_t qy = align_up((size_t)B * M * C * sizeof(float), 1024);
+  const size_t sx = align_up((size_t)B * N * sizeof(float), 1024);
+  float* x_hi = reinterpret_cast<float*>(base);
+  float* x_lo = reinterpret_cast<float*>(base + qx);
+  float* y_hi = reinterpret_cast<float*>(base + 2 * qx);
+  float* y_lo = reinterpret_cast<float*>(base + 2 * qx + qy);
+  float* x_sq = reinterpret_cast<float*>(base + 2 * qx + 2 * qy);
+  float* y_sq = reinterpret_cast<float*>(base + 2 * qx + 2 * qy + sx);
+
+  const int mode = use_tc ? (dtype == GRAFP_F32 ? 1 : 2) : 0;
+  int rc;
+  if (dtype == GRAFP_F32) {
+    rc = launch_knn_normalize<float>(x, x_hi, x_lo, x_sq, (long long)B * N, C, mode, normalize != 0, s);
+    if (rc == GRAFP_OK && y) rc = launch_knn_normalize<float>(y, y_hi, y_lo, y_sq, (long long)B * M, C, mode, normalize != 0, s);
+  } else {
+    rc = launch_knn_normalize<__nv_bfloat16>(x, x_hi, x_lo, x_sq, (long long)B * N, C, mode, normalize != 0, s);
+    if (rc == GRAFP_OK && y) rc = launch_knn_normalize<__nv_bfloat16>(y, y_hi, y_lo, y_sq, (long long)B * M, C, mode, normalize != 0, s);
+  }
+  if (rc != GRAFP_OK) return rc;
+  if (!y) { y_hi = x_hi; y_lo = x_lo; y_sq = x_sq; }
+
+  const int k_out = emit_all ? (int)K : k;
+  const int stride = emit_all ? 1 : dilation;
+  if (use_tc) {
+    g_knn_algo = "tcgen05";
+    return launch_knn_tc(x_hi, x_lo, x_sq, y_hi, y_lo, y_sq, relpos, reinterpret_cast<long long*>(nn_idx), nn_idx32, B, N,
+                         M, C, (int)K, k_out, stride, dtype, s);
+  }
+  g_knn_algo = "simt";
+  return launch_knn_simt(x_hi, x_sq, y_hi, y_sq, relpos, reinterpret_cast<long long*>(nn_idx), nn_idx32, B, N, M, C,
+                         (int)K, k_out, stride, s);
+}
+
+#define DISPATCH_DTYPE(call_f32, call_bf16) (dtype == GRAFP_F32 ? (call_f32) : (call_bf16))
+
+int grafp_mr_aggregate_fwd(const void* x, const void* y, const void* nbr_idx, const void* ctr_idx, int idx_is_i64,
+                           void* out, uint8_t* argmax, int B, int N, int M, int C, int k, int dtype, void* stream) {
+  COMMON_SHAPE_CHECKS("grafp_mr_aggregate_fwd");
+  GRAFP_REQUIRE(x && nbr_idx && out, GRAFP_EINVAL, "grafp_mr_aggregate_fwd: x, nbr_idx and out must be non-null");
+  GRAFP_REQUIRE(y != nullptr || M == N, GRAFP_EINVAL, "grafp_mr_aggregate_fwd: M must equal N when y is null");
+  { int rc = require_device_ptr("grafp_mr_aggregate_fwd", "x", x); if (rc) return rc; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return DISPATCH_DTYPE(launch_mr_aggregate_fwd<float>(x, y, nbr_idx, ctr_idx, idx_is_i64, out, argmax, B, N, M, C, k, s),
+                        launch_mr_aggregate_fwd<__nv_bfloat16>(x, y, nbr_idx, ctr_idx, idx_is_i64, out, argmax, B, N, M, C, k, s));
+}
+
+int grafp_mr_aggregate_bwd(const void* grad_out, const uint8_t* argmax, const void* nbr_idx, const void* ctr_idx,
+                           int idx_is_i64, void* grad_x, void* grad_y, int B, int N, int M, int C, int k, int dtype,
+                           void* stream) {
+  COMMON_SHAPE_CHECKS("grafp_mr_aggregate_bwd");
+  GRAFP_REQUIRE(grad_out && argmax && nbr_idx && grad_x, GRAFP_EINVAL,
+                "grafp_mr_aggregate_bwd: grad_out, argmax, nbr_idx and grad_x must be non-null");
+  GRAFP_REQUIRE(grad_y != nullptr || M == N, GRAFP_EINVAL, "grafp_mr_aggregate_bwd: M must equal N when grad_y is null");
+  { int rc = require_device_ptr("grafp_mr_aggregate_bwd", "grad_out", grad_out); if (rc) return rc; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return DISPATCH_DTYPE(launch_mr_aggregate_bwd<float>(grad_out, argmax, nbr_idx, ctr_idx, idx_is_i64, grad_x, grad_y, B, N, M, C, k, s),
+                        launch_mr_aggregate_bwd<__nv_bfloat16>(grad_out, argmax, nbr_idx, ctr_idx, idx_is_i64, grad_x, grad_y, B, N, M, C, k, s));
+}
+
+int grafp_gather_fwd(const void* src, const void* idx, int idx_is_i64, void* out, int B, int N, int M, int C, int k,
+                     int dtype, void* stream) {
+  COMMON_SHAPE_CHECKS("grafp_gather_fwd");
+  GRAFP_REQUIRE(src && idx && out, GRAFP_EINVAL, "grafp_gather_fwd: src, idx and out must be non-null");
+  { int rc = require_device_ptr("grafp_gather_fwd", "src", src); if (rc) return rc; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return DISPATCH_DTYPE(launch_gather_fwd<float>(src, idx, idx_is_i64, out, B, N, M, C, k, s),
+                        launch_gather_fwd<__nv_bfloat16>(src, idx, idx_is_i64, out, B, N, M, C, k, s));
+}
+
+int grafp_gather_bwd(const void* grad_out, const void* idx, int idx_is_i64, void* grad_src, int B, int N, int M, int C,
+                     int k, int dtype, void* stream) {
+  COMMON_SHAPE_CHECKS("grafp_gather_bwd");
+  GRAFP_REQUIRE(grad_out && idx && grad_src, GRAFP_EINVAL, "grafp_gather_bwd: grad_out, idx and grad_src must be non-null");
+  { int rc = require_device_ptr("grafp_gather_bwd", "grad_out", grad_out); if (rc) return rc; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return DISPATCH_DTYPE(launch_gather_bwd<float>(grad_out, idx, idx_is_i64, grad_src, B, N, M, C, k, s),
+                        launch_gather_bwd<__nv_bfloat16>(grad_out, idx, idx_is_i64, grad_src, B, N, M, C, k, s));
+}
+
+int grafp_edge_gather_fwd(const void* x, const void* y, const void* nbr_idx, const void* ctr_idx, int idx_is_i64,
+                          void* out, int B, int N, int M, int C, int k, int dtype, void* stream) {
+  COMMON_SHAPE_CHECKS("grafp_edge_gather_fwd");
+  GRAFP_REQUIRE(x && nbr_idx && out, GRAFP_EINVAL, "grafp_edge_gather_fwd: x, nbr_idx and out must be non-null");
+  GRAFP_REQUIRE(y != nullptr || M == N, GRAFP_EINVAL, "grafp_edge_gather_fwd: M must equal N when y is null");
+  { int rc = require_device_ptr("grafp_edge_gather_fwd", "x", x); if (rc) return rc; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return DISPATCH_DTYPE(launch_edge_gather_fwd<float>(x, y, nbr_idx, ctr_idx, idx_is_i64, out, B, N, M, C, k, s),
+                        launch_edge_gather_fwd<__nv_bfloat16>(x, y, nbr_idx, ctr_idx, idx_is_i64, out, B, N, M, C, k, s));
+}
+
+int grafp_edge_gather_bwd(const void* grad_out, const void* nbr_idx, const void* ctr_idx, int idx_is_i64, void* grad_x,
+                          void* grad_y, int B, int N, int M, int C, int k, int dtype, void* stream) {
+  COMMON_SHAPE_CHECKS("grafp_edge_gather_bwd");
+  GRAFP_REQUIRE(grad_out && nbr_idx && grad_x, GRAFP_EINVAL, "grafp_edge_gather_bwd: grad_out, nbr_idx and grad_x must be non-null");
+  GRAFP_REQUIRE(grad_y != nullptr || M == N, GRAFP_EINVAL, "grafp_edge_gather_bwd: M must equal N when grad_y is null");
+  { int rc = require_device_ptr("grafp_edge_gather_bwd", "grad_out", grad_out); if (rc) return rc; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return DISPATCH_DTYPE(launch_edge_gather_bwd<float>(grad_out, nbr_idx, ctr_idx, idx_is_i64, grad_x, grad_y, B, N, M, C, k, s),
+                        launch_edge_gather_bwd<__nv_bfloat16>(grad_out, nbr_idx, ctr_idx, idx_is_i64, grad_x, grad_y, B, N, M, C, k, s));
+}
+
+int grafp_max_over_k_fwd(const void* h, void* out, uint8_t* argmax, int B, int N, int C, int k, int dtype, void* stream) {
+  const int M = 1;
+  COMMON_SHAPE_CHECKS("grafp_max_over_k_fwd");
+  GRAFP_REQUIRE(h && out, GRAFP_EINVAL, "grafp_max_over_k_fwd: h and out must be non-null");
+  { int rc = require_device_ptr("grafp_max_over_k_fwd", "h", h); if (rc) return rc; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return DISPATCH_DTYPE(launch_max_over_k_fwd<float>(h, out, argmax, B, N, C, k, s),
+                        launch_max_over_k_fwd<__nv_bfloat16>(h, out, argmax, B, N, C, k, s));
+}
+
+int grafp_max_over_k_bwd(const void* grad_out, const uint8_t* argmax, void* grad_h, int B, int N, int C, int k, int dtype,
+                         void* stream) {
+  const int M = 1;
+  COMMON_SHAPE_CHECKS("grafp_max_over_k_bwd");
+  GRAFP_REQUIRE(grad_out && argmax && grad_h, GRAFP_EINVAL, "grafp_max_over_k_bwd: grad_out, argmax and grad_h must be non-null");
+  { int rc = require_device_ptr("grafp_max_over_k_bwd", "grad_out", grad_out); if (rc) return rc; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return DISPATCH_DTYPE(launch_max_over_k_bwd<float>(grad_out, argmax, grad_h, B, N, C, k, s),
+                        launch_max_over_k_bwd<__nv_bfloat16>(grad_out, argmax, grad_h, B, N, C, k, s));
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+// Shared device/host helpers for libgrafp_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <type_traits>
+
+#include "../../include/grafp_b200.h"
+
+namespace grafp {
+
+// ---- host-side error plumbing (thread local; no exceptions cross the ABI) ----
+void set_error(const char* fmt, ...);
+void clear_error();
+int check_launch(const char* what);  // cudaGetLastError -> return code + message
+int num_sms();
+
+#define GRAFP_REQUIRE(cond, code, ...)  \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::grafp::set_error(__VA_ARGS__);  \
+      return (code);                    \
+    }                                   \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- element access: VEC consecutive channels as fp32 registers ----
+template <typename T, int VEC>
+struct Pack;
+
+template <>
+struct Pack<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  static __device__ __forceinline__ void red_add(float* p, const float (&v)[4]) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3])
+                 : "memory");
+  }
+};
+
+template <>
+struct Pack<float, 1> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { *p = v[0]; }
+  static __device__ __forceinline__ void red_add(float* p, const float (&v)[1]) { atomicAdd(p, v[0]); }
+};
+
+template <>
+struct Pack<__nv_bfloat16, 4> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a);
+    t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+  static __device__ __forceinline__ void red_add(__nv_bfloat16* p, const float (&v)[4]) {
+    atomicAdd(reinterpret_cast<__nv_bfloat162*>(p), __floats2bfloat162_rn(v[0], v[1]));
+    atomicAdd(reinterpret_cast<__nv_bfloat162*>(p) + 1, __floats2bfloat162_rn(v[2], v[3]));
+  }
+};
+
+template <>
+struct Pack<__nv_bfloat16, 1> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[1]) { v[0] = __bfloat162float(*p); }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[1]) { *p = __float2bfloat16_rn(v[0]); }
+  static __device__ __forceinline__ void red_add(__nv_bfloat16* p, const float (&v)[1]) {
+    atomicAdd(p, __float2bfloat16_rn(v[0]));
+  }
+};
+
+template <bool I64>
+__device__ __forceinline__ int load_index(const void* idx, long long pos) {
+  if constexpr (I64) {
+    return static_cast<int>(__ldg(reinterpret_cast<const long long*>(idx) + pos));
+  } else {
+    return __ldg(reinterpret_cast<const int*>(idx) + pos);
+  }
+}
+
+// Launch geometry for grid-stride element-wise kernels: a whole number of waves of
+// `ctas_per_sm` resident CTAs on every SM.
+inline int grid_for(long long items, int threads, int ctas_per_sm) {
+  long long need = (items + threads - 1) / threads;
+  long long cap = static_cast<long long>(num_sms()) * ctas_per_sm;
+  if (need < 1) need = 1;
+  return static_cast<int>(need < cap ? need : cap);
+}
+
+// ---- launchers implemented in aggregate.cu ----
+template <typename T>
+int launch_mr_aggregate_fwd(const void* x, const void* y, const void* nbr, const void* ctr, int idx_is_i64, void* out,
+                            uint8_t* argmax, int B, int N, int M, int C, int k, cudaStream_t s);
+template <typename T>
+int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nbr, const void* ctr, int idx_is_i64,
+                            void* grad_x, void* grad_y, int B, int N, int M, int C, int k, cudaStream_t s);
+template <typename T>
+int launch_gather_fwd(const void* src, const void* idx, int idx_is_i64, void* out, int B, int N, int M, int C, int k,
+                      cudaStream_t s);
+template <typename T>
+int launch_gather_bwd(const void* g, const void* idx, int idx_is_i64, void* grad_src, int B, int N, int M, int C, int k,
+                      cudaStream_t s);
+template <typename T>
+int launch_edge_gather_fwd(const void* x, const void* y, const void* nbr, const void* ctr, int idx_is_i64, void* out,
+                           int B, int N, int M, int C, int k, cudaStream_t s);
+template <typename T>
+int launch_edge_gather_bwd(const void* g, const void* nbr, const void* ctr, int idx_is_i64, void* grad_x, void* grad_y,
+                           int B, int N, int M, int C, int k, cudaStream_t s);
+template <typename T>
+int launch_max_over_k_fwd(const void* h, void* out, uint8_t* argmax, int B, int N, int C, int k, cudaStream_t s);
+template <typename T>
+int launch_max_over_k_bwd(const void* g, const uint8_t* argmax, void* grad_h, int B, int N, int C, int k,
+                          cudaStream_t s);
+
+}  // namespace grafp

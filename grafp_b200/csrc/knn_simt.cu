@@ -1,0 +1,207 @@
+// k-NN graph, CUDA-core path: node normalisation (shared with the tensor-core path)
+// and an exact-fp32 tiled Gram kernel with the top-k selection fused behind every
+// 64x64 distance tile, so the N x M distance matrix only ever exists tile by tile in
+// shared memory.  This path handles every shape (any C, N, M, K <= 64) and is the
+// on-device cross-check for the tcgen05 path.
+#include "knn.cuh"
+
+namespace grafp {
+
+// ------------------------------------------------------------------------------------
+// normalisation: x_hat = x / max(||x||_2, 1e-12) per node (F.normalize, torch_edge.py:281)
+// one warp per node row; optionally also emits the TF32 hi/lo split used by the
+// tensor-core path and the squared norm of x_hat (torch_edge.py:17).
+// ------------------------------------------------------------------------------------
+template <typename T, int MODE>  // MODE 0: x_hat fp32; 1: hi/lo tf32 split; 2: x_hat bf16
+__global__ void __launch_bounds__(256)
+knn_normalize_kernel(const T* __restrict__ x, float* __restrict__ xhat, float* __restrict__ lo,
+                     float* __restrict__ sq, long long rows, int C, bool normalize) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const T* xr = x + row * C;
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float v = to_float(xr[c]);
+      ss = fmaf(v, v, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float denom = normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+    float s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      float v = __fdiv_rn(to_float(xr[c]), denom);
+      if constexpr (MODE == 1) {
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const float l = v - hi;  // exact
+        xhat[row * C + c] = hi;
+        lo[row * C + c] = __uint_as_float(__float_as_uint(l) & 0xffffe000u);
+      } else if constexpr (MODE == 2) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        reinterpret_cast<__nv_bfloat16*>(xhat)[row * C + c] = h;
+        v = __bfloat162float(h);  // the Gram runs on the rounded values, so must |x|^2
+      } else {
+        xhat[row * C + c] = v;
+      }
+      s2 = fmaf(v, v, s2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (lane == 0) sq[row] = s2;
+  }
+}
+
+template <typename T>
+int launch_knn_normalize(const void* x, float* xhat, float* lo, float* sq, long long rows, int C, int mode,
+                         bool normalize, cudaStream_t s) {
+  const int threads = 256;
+  long long blocks = (rows + 7) / 8;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const T* xs = static_cast<const T*>(x);
+  if (mode == 0) knn_normalize_kernel<T, 0><<<(int)blocks, threads, 0, s>>>(xs, xhat, lo, sq, rows, C, normalize);
+  else if (mode == 1) knn_normalize_kernel<T, 1><<<(int)blocks, threads, 0, s>>>(xs, xhat, lo, sq, rows, C, normalize);
+  else knn_normalize_kernel<T, 2><<<(int)blocks, threads, 0, s>>>(xs, xhat, lo, sq, rows, C, normalize);
+  return check_launch("knn_normalize");
+}
+template int launch_knn_normalize<float>(const void*, float*, float*, float*, long long, int, int, bool, cudaStream_t);
+template int launch_knn_normalize<__nv_bfloat16>(const void*, float*, float*, float*, long long, int, int, bool, cudaStream_t);
+
+// ------------------------------------------------------------------------------------
+// exact fp32 Gram + fused top-K
+//   CTA = 64 query rows of one segment, 256 threads, 4x4 register micro-tiles.
+//   For every 64-key tile: accumulate x_hat . y_hat over C in chunks of 16 through shared
+//   memory, form D = (|x|^2 + (-2 s)) + |y|^2 (+ relpos) in that order (torch_edge.py:16-18),
+//   park the tile in shared memory and let one thread per query row merge it into that
+//   row's sorted top-K list (ties: lower key id first).
+// ------------------------------------------------------------------------------------
+constexpr int TQ = 64, TK = 64, TC = 16;
+
+__global__ void __launch_bounds__(256)
+knn_simt_kernel(const float* __restrict__ xh, const float* __restrict__ xsq, const float* __restrict__ yh,
+                const float* __restrict__ ysq, const float* __restrict__ relpos, long long* __restrict__ nn_idx,
+                int* __restrict__ nn_idx32, int N, int M, int C, int K, int k_out, int stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* As = reinterpret_cast<float*>(smem_raw);         // [TC][TQ]
+  float* Bs = As + TC * TQ;                               // [TC][TK]
+  float* Ds = Bs + TC * TK;                               // [TQ][TK + 1]
+  float* Ld = Ds + TQ * (TK + 1);                         // [TQ][K] distances, ascending
+  int* Li = reinterpret_cast<int*>(Ld + TQ * K);          // [TQ][K] key ids
+
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * TQ;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const float* xb = xh + (long long)b * N * C;
+  const float* yb = yh + (long long)b * M * C;
+
+  for (int i = tid; i < TQ * K; i += 256) { Ld[i] = INFINITY; Li[i] = 0; }
+
+  const int lrow = tid >> 2;        // 0..63: tile row loaded by this thread
+  const int lc = (tid & 3) * 4;     // 0,4,8,12: first of its 4 channels
+  const bool vec_ok = (C % 4 == 0);
+
+  for (int k0 = 0; k0 < M; k0 += TK) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int c0 = 0; c0 < C; c0 += TC) {
+      float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+      const int qa = q0 + lrow, kb = k0 + lrow, cc = c0 + lc;
+      if (vec_ok && cc + 3 < C) {
+        if (qa < N) { const float4 t = *reinterpret_cast<const float4*>(xb + (long long)qa * C + cc); av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w; }
+        if (kb < M) { const float4 t = *reinterpret_cast<const float4*>(yb + (long long)kb * C + cc); bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (qa < N && cc + e < C) av[e] = xb[(long long)qa * C + cc + e];
+          if (kb < M && cc + e < C) bv[e] = yb[(long long)kb * C + cc + e];
+        }
+      }
+      __syncthreads();  // previous chunk fully consumed
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { As[(lc + e) * TQ + lrow] = av[e]; Bs[(lc + e) * TK + lrow] = bv[e]; }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < TC; ++c) {
+        const float4 a = *reinterpret_cast<const float4*>(As + c * TQ + ty * 4);
+        const float4 bq = *reinterpret_cast<const float4*>(Bs + c * TK + tx * 4);
+        const float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+    }
+
+    // distances of this tile -> shared
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = q0 + ty * 4 + i;
+      const float sqq = (q < N) ? xsq[(long long)b * N + q] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = k0 + tx * 4 + j;
+        float d = INFINITY;
+        if (q < N && key < M) {
+          d = __fadd_rn(fmaf(-2.f, acc[i][j], sqq), ysq[(long long)b * M + key]);
+          if (relpos != nullptr) d = __fadd_rn(d, relpos[(long long)q * M + key]);
+        }
+        Ds[(ty * 4 + i) * (TK + 1) + tx * 4 + j] = d;
+      }
+    }
+    __syncthreads();
+
+    if (tid < TQ) {
+      float* ld = Ld + tid * K;
+      int* li = Li + tid * K;
+      float worst = ld[K - 1];
+      const int lim = min(TK, M - k0);
+      for (int j = 0; j < lim; ++j) {
+        const float d = Ds[tid * (TK + 1) + j];
+        if (d < worst) {
+          int p = K - 1;
+          while (p > 0 && ld[p - 1] > d) { ld[p] = ld[p - 1]; li[p] = li[p - 1]; --p; }
+          ld[p] = d; li[p] = k0 + j;
+          worst = ld[K - 1];
+        }
+      }
+    }
+    // the next tile's first __syncthreads() orders the Ds reads before its rewrite
+  }
+  __syncthreads();
+
+  // emit ranks 0, stride, 2*stride, ...
+  for (int i = tid; i < TQ * k_out; i += 256) {
+    const int r = i / k_out, j = i - r * k_out;
+    const int q = q0 + r;
+    if (q < N) {
+      const int id = Li[r * K + j * stride];
+      const long long o = ((long long)b * N + q) * k_out + j;
+      nn_idx[o] = id;
+      if (nn_idx32 != nullptr) nn_idx32[o] = id;
+    }
+  }
+}
+
+int launch_knn_simt(const float* xh, const float* xsq, const float* yh, const float* ysq, const float* relpos,
+                    long long* nn_idx, int* nn_idx32, int B, int N, int M, int C, int K, int k_out, int stride,
+                    cudaStream_t s) {
+  const size_t smem = sizeof(float) * (TC * TQ + TC * TK + TQ * (TK + 1)) + (sizeof(float) + sizeof(int)) * TQ * K;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(knn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(knn_simt): %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  dim3 grid((N + TQ - 1) / TQ, B);
+  knn_simt_kernel<<<grid, 256, smem, s>>>(xh, xsq, yh, ysq, relpos, nn_idx, nn_idx32, N, M, C, K, k_out, stride);
+  return check_launch("knn_simt");
+}
+
+}  // namespace grafp

@@ -1,0 +1,347 @@
+"""PyTorch-facing operators over the C ABI: the dilated k-NN graph and the graph-conv
+aggregations, forward and backward (torch.autograd.Function), on CUDA tensors only.
+
+Logical tensor shapes follow the reference (node features (B, C, N, 1), edge features
+(B, C, N, k)); physically every tensor handed to the library is channels-last, i.e. rows
+(B, N, C) / (B, N, k, C).  Inputs in any other layout are converted once.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native
+
+_DTYPES = {torch.float32: 0, torch.bfloat16: 1}
+
+
+class KernelTimer:
+    """Optional per-call instrumentation (bench.py): CUDA events around every C-ABI call on the
+    launching stream, plus a count of the kernels this package launched."""
+
+    def __init__(self, timing: bool = True):
+        self.timing = timing
+        self.launches = 0
+        self.records = []  # (op name, meta dict, start event, end event)
+
+    def summary(self):
+        """name -> {calls, ms_total, meta of the costliest shape}; call after torch.cuda.synchronize()."""
+        out = {}
+        for name, meta, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            slot = out.setdefault(name, {"calls": 0, "ms_total": 0.0, "by_shape": {}})
+            slot["calls"] += 1
+            slot["ms_total"] += ms
+            key = tuple(sorted(meta.items()))
+            sh = slot["by_shape"].setdefault(key, {"calls": 0, "ms_total": 0.0})
+            sh["calls"] += 1
+            sh["ms_total"] += ms
+        return out
+
+
+_TIMER: Optional[KernelTimer] = None
+
+
+def set_timer(timer: Optional[KernelTimer]) -> None:
+    global _TIMER
+    _TIMER = timer
+
+
+def _call(name: str, n_kernels: int, meta: dict, fn, *args) -> None:
+    """Invoke one C-ABI entry point, raising on a non-zero return code."""
+    t = _TIMER
+    if t is None:
+        _native.check(fn(*args), name)
+        return
+    t.launches += n_kernels
+    if t.timing:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _native.check(fn(*args), name)
+        e1.record()
+        t.records.append((name, meta, e0, e1))
+    else:
+        _native.check(fn(*args), name)
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"grafp_b200: dtype {t.dtype} is not supported (float32 and bfloat16 are)") from None
+
+
+def _require_cuda(*tensors: Optional[torch.Tensor]) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("grafp_b200: expected CUDA tensors - the B200 path has no CPU fallback")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def as_rows(x: torch.Tensor) -> torch.Tensor:
+    """Return ``x`` (B, C, N, 1) backed by row-major (B, N, C) memory, copying only if needed."""
+    if x.dim() != 4 or x.shape[3] != 1:
+        raise RuntimeError(f"grafp_b200: expected a (B, C, N, 1) tensor, got {tuple(x.shape)}")
+    B, C, N, _ = x.shape
+    s = x.stride()
+    if (C == 1 or s[1] == 1) and (N == 1 or s[2] == C) and (B == 1 or s[0] == N * C):
+        return x
+    return x.permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)
+
+
+def as_edge_rows(h: torch.Tensor) -> torch.Tensor:
+    """Return ``h`` (B, C, N, k) backed by (B, N, k, C) memory."""
+    B, C, N, k = h.shape
+    s = h.stride()
+    if (C == 1 or s[1] == 1) and (k == 1 or s[3] == C) and (N == 1 or s[2] == k * C) and (B == 1 or s[0] == N * k * C):
+        return h
+    return h.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+
+
+def _new_rows(B: int, C: int, N: int, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty((B, N, C, 1), dtype=like.dtype, device=like.device).permute(0, 2, 1, 3)
+
+
+def _new_edge_rows(B: int, C: int, N: int, k: int, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty((B, N, k, C), dtype=like.dtype, device=like.device).permute(0, 3, 1, 2)
+
+
+def _index_arg(idx: torch.Tensor) -> Tuple[torch.Tensor, int]:
+    if idx.dtype not in (torch.int64, torch.int32):
+        raise RuntimeError(f"grafp_b200: index tensors must be int64 or int32, got {idx.dtype}")
+    return idx.contiguous(), int(idx.dtype == torch.int64)
+
+
+# --------------------------------------------------------------------------------------
+# k-NN graph
+# --------------------------------------------------------------------------------------
+
+def knn_graph(x: torch.Tensor, k: int, dilation: int = 1, y: Optional[torch.Tensor] = None,
+              relative_pos: Optional[torch.Tensor] = None, emit_all: bool = False, normalize: bool = True,
+              want_i32: bool = True, algo: int = _native.KNN_AUTO,
+              out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Neighbour ids of the dilated k-NN graph (reference: torch_edge.py:270-284).
+
+    x: (B, C, N, 1) queries, y: (B, C, M, 1) keys or None, relative_pos: (1, N, M) or None.
+    Returns (nn_idx int64 (B, N, k_out), nn_idx32 int32 or None), k_out = k (or k*dilation with
+    ``emit_all``).  ``out`` may be a preallocated contiguous int64 (B, N, k_out) destination
+    (e.g. ``edge_index[0]``).  Not differentiable, like the reference (no_grad + detach).
+    """
+    _require_cuda(x, y, relative_pos)
+    lib = _native.load()
+    with torch.no_grad():
+        xr = as_rows(x.detach())
+        B, C, N, _ = xr.shape
+        yr = None
+        M = N
+        if y is not None:
+            yr = as_rows(y.detach().to(xr.dtype))
+            if yr.shape[0] != B or yr.shape[1] != C:
+                raise RuntimeError("grafp_b200.knn_graph: x and y must agree in batch and channel size")
+            M = yr.shape[2]
+        rp = None
+        if relative_pos is not None:
+            rp = relative_pos.detach().to(torch.float32).reshape(-1, relative_pos.shape[-1]).contiguous()
+            if rp.shape != (N, M):
+                raise RuntimeError(f"grafp_b200.knn_graph: relative_pos must be (1, {N}, {M}), got {tuple(relative_pos.shape)}")
+        K = int(k) * int(dilation)
+        k_out = K if emit_all else int(k)
+        if out is None:
+            out = torch.empty((B, N, k_out), dtype=torch.int64, device=x.device)
+        elif out.shape != (B, N, k_out) or out.dtype != torch.int64 or not out.is_contiguous():
+            raise RuntimeError("grafp_b200.knn_graph: `out` must be a contiguous int64 (B, N, k_out) tensor")
+        out32 = torch.empty((B, N, k_out), dtype=torch.int32, device=x.device) if want_i32 else None
+        dt = _dtype_code(xr)
+        ws_bytes = lib.grafp_knn_workspace_bytes(B, N, M, C, K, dt)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        _call("knn_fwd", 2 if yr is None else 3, dict(B=B, N=N, M=M, C=C, K=K, dtype=dt), lib.grafp_knn_fwd,
+              xr.data_ptr(), yr.data_ptr() if yr is not None else None,
+              rp.data_ptr() if rp is not None else None, out.data_ptr(),
+              out32.data_ptr() if out32 is not None else None,
+              B, N, M, C, int(k), int(dilation), int(emit_all), int(normalize), dt, int(algo),
+              ws.data_ptr(), ws_bytes, _stream())
+    return out, out32
+
+
+def knn_last_algo() -> str:
+    return _native.load().grafp_knn_last_algo().decode()
+
+
+# --------------------------------------------------------------------------------------
+# max-relative aggregation (MRConv2d body)
+# --------------------------------------------------------------------------------------
+
+class _MRAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, nbr, ctr):
+        lib = _native.load()
+        xr = as_rows(x)
+        B, C, N, _ = xr.shape
+        yr = as_rows(y.to(xr.dtype)) if y is not None else None
+        M = yr.shape[2] if yr is not None else N
+        nbr_c, i64 = _index_arg(nbr)
+        ctr_c = None
+        if ctr is not None:
+            ctr_c = ctr.to(nbr_c.dtype).contiguous()
+        k = nbr_c.shape[-1]
+        if nbr_c.shape != (B, N, k):
+            raise RuntimeError(f"grafp_b200.mr_aggregate: neighbour index must be ({B}, {N}, k), got {tuple(nbr.shape)}")
+        need_grad = any(ctx.needs_input_grad[:2])
+        out = _new_rows(B, 2 * C, N, xr)
+        argmax = torch.empty((B, N, C), dtype=torch.uint8, device=x.device) if need_grad else None
+        _call("mr_aggregate_fwd", 1, dict(B=B, N=N, M=M, C=C, k=k, dtype=_dtype_code(xr), i64=i64,
+                                          argmax=int(argmax is not None)),
+              lib.grafp_mr_aggregate_fwd, xr.data_ptr(), yr.data_ptr() if yr is not None else None, nbr_c.data_ptr(),
+              ctr_c.data_ptr() if ctr_c is not None else None, i64, out.data_ptr(),
+              argmax.data_ptr() if argmax is not None else None, B, N, M, C, k, _dtype_code(xr), _stream())
+        ctx.save_for_backward(nbr_c, ctr_c, argmax)
+        ctx.dims = (B, N, M, C, k, i64, y is not None, _dtype_code(xr))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _native.load()
+        nbr_c, ctr_c, argmax = ctx.saved_tensors
+        B, N, M, C, k, i64, has_y, dt = ctx.dims
+        g = as_rows(grad_out)
+        grad_x = _new_rows(B, C, N, g)
+        grad_y = _new_rows(B, C, M, g) if has_y else None
+        _call("mr_aggregate_bwd", 2, dict(B=B, N=N, M=M, C=C, k=k, dtype=dt, i64=i64),
+              lib.grafp_mr_aggregate_bwd, g.data_ptr(), argmax.data_ptr(), nbr_c.data_ptr(),
+              ctr_c.data_ptr() if ctr_c is not None else None, i64, grad_x.data_ptr(),
+              grad_y.data_ptr() if grad_y is not None else None, B, N, M, C, k, dt, _stream())
+        return grad_x, grad_y, None, None
+
+
+def mr_aggregate(x: torch.Tensor, nbr: torch.Tensor, y: Optional[torch.Tensor] = None,
+                 ctr: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B, 2C, N, 1) interleaved [x_c, max_j(x_j - x_i)_c] (reference: torch_vertex.py:21-32).
+
+    nbr / ctr: (B, N, k) neighbour / centre ids; ``ctr=None`` means the centre of row n is n.
+    """
+    _require_cuda(x, y, nbr, ctr)
+    return _MRAggregate.apply(x, y, nbr, ctr)
+
+
+# --------------------------------------------------------------------------------------
+# plain gather (batched_index_select)
+# --------------------------------------------------------------------------------------
+
+class _Gather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, idx):
+        lib = _native.load()
+        sr = as_rows(src)
+        B, C, M, _ = sr.shape
+        idx_c, i64 = _index_arg(idx)
+        _, N, k = idx_c.shape
+        out = _new_edge_rows(B, C, N, k, sr)
+        _call("gather_fwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_gather_fwd, sr.data_ptr(), idx_c.data_ptr(),
+              i64, out.data_ptr(), B, N, M, C, k, _dtype_code(sr), _stream())
+        ctx.save_for_backward(idx_c)
+        ctx.dims = (B, N, M, C, k, i64, _dtype_code(sr))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _native.load()
+        (idx_c,) = ctx.saved_tensors
+        B, N, M, C, k, i64, dt = ctx.dims
+        g = as_edge_rows(grad_out)
+        grad_src = _new_rows(B, C, M, g)
+        _call("gather_bwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_gather_bwd, g.data_ptr(), idx_c.data_ptr(), i64,
+              grad_src.data_ptr(), B, N, M, C, k, dt, _stream())
+        return grad_src, None
+
+
+def gather_neighbors(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """out[b, c, n, j] = src[b, c, idx[b, n, j]] as a (B, C, N, k) tensor (reference: torch_nn.py:79-98)."""
+    _require_cuda(src, idx)
+    if idx.dim() != 3 or idx.shape[0] != src.shape[0]:
+        raise RuntimeError("grafp_b200.gather_neighbors: idx must be (B, N, k)")
+    return _Gather.apply(src, idx)
+
+
+# --------------------------------------------------------------------------------------
+# EdgeConv features and max over k
+# --------------------------------------------------------------------------------------
+
+class _EdgeGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, nbr, ctr):
+        lib = _native.load()
+        xr = as_rows(x)
+        B, C, N, _ = xr.shape
+        yr = as_rows(y.to(xr.dtype)) if y is not None else None
+        M = yr.shape[2] if yr is not None else N
+        nbr_c, i64 = _index_arg(nbr)
+        ctr_c = ctr.to(nbr_c.dtype).contiguous() if ctr is not None else None
+        k = nbr_c.shape[-1]
+        out = _new_edge_rows(B, 2 * C, N, k, xr)
+        _call("edge_gather_fwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_edge_gather_fwd, xr.data_ptr(),
+              yr.data_ptr() if yr is not None else None, nbr_c.data_ptr(),
+              ctr_c.data_ptr() if ctr_c is not None else None, i64, out.data_ptr(),
+              B, N, M, C, k, _dtype_code(xr), _stream())
+        ctx.save_for_backward(nbr_c, ctr_c)
+        ctx.dims = (B, N, M, C, k, i64, y is not None, _dtype_code(xr))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _native.load()
+        nbr_c, ctr_c = ctx.saved_tensors
+        B, N, M, C, k, i64, has_y, dt = ctx.dims
+        g = as_edge_rows(grad_out)
+        grad_x = _new_rows(B, C, N, g)
+        grad_y = _new_rows(B, C, M, g) if has_y else None
+        _call("edge_gather_bwd", 2 if ctr_c is None else 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_edge_gather_bwd,
+              g.data_ptr(), nbr_c.data_ptr(), ctr_c.data_ptr() if ctr_c is not None else None,
+              i64, grad_x.data_ptr(), grad_y.data_ptr() if grad_y is not None else None,
+              B, N, M, C, k, dt, _stream())
+        return grad_x, grad_y, None, None
+
+
+def edge_features(x: torch.Tensor, nbr: torch.Tensor, y: Optional[torch.Tensor] = None,
+                  ctr: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B, 2C, N, k) = cat([x_i, x_j - x_i], dim=1) (reference: torch_vertex.py:46-51)."""
+    _require_cuda(x, y, nbr, ctr)
+    return _EdgeGather.apply(x, y, nbr, ctr)
+
+
+class _MaxOverK(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h):
+        lib = _native.load()
+        hr = as_edge_rows(h)
+        B, C, N, k = hr.shape
+        out = _new_rows(B, C, N, hr)
+        argmax = torch.empty((B, N, C), dtype=torch.uint8, device=h.device) if ctx.needs_input_grad[0] else None
+        _call("max_over_k_fwd", 1, dict(B=B, N=N, C=C, k=k), lib.grafp_max_over_k_fwd, hr.data_ptr(), out.data_ptr(),
+              argmax.data_ptr() if argmax is not None else None, B, N, C, k, _dtype_code(hr), _stream())
+        ctx.save_for_backward(argmax)
+        ctx.dims = (B, N, C, k, _dtype_code(hr))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _native.load()
+        (argmax,) = ctx.saved_tensors
+        B, N, C, k, dt = ctx.dims
+        g = as_rows(grad_out)
+        grad_h = _new_edge_rows(B, C, N, k, g)
+        _call("max_over_k_bwd", 1, dict(B=B, N=N, C=C, k=k), lib.grafp_max_over_k_bwd, g.data_ptr(), argmax.data_ptr(),
+              grad_h.data_ptr(), B, N, C, k, dt, _stream())
+        return grad_h
+
+
+def max_over_k(h: torch.Tensor) -> torch.Tensor:
+    """torch.max(h, -1, keepdim=True).values for h (B, C, N, k) (reference: torch_vertex.py:51,69)."""
+    _require_cuda(h)
+    if h.dim() != 4:
+        raise RuntimeError("grafp_b200.max_over_k: expected a (B, C, N, k) tensor")
+    return _MaxOverK.apply(h)

@@ -1,0 +1,136 @@
+/*
+ * grafp_b200.h - C ABI of the B200-native GraFP GraphEncoder hot path.
+ *
+ * One shared library (libgrafp_b200.so, sm_100a only) replaces the PyTorch-eager op
+ * sequences of the reference's dynamic k-NN graph and graph-convolution aggregation.
+ * Citations are into the upstream chymaera96/GraFP checkout.
+ *
+ * Conventions
+ *  - Every tensor is a plain device pointer owned by the caller; the library never
+ *    allocates, frees or retains device memory.  All work is enqueued on `stream`
+ *    (a cudaStream_t / CUstream passed as void*); calls return after launch and are
+ *    CUDA-graph capturable.  There is NO CPU path: host pointers are an error.
+ *  - Node features are stored as rows: x[b][n][c] contiguous ("channels last" of the
+ *    reference's logical (B, C, N, 1) tensors).  dtype: 0 = float32, 1 = bfloat16.
+ *  - Index tensors are (B, N, k) contiguous, int64 (the reference's edge_index
+ *    element type) when idx_is_i64 != 0, else int32.  Neighbour ids address the key
+ *    set (y when given, else x) of the same batch item, in [0, M).
+ *  - Return value: 0 = success; < 0 = GRAFP_E* argument/shape error; > 0 = the
+ *    cudaError_t of a failed launch.  grafp_last_error() returns a thread-local
+ *    message for the last failing call on this thread.
+ */
+#ifndef GRAFP_B200_H_
+#define GRAFP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRAFP_ABI_VERSION 1
+
+#define GRAFP_OK 0
+#define GRAFP_EINVAL (-1)       /* null / misaligned pointer, non-positive size, k > M ... */
+#define GRAFP_EUNSUPPORTED (-2) /* shape or dtype outside what the kernels implement      */
+#define GRAFP_EWORKSPACE (-3)   /* workspace smaller than grafp_knn_workspace_bytes()     */
+#define GRAFP_ENODEVICE (-4)    /* no sm_100 device is current                            */
+
+#define GRAFP_F32 0
+#define GRAFP_BF16 1
+
+/* k-NN kernel selection for grafp_knn_fwd */
+#define GRAFP_KNN_AUTO 0 /* tcgen05 path when the shape allows it, else the SIMT path */
+#define GRAFP_KNN_SIMT 1 /* exact-fp32 CUDA-core Gram + fused top-k                   */
+#define GRAFP_KNN_TC 2   /* TMA + tcgen05 (3xTF32 for f32, bf16 MMA for bf16) + fused top-k */
+
+#define GRAFP_KNN_MAX_K 64 /* k * dilation */
+
+int grafp_abi_version(void);
+const char* grafp_last_error(void);
+
+/* Diagnostic: name of the k-NN kernel the last grafp_knn_fwd call on this thread launched
+ * ("simt", "tcgen05"). */
+const char* grafp_knn_last_algo(void);
+
+/*
+ * Dilated k-NN graph.  Replaces DenseDilatedKnnGraph.forward
+ * (encoder/gcn_lib/torch_edge.py:270-284) = F.normalize (:274-275,281) +
+ * pairwise_distance / xy_pairwise_distance (:7-18, :37-53) + optional relative_pos
+ * bias (:97-99, :160-162) + topk (:100, :163) + DenseDilated [..., ::d] (:252-254),
+ * without ever writing the N x M distance matrix to HBM.
+ *
+ *  x        (B, N, C) query node features.
+ *  normalize != 0: L2-normalise every node over C first (what DenseDilatedKnnGraph.forward does);
+ *           0: use the features as given (dense_knn_matrix / xy_dense_knn_matrix called directly).
+ *  y        (B, M, C) key node features or NULL (keys = x, M must equal N).
+ *  relpos   (N, M) float32 bias added to the squared distances, or NULL.
+ *  nn_idx   (B, N, k_out) int64 out: neighbour ids sorted by ascending distance, ties by
+ *           lowest id; k_out = k (ranks 0, d, 2d, ...) or k*dilation when emit_all != 0
+ *           (the caller then applies DenseDilated's stochastic branch, :246-250).
+ *  nn_idx32 optional int32 copy of nn_idx (same shape) or NULL.
+ *  The centre ids (edge_index[1], :102) are arange(N) and are not produced here.
+ */
+size_t grafp_knn_workspace_bytes(int B, int N, int M, int C, int K, int dtype);
+int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn_idx, int32_t* nn_idx32,
+                  int B, int N, int M, int C, int k, int dilation, int emit_all, int normalize, int dtype,
+                  int algo, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Max-relative aggregation.  Replaces the body of MRConv2d.forward before self.nn
+ * (encoder/gcn_lib/torch_vertex.py:21-32): two batched_index_select gathers
+ * (torch_nn.py:79-98), x_j - x_i, max over k, and the channel-interleaving cat.
+ *
+ *  out[b][n][2c] = x[b][n][c]
+ *  out[b][n][2c+1] = max_j ( src[b][nbr[b][n][j]][c] - x[b][ctr[b][n][j]][c] ),  src = y ? y : x
+ *  argmax[b][n][c] = first j attaining the max (uint8; NULL when no backward is needed)
+ *  ctr == NULL means ctr[b][n][j] = n (what the k-NN graph produces, torch_edge.py:102).
+ *
+ * The backward overwrites grad_x (B, N, C) and, when y was given, grad_y (B, M, C):
+ *  grad_x[b][n][c]  = g[b][n][2c] + sum over (m, j = argmax[b][m][c]) of
+ *                     ( -g[b][m][2c+1] if ctr[b][m][j] == n )  ( +g[b][m][2c+1] if y == NULL and nbr[b][m][j] == n )
+ * Floating-point accumulation order of the scatter is not fixed (atomics).
+ */
+int grafp_mr_aggregate_fwd(const void* x, const void* y, const void* nbr_idx, const void* ctr_idx, int idx_is_i64,
+                           void* out, uint8_t* argmax, int B, int N, int M, int C, int k, int dtype, void* stream);
+int grafp_mr_aggregate_bwd(const void* grad_out, const uint8_t* argmax, const void* nbr_idx, const void* ctr_idx,
+                           int idx_is_i64, void* grad_x, void* grad_y, int B, int N, int M, int C, int k, int dtype,
+                           void* stream);
+
+/*
+ * Plain neighbour gather.  Replaces batched_index_select (torch_nn.py:79-98).
+ *  out[b][n][j][c] = src[b][idx[b][n][j]][c]          out is (B, N, k, C)
+ * Backward (index_put_ accumulate of the reference's autograd) overwrites grad_src (B, M, C).
+ */
+int grafp_gather_fwd(const void* src, const void* idx, int idx_is_i64, void* out, int B, int N, int M, int C, int k,
+                     int dtype, void* stream);
+int grafp_gather_bwd(const void* grad_out, const void* idx, int idx_is_i64, void* grad_src, int B, int N, int M, int C,
+                     int k, int dtype, void* stream);
+
+/*
+ * EdgeConv feature construction.  Replaces cat([x_i, x_j - x_i], dim=1) of
+ * EdgeConv2d.forward (torch_vertex.py:46-51).
+ *  out[b][n][j][c]     = x[b][ctr[b][n][j]][c]
+ *  out[b][n][j][C + c] = src[b][nbr[b][n][j]][c] - x[b][ctr[b][n][j]][c]      out is (B, N, k, 2C)
+ * Backward overwrites grad_x (and grad_y when y was given).
+ */
+int grafp_edge_gather_fwd(const void* x, const void* y, const void* nbr_idx, const void* ctr_idx, int idx_is_i64,
+                          void* out, int B, int N, int M, int C, int k, int dtype, void* stream);
+int grafp_edge_gather_bwd(const void* grad_out, const void* nbr_idx, const void* ctr_idx, int idx_is_i64, void* grad_x,
+                          void* grad_y, int B, int N, int M, int C, int k, int dtype, void* stream);
+
+/*
+ * Max over the neighbour axis.  Replaces torch.max(h, -1, keepdim=True) of
+ * EdgeConv2d.forward (torch_vertex.py:51) and GraphSAGE.forward (:69).
+ *  out[b][n][c] = max_j h[b][n][j][c],  argmax = first such j.   h is (B, N, k, C)
+ * Backward overwrites grad_h with grad_out routed to the argmax slot and zeros elsewhere.
+ */
+int grafp_max_over_k_fwd(const void* h, void* out, uint8_t* argmax, int B, int N, int C, int k, int dtype, void* stream);
+int grafp_max_over_k_bwd(const void* grad_out, const uint8_t* argmax, void* grad_h, int B, int N, int C, int k, int dtype,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAFP_B200_H_ */

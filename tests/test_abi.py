@@ -1,0 +1,65 @@
+"""The C-ABI library builds, loads and exports exactly what include/grafp_b200.h declares (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from grafp_b200 import _native, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "grafp_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(grafp_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    return build.build()
+
+
+def test_header_and_binding_agree():
+    assert declared_functions() == sorted(_native.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    for name in declared_functions():
+        assert hasattr(lib, name), name
+
+
+def test_library_links_without_the_cuda_driver(lib_path):
+    import subprocess
+    out = subprocess.run(["ldd", lib_path], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out and "not found" not in out
+
+
+def test_abi_version_and_sizes(lib_path):
+    lib = _native.load()
+    assert lib.grafp_abi_version() == _native.ABI_VERSION == 1
+    assert lib.grafp_knn_workspace_bytes(0, 1, 1, 1, 1, 0) == 0
+    need = lib.grafp_knn_workspace_bytes(4, 256, 256, 64, 3, 0)
+    assert need >= 4 * 4 * 256 * 64 * 4  # hi + lo for queries and keys
+
+
+def test_calls_fail_loudly_without_a_device(lib_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    lib = _native.load()
+    rc = lib.grafp_max_over_k_fwd(None, None, None, 1, 1, 4, 1, 0, None)
+    assert rc == -4  # GRAFP_ENODEVICE: no CPU path
+    assert b"no CPU path" in lib.grafp_last_error()
+    rc = lib.grafp_knn_fwd(None, None, None, None, None, 1, 8, 8, 4, 9, 1, 0, 1, 0, 0, None, 0, None)
+    assert rc != 0
+
+
+def test_missing_library_is_an_error(monkeypatch, tmp_path):
+    monkeypatch.setenv("GRAFP_B200_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_native, "_lib", None)
+    with pytest.raises(RuntimeError, match="no PyTorch/CPU fallback"):
+        _native.load()

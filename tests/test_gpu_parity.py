@@ -1,0 +1,409 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Bars (SURVEY.md section 8c / BASELINE.json north_star):
+  * k-NN neighbour ids: identical to the reference except documented equal-distance ties
+    (a differing id is accepted only if the fp64 distance gap is below the fp32 evaluation noise);
+  * aggregation / gather / edge features / max-over-k forward: bit-exact in fp32;
+  * gradients and model-level outputs: <= 1e-4 relative error in fp32 (atomics reorder sums);
+  * bf16: stated looser bounds next to each test.
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_io as gio
+from grafp_b200 import _native, ops, synth
+from grafp_b200.encoder.gcn_lib import torch_edge, torch_nn, torch_vertex
+from grafp_b200.encoder.graph_encoder import GraphEncoder
+from grafp_b200.simclr.simclr import SimCLR
+from grafp_b200.simclr.ntxent import ntxent_loss
+from oracle import grafp_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+REL_TOL = 1e-4
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_library_math():
+    # the parity bar is fp32: keep cuDNN / cuBLAS off TF32 for the PyTorch layers around our kernels
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def load_synth(module, seed):
+    sd = module.state_dict()
+    keep = {k: v for k, v in sd.items() if k.endswith("relative_pos")}
+    module.load_state_dict(synth.synth_state_dict({k: v.shape for k, v in sd.items()}, seed, keep))
+    return module
+
+
+def assert_knn_ok(x, nn_idx, k, d, y=None, rp=None, max_mismatch_frac=0.02, what=""):
+    rep = O.knn_mismatch_report(x.cpu(), nn_idx.cpu(), k * d, None if y is None else y.cpu(),
+                                None if rp is None else rp.cpu(), ordered=True, dilation=d)
+    assert rep["hard"] == 0, f"{what}: non-tie neighbour mismatches {rep}"
+    assert rep["mismatch"] <= max_mismatch_frac * rep["entries"], f"{what}: too many tie-order differences {rep}"
+    return rep
+
+
+# ----------------------------------------------------------------------------------------
+# k-NN graph
+# ----------------------------------------------------------------------------------------
+
+def test_library_is_the_native_one():
+    lib = _native.load()
+    assert lib.grafp_abi_version() == 1
+    x = torch.randn(2, 16, 64, 1, device=DEV)
+    ops.knn_graph(x, 3)
+    assert ops.knn_last_algo() in ("simt", "tcgen05")
+
+
+@pytest.mark.parametrize("name", [str(n) for n in gio.load("knn")["names"]])
+@pytest.mark.parametrize("algo", ["simt", "auto"])
+def test_knn_matches_reference_golden(name, algo):
+    gold = gio.load("knn")
+    x = gio.t(gold[f"{name}.x"]).to(DEV)
+    y = gio.t(gold[f"{name}.y"]).to(DEV) if f"{name}.y" in gold else None
+    rp = gio.t(gold[f"{name}.relative_pos"]).to(DEV) if f"{name}.relative_pos" in gold else None
+    k, d = (int(v) for v in gold[f"{name}.kd"])
+    ref = gio.t(gold[f"{name}.edge_index"])
+    if algo == "simt":
+        nn_idx, nn32 = ops.knn_graph(x, k, d, y, rp, algo=_native.KNN_SIMT)
+        assert torch.equal(nn_idx, nn32.long())
+        edge0 = nn_idx.cpu()
+    else:
+        edge = torch_edge.DenseDilatedKnnGraph(k=k, dilation=d)(x, y, rp)
+        assert edge.shape == ref.shape and edge.dtype == torch.int64
+        assert torch.equal(edge[1].cpu(), ref[1])
+        edge0 = edge[0].cpu()
+    assert_knn_ok(x, edge0, k, d, y, rp, what=name)
+    # with random N(0,1) features there are no exact ties: all but a couple of near-tie entries are identical
+    if name in ("plain_k3", "dil2_k4", "ragged_n", "xy_pooled", "k_equals_n"):
+        assert int((edge0 != ref[0]).sum()) <= 2, name
+
+
+STAGES = [(1024, 64), (512, 128), (256, 256), (128, 512)]
+
+
+@pytest.mark.parametrize("N,C", STAGES)
+@pytest.mark.parametrize("algo", [_native.KNN_SIMT, _native.KNN_AUTO])
+def test_knn_encoder_stage_shapes_vs_oracle(N, C, algo):
+    B, k = 3, 3
+    x = synth.synth_point_cloud(B, C, N, 1000 + N, relu=True)
+    x[0, :, 7] = x[0, :, 3]      # exact duplicate nodes (equal distances everywhere)
+    x[1, :, 11] = 0              # all-zero node: normalises to 0
+    nn_idx, _ = ops.knn_graph(x.to(DEV), k, 1, algo=algo)
+    assert_knn_ok(x, nn_idx, k, 1, what=f"stage N={N} C={C} algo={ops.knn_last_algo()}")
+
+
+@pytest.mark.parametrize("C", [64, 256])
+@pytest.mark.parametrize("d", [1, 2, 3, 4])
+@pytest.mark.parametrize("algo", [_native.KNN_SIMT, _native.KNN_AUTO])
+def test_knn_dense_stress_vs_oracle(C, d, algo):
+    B, N, k = 2, 1024, 16
+    x = synth.synth_point_cloud(B, C, N, 2000 + C + d)
+    nn_idx, _ = ops.knn_graph(x.to(DEV), k, d, algo=algo)
+    rep = assert_knn_ok(x, nn_idx, k, d, what=f"stress C={C} d={d} algo={ops.knn_last_algo()}")
+    full, _ = ops.knn_graph(x.to(DEV), k, d, emit_all=True, algo=algo)
+    assert torch.equal(full[..., ::d], nn_idx), "dilated output must equal every d-th rank of the full list"
+    assert rep["mismatch"] <= 0.001 * rep["entries"]
+
+
+def test_knn_full_batch_properties():
+    """BASELINE config 2 size (B=512 segments, stage-0 shape): size-independent properties."""
+    B, C, N, k = 512, 64, 1024, 3
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn(B, C, N, 1, device=DEV, generator=g)
+    a, a32 = ops.knn_graph(x, k)
+    algo = ops.knn_last_algo()
+    b, _ = ops.knn_graph(x, k)
+    assert torch.equal(a, b), "k-NN must be deterministic"
+    assert torch.equal(a, a32.long())
+    assert int(a.min()) >= 0 and int(a.max()) < N
+    assert torch.equal(a[..., 0], torch.arange(N, device=DEV).expand(B, N)), "rank 0 is the node itself"
+    srt = a.sort(-1).values
+    assert bool((srt[..., 1:] != srt[..., :-1]).all()), "neighbour ids are distinct"
+    s, _ = ops.knn_graph(x, k, algo=_native.KNN_SIMT)
+    agree = float((s == a).float().mean())
+    assert agree > 0.9995, f"{algo} vs simt agreement {agree}"
+    pick = [0, 137, 511]
+    assert_knn_ok(x[pick].cpu(), a[pick], k, 1, what="full batch sample")
+    # permuting the nodes of a segment permutes the graph (no dependence on node order beyond ties)
+    perm = torch.randperm(N, device=DEV, generator=g)
+    xp = x[:4][:, :, perm]
+    ap, _ = ops.knn_graph(xp, k)
+    back = perm[ap]                      # neighbour ids mapped to original numbering, rows in permuted order
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(N, device=DEV)
+    same = (back[:, inv] == a[:4]).float().mean()
+    assert float(same) > 0.9995
+
+
+def test_knn_errors():
+    x = torch.randn(1, 8, 16, 1, device=DEV)
+    with pytest.raises(RuntimeError, match="exceeds the number of key nodes"):
+        ops.knn_graph(x, 17)
+    with pytest.raises(RuntimeError, match="exceeds 64"):
+        ops.knn_graph(torch.randn(1, 8, 256, 1, device=DEV), 33, 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.knn_graph(x.cpu(), 3)
+    with pytest.raises(RuntimeError, match="not supported"):
+        ops.knn_graph(x.half(), 3)
+
+
+def test_dense_knn_matrix_uses_features_as_given():
+    x = synth.synth_point_cloud(2, 16, 96, 77) * torch.linspace(0.5, 3.0, 96).view(1, 1, 96, 1)
+    e = torch_edge.dense_knn_matrix(x.to(DEV), k=5).cpu()
+    ref = O.knn_edge_index(x, 5)
+    assert float((e == ref).float().mean()) > 0.999
+
+
+def test_stochastic_dilation_draws_from_the_full_list():
+    torch.manual_seed(0)
+    g = torch_edge.DenseDilatedKnnGraph(k=4, dilation=3, stochastic=True, epsilon=1.0).train()
+    x = synth.synth_point_cloud(2, 16, 96, 5).to(DEV)
+    e = g(x)
+    full, _ = ops.knn_graph(x, 4, 3, emit_all=True)
+    assert e.shape == (2, 2, 96, 4)
+    assert bool((e[0].unsqueeze(-1) == full.unsqueeze(-2)).any(-1).all())
+
+
+# ----------------------------------------------------------------------------------------
+# aggregation ops
+# ----------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("tag", ["self", "xy"])
+def test_aggregation_ops_match_reference_golden(tag):
+    gold = gio.load("aggregate")
+    x = gio.t(gold[f"{tag}.x"]).to(DEV).requires_grad_(True)
+    y = gio.t(gold[f"{tag}.y"]).to(DEV).requires_grad_(True) if f"{tag}.y" in gold else None
+    edge = gio.t(gold[f"{tag}.edge_index"]).to(DEV)
+    src = x if y is None else y
+    assert torch.equal(ops.gather_neighbors(src, edge[0]).cpu(), gio.t(gold[f"{tag}.gather"]))
+    feat = ops.mr_aggregate(x, edge[0], y, edge[1])
+    assert feat.shape == gold[f"{tag}.mr_features"].shape
+    assert torch.equal(feat.cpu(), gio.t(gold[f"{tag}.mr_features"])), "MR features must be bit-exact"
+    feat.backward(gio.t(gold[f"{tag}.mr_upstream"]).to(DEV))
+    assert gio.rel_err(x.grad.cpu(), gio.t(gold[f"{tag}.mr_grad_x"])) < REL_TOL
+    if y is not None:
+        assert gio.rel_err(y.grad.cpu(), gio.t(gold[f"{tag}.mr_grad_y"])) < REL_TOL
+        y.grad = None
+    x.grad = None
+    if tag == "self":  # identity-centre fast path (what DyGraphConv2d uses) must give the same bits
+        feat2 = ops.mr_aggregate(x, edge[0].int(), None, None)
+        assert torch.equal(feat2, feat)
+        feat2.backward(gio.t(gold[f"{tag}.mr_upstream"]).to(DEV))
+        assert gio.rel_err(x.grad.cpu(), gio.t(gold[f"{tag}.mr_grad_x"])) < REL_TOL
+        x.grad = None
+    ef = ops.edge_features(x, edge[0], y, edge[1])
+    assert torch.equal(ef.cpu(), gio.t(gold[f"{tag}.edge_features"])), "edge features must be bit-exact"
+    ef.backward(gio.t(gold[f"{tag}.edge_upstream"]).to(DEV))
+    assert gio.rel_err(x.grad.cpu(), gio.t(gold[f"{tag}.edge_grad_x"])) < REL_TOL
+    if y is not None:
+        assert gio.rel_err(y.grad.cpu(), gio.t(gold[f"{tag}.edge_grad_y"])) < REL_TOL
+
+
+@pytest.mark.parametrize("N,C", STAGES + [(70, 12), (33, 6)])
+@pytest.mark.parametrize("k", [3, 9])
+def test_mr_aggregate_vs_oracle(N, C, k):
+    B = 3
+    x = synth.synth_point_cloud(B, C, N, 300 + N + k, relu=True)
+    x[0, :, 2] = x[0, :, 1]
+    edge = O.dilated_knn_graph(x, k)
+    xg = x.to(DEV).requires_grad_(True)
+    out = ops.mr_aggregate(xg, edge[0].to(DEV).int())
+    xo = x.clone().requires_grad_(True)
+    ref = O.max_relative_features(xo, edge)
+    assert torch.equal(out.cpu(), ref)
+    up = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1))
+    ref.backward(up)
+    out.backward(up.to(DEV))
+    assert gio.rel_err(xg.grad.cpu(), xo.grad) < REL_TOL
+    # plain-contiguous NCHW input (not channels-last) is accepted and converted once
+    x_nchw = x.to(DEV).contiguous()
+    assert torch.equal(ops.mr_aggregate(x_nchw, edge[0].to(DEV)).cpu(), ref)
+
+
+def test_mr_aggregate_full_batch_properties():
+    """B=512, stage-2 shape: forward identities + linearity of the backward in grad_out."""
+    B, C, N, k = 512, 256, 256, 3
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.relu(torch.randn(B, C, N, 1, device=DEV, generator=g)).requires_grad_(True)
+    nbr, nbr32 = ops.knn_graph(x, k)
+    out = ops.mr_aggregate(x, nbr32)
+    assert torch.equal(out[:, 0::2], x.detach()), "even channels carry x itself"
+    assert float(out[:, 1::2].min()) >= 0.0, "self is a neighbour, so max_j(x_j - x_i) >= 0"
+    ref = torch.stack([x.detach()[torch.arange(B, device=DEV)[:, None], :, nbr[:, :, j], 0] for j in range(k)], -1)  # (B,N,C,k)
+    ref = (ref - x.detach().squeeze(-1).transpose(1, 2).unsqueeze(-1)).max(-1).values.transpose(1, 2).unsqueeze(-1)
+    assert torch.equal(out[:, 1::2], ref)
+    g1 = torch.randn(out.shape, device=DEV, generator=g)
+    g2 = torch.randn(out.shape, device=DEV, generator=g)
+    (ga,) = torch.autograd.grad(out, x, g1, retain_graph=True)
+    (gb,) = torch.autograd.grad(out, x, g2, retain_graph=True)
+    (gab,) = torch.autograd.grad(out, x, g1 + 2 * g2)
+    assert gio.rel_err(gab, ga + 2 * gb) < 1e-5
+    assert abs(float(gab.double().sum()) - float((g1 + 2 * g2)[:, 0::2].double().sum())) < 0.05, \
+        "the max-relative part moves gradient between nodes but conserves its sum"
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 64, 4), (3, 128, 100, 9), (2, 6, 33, 5)])
+def test_gather_edge_maxk_vs_oracle(shape):
+    B, C, N, k = shape
+    x = synth.synth_point_cloud(B, C, N, 400 + N)
+    edge = O.dilated_knn_graph(x, k)
+    xg, xo = x.to(DEV).requires_grad_(True), x.clone().requires_grad_(True)
+    up = torch.randn(B, C, N, k, generator=torch.Generator().manual_seed(2))
+    got, ref = torch_nn.batched_index_select(xg, edge[0].to(DEV)), O.gather_neighbors(xo, edge[0])
+    assert got.shape == ref.shape and torch.equal(got.cpu(), ref)
+    got.backward(up.to(DEV)); ref.backward(up)
+    assert gio.rel_err(xg.grad.cpu(), xo.grad) < REL_TOL
+    xg.grad = None; xo.grad = None
+    h, hr = ops.edge_features(xg, edge[0].to(DEV).int()), O.edge_features(xo, edge)
+    assert torch.equal(h.cpu(), hr)
+    m, mr = ops.max_over_k(h), torch.max(hr, -1, keepdim=True).values
+    assert torch.equal(m.cpu(), mr)
+    up2 = torch.randn(mr.shape, generator=torch.Generator().manual_seed(3))
+    m.backward(up2.to(DEV)); mr.backward(up2)
+    assert gio.rel_err(xg.grad.cpu(), xo.grad) < REL_TOL
+
+
+def test_aggregation_bf16():
+    """bf16 (BASELINE config 3): forward is exact on the bf16 inputs up to the final rounding of
+    x_j - x_i (<= 2^-8 relative); gradients within 2e-2 relative (bf16 atomics)."""
+    B, C, N, k = 2, 64, 256, 3
+    x = synth.synth_point_cloud(B, C, N, 9, relu=True).bfloat16()
+    edge = O.dilated_knn_graph(x.float(), k)
+    xg = x.to(DEV).requires_grad_(True)
+    out = ops.mr_aggregate(xg, edge[0].to(DEV).int())
+    assert out.dtype == torch.bfloat16
+    ref = O.max_relative_features(x.float(), edge)
+    assert torch.equal(out.float().cpu(), ref.bfloat16().float())
+    up = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1)).bfloat16()
+    xo = x.float().requires_grad_(True)
+    O.max_relative_features(xo, edge).backward(up.float())
+    out.backward(up.to(DEV))
+    assert gio.rel_err(xg.grad.float().cpu(), xo.grad) < 2e-2
+    nn_idx, _ = ops.knn_graph(x.to(DEV), k)
+    rep = O.knn_mismatch_report(x.float(), nn_idx.cpu(), k, ordered=False)
+    assert rep["rows_differing"] <= 0.05 * B * N, rep  # bf16 Gram: >= 95 % of rows pick the same neighbour set
+
+
+# ----------------------------------------------------------------------------------------
+# modules and the encoder
+# ----------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("conv", ["mr", "edge", "sage", "gin"])
+@pytest.mark.parametrize("d", [1, 2])
+def test_dygraphconv_modules_match_reference_golden(conv, d):
+    gold = gio.load("gconv")
+    B, C, N, k = (int(v) for v in gold["cfg"])
+    tag = f"{conv}_d{d}"
+    mod = torch_vertex.DyGraphConv2d(C, 2 * C, kernel_size=k, dilation=d, conv=conv, act="relu", norm="batch",
+                                     bias=True, stochastic=False, epsilon=0.0, r=1)
+    load_synth(mod, 40 + d).to(DEV).train()
+    x = gio.t(gold["x"]).to(DEV).requires_grad_(True)
+    out = mod(x)
+    assert gio.rel_err(out.cpu(), gio.t(gold[f"{tag}.out"])) < REL_TOL
+    out.backward(gio.t(gold[f"{tag}.upstream"]).to(DEV))
+    assert gio.rel_err(x.grad.cpu(), gio.t(gold[f"{tag}.grad_x"])) < REL_TOL
+    for name, p in mod.named_parameters():
+        assert gio.rel_err(p.grad.cpu(), gio.t(gold[f"{tag}.grad.{name}"])) < REL_TOL, name
+    for name, b in mod.named_buffers():
+        if b.dtype.is_floating_point:
+            assert gio.rel_err(b.cpu(), gio.t(gold[f"{tag}.buf.{name}"])) < REL_TOL, name
+
+
+def test_grapher_block_matches_reference_golden():
+    gold = gio.load("grapher")
+    B, C, N, k, d = (int(v) for v in gold["cfg"])
+    mod = torch_vertex.Grapher(C, k, d, "mr", "relu", "batch", True, False, 0.2, 1, n=N, drop_path=0.0, relative_pos=True)
+    assert torch.allclose(mod.relative_pos, gio.t(gold["relative_pos"]), atol=1e-6)
+    load_synth(mod, 61).to(DEV).train()
+    x = gio.t(gold["x"]).to(DEV).requires_grad_(True)
+    out = mod(x)
+    assert gio.rel_err(out.cpu(), gio.t(gold["out"])) < REL_TOL
+    out.backward(gio.t(gold["upstream"]).to(DEV))
+    assert gio.rel_err(x.grad.cpu(), gio.t(gold["grad_x"])) < REL_TOL
+    for name, p in mod.named_parameters():
+        if p.requires_grad:
+            assert gio.rel_err(p.grad.cpu(), gio.t(gold[f"grad.{name}"])) < REL_TOL, name
+    mod.eval()
+    with torch.no_grad():
+        assert gio.rel_err(mod(x.detach()).cpu(), gio.t(gold["out_eval"])) < REL_TOL
+
+
+def test_graph_encoder_matches_reference_golden():
+    gold = gio.load("encoder")
+    cfg = dict(synth.DEFAULT_CFG)
+    enc = GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3)
+    load_synth(enc, 81).to(DEV).train()
+    x = gio.t(gold["x"]).to(DEV).requires_grad_(True)
+    out = enc(x)
+    assert out.shape == (4, 1024)
+    assert gio.rel_err(out.cpu(), gio.t(gold["out_train"])) < REL_TOL
+    (out * gio.t(gold["upstream"]).to(DEV)).sum().backward()
+    assert gio.rel_err(x.grad.cpu(), gio.t(gold["grad_x"])) < REL_TOL
+    norms = dict(zip((str(n) for n in gold["grad_names"]), gold["grad_norm"]))
+    for name, p in enc.named_parameters():
+        if p.requires_grad:
+            got = float(p.grad.double().norm())
+            assert abs(got - norms[name]) <= REL_TOL * max(norms[name], 1e-12), name
+    assert gio.rel_err(enc.stem[0].weight.grad.cpu(), gio.t(gold["grad.stem.0.weight"])) < REL_TOL
+    assert gio.rel_err(enc.backbone[0][0].graph_conv.gconv.nn[0].weight.grad.cpu(),
+                       gio.t(gold["grad.backbone.0.0.graph_conv.gconv.nn.0.weight"])) < REL_TOL
+    assert gio.rel_err(enc.backbone[8][0].fc1[0].weight.grad.flatten()[:4096].cpu(),
+                       gio.t(gold["grad.backbone.8.0.fc1.0.weight.head"])) < REL_TOL
+    assert gio.rel_err(enc.stem[1].running_mean.cpu(), gio.t(gold["bn_running_mean.stem.1"])) < REL_TOL
+    assert gio.rel_err(enc.backbone[14][1].fc2[1].running_var.cpu(),
+                       gio.t(gold["bn_running_var.backbone.14.1.fc2.1"])) < REL_TOL
+    enc.eval()
+    with torch.no_grad():
+        assert gio.rel_err(enc(x.detach()).cpu(), gio.t(gold["out_eval"])) < REL_TOL
+
+
+def test_graph_encoder_vs_oracle_fresh_seed():
+    """Same check against the oracle itself (not a stored fixture) on another seed and batch."""
+    cfg = dict(synth.DEFAULT_CFG)
+    enc = GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3)
+    load_synth(enc, 555)
+    p = {k: v.clone() for k, v in enc.state_dict().items() if not k.endswith("relative_pos")}
+    x = torch.rand(6, 8, 1024, generator=torch.Generator().manual_seed(8))
+    ref = O.graph_encoder(p, x, True, k=3)
+    enc.to(DEV).train()
+    out = enc(x.to(DEV))
+    assert gio.rel_err(out.cpu(), ref) < REL_TOL
+
+
+def test_simclr_step_and_retrieval_match_reference_golden():
+    gold = gio.load("simclr")
+    cfg = dict(synth.DEFAULT_CFG)
+    model = SimCLR(cfg, GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3))
+    load_synth(model, 101).to(DEV).train()
+    s_i, s_j = gio.t(gold["spec_i"]).to(DEV), gio.t(gold["spec_j"]).to(DEV)
+    h_i, h_j, z_i, z_j = model(s_i, s_j)
+    assert gio.rel_err(z_i.cpu(), gio.t(gold["z_i"])) < REL_TOL and gio.rel_err(z_j.cpu(), gio.t(gold["z_j"])) < REL_TOL
+    loss = ntxent_loss(z_i, z_j, cfg)
+    assert abs(float(loss) - float(gold["loss"])) < REL_TOL * abs(float(gold["loss"]))
+    loss.backward()
+    norms = dict(zip((str(n) for n in gold["grad_names"]), gold["grad_norm"]))
+    worst = max(abs(float(p.grad.double().norm()) - norms[n]) / max(norms[n], 1e-12)
+                for n, p in model.named_parameters() if p.requires_grad)
+    assert worst < 5e-4, worst  # loss at tau=0.05 amplifies embedding noise ~20x into the gradients
+    model.eval()
+    with torch.no_grad():
+        db_specs, q_specs = synth.synth_spec(32, 121)
+        _, _, db, _ = model(db_specs.to(DEV), db_specs.to(DEV))
+        _, _, q, _ = model(q_specs[:8].to(DEV), q_specs[:8].to(DEV))
+    assert gio.rel_err(db.cpu(), gio.t(gold["db"])) < REL_TOL
+    assert torch.equal(O.top1_retrieval(db.cpu(), q.cpu()), gio.t(gold["top1"])), "identical top-1 retrieval hits"
+
+
+def test_state_dict_cross_loads_strict():
+    cfg = dict(synth.DEFAULT_CFG)
+    a = SimCLR(cfg, GraphEncoder(cfg=cfg, in_channels=8, k=3))
+    gold = gio.load("simclr")
+    sd = synth.synth_state_dict(gio.shapes_from(gold), 7)
+    a.load_state_dict(sd, strict=True)
