@@ -280,7 +280,7 @@ def run_ours(args):
     for _ in range(args.steps):
         x_i = host_i.to(dev, non_blocking=True)
         x_j = host_j.to(dev, non_blocking=True)
-        losses.append(float(step(x_i, x_j)))  # .item(): device -> host read of the step's result
+        losses.append(step(x_i, x_j).item())  # .item(): device -> host read of the step's result
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)

@@ -126,9 +126,9 @@ class GraphEncoder(nn.Module):
 
     def forward(self, x):
         """x: (B, C, num_points) -> (B, 1024)."""
-        # (B, C, N) -> logical (B, C, N, 1) stored as node rows (B, N, C): one transposing copy of the
-        # 8-channel input, after which every layer keeps the channels-last layout
-        x = x.transpose(1, 2).contiguous().transpose(1, 2).unsqueeze(-1)
+        # (B, C, N) -> logical (B, C, N, 1) stored as node rows (B, N, C) (canonical channels-last strides):
+        # one transposing copy of the 8-channel input, after which every layer keeps that layout
+        x = x.unsqueeze(-1).contiguous(memory_format=torch.channels_last)
         x = self.stem(x)
         for block in self.backbone:
             x = block(x)

@@ -91,7 +91,10 @@ def as_rows(x: torch.Tensor) -> torch.Tensor:
     s = x.stride()
     if (C == 1 or s[1] == 1) and (N == 1 or s[2] == C) and (B == 1 or s[0] == N * C):
         return x
-    return x.permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)
+    # canonical channels-last strides (N*C, 1, C, C): PyTorch / cuDNN recognise the result as NHWC
+    out = torch.empty_like(x, memory_format=torch.channels_last)
+    out.copy_(x)
+    return out
 
 
 def as_edge_rows(h: torch.Tensor) -> torch.Tensor:
@@ -100,15 +103,19 @@ def as_edge_rows(h: torch.Tensor) -> torch.Tensor:
     s = h.stride()
     if (C == 1 or s[1] == 1) and (k == 1 or s[3] == C) and (N == 1 or s[2] == k * C) and (B == 1 or s[0] == N * k * C):
         return h
-    return h.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    out = torch.empty_like(h, memory_format=torch.channels_last)
+    out.copy_(h)
+    return out
 
 
 def _new_rows(B: int, C: int, N: int, like: torch.Tensor) -> torch.Tensor:
-    return torch.empty((B, N, C, 1), dtype=like.dtype, device=like.device).permute(0, 2, 1, 3)
+    # strides (N*C, 1, C, C): rows (B, N, C) in memory *and* canonical torch.channels_last, so the
+    # cuDNN convolutions / batch norms that follow consume it without a layout copy
+    return torch.empty((B, C, N, 1), dtype=like.dtype, device=like.device, memory_format=torch.channels_last)
 
 
 def _new_edge_rows(B: int, C: int, N: int, k: int, like: torch.Tensor) -> torch.Tensor:
-    return torch.empty((B, N, k, C), dtype=like.dtype, device=like.device).permute(0, 3, 1, 2)
+    return torch.empty((B, C, N, k), dtype=like.dtype, device=like.device, memory_format=torch.channels_last)
 
 
 def _index_arg(idx: torch.Tensor) -> Tuple[torch.Tensor, int]:

@@ -23,3 +23,14 @@ def shapes_from(gold):
 def rel_err(a, b):
     a, b = a.detach().double(), b.detach().double()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def close(a, b, rel=1e-4, scale=0.0):
+    """||a - b|| <= rel * max(||b||, 0.1 * scale).
+
+    ``scale`` (the largest gradient norm of the module under test) gives a floor for gradients that
+    are mathematically zero - e.g. a conv bias feeding a train-mode BatchNorm - where both sides hold
+    nothing but rounding noise proportional to the other gradients.
+    """
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm()) <= rel * max(float(b.norm()), 0.1 * scale)

@@ -96,7 +96,9 @@ def test_ops_refuse_cpu_tensors():
 def test_as_rows_layouts():
     x = torch.randn(2, 8, 16, 1)
     r = ops.as_rows(x)
-    assert torch.equal(r, x) and r.permute(0, 2, 1, 3).is_contiguous()
+    assert torch.equal(r, x) and r.permute(0, 2, 1, 3).is_contiguous() and r.is_contiguous(memory_format=torch.channels_last)
+    assert ops._new_rows(2, 8, 16, x).is_contiguous(memory_format=torch.channels_last)
+    assert ops._new_edge_rows(2, 8, 16, 3, x).permute(0, 2, 3, 1).is_contiguous()
     cl = x.contiguous(memory_format=torch.channels_last)
     assert ops.as_rows(cl).data_ptr() == cl.data_ptr()
     h = torch.randn(2, 8, 16, 3)
