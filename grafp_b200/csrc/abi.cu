@@ -122,7 +122,7 @@ int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn
   { int rc = require_device_ptr("grafp_knn_fwd", "nn_idx", nn_idx); if (rc) return rc; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
-  const bool tc_ok = knn_tc_supported(N, M, C, (int)K, dtype);
+  const bool tc_ok = knn_tc_supported(N, M, C, (int)K, dtype) && relpos == nullptr;
   if (algo == GRAFP_KNN_TC && !tc_ok) {
     set_error("grafp_knn_fwd: the tcgen05 path does not support N=%d M=%d C=%d K=%lld dtype=%d", N, M, C, K, dtype);
     return GRAFP_EUNSUPPORTED;

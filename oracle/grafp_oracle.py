@@ -352,8 +352,9 @@ class GraphReplay:
     pick is a documented tie (``hard == 0``).
     """
 
-    def __init__(self, recorded):
+    def __init__(self, recorded, classify: bool = True):
         self.recorded = list(recorded)
+        self.classify = classify
         self.pos = 0
         self.mismatch = 0
         self.hard = 0
@@ -362,11 +363,12 @@ class GraphReplay:
     def __call__(self, x, k, dilation, y, relative_pos):
         nbr = self.recorded[self.pos].to(x.device).long()
         self.pos += 1
-        rep = knn_mismatch_report(x.detach(), nbr, k * dilation, None if y is None else y.detach(), relative_pos,
-                                  ordered=True, dilation=dilation)
-        self.mismatch += rep["mismatch"]
-        self.hard += rep["hard"]
-        self.entries += rep["entries"]
+        if self.classify:
+            rep = knn_mismatch_report(x.detach(), nbr, k * dilation, None if y is None else y.detach(), relative_pos,
+                                      ordered=True, dilation=dilation)
+            self.mismatch += rep["mismatch"]
+            self.hard += rep["hard"]
+            self.entries += rep["entries"]
         B, N, kk = nbr.shape
         centre = torch.arange(N, device=x.device).view(1, N, 1).expand(B, N, kk)
         return torch.stack((nbr, centre), dim=0)
