@@ -1,0 +1,19 @@
+"""Run the hot-path kernels alone at the benchmark batch (for `ncu --set full` captures)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from grafp_b200 import ops
+
+dev = "cuda"
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+for (N, C) in [(1024, 64), (512, 128), (256, 256), (128, 512)]:
+    x = torch.relu(torch.randn(B, C, N, 1, device=dev)).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    for _ in range(reps):
+        nbr, nbr32 = ops.knn_graph(x, 3)
+        out = ops.mr_aggregate(x, nbr32)
+        g = torch.randn_like(out)
+        (gx,) = torch.autograd.grad(out, x, g)
+    torch.cuda.synchronize()
+print("done", ops.knn_last_algo())

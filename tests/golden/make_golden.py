@@ -256,27 +256,28 @@ def make_simclr(ref):
                                     for _, p in model.named_parameters()])
     arrays["grad_names"] = np.array([n for n, _ in model.named_parameters()])
     arrays["peaks_i"] = model.peak_extractor(s_i)
-    # eval-mode fingerprints + retrieval on a small synthetic DB (config 5 in miniature)
-    model.eval()
+    # fingerprints + retrieval on a small synthetic DB (config 5 in miniature).  Like generate.py
+    # (:34-47,67-72), which never calls model.eval(), BatchNorm runs on batch statistics here.
     with torch.no_grad():
         db_specs, q_specs = synth.synth_spec(32, 121)
         _, _, db, _ = model(db_specs, db_specs)
-        _, _, q, _ = model(q_specs[:8], q_specs[:8])
+        _, _, q, _ = model(q_specs[:16], q_specs[:16])
     arrays.update(db=db, queries=q)
     d = (q * q).sum(1, keepdim=True) - 2 * q @ db.T + (db * db).sum(1)[None]
     arrays["top1"] = torch.argmin(d, dim=1)
+    best2 = torch.topk(-d, 2, dim=1).values
+    print("retrieval top1", arrays["top1"].tolist(), "min margin", float((best2[:, 0] - best2[:, 1]).min()))
     save("simclr", **arrays)
 
 
 def main():
     ref = _reference_import.load()
     torch.manual_seed(0)
-    make_knn(ref)
-    make_aggregate(ref)
-    make_gconv(ref)
-    make_grapher(ref)
-    make_encoder(ref)
-    make_simclr(ref)
+    only = set(sys.argv[1:])
+    for name, fn in (("knn", make_knn), ("aggregate", make_aggregate), ("gconv", make_gconv),
+                     ("grapher", make_grapher), ("encoder", make_encoder), ("simclr", make_simclr)):
+        if not only or name in only:
+            fn(ref)
 
 
 if __name__ == "__main__":

@@ -112,6 +112,33 @@ def test_knn_dense_stress_vs_oracle(C, d, algo):
     assert rep["mismatch"] <= 0.001 * rep["entries"]
 
 
+@pytest.mark.parametrize("B,C,N,M,k,d", [
+    (3, 48, 300, 0, 5, 1),      # ragged N and C: TMA zero-fills the tile edges
+    (2, 36, 130, 0, 3, 2),
+    (2, 64, 1000, 0, 3, 1),
+    (2, 64, 512, 128, 4, 1),    # separate key set (y): 128 keys -> one 128-wide key tile
+    (2, 32, 384, 200, 6, 2),    # separate key set, ragged
+    (2, 64, 1024, 0, 9, 1),     # K = 9: shared-memory list variant
+    (1, 512, 128, 0, 64, 1),    # K = 64 of 128 keys
+])
+def test_knn_tensor_core_path_vs_oracle(B, C, N, M, k, d):
+    x = synth.synth_point_cloud(B, C, N, 3000 + N + C)
+    y = synth.synth_point_cloud(B, C, M, 4000 + M) if M else None
+    nn_idx, _ = ops.knn_graph(x.to(DEV), k, d, None if y is None else y.to(DEV), algo=_native.KNN_TC)
+    assert ops.knn_last_algo() == "tcgen05"
+    assert_knn_ok(x, nn_idx, k, d, y, what=f"tc N={N} M={M} C={C} k={k} d={d}")
+
+
+def test_auto_picks_the_tensor_core_path_for_encoder_shapes():
+    for N, C in STAGES:
+        ops.knn_graph(torch.randn(2, C, N, 1, device=DEV), 3)
+        assert ops.knn_last_algo() == "tcgen05", (N, C)
+    ops.knn_graph(torch.randn(2, 16, 64, 1, device=DEV), 3)
+    assert ops.knn_last_algo() == "simt"
+    with pytest.raises(RuntimeError, match="tcgen05 path does not support"):
+        ops.knn_graph(torch.randn(2, 16, 64, 1, device=DEV), 3, algo=_native.KNN_TC)
+
+
 def test_knn_full_batch_properties():
     """BASELINE config 2 size (B=512 segments, stage-0 shape): size-independent properties."""
     B, C, N, k = 512, 64, 1024, 3
@@ -487,12 +514,12 @@ def test_simclr_step_and_retrieval_match_reference_golden():
     assert_grads_as_accurate_as_reference(ours, g32, g64, trainable)
     if replay.mismatch == 0:
         assert abs(float(loss) - float(gold["loss"])) < REL_TOL * abs(float(gold["loss"]))
-    # config 5 in miniature: eval-mode fingerprints of a synthetic DB, identical top-1 retrieval hits
-    model.eval()
+    # config 5 in miniature: fingerprints of a synthetic DB (BatchNorm on batch statistics, as generate.py
+    # leaves the model), identical top-1 retrieval hits
     with torch.no_grad():
         db_specs, q_specs = synth.synth_spec(32, 121)
         _, _, db, _ = model(db_specs.to(DEV), db_specs.to(DEV))
-        _, _, q, _ = model(q_specs[:8].to(DEV), q_specs[:8].to(DEV))
+        _, _, q, _ = model(q_specs[:16].to(DEV), q_specs[:16].to(DEV))
     assert gio.rel_err(db.cpu(), gio.t(gold["db"])) < 5e-2
     assert torch.equal(O.top1_retrieval(db.cpu(), q.cpu()), gio.t(gold["top1"])), "identical top-1 retrieval hits"
 

@@ -151,10 +151,10 @@ def test_simclr_step_and_retrieval_match_reference():
     assert gio.rel_err(z_j, gio.t(gold["z_j"])) < 1e-5
     loss = O.ntxent_loss(z_i, z_j, synth.DEFAULT_CFG["tau"])
     assert abs(float(loss) - float(gold["loss"])) < 1e-5 * abs(float(gold["loss"]))
-    with torch.no_grad():
+    with torch.no_grad():  # BatchNorm on batch statistics, as generate.py leaves the model (never .eval())
         db_specs, q_specs = synth.synth_spec(32, 121)
-        _, _, db, _ = O.simclr_forward(p, db_specs, db_specs, False)
-        _, _, q, _ = O.simclr_forward(p, q_specs[:8], q_specs[:8], False)
+        _, _, db, _ = O.simclr_forward(p, db_specs, db_specs, True)
+        _, _, q, _ = O.simclr_forward(p, q_specs[:16], q_specs[:16], True)
     assert gio.rel_err(db, gio.t(gold["db"])) < 1e-5
     assert torch.equal(O.top1_retrieval(db, q), gio.t(gold["top1"]))
     assert np.array_equal(O.top1_retrieval(gio.t(gold["db"]), gio.t(gold["queries"])).numpy(), gold["top1"])
