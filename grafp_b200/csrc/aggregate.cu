@@ -75,6 +75,94 @@ mr_aggregate_fwd_kernel(const T* __restrict__ x, const T* __restrict__ src, cons
   }
 }
 
+// Fast path (4-channel packs, C/4 a power of two <= 256, centre == row): grid.y = segment, so all index
+// arithmetic is 32-bit shifts/masks (the generic kernel spends most of its issue slots on 64-bit
+// divisions).  Every thread keeps U independent (row, 4-channel) items in flight so the dependent chain
+// id -> neighbour row -> store is overlapped U-deep.
+template <typename T, bool I64, int U>
+__global__ void __launch_bounds__(kThreads)
+mr_aggregate_fwd_fast_kernel(const T* __restrict__ x, const T* __restrict__ src, const void* __restrict__ nbr,
+                             T* __restrict__ out, uint8_t* __restrict__ argmax, int N, int M, int C, int k,
+                             int cv_shift) {
+  const int b = blockIdx.y;
+  const int rpb = kThreads >> cv_shift;                       // rows per block pass
+  const int r_local = threadIdx.x >> cv_shift;
+  const int c = (threadIdx.x & ((1 << cv_shift) - 1)) * 4;
+  const T* xb = x + (long long)b * N * C + c;
+  const T* sb = src + (long long)b * M * C + c;
+  T* ob = out + (long long)b * N * 2 * C + 2 * c;
+  uint8_t* ab = argmax ? argmax + (long long)b * N * C + c : nullptr;
+  const long long ib = (long long)b * N * k;
+  for (int n0 = blockIdx.x * rpb * U + r_local; n0 < N; n0 += gridDim.x * rpb * U) {
+    int n[U];
+    float self[U][4], best[U][4];
+    int arg[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      n[u] = min(n0 + u * rpb, N - 1);  // clamp: dead lanes recompute the last row, stores are guarded
+      Pack<T, 4>::load(xb + (long long)n[u] * C, self[u]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { best[u][e] = -INFINITY; arg[u][e] = 0; }
+    }
+    // The compare chain is the issue-slot bottleneck (FSETP/FSEL/SEL all share the ALU pipe), so it is
+    // kept to one compare + two selects per element; NaN / inf inputs are detected on the FMA pipe
+    // (d * 0 accumulates to NaN) and such rows are redone by the exact slow path below.
+    float poison[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) poison[u] = 0.f;
+    for (int j = 0; j < k; ++j) {
+      int nb[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) nb[u] = load_index<I64>(nbr, ib + n[u] * k + j);
+      float xj[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u) Pack<T, 4>::load(sb + (long long)nb[u] * C, xj[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float d = xj[u][e] - self[u][e];
+          poison[u] = fmaf(d, 0.f, poison[u]);
+          const bool gt = d > best[u][e];  // strict: the first maximiser wins
+          best[u][e] = gt ? d : best[u][e];
+          arg[u][e] = gt ? j : arg[u][e];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (poison[u] != 0.f) {  // NaN or inf seen: redo with torch.max semantics (NaN propagates, first NaN wins)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { best[u][e] = -INFINITY; arg[u][e] = 0; }
+        for (int j = 0; j < k; ++j) {
+          const int nbj = load_index<I64>(nbr, ib + n[u] * k + j);
+          float xj[4];
+          Pack<T, 4>::load(sb + (long long)nbj * C, xj);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float d = xj[e] - self[u][e];
+            if (d > best[u][e] || d != d) {
+              if (!(best[u][e] != best[u][e])) { best[u][e] = d; arg[u][e] = j; }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (n0 + u * rpb >= N) continue;
+      T* o = ob + (long long)n[u] * 2 * C;
+      const float il[8] = {self[u][0], best[u][0], self[u][1], best[u][1], self[u][2], best[u][2], self[u][3], best[u][3]};
+      Pack8<T>::store(o, il);  // one full-sector store per thread
+      if (ab != nullptr) {
+        const unsigned int packed = (unsigned)arg[u][0] | ((unsigned)arg[u][1] << 8) | ((unsigned)arg[u][2] << 16) |
+                                    ((unsigned)arg[u][3] << 24);
+        *reinterpret_cast<unsigned int*>(ab + (long long)n[u] * C) = packed;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // K3 (generic form): dense pass + atomic scatter pass, ordered by the stream.
 //   dense:   grad_x[row][c] = g[row][2c] (- g[row][2c+1] when the centre is the row itself)
@@ -190,6 +278,159 @@ mr_aggregate_bwd_scatter_kernel(const T* __restrict__ g, const uint8_t* __restri
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------
+// K3 (fused form, the one the k-NN graphs of the encoder use): one thread-block cluster per
+// segment.  Phase 1: every CTA streams its share of grad_out rows once, writes the dense part
+// of grad_x with plain stores and parks g[.., 2c+1] + argmax in shared memory.  A cluster
+// barrier orders all dense stores of the segment before phase 2, which routes the parked
+// values to their winning neighbour rows with vector reductions (red.global.add.v4.f32) that
+// hit the just-written, L2-resident grad_x rows.  HBM traffic = algorithmic bytes: grad_out,
+// argmax and the ids are read once, grad_x is written once.
+// ------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 256;
+
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <typename T, bool I64, int U>
+__global__ void __launch_bounds__(kFusedThreads, 4)
+mr_aggregate_bwd_fused_kernel(const T* __restrict__ g, const uint8_t* __restrict__ argmax, const void* __restrict__ nbr,
+                              T* __restrict__ grad_x, int N, int C, int k, int rows_per_cta, int cv_shift) {
+  extern __shared__ __align__(16) unsigned char fused_smem[];
+  const int cv = 1 << cv_shift;
+  float4* g1s = reinterpret_cast<float4*>(fused_smem);                                     // [rows_per_cta * cv]
+  unsigned int* ams = reinterpret_cast<unsigned int*>(fused_smem + (size_t)rows_per_cta * cv * 16);
+  const unsigned csize = cluster_nctarank();
+  const long long b = blockIdx.x / csize;
+  const int row0 = static_cast<int>(cluster_ctarank()) * rows_per_cta;
+  const int nrows = max(0, min(rows_per_cta, N - row0));
+  const int items = nrows << cv_shift;
+  const T* gb = g + b * (long long)N * 2 * C;
+  const uint8_t* ab = argmax + b * (long long)N * C;
+  T* gxb = grad_x + b * (long long)N * C;
+  const long long ib = b * (long long)N * k;
+
+  // phase 1: U independent items per thread in flight (loads first, then the dependent id look-ups)
+  for (int it0 = threadIdx.x; it0 < items; it0 += kFusedThreads * U) {
+    float g0[U][4], g1[U][4];
+    unsigned int packed[U];
+    int n[U], c[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int it = min(it0 + u * kFusedThreads, items - 1);
+      n[u] = row0 + (it >> cv_shift);
+      c[u] = (it & (cv - 1)) * 4;
+      {
+        float gp[8];
+        Pack8<T>::load(gb + (long long)n[u] * 2 * C + 2 * c[u], gp);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { g0[u][e] = gp[2 * e]; g1[u][e] = gp[2 * e + 1]; }
+      }
+      packed[u] = __ldg(reinterpret_cast<const unsigned int*>(ab + (long long)n[u] * C + c[u]));
+    }
+    int nb[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) nb[u][e] = load_index<I64>(nbr, ib + n[u] * k + ((packed[u] >> (8 * e)) & 0xff));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int it = it0 + u * kFusedThreads;
+      if (it >= items) continue;
+      float r[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r[e] = (nb[u][e] == n[u]) ? g0[u][e] : g0[u][e] - g1[u][e];
+      Pack<T, 4>::store(gxb + (long long)n[u] * C + c[u], r);
+      g1s[it] = make_float4(g1[u][0], g1[u][1], g1[u][2], g1[u][3]);
+      ams[it] = packed[u];
+    }
+  }
+  __threadfence();
+  cluster_sync_all();
+
+  // phase 2: route the parked values to the winning neighbour rows of this segment
+  for (int it = threadIdx.x; it < items; it += kFusedThreads) {
+    const int n = row0 + (it >> cv_shift);
+    const int c = (it & (cv - 1)) * 4;
+    const float4 gv = g1s[it];
+    const unsigned int packed = ams[it];
+    const float g1[4] = {gv.x, gv.y, gv.z, gv.w};
+    // One 16-byte reduction per distinct winning neighbour (channels that picked another neighbour add 0):
+    // the reduction issue rate, not the bytes, bounds this phase.
+    int a[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) a[e] = (packed >> (8 * e)) & 0xff;
+    unsigned todo = 0xf;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (todo & (1u << e)) {
+        const int j = a[e];
+        float v[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          const bool hit = (a[f] == j);
+          v[f] = hit ? g1[f] : 0.f;
+          if (hit) todo &= ~(1u << f);
+        }
+        const int nb = load_index<I64>(nbr, ib + n * k + j);
+        if (nb != n) Pack<T, 4>::red_add(gxb + (long long)nb * C + c, v);
+      }
+    }
+  }
+}
+
+template <typename T, bool I64, int U>
+int launch_mr_bwd_fused(const T* g, const uint8_t* argmax, const void* nbr, T* grad_x, int B, int N, int C, int k,
+                        cudaStream_t s, bool* launched) {
+  *launched = false;
+  const int cv = C / 4;
+  if ((cv & (cv - 1)) != 0 || !aligned32(g)) return GRAFP_OK;  // C/4 a power of two (shift/mask indexing), 256-bit loads
+  int cv_shift = 0;
+  while ((1 << cv_shift) < cv) ++cv_shift;
+  // cluster of 8 CTAs per segment when the per-CTA share (g1 stash 4 B + argmax 1 B per element) fits
+  // 48 KB (4 CTAs resident per SM in different phases), else the smallest cluster that fits 96 KB
+  int cl = 0;
+  if (N >= 64 && (long long)((N + 7) / 8) * C * 5 <= 48 * 1024) cl = 8;
+  else {
+    for (int cand : {2, 4, 8}) {
+      const long long rows = (N + cand - 1) / cand;
+      if (rows * C * 5 <= 96 * 1024) { cl = cand; break; }
+    }
+  }
+  if (cl == 0) return GRAFP_OK;
+  if ((long long)B * cl > 0x7fffffffLL) return GRAFP_OK;
+  const int rows_per_cta = (N + cl - 1) / cl;
+  const size_t smem = (size_t)rows_per_cta * C * 5;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mr_aggregate_bwd_fused_kernel<T, I64, U>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_bwd_fused): %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * cl));
+  cfg.blockDim = dim3(kFusedThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mr_aggregate_bwd_fused_kernel<T, I64, U>, g, argmax, nbr, grad_x, N, C, k,
+                                     rows_per_cta, cv_shift);
+  if (e != cudaSuccess) { set_error("mr_aggregate_bwd_fused launch: %s", cudaGetErrorString(e)); return (int)e; }
+  *launched = true;
+  return check_launch("mr_aggregate_bwd_fused");
 }
 
 // ------------------------------------------------------------------------------------
@@ -379,6 +620,25 @@ max_over_k_bwd_kernel(const T* __restrict__ g, const uint8_t* __restrict__ argma
 // ------------------------------------------------------------------------------------
 namespace {
 
+// development switches: GRAFP_MR_FWD_VARIANT = 0 generic kernel, 1 / 2 / 4 fast kernel with that many items in
+// flight per thread (default 4); GRAFP_MR_BWD_VARIANT = 0 two-kernel form, 1 / 2 / 4 fused cluster form (default 2)
+int fwd_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GRAFP_MR_FWD_VARIANT");
+    v = e ? atoi(e) : 4;
+  }
+  return v;
+}
+int bwd_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GRAFP_MR_BWD_VARIANT");
+    v = e ? atoi(e) : 2;
+  }
+  return v;
+}
+
 template <typename F>
 int dispatch_vec_idx(int C, bool ptrs_aligned, int idx_is_i64, F&& f) {
   const bool vec4 = (C % 4 == 0) && ptrs_aligned;
@@ -403,6 +663,26 @@ int launch_mr_aggregate_fwd(const void* x, const void* y, const void* nbr, const
     constexpr int VEC = decltype(vec)::value;
     constexpr bool I64 = decltype(i64)::value;
     const int grid = grid_for(rows * (C / VEC), kThreads, 8);
+    if constexpr (VEC == 4) {
+      const int cv = C / 4;
+      const int variant = fwd_variant();
+      if (!ctr && variant > 0 && (cv & (cv - 1)) == 0 && cv <= kThreads && B <= 65535 && aligned32(out)) {
+        int cv_shift = 0;
+        while ((1 << cv_shift) < cv) ++cv_shift;
+        const int rpb = kThreads >> cv_shift;
+        const int u = variant;  // items in flight per thread: 1, 2 or 4
+        const int passes = (N + rpb * u - 1) / (rpb * u);
+        int gx = (num_sms() * 8 + B - 1) / B;  // about 8 resident CTAs per SM across the whole batch
+        if (gx > passes) gx = passes;
+        if (gx < 1) gx = 1;
+        dim3 grid2(gx, B);
+        T* o = static_cast<T*>(out);
+        if (u == 1) mr_aggregate_fwd_fast_kernel<T, I64, 1><<<grid2, kThreads, 0, s>>>(xs, src, nbr, o, argmax, N, M, C, k, cv_shift);
+        else if (u == 2) mr_aggregate_fwd_fast_kernel<T, I64, 2><<<grid2, kThreads, 0, s>>>(xs, src, nbr, o, argmax, N, M, C, k, cv_shift);
+        else mr_aggregate_fwd_fast_kernel<T, I64, 4><<<grid2, kThreads, 0, s>>>(xs, src, nbr, o, argmax, N, M, C, k, cv_shift);
+        return check_launch("mr_aggregate_fwd");
+      }
+    }
     if (ctr) {
       mr_aggregate_fwd_kernel<T, VEC, I64, true><<<grid, kThreads, 0, s>>>(xs, src, nbr, ctr, static_cast<T*>(out),
                                                                             argmax, rows, N, M, C, k);
@@ -431,6 +711,16 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
     const int grid = grid_for(rows * (C / VEC), kThreads, 8);
     const T* gs = static_cast<const T*>(g);
     const bool self_skip = (ctr == nullptr) && (grad_y == nullptr);
+    if constexpr (VEC == 4) {
+      const int bv = bwd_variant();  // 0: two-kernel form; 1 / 2 / 4: fused form with that many items in flight
+      if (self_skip && bv > 0) {
+        bool launched = false;
+        const int rc = bv == 1 ? launch_mr_bwd_fused<T, I64, 1>(gs, argmax, nbr, gx, B, N, C, k, s, &launched)
+                     : bv == 2 ? launch_mr_bwd_fused<T, I64, 2>(gs, argmax, nbr, gx, B, N, C, k, s, &launched)
+                               : launch_mr_bwd_fused<T, I64, 4>(gs, argmax, nbr, gx, B, N, C, k, s, &launched);
+        if (rc != GRAFP_OK || launched) return rc;
+      }
+    }
     if (self_skip) {
       mr_aggregate_bwd_dense_kernel<T, VEC, I64, true><<<grid, kThreads, 0, s>>>(gs, argmax, nbr, gx, rows, N, C, k, true);
       mr_aggregate_bwd_scatter_kernel<T, VEC, I64, false, true><<<grid, kThreads, 0, s>>>(gs, argmax, nbr, ctr, gx, gsrc,

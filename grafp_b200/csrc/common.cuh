@@ -7,6 +7,8 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <initializer_list>
 #include <type_traits>
 
 #include "../../include/grafp_b200.h"
@@ -42,6 +44,9 @@ struct Pack<float, 4> {
   static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
+  static __device__ __forceinline__ void store_streaming(float* p, const float (&v)[4]) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  }
   static __device__ __forceinline__ void red_add(float* p, const float (&v)[4]) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                  "f"(v[3])
@@ -72,6 +77,14 @@ struct Pack<__nv_bfloat16, 4> {
     t.y = *reinterpret_cast<uint32_t*>(&b);
     *reinterpret_cast<uint2*>(p) = t;
   }
+  static __device__ __forceinline__ void store_streaming(__nv_bfloat16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a);
+    t.y = *reinterpret_cast<uint32_t*>(&b);
+    __stcs(reinterpret_cast<uint2*>(p), t);
+  }
   static __device__ __forceinline__ void red_add(__nv_bfloat16* p, const float (&v)[4]) {
     atomicAdd(reinterpret_cast<__nv_bfloat162*>(p), __floats2bfloat162_rn(v[0], v[1]));
     atomicAdd(reinterpret_cast<__nv_bfloat162*>(p) + 1, __floats2bfloat162_rn(v[2], v[3]));
@@ -86,6 +99,50 @@ struct Pack<__nv_bfloat16, 1> {
     atomicAdd(p, __float2bfloat16_rn(v[0]));
   }
 };
+
+// 8 consecutive elements (32 bytes of fp32 -> one 256-bit LDG/STG on sm_100; 16 bytes of bf16)
+template <typename T>
+struct Pack8;
+
+template <>
+struct Pack8<float> {
+  static constexpr int kAlign = 32;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+  }
+};
+
+template <>
+struct Pack8<__nv_bfloat16> {
+  static constexpr int kAlign = 16;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
 template <bool I64>
 __device__ __forceinline__ int load_index(const void* idx, long long pos) {

@@ -52,6 +52,87 @@ knn_normalize_kernel(const T* __restrict__ x, float* __restrict__ xhat, float* _
   }
 }
 
+// Vectorised form for C % 4 == 0 and C <= 1024: a group of LPR lanes owns one node row, every lane
+// keeps its 4-channel packs in registers (one 16-byte load per pack), the two reductions are
+// xor-shuffles inside the group.  LPR = min(32, pow2 >= C/4), so a warp covers 32/LPR rows.
+template <typename T, int MODE, int LPR, int PACKS>
+__global__ void __launch_bounds__(256)
+knn_normalize_vec_kernel(const T* __restrict__ x, float* __restrict__ xhat, float* __restrict__ lo,
+                         float* __restrict__ sq, long long rows, int C, bool normalize) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  constexpr int RPW = 32 / LPR;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int cv = C / 4;
+  for (long long rb = warp0 * RPW; rb < rows; rb += nwarps * RPW) {
+    const long long row = rb + lane / LPR;
+    const bool live = row < rows;
+    float v[PACKS][4];
+    float ss = 0.f;
+#pragma unroll
+    for (int p = 0; p < PACKS; ++p) {
+      const int c4 = sub + p * LPR;
+      if (live && c4 < cv) Pack<T, 4>::load(x + row * C + c4 * 4, v[p]);
+      else { v[p][0] = v[p][1] = v[p][2] = v[p][3] = 0.f; }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ss = fmaf(v[p][e], v[p][e], ss);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float denom = normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+    float s2 = 0.f;
+#pragma unroll
+    for (int p = 0; p < PACKS; ++p) {
+      const int c4 = sub + p * LPR;
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float q = __fdiv_rn(v[p][e], denom);
+        if constexpr (MODE == 1) {
+          h[e] = __uint_as_float(__float_as_uint(q) & 0xffffe000u);
+          l[e] = __uint_as_float(__float_as_uint(q - h[e]) & 0xffffe000u);
+        } else if constexpr (MODE == 2) {
+          h[e] = q;
+          q = __bfloat162float(__float2bfloat16_rn(q));
+        } else {
+          h[e] = q;
+        }
+        s2 = fmaf(q, q, s2);
+      }
+      if (live && c4 < cv) {
+        if constexpr (MODE == 2) {
+          Pack<__nv_bfloat16, 4>::store(reinterpret_cast<__nv_bfloat16*>(xhat) + row * C + c4 * 4, h);
+        } else {
+          Pack<float, 4>::store(xhat + row * C + c4 * 4, h);
+          if constexpr (MODE == 1) Pack<float, 4>::store(lo + row * C + c4 * 4, l);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (live && sub == 0) sq[row] = s2;
+  }
+}
+
+template <typename T, int MODE>
+static bool launch_normalize_vec(const T* xs, float* xhat, float* lo, float* sq, long long rows, int C, bool normalize,
+                                 int blocks, cudaStream_t s) {
+  const int cv = C / 4;
+#define GRAFP_NORM_CASE(LPR_, PACKS_)                                                                        \
+  knn_normalize_vec_kernel<T, MODE, LPR_, PACKS_><<<blocks, 256, 0, s>>>(xs, xhat, lo, sq, rows, C, normalize); \
+  return true;
+  if (cv <= 4) { GRAFP_NORM_CASE(4, 1) }
+  if (cv <= 8) { GRAFP_NORM_CASE(8, 1) }
+  if (cv <= 16) { GRAFP_NORM_CASE(16, 1) }
+  if (cv <= 32) { GRAFP_NORM_CASE(32, 1) }
+  if (cv <= 64) { GRAFP_NORM_CASE(32, 2) }
+  if (cv <= 128) { GRAFP_NORM_CASE(32, 4) }
+  if (cv <= 256) { GRAFP_NORM_CASE(32, 8) }
+#undef GRAFP_NORM_CASE
+  return false;
+}
+
 template <typename T>
 int launch_knn_normalize(const void* x, float* xhat, float* lo, float* sq, long long rows, int C, int mode,
                          bool normalize, cudaStream_t s) {
@@ -61,6 +142,14 @@ int launch_knn_normalize(const void* x, float* xhat, float* lo, float* sq, long 
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   const T* xs = static_cast<const T*>(x);
+  const bool vec = (C % 4 == 0) && aligned16(x) && aligned16(xhat) && aligned16(lo);
+  if (vec) {
+    bool done = false;
+    if (mode == 0) done = launch_normalize_vec<T, 0>(xs, xhat, lo, sq, rows, C, normalize, (int)blocks, s);
+    else if (mode == 1) done = launch_normalize_vec<T, 1>(xs, xhat, lo, sq, rows, C, normalize, (int)blocks, s);
+    else done = launch_normalize_vec<T, 2>(xs, xhat, lo, sq, rows, C, normalize, (int)blocks, s);
+    if (done) return check_launch("knn_normalize");
+  }
   if (mode == 0) knn_normalize_kernel<T, 0><<<(int)blocks, threads, 0, s>>>(xs, xhat, lo, sq, rows, C, normalize);
   else if (mode == 1) knn_normalize_kernel<T, 1><<<(int)blocks, threads, 0, s>>>(xs, xhat, lo, sq, rows, C, normalize);
   else knn_normalize_kernel<T, 2><<<(int)blocks, threads, 0, s>>>(xs, xhat, lo, sq, rows, C, normalize);
