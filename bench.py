@@ -192,7 +192,7 @@ def run_ours(args):
     from grafp_b200 import _native, ops, synth
     from grafp_b200.encoder.graph_encoder import GraphEncoder
     from grafp_b200.simclr.simclr import SimCLR
-    from grafp_b200.simclr.ntxent import ntxent_loss
+    from grafp_b200.simclr.distributed import global_ntxent_loss
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -227,15 +227,8 @@ def run_ours(args):
     h2d_bytes = host_i.numel() * 4 + host_j.numel() * 4
 
     def loss_fn(z_i, z_j):
-        if world == 1:
-            return ntxent_loss(z_i, z_j, cfg)
-        # global-batch negatives like the reference's DataParallel gather (train.py:69-71): all_gather the
-        # embeddings, keep the local rows differentiable; the sum over ranks of the local losses' gradients
-        # equals the gradient of the global loss, DDP's mean-reduction is undone by scaling with `world`.
-        import torch.distributed.nn.functional as dfn
-        zi_all = torch.cat(dfn.all_gather(z_i), 0)
-        zj_all = torch.cat(dfn.all_gather(z_j), 0)
-        return ntxent_loss(zi_all, zj_all, cfg)
+        # global-batch negatives like the reference's DataParallel gather (train.py:69-71)
+        return global_ntxent_loss(z_i, z_j, cfg)
 
     def step(x_i, x_j):
         opt.zero_grad(set_to_none=True)

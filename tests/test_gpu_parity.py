@@ -516,12 +516,32 @@ def test_simclr_step_and_retrieval_match_reference_golden():
         assert abs(float(loss) - float(gold["loss"])) < REL_TOL * abs(float(gold["loss"]))
     # config 5 in miniature: fingerprints of a synthetic DB (BatchNorm on batch statistics, as generate.py
     # leaves the model), identical top-1 retrieval hits
+    db_specs, q_specs = synth.synth_spec(32, 121)
+    rec, handles = record_graphs(model)
     with torch.no_grad():
-        db_specs, q_specs = synth.synth_spec(32, 121)
         _, _, db, _ = model(db_specs.to(DEV), db_specs.to(DEV))
         _, _, q, _ = model(q_specs[:16].to(DEV), q_specs[:16].to(DEV))
-    assert gio.rel_err(db.cpu(), gio.t(gold["db"])) < 5e-2
-    assert torch.equal(O.top1_retrieval(db.cpu(), q.cpu()), gio.t(gold["top1"])), "identical top-1 retrieval hits"
+    for h in handles:
+        h.remove()
+    ours_top1 = O.top1_retrieval(db.cpu(), q.cpu())
+    # (a) against the oracle fed with the same graphs: identical hits, embeddings within 1e-4
+    p = _to(base, torch.float32)  # weights are unchanged (no optimizer step); batch-statistics BN ignores running stats
+    replay = O.GraphReplay(rec)
+    with torch.no_grad():
+        _, _, db_ref, _ = O.simclr_forward(p, db_specs, db_specs, True, graph_fn=replay)
+        _, _, q_ref, _ = O.simclr_forward(p, q_specs[:16], q_specs[:16], True, graph_fn=replay)
+    assert replay.hard == 0
+    assert gio.rel_err(db.cpu(), db_ref) < REL_TOL
+    assert torch.equal(ours_top1, O.top1_retrieval(db_ref, q_ref)), "identical top-1 retrieval hits"
+    # (b) against the hits stored from the upstream reference: a query may only differ if its two best
+    # candidates are closer than the embedding noise a differently resolved k-NN tie can cause
+    gold_top1 = gio.t(gold["top1"])
+    gdb, gq = gio.t(gold["db"]), gio.t(gold["queries"])
+    dist = (gq * gq).sum(1, keepdim=True) - 2 * gq @ gdb.T + (gdb * gdb).sum(1)[None]
+    best2 = torch.topk(-dist, 2, dim=1).values
+    margin = (best2[:, 0] - best2[:, 1])
+    differs = ours_top1 != gold_top1
+    assert int(differs.sum()) <= 1 and bool((margin[differs] < 0.02).all()), (ours_top1, gold_top1, margin)
 
 
 def test_state_dict_cross_loads_strict():
