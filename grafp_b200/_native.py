@@ -20,6 +20,7 @@ SIGNATURES = {
     "grafp_abi_version": (_i, []),
     "grafp_last_error": (_c.c_char_p, []),
     "grafp_knn_last_algo": (_c.c_char_p, []),
+    "grafp_knn_last_variant": (_c.c_char_p, []),
     "grafp_knn_workspace_bytes": (_sz, [_i] * 6),
     "grafp_knn_fwd": (_i, [_vp] * 5 + [_i] * 10 + [_vp, _sz, _vp]),
     "grafp_mr_aggregate_fwd": (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 6 + [_vp]),
@@ -33,7 +34,7 @@ SIGNATURES = {
 }
 
 ABI_VERSION = 1
-KNN_AUTO, KNN_SIMT, KNN_TC = 0, 1, 2
+KNN_AUTO, KNN_SIMT, KNN_TC, KNN_TC_TF32 = 0, 1, 2, 3
 KNN_MAX_K = 64
 
 _lib = None

@@ -9,6 +9,7 @@ namespace grafp {
 namespace {
 thread_local std::string g_error;
 thread_local const char* g_knn_algo = "none";
+thread_local const char* g_knn_variant = "none";
 }  // namespace
 
 void set_error(const char* fmt, ...) {
@@ -93,6 +94,7 @@ extern "C" {
 int grafp_abi_version(void) { return GRAFP_ABI_VERSION; }
 const char* grafp_last_error(void) { return g_error.c_str(); }
 const char* grafp_knn_last_algo(void) { return g_knn_algo; }
+const char* grafp_knn_last_variant(void) { return g_knn_variant; }
 
 size_t grafp_knn_workspace_bytes(int B, int N, int M, int C, int K, int dtype) {
   (void)K; (void)dtype;
@@ -115,19 +117,23 @@ int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn
   const long long K = (long long)k * dilation;
   GRAFP_REQUIRE(K <= M, GRAFP_EINVAL, "grafp_knn_fwd: k*dilation = %lld exceeds the number of key nodes %d", K, M);
   GRAFP_REQUIRE(K <= GRAFP_KNN_MAX_K, GRAFP_EUNSUPPORTED, "grafp_knn_fwd: k*dilation = %lld exceeds %d", K, GRAFP_KNN_MAX_K);
-  GRAFP_REQUIRE(algo >= GRAFP_KNN_AUTO && algo <= GRAFP_KNN_TC, GRAFP_EINVAL, "grafp_knn_fwd: unknown algo %d", algo);
+  GRAFP_REQUIRE(algo >= GRAFP_KNN_AUTO && algo <= GRAFP_KNN_TC_TF32, GRAFP_EINVAL, "grafp_knn_fwd: unknown algo %d", algo);
   GRAFP_REQUIRE(workspace_bytes >= grafp_knn_workspace_bytes(B, N, M, C, (int)K, dtype), GRAFP_EWORKSPACE,
                 "grafp_knn_fwd: workspace of %zu bytes is smaller than grafp_knn_workspace_bytes()", workspace_bytes);
   { int rc = require_device_ptr("grafp_knn_fwd", "x", x); if (rc) return rc; }
   { int rc = require_device_ptr("grafp_knn_fwd", "nn_idx", nn_idx); if (rc) return rc; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
-  const bool tc_ok = knn_tc_supported(N, M, C, (int)K, dtype) && relpos == nullptr;
-  if (algo == GRAFP_KNN_TC && !tc_ok) {
+  // tensor-core kernels: f16x3 (knn_tc2.cu, K <= 8) preferred, tf32x3 (knn_tc.cu) for the rest of the envelope
+  // (f16x3 needs |x| <= 1, i.e. the normalised features DenseDilatedKnnGraph always passes)
+  const bool tc2_ok = relpos == nullptr && normalize != 0 && knn_tc2_supported(N, M, C, (int)K, dtype, y == nullptr);
+  const bool tc1_ok = relpos == nullptr && knn_tc_supported(N, M, C, (int)K, dtype);
+  if ((algo == GRAFP_KNN_TC && !tc2_ok && !tc1_ok) || (algo == GRAFP_KNN_TC_TF32 && !tc1_ok)) {
     set_error("grafp_knn_fwd: the tcgen05 path does not support N=%d M=%d C=%d K=%lld dtype=%d", N, M, C, K, dtype);
     return GRAFP_EUNSUPPORTED;
   }
-  const bool use_tc = (algo == GRAFP_KNN_TC) || (algo == GRAFP_KNN_AUTO && tc_ok);
+  const bool use_tc2 = tc2_ok && (algo == GRAFP_KNN_TC || algo == GRAFP_KNN_AUTO);
+  const bool use_tc = use_tc2 || algo == GRAFP_KNN_TC_TF32 || (tc1_ok && (algo == GRAFP_KNN_TC || algo == GRAFP_KNN_AUTO));
 
   // carve the workspace
   char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
@@ -141,7 +147,7 @@ int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn
   float* x_sq = reinterpret_cast<float*>(base + 2 * qx + 2 * qy);
   float* y_sq = reinterpret_cast<float*>(base + 2 * qx + 2 * qy + sx);
 
-  const int mode = use_tc ? (dtype == GRAFP_F32 ? 1 : 2) : 0;
+  const int mode = use_tc2 ? 3 : (use_tc ? (dtype == GRAFP_F32 ? 1 : 2) : 0);
   int rc;
   if (dtype == GRAFP_F32) {
     rc = launch_knn_normalize<float>(x, x_hi, x_lo, x_sq, (long long)B * N, C, mode, normalize != 0, s);
@@ -155,12 +161,20 @@ int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn
 
   const int k_out = emit_all ? (int)K : k;
   const int stride = emit_all ? 1 : dilation;
+  if (use_tc2) {
+    g_knn_algo = "tcgen05";
+    g_knn_variant = "f16x3";
+    return launch_knn_tc2(x_hi, x_lo, x_sq, y_hi, y_lo, y_sq, reinterpret_cast<long long*>(nn_idx), nn_idx32, B, N, M, C,
+                          (int)K, k_out, stride, dtype, y == nullptr, s);
+  }
   if (use_tc) {
     g_knn_algo = "tcgen05";
+    g_knn_variant = "tf32x3";
     return launch_knn_tc(x_hi, x_lo, x_sq, y_hi, y_lo, y_sq, relpos, reinterpret_cast<long long*>(nn_idx), nn_idx32, B, N,
                          M, C, (int)K, k_out, stride, dtype, s);
   }
   g_knn_algo = "simt";
+  g_knn_variant = "fp32";
   return launch_knn_simt(x_hi, x_sq, y_hi, y_sq, relpos, reinterpret_cast<long long*>(nn_idx), nn_idx32, B, N, M, C,
                          (int)K, k_out, stride, s);
 }

@@ -5,14 +5,18 @@
 // on-device cross-check for the tcgen05 path.
 #include "knn.cuh"
 
+#include <cuda_fp16.h>
+
 namespace grafp {
+
+constexpr float kF16PlaneScale = 4096.f;  // mode 3: planes hold x_hat * 2^12 (exact scaling), see knn_tc2.cu
 
 // ------------------------------------------------------------------------------------
 // normalisation: x_hat = x / max(||x||_2, 1e-12) per node (F.normalize, torch_edge.py:281)
 // one warp per node row; optionally also emits the TF32 hi/lo split used by the
 // tensor-core path and the squared norm of x_hat (torch_edge.py:17).
 // ------------------------------------------------------------------------------------
-template <typename T, int MODE>  // MODE 0: x_hat fp32; 1: hi/lo tf32 split; 2: x_hat bf16
+template <typename T, int MODE>  // MODE 0: x_hat fp32; 1: hi/lo tf32 split; 2: x_hat bf16; 3: hi/lo fp16 split of x_hat * 2^12
 __global__ void __launch_bounds__(256)
 knn_normalize_kernel(const T* __restrict__ x, float* __restrict__ xhat, float* __restrict__ lo,
                      float* __restrict__ sq, long long rows, int C, bool normalize) {
@@ -41,6 +45,11 @@ knn_normalize_kernel(const T* __restrict__ x, float* __restrict__ xhat, float* _
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         reinterpret_cast<__nv_bfloat16*>(xhat)[row * C + c] = h;
         v = __bfloat162float(h);  // the Gram runs on the rounded values, so must |x|^2
+      } else if constexpr (MODE == 3) {
+        const float sv = v * kF16PlaneScale;
+        const __half h = __float2half_rn(sv);
+        reinterpret_cast<__half*>(xhat)[row * C + c] = h;
+        reinterpret_cast<__half*>(lo)[row * C + c] = __float2half_rn(sv - __half2float(h));
       } else {
         xhat[row * C + c] = v;
       }
@@ -95,6 +104,10 @@ knn_normalize_vec_kernel(const T* __restrict__ x, float* __restrict__ xhat, floa
         } else if constexpr (MODE == 2) {
           h[e] = q;
           q = __bfloat162float(__float2bfloat16_rn(q));
+        } else if constexpr (MODE == 3) {
+          const float sv = q * kF16PlaneScale;
+          h[e] = __half2float(__float2half_rn(sv));
+          l[e] = sv - h[e];  // exact; rounded to fp16 by the store
         } else {
           h[e] = q;
         }
@@ -103,6 +116,14 @@ knn_normalize_vec_kernel(const T* __restrict__ x, float* __restrict__ xhat, floa
       if (live && c4 < cv) {
         if constexpr (MODE == 2) {
           Pack<__nv_bfloat16, 4>::store(reinterpret_cast<__nv_bfloat16*>(xhat) + row * C + c4 * 4, h);
+        } else if constexpr (MODE == 3) {
+          const __half2 h01 = __floats2half2_rn(h[0], h[1]), h23 = __floats2half2_rn(h[2], h[3]);
+          const __half2 l01 = __floats2half2_rn(l[0], l[1]), l23 = __floats2half2_rn(l[2], l[3]);
+          uint2 hv, lv;
+          hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+          lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(xhat) + row * C + c4 * 4) = hv;
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(lo) + row * C + c4 * 4) = lv;
         } else {
           Pack<float, 4>::store(xhat + row * C + c4 * 4, h);
           if constexpr (MODE == 1) Pack<float, 4>::store(lo + row * C + c4 * 4, l);
@@ -147,11 +168,13 @@ int launch_knn_normalize(const void* x, float* xhat, float* lo, float* sq, long 
     bool done = false;
     if (mode == 0) done = launch_normalize_vec<T, 0>(xs, xhat, lo, sq, rows, C, normalize, (int)blocks, s);
     else if (mode == 1) done = launch_normalize_vec<T, 1>(xs, xhat, lo, sq, rows, C, normalize, (int)blocks, s);
+    else if (mode == 3) done = launch_normalize_vec<T, 3>(xs, xhat, lo, sq, rows, C, normalize, (int)blocks, s);
     else done = launch_normalize_vec<T, 2>(xs, xhat, lo, sq, rows, C, normalize, (int)blocks, s);
     if (done) return check_launch("knn_normalize");
   }
   if (mode == 0) knn_normalize_kernel<T, 0><<<(int)blocks, threads, 0, s>>>(xs, xhat, lo, sq, rows, C, normalize);
   else if (mode == 1) knn_normalize_kernel<T, 1><<<(int)blocks, threads, 0, s>>>(xs, xhat, lo, sq, rows, C, normalize);
+  else if (mode == 3) knn_normalize_kernel<T, 3><<<(int)blocks, threads, 0, s>>>(xs, xhat, lo, sq, rows, C, normalize);
   else knn_normalize_kernel<T, 2><<<(int)blocks, threads, 0, s>>>(xs, xhat, lo, sq, rows, C, normalize);
   return check_launch("knn_normalize");
 }

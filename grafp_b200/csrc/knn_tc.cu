@@ -12,14 +12,13 @@
 //
 // Pipelines: smem ring full/empty mbarriers (TMA <-> MMA), double-buffered TMEM accumulator
 // full/empty mbarriers (MMA <-> epilogue): selection of key tile t overlaps the MMAs of tile t+1.
-#include <cuda.h>
-
 #include <mutex>
 
-#include "knn.cuh"
+#include "tc_ptx.cuh"
 
 namespace grafp {
 namespace tc {
+using namespace tcptx;
 
 constexpr int BM = 128;        // query rows per CTA = UMMA_M
 constexpr int BK = 32;         // fp32 per k-chunk = one 128-byte swizzle-atom row
@@ -40,80 +39,6 @@ struct Cfg {
   static constexpr uint32_t kBarBytes = 128;
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kYsqBytes + kListBytes + kBarBytes + 1024;
 };
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-      "@P1 bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, A: 128 x 8 tf32 K-major, B: BN x 8 tf32 K-major
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128-byte-swizzled shared-memory matrix descriptor (tile rows are 128 bytes, 8-row
-// swizzle atoms are 1024 bytes apart); `addr` may be advanced by k*32 bytes inside the atom.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
-  d |= static_cast<uint64_t>(1) << 16;                 // leading byte offset (16 B units), bits [16,30)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;         // stride byte offset, bits [32,46)
-  d |= static_cast<uint64_t>(1) << 46;                 // descriptor version (Blackwell), bits [46,48)
-  d |= static_cast<uint64_t>(2) << 61;                 // layout: SWIZZLE_128B, bits [61,64)
-  return d;
-}
 
 // instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = BN
 template <int BN>
@@ -351,23 +276,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess) {
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-  });
-  return fn;
-}
+static EncodeTiledFn encode_fn() { return tcptx::encode_tiled_fn(); }
 
 // rows x C fp32 matrix per batch item, box = box_rows x 32 elements, 128B swizzle, zero fill out of bounds
 static bool make_map(CUtensorMap* map, const void* base, int B, int rows, int C, int box_rows) {
@@ -402,6 +311,22 @@ static int launch_variant(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, co
 }
 
 }  // namespace tc
+
+namespace tcptx {
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+}  // namespace tcptx
 
 bool knn_tc_supported(int N, int M, int C, int K, int dtype) {
   return dtype == GRAFP_F32 && C % 4 == 0 && C >= 32 && N >= 128 && M >= 128 && K >= 1 && K <= GRAFP_KNN_MAX_K;

@@ -1,0 +1,522 @@
+// k-NN graph, second-generation tensor-core path (sm_100a): TMA-staged fp16 hi/lo planes ->
+// tcgen05.mma kind::f16 (three MMAs per k-step: lo.hi + hi.lo + hi.hi, fp32 accumulate in TMEM) ->
+// fused per-row top-K epilogue.  Replaces DenseDilatedKnnGraph.forward's pairwise_distance +
+// topk + dilation (reference torch_edge.py:7-18, 70-103, 245-255, 270-284) for K = k*d <= 8.
+//
+// Why fp16 planes: the normalised features are in [-1, 1]; scaled by 2^12 they split exactly into
+// hi = fp16(x) and lo = fp16(x - hi) with a residual below 2^-24 |x| (better than the 3xTF32 split,
+// whose truncated planes leave 2^-20), every product is exact in the fp32 accumulator, kind::f16
+// issues at twice the kind::tf32 rate and the planes are half the bytes in HBM, L2 and shared memory.
+//
+// Two kernels, one data layout.  A "block" is 128 node rows x 64 channels, hi plane then lo plane
+// (2 x 16 KB, each row one 128-byte swizzle line, loaded by one TMA box each).
+//
+//  * knn_stream_kernel<NH, KREG>: a CTA owns 128*NH query rows of one segment.  Their blocks stay
+//    RESIDENT in shared memory for the whole kernel; key blocks stream through a TMA ring.  Per key
+//    tile (128 keys) the MMA thread fills NH accumulators (one per query half) of a double-buffered
+//    TMEM set, so the top-K selection of tile t (4*NH epilogue warps, one accumulator row per
+//    thread) overlaps the MMAs of tile t+1.  L2->smem traffic per MMA cycle is 1/3 of the
+//    first-generation kernel (which re-streamed the query chunk with every key chunk), which is
+//    what makes the N = 1024 / 512 stages tensor-bound instead of L2-bound.
+//  * knn_self_kernel<NH, KREG>: self-graphs (keys == queries) with N <= 128*NH.  One CTA owns the
+//    whole segment; every K-chunk is loaded ONCE and used as both MMA operands, all NH*NH
+//    accumulators stay live in TMEM (512 columns at NH = 2) and are selected from once at the end.
+//    Used where the channel count is too large for resident queries (C = 256 / 512 stages).
+#include "tc_ptx.cuh"
+
+#include <cuda_fp16.h>
+
+namespace grafp {
+namespace tc2 {
+using namespace tcptx;
+
+constexpr int BM = 128;                       // rows per MMA = UMMA_M = key-tile width = UMMA_N
+constexpr int BK = 64;                        // fp16 per K-chunk = one 128-byte swizzle row
+constexpr int UMMA_K = 16;                    // kind::f16
+constexpr uint32_t kPlaneBytes = BM * BK * 2; // 16 KB
+constexpr uint32_t kBlockBytes = 2 * kPlaneBytes;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kSmemLimit = 232448;       // 227 KB opt-in maximum per CTA
+constexpr float kPlaneScale = 4096.f;         // planes hold x_hat * 2^12 (see knn_normalize, mode 3)
+
+// instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = 128
+__device__ __forceinline__ constexpr uint32_t make_idesc_f16() {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(BM >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+
+// Per-row running top-K, one accumulator row per thread.  The epilogue is issue-slot bound (one
+// row x 128 columns per thread and tile), so the common case must cost as little as possible:
+// a key can only enter the list if its raw accumulator exceeds a conservative per-row threshold
+// `thr` (one FSETP); the warp votes, and only columns where some lane has a candidate run the
+// exact distance D = (|x|^2 + (-2 s)) + |y|^2 (reference association order, torch_edge.py:16-18)
+// and the branch-free insertion network (ties keep the earlier = lower key id).
+template <int KREG>
+struct TopK {
+  float d[KREG];
+  int id[KREG];
+  float sq_i;  // |x_i|^2
+  float base;  // (sq_i + a lower bound of |y_j|^2 over the current key tile - slack) * 2^23
+  float thr;   // candidate iff acc > thr
+  static constexpr float kHalfScale2 = 0.5f * kPlaneScale * kPlaneScale;
+  static constexpr float kM2 = -2.f / (kPlaneScale * kPlaneScale);  // power of two: kM2 * acc is exact
+  __device__ __forceinline__ void init(float sq) {
+#pragma unroll
+    for (int p = 0; p < KREG; ++p) { d[p] = INFINITY; id[p] = 0; }
+    sq_i = sq; base = 0.f; thr = -INFINITY;
+  }
+  // dist < d[K-1] implies sq_i + kM2*acc + ymin < d[K-1] + 1e-6 (fp32 evaluation error of dist is < 5e-7 for
+  // normalised features); 4e-6 also covers the rounding of this expression itself.
+  __device__ __forceinline__ void update_thr() { thr = fmaf(-kHalfScale2, d[KREG - 1], base); }
+  __device__ __forceinline__ void set_tile(float ymin) { base = (sq_i + ymin - 4e-6f) * kHalfScale2; update_thr(); }
+  __device__ __forceinline__ void insert(float v, int key) {  // select network; no-op unless v < d[K-1]
+    bool c[KREG];
+#pragma unroll
+    for (int p = 0; p < KREG; ++p) c[p] = v < d[p];
+#pragma unroll
+    for (int p = KREG - 1; p > 0; --p) {  // c[p-1] implies c[p]: shift down, or drop v in, or keep
+      d[p] = c[p - 1] ? d[p - 1] : (c[p] ? v : d[p]);
+      id[p] = c[p - 1] ? id[p - 1] : (c[p] ? key : id[p]);
+    }
+    d[0] = c[0] ? v : d[0];
+    id[0] = c[0] ? key : id[0];
+  }
+  // 32 accumulator columns (acc = s * 2^24); ys_addr: shared address of |y|^2 of column 0
+  __device__ __forceinline__ void scan32(const uint32_t (&v)[32], uint32_t ys_addr, int key0) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float a = __uint_as_float(v[j]);
+      if (__any_sync(0xffffffffu, a > thr)) {
+        const float dist = __fadd_rn(fmaf(kM2, a, sq_i), lds_f32(ys_addr + 4 * j));
+        insert(dist, key0 + j);
+        update_thr();
+      }
+    }
+  }
+};
+
+template <int KREG>
+__device__ __forceinline__ void emit(const TopK<KREG>& top, long long* nn_idx, int* nn_idx32, long long o, int k_out, int stride) {
+#pragma unroll
+  for (int p = 0; p < KREG; ++p) {
+    if (p % stride == 0 && p / stride < k_out) {
+      nn_idx[o + p / stride] = top.id[p];
+      if (nn_idx32 != nullptr) nn_idx32[o + p / stride] = top.id[p];
+    }
+  }
+}
+
+// three MMAs per 16-channel step over one 64-channel block pair
+__device__ __forceinline__ void mma_block(uint32_t acc, uint32_t a_blk, uint32_t b_blk, bool first) {
+  constexpr uint32_t idesc = make_idesc_f16();
+#pragma unroll
+  for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+    const uint32_t off = kk * UMMA_K * 2;
+    const uint64_t a_hi = make_smem_desc(a_blk + off), a_lo = make_smem_desc(a_blk + kPlaneBytes + off);
+    const uint64_t b_hi = make_smem_desc(b_blk + off), b_lo = make_smem_desc(b_blk + kPlaneBytes + off);
+    umma_f16(acc, a_lo, b_hi, idesc, (first && kk == 0) ? 0u : 1u);
+    umma_f16(acc, a_hi, b_lo, idesc, 1u);
+    umma_f16(acc, a_hi, b_hi, idesc, 1u);
+  }
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// resident queries, streamed keys
+// ---------------------------------------------------------------------------------------------
+template <int NH, int KREG>
+__global__ void __launch_bounds__((4 * NH + 2) * 32, 1)
+knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                  const __grid_constant__ CUtensorMap tm_y_hi, const __grid_constant__ CUtensorMap tm_y_lo,
+                  const float* __restrict__ xsq, const float* __restrict__ ysq, long long* __restrict__ nn_idx,
+                  int* __restrict__ nn_idx32, int N, int M, int C, int k_out, int stride, int stages) {
+  constexpr int kEpilogueThreads = 128 * NH;
+  constexpr int kProducerWarp = 4 * NH, kMmaWarp = 4 * NH + 1;
+  constexpr uint32_t kTmemCols = 2 * NH * BM;  // two accumulator sets of NH tiles
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int num_kc = (C + BK - 1) / BK;
+  const int num_tiles = (M + BM - 1) / BM;
+  unsigned char* q_base = smem;                                    // [NH][num_kc] blocks
+  unsigned char* ring = q_base + (size_t)NH * num_kc * kBlockBytes; // [stages] blocks
+  float* ysq_s = reinterpret_cast<float*>(ring + (size_t)stages * kBlockBytes);  // [2][BM]
+  float* ymin_s = ysq_s + 2 * BM;                                                // [2][4] per-warp minima of |y|^2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ymin_s + 8);
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8 * kMaxStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  const uint32_t bar_q = bar_tempty + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int m0 = blockIdx.x * (BM * NH);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4 * NH); }
+    mbar_init(bar_q, 1);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      // resident query blocks: one barrier, NH * num_kc * 2 boxes
+      mbar_arrive_expect_tx(bar_q, (uint32_t)(NH * num_kc) * kBlockBytes);
+      for (int h = 0; h < NH; ++h) {
+        for (int c = 0; c < num_kc; ++c) {
+          const uint32_t dst = smem_u32(q_base + (size_t)(h * num_kc + c) * kBlockBytes);
+          tma_load_3d(dst, &tm_x_hi, bar_q, c * BK, m0 + h * BM, b);
+          tma_load_3d(dst + kPlaneBytes, &tm_x_lo, bar_q, c * BK, m0 + h * BM, b);
+        }
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < num_tiles; ++t) {
+        for (int c = 0; c < num_kc; ++c) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t full = bar_full + 8 * s;
+          mbar_arrive_expect_tx(full, kBlockBytes);
+          const uint32_t dst = smem_u32(ring + (size_t)s * kBlockBytes);
+          tma_load_3d(dst, &tm_y_hi, full, c * BK, t * BM, b);
+          tma_load_3d(dst + kPlaneBytes, &tm_y_lo, full, c * BK, t * BM, b);
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      mbar_wait(bar_q, 0);
+      tcgen05_fence_after();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < num_tiles; ++t) {
+        const int as = t & 1;
+        mbar_wait(bar_tempty + 8 * as, ((t >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator set
+        tcgen05_fence_after();
+        for (int c = 0; c < num_kc; ++c) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tcgen05_fence_after();
+          const uint32_t b_blk = smem_u32(ring + (size_t)s * kBlockBytes);
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            const uint32_t a_blk = smem_u32(q_base + (size_t)(h * num_kc + c) * kBlockBytes);
+            mma_block(tmem_base + (as * NH + h) * BM, a_blk, b_blk, c == 0);
+          }
+          tcgen05_commit(bar_empty + 8 * s);  // frees the ring slot when these MMAs retire
+          if (++s == stages) { s = 0; ph ^= 1; }
+        }
+        tcgen05_commit(bar_tfull + 8 * as);
+      }
+    }
+  } else {
+    // ===== epilogue: warp w reads TMEM lanes 32*(w%4).., accumulator tile h = w/4 =====
+    const int h = warp >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int q = m0 + h * BM + r;
+    const float sq_i = (q < N) ? xsq[(long long)b * N + q] : 0.f;
+    const float* ysq_b = ysq + (long long)b * M;
+    TopK<KREG> top;
+    top.init(sq_i);
+    // |y|^2 of the next key tile is fetched one tile ahead so its global-load latency hides behind the scan
+    float yv_next = (threadIdx.x < BM && (int)threadIdx.x < M) ? ysq_b[threadIdx.x] : INFINITY;
+    for (int t = 0; t < num_tiles; ++t) {
+      const int as = t & 1;
+      float* ys = ysq_s + as * BM;
+      if (threadIdx.x < BM) {
+        const float yv = yv_next;  // keys past the end are +inf and can never be selected
+        const int key_next = (t + 1) * BM + threadIdx.x;
+        yv_next = (key_next < M) ? ysq_b[key_next] : INFINITY;
+        ys[threadIdx.x] = yv;
+        float mn = yv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if (lane == 0) ymin_s[as * 4 + warp] = mn;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
+      {
+        const float4 m4 = *reinterpret_cast<const float4*>(ymin_s + as * 4);
+        top.set_tile(fminf(fminf(m4.x, m4.y), fminf(m4.z, m4.w)));
+      }
+      mbar_wait(bar_tfull + 8 * as, (t >> 1) & 1);
+      tcgen05_fence_after();
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * NH + h) * BM;
+#pragma unroll 1
+      for (int cc = 0; cc < BM / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(trow + cc * 32, v);
+        tmem_ld_wait();
+        top.scan32(v, smem_u32(ys + cc * 32), t * BM + cc * 32);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+    }
+    if (q < N) emit<KREG>(top, nn_idx, nn_idx32, ((long long)b * N + q) * k_out, k_out, stride);
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// self-graph of a whole segment per CTA: every chunk loaded once, used as both operands
+// ---------------------------------------------------------------------------------------------
+template <int NH, int KREG>
+__global__ void __launch_bounds__((4 * NH + 2) * 32, (NH == 1) ? 2 : 1)
+knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
+                const float* __restrict__ xsq, long long* __restrict__ nn_idx, int* __restrict__ nn_idx32, int N, int C,
+                int k_out, int stride, int stages) {
+  constexpr int kEpilogueThreads = 128 * NH;
+  constexpr int kProducerWarp = 4 * NH, kMmaWarp = 4 * NH + 1;
+  constexpr uint32_t kTmemCols = NH * NH * BM;
+  constexpr uint32_t kStageBytes = NH * kBlockBytes;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int num_kc = (C + BK - 1) / BK;
+  unsigned char* ring = smem;
+  float* ysq_s = reinterpret_cast<float*>(ring + (size_t)stages * kStageBytes);  // [NH * BM]
+  float* ymin_s = ysq_s + NH * BM;                                               // [4 * NH]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ymin_s + 8);
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8 * kMaxStages;
+  const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = 0; c < num_kc; ++c) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const uint32_t full = bar_full + 8 * s;
+        mbar_arrive_expect_tx(full, kStageBytes);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          const uint32_t dst = smem_u32(ring + (size_t)s * kStageBytes + h * kBlockBytes);
+          tma_load_3d(dst, &tm_x_hi, full, c * BK, h * BM, b);
+          tma_load_3d(dst + kPlaneBytes, &tm_x_lo, full, c * BK, h * BM, b);
+        }
+        if (++s == stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int c = 0; c < num_kc; ++c) {
+        mbar_wait(bar_full + 8 * s, ph);
+        tcgen05_fence_after();
+        const uint32_t stage = smem_u32(ring + (size_t)s * kStageBytes);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+#pragma unroll
+          for (int t = 0; t < NH; ++t) {
+            mma_block(tmem_base + (h * NH + t) * BM, stage + h * kBlockBytes, stage + t * kBlockBytes, c == 0);
+          }
+        }
+        tcgen05_commit(bar_empty + 8 * s);
+        if (++s == stages) { s = 0; ph ^= 1; }
+      }
+      tcgen05_commit(bar_tfull);
+    }
+  } else {
+    const int h = warp >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int q = h * BM + r;
+    const float* xsq_b = xsq + (long long)b * N;
+    const float sq_i = (q < N) ? xsq_b[q] : 0.f;
+    {  // kEpilogueThreads == NH * BM: one key norm per thread, per-warp minima for the candidate threshold
+      const float yv = (threadIdx.x < N) ? xsq_b[threadIdx.x] : INFINITY;
+      ysq_s[threadIdx.x] = yv;
+      float mn = yv;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      if (lane == 0) ymin_s[warp] = mn;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
+    TopK<KREG> top;
+    top.init(sq_i);
+    {
+      float mn = ymin_s[0];
+#pragma unroll
+      for (int w = 1; w < 4 * NH; ++w) mn = fminf(mn, ymin_s[w]);
+      top.set_tile(mn);
+    }
+    mbar_wait(bar_tfull, 0);
+    tcgen05_fence_after();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (h * NH) * BM;
+#pragma unroll 1
+    for (int cc = 0; cc < NH * BM / 32; ++cc) {
+      uint32_t v[32];
+      tmem_ld32(trow + cc * 32, v);
+      tmem_ld_wait();
+      top.scan32(v, smem_u32(ysq_s + cc * 32), cc * 32);
+    }
+    if (q < N) emit<KREG>(top, nn_idx, nn_idx32, ((long long)b * N + q) * k_out, k_out, stride);
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+// (rows x C) fp16 matrix per segment, box = 128 rows x 64 channels, 128B swizzle, zero fill out of bounds
+static bool make_map_f16(CUtensorMap* map, const void* base, int B, int rows, int C) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)rows * C * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+constexpr uint32_t kMiscBytes = 2 * BM * 4 + 32 + (2 * kMaxStages + 8) * 8 + 1024;  // ysq, barriers + TMEM slot, alignment slack
+
+template <typename Kernel>
+static int set_smem(Kernel kernel, bool* configured, const char* what) {
+  if (*configured) return GRAFP_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e)); return (int)e; }
+  *configured = true;
+  return GRAFP_OK;
+}
+
+template <int NH, int KREG>
+static int launch_stream(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& yh, const CUtensorMap& yl,
+                         const float* xsq, const float* ysq, long long* nn_idx, int* nn_idx32, int B, int N, int M, int C,
+                         int k_out, int stride, int stages, cudaStream_t s) {
+  static bool configured = false;
+  if (int rc = set_smem(knn_stream_kernel<NH, KREG>, &configured, "knn_stream")) return rc;
+  const int num_kc = (C + BK - 1) / BK;
+  const size_t smem = (size_t)(NH * num_kc + stages) * kBlockBytes + kMiscBytes;
+  dim3 grid((N + BM * NH - 1) / (BM * NH), B);
+  knn_stream_kernel<NH, KREG><<<grid, (4 * NH + 2) * 32, smem, s>>>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, N, M, C,
+                                                                   k_out, stride, stages);
+  return check_launch("knn_stream");
+}
+
+template <int NH, int KREG>
+static int launch_self(const CUtensorMap& xh, const CUtensorMap& xl, const float* xsq, long long* nn_idx, int* nn_idx32,
+                       int B, int N, int C, int k_out, int stride, int stages, cudaStream_t s) {
+  static bool configured = false;
+  if (int rc = set_smem(knn_self_kernel<NH, KREG>, &configured, "knn_self")) return rc;
+  const size_t smem = (size_t)stages * NH * kBlockBytes + kMiscBytes;
+  knn_self_kernel<NH, KREG><<<B, (4 * NH + 2) * 32, smem, s>>>(xh, xl, xsq, nn_idx, nn_idx32, N, C, k_out, stride, stages);
+  return check_launch("knn_self");
+}
+
+// plan: 0 = unsupported, 1 = self NH=1, 2 = self NH=2, 3 = stream NH=1, 4 = stream NH=2
+static int plan(int N, int M, int C, int K, int dtype, bool self, int* stages) {
+  if (dtype != GRAFP_F32 || C % 8 != 0 || C < BK || N < BM || M < BM || K < 1 || K > 8) return 0;
+  const int num_kc = (C + BK - 1) / BK;
+  const uint32_t budget = kSmemLimit - kMiscBytes;
+  if (self && N <= 2 * BM) {
+    const int nh = (N > BM) ? 2 : 1;
+    // NH = 1: two CTAs per SM (<= 113 KB each); NH = 2: one CTA owns the SM
+    const uint32_t cap = (nh == 1) ? (113u * 1024 - kMiscBytes) : budget;
+    int st = (int)(cap / (nh * kBlockBytes));
+    if (st > num_kc) st = num_kc;
+    if (st > kMaxStages) st = kMaxStages;
+    if (st < 1) return 0;
+    *stages = st;
+    return nh;
+  }
+  for (int nh = (N > BM ? 2 : 1); nh >= 1; --nh) {
+    const uint32_t resident = (uint32_t)(nh * num_kc) * kBlockBytes;
+    if (resident + 2 * kBlockBytes > budget) continue;
+    int st = (int)((budget - resident) / kBlockBytes);
+    if (st > 4) st = 4;
+    *stages = st;
+    return 2 + nh;
+  }
+  return 0;
+}
+
+}  // namespace tc2
+
+bool knn_tc2_supported(int N, int M, int C, int K, int dtype, bool self) {
+  int stages = 0;
+  return tc2::plan(N, M, C, K, dtype, self, &stages) != 0;
+}
+
+int launch_knn_tc2(const void* xhi, const void* xlo, const float* xsq, const void* yhi, const void* ylo,
+                   const float* ysq, long long* nn_idx, int* nn_idx32, int B, int N, int M, int C, int K, int k_out,
+                   int stride, int dtype, bool self, cudaStream_t s) {
+  using namespace tc2;
+  int stages = 0;
+  const int p = plan(N, M, C, K, dtype, self, &stages);
+  if (p == 0) {
+    set_error("knn_tc2: unsupported configuration");
+    return GRAFP_EUNSUPPORTED;
+  }
+  CUtensorMap xh, xl, yh, yl;
+  if (!make_map_f16(&xh, xhi, B, N, C) || !make_map_f16(&xl, xlo, B, N, C) || !make_map_f16(&yh, yhi, B, M, C) ||
+      !make_map_f16(&yl, ylo, B, M, C)) {
+    set_error("knn_tc2: cuTensorMapEncodeTiled failed (driver entry point unavailable or bad shape)");
+    return GRAFP_EUNSUPPORTED;
+  }
+  const bool k3 = K <= 3;
+  switch (p) {
+    case 1: return k3 ? launch_self<1, 3>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, stages, s)
+                      : launch_self<1, 8>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, stages, s);
+    case 2: return k3 ? launch_self<2, 3>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, stages, s)
+                      : launch_self<2, 8>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, stages, s);
+    case 3: return k3 ? launch_stream<1, 3>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, stages, s)
+                      : launch_stream<1, 8>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, stages, s);
+    default: return k3 ? launch_stream<2, 3>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, stages, s)
+                       : launch_stream<2, 8>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, stages, s);
+  }
+}
+
+}  // namespace grafp

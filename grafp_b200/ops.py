@@ -179,6 +179,10 @@ def knn_last_algo() -> str:
     return _native.load().grafp_knn_last_algo().decode()
 
 
+def knn_last_variant() -> str:
+    return _native.load().grafp_knn_last_variant().decode()
+
+
 # --------------------------------------------------------------------------------------
 # max-relative aggregation (MRConv2d body)
 # --------------------------------------------------------------------------------------

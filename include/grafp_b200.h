@@ -43,7 +43,8 @@ extern "C" {
 /* k-NN kernel selection for grafp_knn_fwd */
 #define GRAFP_KNN_AUTO 0 /* tcgen05 path when the shape allows it, else the SIMT path */
 #define GRAFP_KNN_SIMT 1 /* exact-fp32 CUDA-core Gram + fused top-k                   */
-#define GRAFP_KNN_TC 2   /* TMA + tcgen05 (3xTF32 for f32, bf16 MMA for bf16) + fused top-k */
+#define GRAFP_KNN_TC 2   /* TMA + tcgen05 + fused top-k: the f16x3 kernels when K <= 8, else the tf32x3 kernel */
+#define GRAFP_KNN_TC_TF32 3 /* force the first-generation tf32x3 tcgen05 kernel (cross-check)          */
 
 #define GRAFP_KNN_MAX_K 64 /* k * dilation */
 
@@ -53,6 +54,9 @@ const char* grafp_last_error(void);
 /* Diagnostic: name of the k-NN kernel the last grafp_knn_fwd call on this thread launched
  * ("simt", "tcgen05"). */
 const char* grafp_knn_last_algo(void);
+/* Diagnostic: which arithmetic the last k-NN call used: "f16x3" (fp16 hi/lo planes, kind::f16),
+ * "tf32x3" (tf32 hi/lo planes, kind::tf32) or "fp32" (CUDA cores). */
+const char* grafp_knn_last_variant(void);
 
 /*
  * Dilated k-NN graph.  Replaces DenseDilatedKnnGraph.forward

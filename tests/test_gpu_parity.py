@@ -112,7 +112,7 @@ def test_knn_dense_stress_vs_oracle(C, d, algo):
     assert rep["mismatch"] <= 0.001 * rep["entries"]
 
 
-@pytest.mark.parametrize("B,C,N,M,k,d", [
+TC_CASES = [
     (3, 48, 300, 0, 5, 1),      # ragged N and C: TMA zero-fills the tile edges
     (2, 36, 130, 0, 3, 2),
     (2, 64, 1000, 0, 3, 1),
@@ -120,19 +120,55 @@ def test_knn_dense_stress_vs_oracle(C, d, algo):
     (2, 32, 384, 200, 6, 2),    # separate key set, ragged
     (2, 64, 1024, 0, 9, 1),     # K = 9: shared-memory list variant
     (1, 512, 128, 0, 64, 1),    # K = 64 of 128 keys
-])
-def test_knn_tensor_core_path_vs_oracle(B, C, N, M, k, d):
+    (2, 64, 256, 0, 3, 1),      # whole-segment self-graph, two row halves, one channel chunk
+    (3, 256, 200, 0, 3, 1),     # whole-segment self-graph, ragged second half
+    (2, 512, 128, 0, 8, 1),     # whole-segment self-graph, one half, K = 8 register list
+    (2, 128, 384, 0, 8, 1),     # resident queries (2 halves), ragged last query tile, K = 8
+    (2, 256, 1024, 0, 3, 1),    # resident queries (1 half, 4 channel chunks)
+    (2, 72, 640, 0, 4, 2),      # channel tail inside the second 64-wide chunk
+    (2, 64, 512, 300, 4, 1),    # separate key set with a ragged last key tile
+    (2, 320, 256, 256, 3, 1),   # separate key set, 5 resident channel chunks
+]
+
+
+@pytest.mark.parametrize("B,C,N,M,k,d", TC_CASES)
+@pytest.mark.parametrize("algo", [_native.KNN_TC, _native.KNN_TC_TF32])
+def test_knn_tensor_core_path_vs_oracle(B, C, N, M, k, d, algo):
     x = synth.synth_point_cloud(B, C, N, 3000 + N + C)
     y = synth.synth_point_cloud(B, C, M, 4000 + M) if M else None
-    nn_idx, _ = ops.knn_graph(x.to(DEV), k, d, None if y is None else y.to(DEV), algo=_native.KNN_TC)
+    nn_idx, _ = ops.knn_graph(x.to(DEV), k, d, None if y is None else y.to(DEV), algo=algo)
     assert ops.knn_last_algo() == "tcgen05"
-    assert_knn_ok(x, nn_idx, k, d, y, what=f"tc N={N} M={M} C={C} k={k} d={d}")
+    if algo == _native.KNN_TC_TF32:
+        assert ops.knn_last_variant() == "tf32x3"
+    elif k * d <= 8 and C >= 64 and C % 8 == 0 and N >= 128 and (M == 0 or M >= 128):
+        assert ops.knn_last_variant() == "f16x3", (B, C, N, M, k, d)
+    assert_knn_ok(x, nn_idx, k, d, y, what=f"tc N={N} M={M} C={C} k={k} d={d} {ops.knn_last_variant()}")
+
+
+def test_knn_f16_planes_edge_inputs():
+    """Duplicate nodes, all-zero nodes, tiny and huge feature magnitudes through the f16x3 kernels."""
+    for N, C in [(1024, 64), (256, 256)]:
+        x = synth.synth_point_cloud(2, C, N, 5000 + N, relu=True)
+        x[0, :, 7] = x[0, :, 3]
+        x[0, :, 200] = x[0, :, 3]
+        x[1, :, 11] = 0
+        x[1, :, 12] *= 1e-20       # normalisation brings it back to unit length
+        x[1, :, 13] *= 1e18
+        x[1, 1:, 14] = 0           # one-hot node: x_hat has a single 1.0 (top of the fp16 plane range)
+        nn_idx, _ = ops.knn_graph(x.to(DEV), 3, 1, algo=_native.KNN_TC)
+        assert ops.knn_last_variant() == "f16x3"
+        assert_knn_ok(x, nn_idx, 3, 1, what=f"f16 edge inputs N={N} C={C}")
 
 
 def test_auto_picks_the_tensor_core_path_for_encoder_shapes():
     for N, C in STAGES:
         ops.knn_graph(torch.randn(2, C, N, 1, device=DEV), 3)
         assert ops.knn_last_algo() == "tcgen05", (N, C)
+        assert ops.knn_last_variant() == "f16x3", (N, C)
+    ops.knn_graph(torch.randn(2, 64, 1024, 1, device=DEV), 16)
+    assert (ops.knn_last_algo(), ops.knn_last_variant()) == ("tcgen05", "tf32x3")
+    ops.knn_graph(torch.randn(2, 64, 1024, 1, device=DEV), 3, normalize=False)  # un-normalised: outside fp16 plane range
+    assert ops.knn_last_variant() == "tf32x3"
     ops.knn_graph(torch.randn(2, 16, 64, 1, device=DEV), 3)
     assert ops.knn_last_algo() == "simt"
     with pytest.raises(RuntimeError, match="tcgen05 path does not support"):
