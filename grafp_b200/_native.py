@@ -24,7 +24,8 @@ SIGNATURES = {
     "grafp_knn_workspace_bytes": (_sz, [_i] * 6),
     "grafp_knn_fwd": (_i, [_vp] * 5 + [_i] * 10 + [_vp, _sz, _vp]),
     "grafp_mr_aggregate_fwd": (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 6 + [_vp]),
-    "grafp_mr_aggregate_bwd": (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 6 + [_vp]),
+    "grafp_mr_aggregate_bwd_workspace_bytes": (_sz, [_i] * 3),
+    "grafp_mr_aggregate_bwd": (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 6 + [_vp, _sz, _vp]),
     "grafp_gather_fwd": (_i, [_vp] * 2 + [_i] + [_vp] + [_i] * 6 + [_vp]),
     "grafp_gather_bwd": (_i, [_vp] * 2 + [_i] + [_vp] + [_i] * 6 + [_vp]),
     "grafp_edge_gather_fwd": (_i, [_vp] * 4 + [_i] + [_vp] + [_i] * 6 + [_vp]),
@@ -33,7 +34,7 @@ SIGNATURES = {
     "grafp_max_over_k_bwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 KNN_AUTO, KNN_SIMT, KNN_TC, KNN_TC_TF32 = 0, 1, 2, 3
 KNN_MAX_K = 64
 

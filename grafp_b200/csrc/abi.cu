@@ -192,17 +192,22 @@ int grafp_mr_aggregate_fwd(const void* x, const void* y, const void* nbr_idx, co
                         launch_mr_aggregate_fwd<__nv_bfloat16>(x, y, nbr_idx, ctr_idx, idx_is_i64, out, argmax, B, N, M, C, k, s));
 }
 
+size_t grafp_mr_aggregate_bwd_workspace_bytes(int B, int N, int k) {
+  if (B <= 0 || N <= 0 || k <= 0) return 0;
+  return mr_bwd_workspace_bytes(B, N, k);
+}
+
 int grafp_mr_aggregate_bwd(const void* grad_out, const uint8_t* argmax, const void* nbr_idx, const void* ctr_idx,
                            int idx_is_i64, void* grad_x, void* grad_y, int B, int N, int M, int C, int k, int dtype,
-                           void* stream) {
+                           void* workspace, size_t workspace_bytes, void* stream) {
   COMMON_SHAPE_CHECKS("grafp_mr_aggregate_bwd");
   GRAFP_REQUIRE(grad_out && argmax && nbr_idx && grad_x, GRAFP_EINVAL,
                 "grafp_mr_aggregate_bwd: grad_out, argmax, nbr_idx and grad_x must be non-null");
   GRAFP_REQUIRE(grad_y != nullptr || M == N, GRAFP_EINVAL, "grafp_mr_aggregate_bwd: M must equal N when grad_y is null");
   { int rc = require_device_ptr("grafp_mr_aggregate_bwd", "grad_out", grad_out); if (rc) return rc; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return DISPATCH_DTYPE(launch_mr_aggregate_bwd<float>(grad_out, argmax, nbr_idx, ctr_idx, idx_is_i64, grad_x, grad_y, B, N, M, C, k, s),
-                        launch_mr_aggregate_bwd<__nv_bfloat16>(grad_out, argmax, nbr_idx, ctr_idx, idx_is_i64, grad_x, grad_y, B, N, M, C, k, s));
+  return DISPATCH_DTYPE(launch_mr_aggregate_bwd<float>(grad_out, argmax, nbr_idx, ctr_idx, idx_is_i64, grad_x, grad_y, B, N, M, C, k, workspace, workspace_bytes, s),
+                        launch_mr_aggregate_bwd<__nv_bfloat16>(grad_out, argmax, nbr_idx, ctr_idx, idx_is_i64, grad_x, grad_y, B, N, M, C, k, workspace, workspace_bytes, s));
 }
 
 int grafp_gather_fwd(const void* src, const void* idx, int idx_is_i64, void* out, int B, int N, int M, int C, int k,

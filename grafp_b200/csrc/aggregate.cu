@@ -164,6 +164,124 @@ mr_aggregate_fwd_fast_kernel(const T* __restrict__ x, const T* __restrict__ src,
 }
 
 // ------------------------------------------------------------------------------------
+// K2, pipelined form (fp32, k = KN neighbours, centre == row, C/4 a power of two): persistent CTAs,
+// one (row, 4-channel) item per thread and iteration.  The item's own 16 bytes and its KN
+// neighbour slices are fetched with cp.async into a per-thread shared-memory slot D iterations
+// ahead, so D * (KN + 1) * 16 bytes per thread are in flight without holding registers, and the
+// neighbour ids (the dependent load in front of the gathers) are read one iteration earlier
+// still.  The gathers are L2 hits (a segment's features are 256 KiB); HBM sees the algorithmic
+// bytes only: x and the ids once, the interleaved output and the argmax once.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+template <bool I64, int KN, int D>
+__global__ void __launch_bounds__(kThreads)
+mr_aggregate_fwd_pipe_kernel(const float* __restrict__ x, const float* __restrict__ src, const void* __restrict__ nbr,
+                             float* __restrict__ out, uint8_t* __restrict__ argmax, int N, int M, int C, int cv_shift,
+                             int ips_shift, int total_iters) {
+  extern __shared__ __align__(16) unsigned char pipe_smem[];
+  // slot (stage s, operand o, thread t) -> 16 bytes; consecutive threads are consecutive: conflict-free
+  const uint32_t slot0 = static_cast<uint32_t>(__cvta_generic_to_shared(pipe_smem)) + threadIdx.x * 16;
+  auto slot = [&](int s, int o) { return slot0 + (uint32_t)((s * (KN + 1) + o) * kThreads * 16); };
+  const int cmask = (1 << cv_shift) - 1;
+  const int c = (threadIdx.x & cmask) * 4;  // 256 % cv == 0: the channel pack of a thread never changes
+
+  // work item w = (segment b, chunk of 256 items): b = w >> ips_shift
+  auto row_of = [&](int w, long long& rowg, int& b) {
+    b = w >> ips_shift;
+    const int chunk = w & ((1 << ips_shift) - 1);
+    const int n = (chunk * kThreads + (int)threadIdx.x) >> cv_shift;
+    rowg = (long long)b * N + n;
+  };
+  auto load_ids = [&](int w, int (&ids)[KN]) {
+    long long rowg; int b;
+    row_of(w, rowg, b);
+#pragma unroll
+    for (int j = 0; j < KN; ++j) ids[j] = load_index<I64>(nbr, rowg * KN + j);
+  };
+  auto issue = [&](int w, int s, const int (&ids)[KN]) {
+    long long rowg; int b;
+    row_of(w, rowg, b);
+    cp_async16(slot(s, 0), x + rowg * C + c);
+    const float* sb = src + (long long)b * M * C + c;
+#pragma unroll
+    for (int j = 0; j < KN; ++j) cp_async16(slot(s, 1 + j), sb + (long long)ids[j] * C);
+  };
+
+  const int w0 = blockIdx.x, stride = gridDim.x;
+  int ids[KN];
+#pragma unroll
+  for (int s = 0; s < D; ++s) {
+    const int w = w0 + s * stride;
+    if (w < total_iters) { load_ids(w, ids); issue(w, s, ids); }
+    cp_async_commit();
+  }
+  if (w0 + D * stride < total_iters) load_ids(w0 + D * stride, ids);
+
+  int s = 0;
+  for (int w = w0; w < total_iters; w += stride) {
+    cp_async_wait<D - 1>();
+    float self[4], best[4];
+    int arg[4];
+    {
+      const float4 v = *reinterpret_cast<const float4*>(pipe_smem + (slot(s, 0) - (slot0 - threadIdx.x * 16)));
+      self[0] = v.x; self[1] = v.y; self[2] = v.z; self[3] = v.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { best[e] = -INFINITY; arg[e] = 0; }
+    float xj[KN][4];
+    float poison = 0.f;
+#pragma unroll
+    for (int j = 0; j < KN; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(pipe_smem + (slot(s, 1 + j) - (slot0 - threadIdx.x * 16)));
+      xj[j][0] = v.x; xj[j][1] = v.y; xj[j][2] = v.z; xj[j][3] = v.w;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = xj[j][e] - self[e];
+        poison = fmaf(d, 0.f, poison);      // NaN / inf anywhere -> NaN
+        const bool gt = d > best[e];        // strict: the first maximiser wins (torch.max)
+        best[e] = gt ? d : best[e];
+        arg[e] = gt ? j : arg[e];
+      }
+    }
+    if (poison != 0.f) {  // redo with exact torch.max semantics (NaN propagates, first NaN wins)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { best[e] = -INFINITY; arg[e] = 0; }
+#pragma unroll
+      for (int j = 0; j < KN; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float d = xj[j][e] - self[e];
+          if (d > best[e] || d != d) {
+            if (!(best[e] != best[e])) { best[e] = d; arg[e] = j; }
+          }
+        }
+      }
+    }
+    long long rowg; int b;
+    row_of(w, rowg, b);
+    const float il[8] = {self[0], best[0], self[1], best[1], self[2], best[2], self[3], best[3]};
+    Pack8<float>::store(out + rowg * 2 * C + 2 * c, il);
+    if (argmax != nullptr) {
+      const unsigned int packed = (unsigned)arg[0] | ((unsigned)arg[1] << 8) | ((unsigned)arg[2] << 16) | ((unsigned)arg[3] << 24);
+      *reinterpret_cast<unsigned int*>(argmax + rowg * C + c) = packed;
+    }
+    // refill this slot D iterations ahead (the slot's values are in registers / stored by now)
+    const int wn = w + D * stride;
+    if (wn < total_iters) issue(wn, s, ids);
+    cp_async_commit();
+    if (wn + stride < total_iters) load_ids(wn + stride, ids);
+    if (++s == D) s = 0;
+  }
+  cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------
 // K3 (generic form): dense pass + atomic scatter pass, ordered by the stream.
 //   dense:   grad_x[row][c] = g[row][2c] (- g[row][2c+1] when the centre is the row itself)
 //            (+ g[row][2c+1] again when the winning neighbour is the row itself, i.e. the
@@ -434,6 +552,180 @@ int launch_mr_bwd_fused(const T* g, const uint8_t* argmax, const void* nbr, T* g
 }
 
 // ------------------------------------------------------------------------------------
+// K3, gather form (fp32, k = KN, graphs built by the k-NN op): no atomics, no zero-fill, no
+// cluster barrier, deterministic.  A small kernel first transposes each segment's graph into
+// reverse CSR (who points at row n, through which neighbour slot), sorted so the summation
+// order is fixed; the main kernel then owns one (row, 4-channel) item per thread and iteration:
+//   grad_x[n][c] = g[n][2c] - [winner(n,c) != n] g[n][2c+1] + sum over in-edges (m, j) of [argmax[m][c] == j] g[m][2c+1]
+// Its own g slice and argmax word arrive through a cp.async pipeline D iterations deep (HBM
+// stream); the in-edge rows are L2 hits (a segment's grad_out is 512 KiB).  HBM traffic = the
+// algorithmic bytes plus the 16 bytes per row of reverse graph.
+// ------------------------------------------------------------------------------------
+template <bool I64>
+__global__ void __launch_bounds__(kThreads)
+mr_bwd_build_reverse_kernel(const void* __restrict__ nbr, int* rev_off, unsigned int* rev_src, int N, int k) {
+  extern __shared__ int rev_smem[];
+  int* off = rev_smem;           // [N + 1] in-degree counts, then exclusive offsets
+  int* cur = rev_smem + N + 1;   // [N] fill cursors
+  __shared__ int wsum[kThreads / 32];
+  const long long b = blockIdx.x;
+  const long long ebase = b * N * k;
+  const int E = N * k;
+  for (int i = threadIdx.x; i <= N; i += kThreads) off[i] = 0;
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += kThreads) {
+    const int m = e / k;
+    const int t = load_index<I64>(nbr, ebase + e);
+    if (t != m) atomicAdd(&off[t], 1);  // self edges cancel against the centre term and are not listed
+  }
+  __syncthreads();
+  // exclusive scan: contiguous span per thread, warp scan of the span sums, then the warp totals
+  const int span = (N + kThreads - 1) / kThreads;
+  const int lo = min((int)threadIdx.x * span, N), hi = min(lo + span, N);
+  int local = 0;
+  for (int i = lo; i < hi; ++i) local += off[i];
+  int incl = local;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  int wbase = 0;
+  for (int w = 0; w < warp; ++w) wbase += wsum[w];
+  int run = wbase + incl - local;
+  for (int i = lo; i < hi; ++i) { const int c = off[i]; off[i] = run; cur[i] = run; run += c; }
+  if (threadIdx.x == kThreads - 1) off[N] = run;
+  __syncthreads();
+  int* ro = rev_off + b * (N + 1);
+  for (int i = threadIdx.x; i <= N; i += kThreads) ro[i] = off[i];
+  unsigned int* rs = rev_src + ebase;
+  for (int e = threadIdx.x; e < E; e += kThreads) {
+    const int m = e / k, j = e - m * k;
+    const int t = load_index<I64>(nbr, ebase + e);
+    if (t != m) rs[atomicAdd(&cur[t], 1)] = (unsigned)m | ((unsigned)j << 24);
+  }
+  __syncthreads();
+  // fixed summation order: sort every (short) list by source row
+  for (int n = threadIdx.x; n < N; n += kThreads) {
+    const int s0 = off[n], s1 = off[n + 1];
+    for (int i = s0 + 1; i < s1; ++i) {
+      const unsigned v = rs[i];
+      int p = i - 1;
+      while (p >= s0 && rs[p] > v) { rs[p + 1] = rs[p]; --p; }
+      rs[p + 1] = v;
+    }
+  }
+}
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <bool I64, int KN, int D>
+__global__ void __launch_bounds__(kThreads)
+mr_aggregate_bwd_gather_kernel(const float* __restrict__ g, const uint8_t* __restrict__ argmax,
+                               const void* __restrict__ nbr, const int* __restrict__ rev_off,
+                               const unsigned int* __restrict__ rev_src, float* __restrict__ grad_x, int N, int C,
+                               int cv_shift, int ips_shift, int total_iters) {
+  extern __shared__ __align__(16) unsigned char pipe_smem[];
+  // per stage: two 16-byte planes (the thread's 8 interleaved grad_out floats) and one 4-byte plane (its argmax word)
+  constexpr int kStageBytes = kThreads * 36;
+  const uint32_t smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(pipe_smem));
+  const int cmask = (1 << cv_shift) - 1;
+  const int c = (threadIdx.x & cmask) * 4;
+
+  auto row_of = [&](int w, int& b, int& n) {
+    b = w >> ips_shift;
+    const int chunk = w & ((1 << ips_shift) - 1);
+    n = (chunk * kThreads + (int)threadIdx.x) >> cv_shift;
+  };
+  auto issue = [&](int w, int s) {
+    int b, n;
+    row_of(w, b, n);
+    const long long rowg = (long long)b * N + n;
+    const uint32_t st = smem0 + s * kStageBytes;
+    const float* gp = g + rowg * 2 * C + 2 * c;
+    cp_async16(st + threadIdx.x * 16, gp);
+    cp_async16(st + kThreads * 16 + threadIdx.x * 16, gp + 4);
+    cp_async4(st + kThreads * 32 + threadIdx.x * 4, argmax + rowg * C + c);
+  };
+  struct Meta { int ids[KN]; int o0, o1; };
+  auto load_meta = [&](int w, Meta& mt) {
+    int b, n;
+    row_of(w, b, n);
+    const long long rowg = (long long)b * N + n;
+#pragma unroll
+    for (int j = 0; j < KN; ++j) mt.ids[j] = load_index<I64>(nbr, rowg * KN + j);
+    const int* ro = rev_off + (long long)b * (N + 1) + n;
+    mt.o0 = __ldg(ro);
+    mt.o1 = __ldg(ro + 1);
+  };
+
+  const int w0 = blockIdx.x, stride = gridDim.x;
+#pragma unroll
+  for (int s = 0; s < D; ++s) {
+    if (w0 + s * stride < total_iters) issue(w0 + s * stride, s);
+    cp_async_commit();
+  }
+  Meta cur, nxt;
+  if (w0 < total_iters) load_meta(w0, cur);
+  nxt = cur;
+
+  int s = 0;
+  for (int w = w0; w < total_iters; w += stride) {
+    if (w + stride < total_iters) load_meta(w + stride, nxt);  // consumed next iteration
+    cp_async_wait<D - 1>();
+    const unsigned char* st = pipe_smem + s * kStageBytes;
+    const float4 ga = *reinterpret_cast<const float4*>(st + threadIdx.x * 16);
+    const float4 gb = *reinterpret_cast<const float4*>(st + kThreads * 16 + threadIdx.x * 16);
+    const unsigned int am = *reinterpret_cast<const unsigned int*>(st + kThreads * 32 + threadIdx.x * 4);
+    int b, n;
+    row_of(w, b, n);
+    const float g0[4] = {ga.x, ga.z, gb.x, gb.z};
+    const float g1[4] = {ga.y, ga.w, gb.y, gb.w};
+    float r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int a = (am >> (8 * e)) & 0xff;
+      int win = cur.ids[KN - 1];
+#pragma unroll
+      for (int j = KN - 2; j >= 0; --j) win = (a == j) ? cur.ids[j] : win;
+      r[e] = (win == n) ? g0[e] : g0[e] - g1[e];
+    }
+    // in-edges: (m, j) pairs whose slot j of row m is this row; two in flight per trip
+    const long long segrow = (long long)b * N;
+    const unsigned int* rs = rev_src + segrow * KN;
+    for (int e0 = cur.o0; e0 < cur.o1; e0 += 2) {
+      const bool two = e0 + 1 < cur.o1;
+      const unsigned ent0 = __ldg(rs + e0);
+      const unsigned ent1 = two ? __ldg(rs + e0 + 1) : ent0;
+      const long long m0 = segrow + (ent0 & 0xffffffu), m1 = segrow + (ent1 & 0xffffffu);
+      const unsigned am0 = __ldg(reinterpret_cast<const unsigned int*>(argmax + m0 * C + c));
+      const unsigned am1 = __ldg(reinterpret_cast<const unsigned int*>(argmax + m1 * C + c));
+      float gm0[8], gm1[8];
+      Pack8<float>::load(g + m0 * 2 * C + 2 * c, gm0);
+      Pack8<float>::load(g + m1 * 2 * C + 2 * c, gm1);
+      const unsigned j0 = ent0 >> 24, j1 = ent1 >> 24;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        r[e] += (((am0 >> (8 * e)) & 0xff) == j0) ? gm0[2 * e + 1] : 0.f;
+        r[e] += (two && ((am1 >> (8 * e)) & 0xff) == j1) ? gm1[2 * e + 1] : 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(grad_x + (segrow + n) * C + c) = make_float4(r[0], r[1], r[2], r[3]);
+    const int wn = w + D * stride;
+    if (wn < total_iters) issue(wn, s);
+    cp_async_commit();
+    cur = nxt;
+    if (++s == D) s = 0;
+  }
+  cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------
 // plain gather (torch_nn.py:79-98) and its scatter-add backward
 // ------------------------------------------------------------------------------------
 template <typename T, int VEC, bool I64>
@@ -621,22 +913,16 @@ max_over_k_bwd_kernel(const T* __restrict__ g, const uint8_t* __restrict__ argma
 namespace {
 
 // development switches: GRAFP_MR_FWD_VARIANT = 0 generic kernel, 1 / 2 / 4 fast kernel with that many items in
-// flight per thread (default 4); GRAFP_MR_BWD_VARIANT = 0 two-kernel form, 1 / 2 / 4 fused cluster form (default 2)
+// flight per thread, 8 (default) the cp.async-pipelined persistent kernel where it applies; GRAFP_MR_BWD_VARIANT = 0 two-kernel form, 1 / 2 / 4 fused cluster form,
+// 8 (default) the gather form over the reverse graph when a workspace is given
+// (read on every call - a getenv is nanoseconds next to a launch - so tests can switch kernels in-process)
 int fwd_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("GRAFP_MR_FWD_VARIANT");
-    v = e ? atoi(e) : 4;
-  }
-  return v;
+  const char* e = getenv("GRAFP_MR_FWD_VARIANT");
+  return e ? atoi(e) : 8;
 }
 int bwd_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("GRAFP_MR_BWD_VARIANT");
-    v = e ? atoi(e) : 2;
-  }
-  return v;
+  const char* e = getenv("GRAFP_MR_BWD_VARIANT");
+  return e ? atoi(e) : 8;
 }
 
 template <typename F>
@@ -669,8 +955,34 @@ int launch_mr_aggregate_fwd(const void* x, const void* y, const void* nbr, const
       if (!ctr && variant > 0 && (cv & (cv - 1)) == 0 && cv <= kThreads && B <= 65535 && aligned32(out)) {
         int cv_shift = 0;
         while ((1 << cv_shift) < cv) ++cv_shift;
+        if constexpr (std::is_same<T, float>::value) {
+          // pipelined persistent form: k == 3 (GraFP's k), whole 256-item chunks, a power-of-two number per segment
+          const long long items_per_seg = (long long)N * cv;
+          const long long ips = items_per_seg / kThreads;
+          if (variant >= 8 && k == 3 && items_per_seg % kThreads == 0 && (ips & (ips - 1)) == 0 && ips >= 1 &&
+              (long long)B * ips < 0x7fffffffLL) {
+            int ips_shift = 0;
+            while ((1LL << ips_shift) < ips) ++ips_shift;
+            const int total = (int)(B * ips);
+            constexpr int D = 4;
+            const size_t smem = (size_t)D * 4 * kThreads * 16;
+            static bool configured = false;
+            if (!configured) {
+              cudaError_t e = cudaFuncSetAttribute(mr_aggregate_fwd_pipe_kernel<I64, 3, D>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+              if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_fwd_pipe): %s", cudaGetErrorString(e)); return (int)e; }
+              configured = true;
+            }
+            int ctas = num_sms() * 3;  // 64 KB of slots per CTA: three CTAs per SM
+            if (ctas > total) ctas = total;
+            mr_aggregate_fwd_pipe_kernel<I64, 3, D><<<ctas, kThreads, smem, s>>>(
+                reinterpret_cast<const float*>(xs), reinterpret_cast<const float*>(src), nbr, reinterpret_cast<float*>(out),
+                argmax, N, M, C, cv_shift, ips_shift, total);
+            return check_launch("mr_aggregate_fwd_pipe");
+          }
+        }
         const int rpb = kThreads >> cv_shift;
-        const int u = variant;  // items in flight per thread: 1, 2 or 4
+        const int u = variant >= 8 ? 4 : variant;  // items in flight per thread: 1, 2 or 4
         const int passes = (N + rpb * u - 1) / (rpb * u);
         int gx = (num_sms() * 8 + B - 1) / B;  // about 8 resident CTAs per SM across the whole batch
         if (gx > passes) gx = passes;
@@ -694,9 +1006,16 @@ int launch_mr_aggregate_fwd(const void* x, const void* y, const void* nbr, const
   });
 }
 
+size_t mr_bwd_workspace_bytes(int B, int N, int k) {
+  // reverse CSR of every segment's graph: offsets (B, N + 1) int32 and sources (B, N * k) uint32
+  const size_t off = ((size_t)B * (N + 1) * 4 + 255) / 256 * 256;
+  return off + (size_t)B * N * k * 4 + 256;
+}
+
 template <typename T>
 int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nbr, const void* ctr, int idx_is_i64,
-                            void* grad_x, void* grad_y, int B, int N, int M, int C, int k, cudaStream_t s) {
+                            void* grad_x, void* grad_y, int B, int N, int M, int C, int k, void* workspace,
+                            size_t workspace_bytes, cudaStream_t s) {
   const long long rows = (long long)B * N;
   T* gx = static_cast<T*>(grad_x);
   T* gsrc = grad_y ? static_cast<T*>(grad_y) : gx;
@@ -711,8 +1030,43 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
     const int grid = grid_for(rows * (C / VEC), kThreads, 8);
     const T* gs = static_cast<const T*>(g);
     const bool self_skip = (ctr == nullptr) && (grad_y == nullptr);
+    if constexpr (VEC == 4 && std::is_same<T, float>::value) {
+      // gather form over the reverse graph (default when the caller passes a workspace)
+      const int cv = C / 4;
+      const long long items_per_seg = (long long)N * cv;
+      const long long ips = items_per_seg / kThreads;
+      if (self_skip && bwd_variant() >= 8 && k == 3 && workspace != nullptr &&
+          workspace_bytes >= mr_bwd_workspace_bytes(B, N, k) && (cv & (cv - 1)) == 0 && cv <= kThreads &&
+          items_per_seg % kThreads == 0 && (ips & (ips - 1)) == 0 && ips >= 1 && (long long)B * ips < 0x7fffffffLL &&
+          N <= 8192 && aligned32(g)) {
+        int cv_shift = 0, ips_shift = 0;
+        while ((1 << cv_shift) < cv) ++cv_shift;
+        while ((1LL << ips_shift) < ips) ++ips_shift;
+        char* wbase = reinterpret_cast<char*>(((uintptr_t)workspace + 255) / 256 * 256);
+        int* rev_off = reinterpret_cast<int*>(wbase);
+        unsigned int* rev_src = reinterpret_cast<unsigned int*>(wbase + ((size_t)B * (N + 1) * 4 + 255) / 256 * 256);
+        const size_t smem_rev = (size_t)(2 * N + 2) * sizeof(int);
+        constexpr int D = 4;
+        const size_t smem_pipe = (size_t)D * kThreads * 36;
+        static bool configured = false;
+        if (!configured) {
+          cudaError_t e = cudaFuncSetAttribute(mr_bwd_build_reverse_kernel<I64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
+          if (e == cudaSuccess) e = cudaFuncSetAttribute(mr_aggregate_bwd_gather_kernel<I64, 3, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
+          if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_bwd_gather): %s", cudaGetErrorString(e)); return (int)e; }
+          configured = true;
+        }
+        mr_bwd_build_reverse_kernel<I64><<<B, kThreads, smem_rev, s>>>(nbr, rev_off, rev_src, N, k);
+        const int total = (int)(B * ips);
+        int ctas = num_sms() * 6;  // 36 KB of slots per CTA
+        if (ctas > total) ctas = total;
+        mr_aggregate_bwd_gather_kernel<I64, 3, D><<<ctas, kThreads, smem_pipe, s>>>(
+            reinterpret_cast<const float*>(gs), argmax, nbr, rev_off, rev_src, reinterpret_cast<float*>(gx), N, C, cv_shift,
+            ips_shift, total);
+        return check_launch("mr_aggregate_bwd_gather");
+      }
+    }
     if constexpr (VEC == 4) {
-      const int bv = bwd_variant();  // 0: two-kernel form; 1 / 2 / 4: fused form with that many items in flight
+      const int bv = bwd_variant() >= 8 ? 2 : bwd_variant();  // 0: two-kernel form; 1 / 2 / 4: fused cluster form
       if (self_skip && bv > 0) {
         bool launched = false;
         const int rc = bv == 1 ? launch_mr_bwd_fused<T, I64, 1>(gs, argmax, nbr, gx, B, N, C, k, s, &launched)
@@ -850,7 +1204,7 @@ int launch_max_over_k_bwd(const void* g, const uint8_t* argmax, void* grad_h, in
   template int launch_mr_aggregate_fwd<T>(const void*, const void*, const void*, const void*, int, void*, uint8_t*,  \
                                           int, int, int, int, int, cudaStream_t);                                    \
   template int launch_mr_aggregate_bwd<T>(const void*, const uint8_t*, const void*, const void*, int, void*, void*,  \
-                                          int, int, int, int, int, cudaStream_t);                                    \
+                                          int, int, int, int, int, void*, size_t, cudaStream_t);                     \
   template int launch_gather_fwd<T>(const void*, const void*, int, void*, int, int, int, int, int, cudaStream_t);    \
   template int launch_gather_bwd<T>(const void*, const void*, int, void*, int, int, int, int, int, cudaStream_t);    \
   template int launch_edge_gather_fwd<T>(const void*, const void*, const void*, const void*, int, void*, int, int,   \

@@ -168,7 +168,9 @@ int launch_mr_aggregate_fwd(const void* x, const void* y, const void* nbr, const
                             uint8_t* argmax, int B, int N, int M, int C, int k, cudaStream_t s);
 template <typename T>
 int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nbr, const void* ctr, int idx_is_i64,
-                            void* grad_x, void* grad_y, int B, int N, int M, int C, int k, cudaStream_t s);
+                            void* grad_x, void* grad_y, int B, int N, int M, int C, int k, void* workspace,
+                            size_t workspace_bytes, cudaStream_t s);
+size_t mr_bwd_workspace_bytes(int B, int N, int k);
 template <typename T>
 int launch_gather_fwd(const void* src, const void* idx, int idx_is_i64, void* out, int B, int N, int M, int C, int k,
                       cudaStream_t s);

@@ -136,6 +136,94 @@ knn_normalize_vec_kernel(const T* __restrict__ x, float* __restrict__ xhat, floa
   }
 }
 
+// Lean fp32 -> fp16 hi/lo plane producer for the f16x3 tensor-core kernels (mode 3, C % 4 == 0, C <= 1024).
+// Same row ownership as the vectorised kernel above, but the warp never diverges (rows past the end are
+// clamped and only their stores are guarded), the quotient x / denom is formed as one reciprocal per row
+// plus a Newton correction per element (q0 = x * r; q = fma(fma(-q0, denom, x), r, q0), which is the
+// correctly rounded quotient except in rare double-rounding cases), and the planes leave as packed
+// 8-byte stores.  ~4x fewer instructions than the generic kernel, which was issue-bound.
+template <int LPR, int PACKS>
+__global__ void __launch_bounds__(256)
+knn_normalize_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+                         float* __restrict__ sq, long long rows, int C, bool normalize) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  constexpr int RPW = 32 / LPR;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int cv = C / 4;
+  for (long long rb = warp0 * RPW; rb < rows; rb += nwarps * RPW) {
+    const long long row_raw = rb + lane / LPR;
+    const bool live = row_raw < rows;
+    const long long row = live ? row_raw : rows - 1;
+    float4 v[PACKS];
+    float ss = 0.f;
+#pragma unroll
+    for (int p = 0; p < PACKS; ++p) {
+      const int c4 = sub + p * LPR;
+      v[p] = (c4 < cv) ? __ldg(reinterpret_cast<const float4*>(x + row * C) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ss = fmaf(v[p].x, v[p].x, ss); ss = fmaf(v[p].y, v[p].y, ss);
+      ss = fmaf(v[p].z, v[p].z, ss); ss = fmaf(v[p].w, v[p].w, ss);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float denom = normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+    const float r = __frcp_rn(denom);
+    float s2 = 0.f;
+#pragma unroll
+    for (int p = 0; p < PACKS; ++p) {
+      const int c4 = sub + p * LPR;
+      const float xin[4] = {v[p].x, v[p].y, v[p].z, v[p].w};
+      float h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float q0 = xin[e] * r;
+        const float q = fmaf(fmaf(-q0, denom, xin[e]), r, q0);
+        s2 = fmaf(q, q, s2);
+        const float sv = q * kF16PlaneScale;
+        h[e] = __half2float(__float2half_rn(sv));
+        l[e] = sv - h[e];  // exact; rounded to fp16 by the store
+      }
+      if (live && c4 < cv) {
+        const __half2 h01 = __floats2half2_rn(h[0], h[1]), h23 = __floats2half2_rn(h[2], h[3]);
+        const __half2 l01 = __floats2half2_rn(l[0], l[1]), l23 = __floats2half2_rn(l[2], l[3]);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(hi + row * C + c4 * 4) = hv;
+        *reinterpret_cast<uint2*>(lo + row * C + c4 * 4) = lv;
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (live && sub == 0) sq[row] = s2;
+  }
+}
+
+static bool launch_normalize_f16(const float* xs, float* hi, float* lo, float* sq, long long rows, int C, bool normalize,
+                                 cudaStream_t s) {
+  const int cv = C / 4;
+  __half* h = reinterpret_cast<__half*>(hi);
+  __half* l = reinterpret_cast<__half*>(lo);
+#define GRAFP_NORM16_CASE(LPR_, PACKS_)                                                              \
+  {                                                                                                  \
+    const long long need = (rows + (256 / LPR_) - 1) / (256 / LPR_);                                 \
+    const long long cap = (long long)num_sms() * 8;                                                  \
+    const int blocks = (int)(need < cap ? (need < 1 ? 1 : need) : cap);                              \
+    knn_normalize_f16_kernel<LPR_, PACKS_><<<blocks, 256, 0, s>>>(xs, h, l, sq, rows, C, normalize); \
+    return true;                                                                                     \
+  }
+  if (cv <= 4) GRAFP_NORM16_CASE(4, 1)
+  if (cv <= 8) GRAFP_NORM16_CASE(8, 1)
+  if (cv <= 16) GRAFP_NORM16_CASE(16, 1)
+  if (cv <= 32) GRAFP_NORM16_CASE(32, 1)
+  if (cv <= 64) GRAFP_NORM16_CASE(32, 2)
+  if (cv <= 128) GRAFP_NORM16_CASE(32, 4)
+  if (cv <= 256) GRAFP_NORM16_CASE(32, 8)
+#undef GRAFP_NORM16_CASE
+  return false;
+}
+
 template <typename T, int MODE>
 static bool launch_normalize_vec(const T* xs, float* xhat, float* lo, float* sq, long long rows, int C, bool normalize,
                                  int blocks, cudaStream_t s) {
@@ -164,6 +252,10 @@ int launch_knn_normalize(const void* x, float* xhat, float* lo, float* sq, long 
   if (blocks < 1) blocks = 1;
   const T* xs = static_cast<const T*>(x);
   const bool vec = (C % 4 == 0) && aligned16(x) && aligned16(xhat) && aligned16(lo);
+  if (vec && mode == 3 && std::is_same<T, float>::value) {
+    if (launch_normalize_f16(reinterpret_cast<const float*>(x), xhat, lo, sq, rows, C, normalize, s))
+      return check_launch("knn_normalize_f16");
+  }
   if (vec) {
     bool done = false;
     if (mode == 0) done = launch_normalize_vec<T, 0>(xs, xhat, lo, sq, rows, C, normalize, (int)blocks, s);

@@ -86,15 +86,26 @@ struct TopK {
     d[0] = c[0] ? v : d[0];
     id[0] = c[0] ? key : id[0];
   }
-  // 32 accumulator columns (acc = s * 2^24); ys_addr: shared address of |y|^2 of column 0
+  // 32 accumulator columns (acc = s * 2^24); ys_addr: shared address of |y|^2 of column 0.
+  // The votes of a group of kVoteGroup columns are taken up front against the threshold as of the group
+  // start (a stale threshold is only looser, the exact test is redone in `insert`), so the
+  // FSETP -> VOTE -> BRA latency chain is paid once per group instead of once per column.
+  static constexpr int kVoteGroup = 4;
   __device__ __forceinline__ void scan32(const uint32_t (&v)[32], uint32_t ys_addr, int key0) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float a = __uint_as_float(v[j]);
-      if (__any_sync(0xffffffffu, a > thr)) {
-        const float dist = __fadd_rn(fmaf(kM2, a, sq_i), lds_f32(ys_addr + 4 * j));
-        insert(dist, key0 + j);
-        update_thr();
+    for (int j0 = 0; j0 < 32; j0 += kVoteGroup) {
+      bool cand[kVoteGroup];
+      const float t = thr;
+#pragma unroll
+      for (int g = 0; g < kVoteGroup; ++g) cand[g] = __any_sync(0xffffffffu, __uint_as_float(v[j0 + g]) > t);
+#pragma unroll
+      for (int g = 0; g < kVoteGroup; ++g) {
+        if (cand[g]) {
+          const int j = j0 + g;
+          const float dist = __fadd_rn(fmaf(kM2, __uint_as_float(v[j]), sq_i), lds_f32(ys_addr + 4 * j));
+          insert(dist, key0 + j);
+          update_thr();
+        }
       }
     }
   }

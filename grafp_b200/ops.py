@@ -222,10 +222,15 @@ class _MRAggregate(torch.autograd.Function):
         g = as_rows(grad_out)
         grad_x = _new_rows(B, C, N, g)
         grad_y = _new_rows(B, C, M, g) if has_y else None
+        ws, ws_bytes = None, 0
+        if ctr_c is None and not has_y:  # k-NN-op graph: gather-form backward over the reverse graph
+            ws_bytes = lib.grafp_mr_aggregate_bwd_workspace_bytes(B, N, k)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
         _call("mr_aggregate_bwd", 2, dict(B=B, N=N, M=M, C=C, k=k, dtype=dt, i64=i64),
               lib.grafp_mr_aggregate_bwd, g.data_ptr(), argmax.data_ptr(), nbr_c.data_ptr(),
               ctr_c.data_ptr() if ctr_c is not None else None, i64, grad_x.data_ptr(),
-              grad_y.data_ptr() if grad_y is not None else None, B, N, M, C, k, dt, _stream())
+              grad_y.data_ptr() if grad_y is not None else None, B, N, M, C, k, dt,
+              ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
         return grad_x, grad_y, None, None
 
 

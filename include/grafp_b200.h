@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GRAFP_ABI_VERSION 1
+#define GRAFP_ABI_VERSION 2
 
 #define GRAFP_OK 0
 #define GRAFP_EINVAL (-1)       /* null / misaligned pointer, non-positive size, k > M ... */
@@ -94,13 +94,18 @@ int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn
  * The backward overwrites grad_x (B, N, C) and, when y was given, grad_y (B, M, C):
  *  grad_x[b][n][c]  = g[b][n][2c] + sum over (m, j = argmax[b][m][c]) of
  *                     ( -g[b][m][2c+1] if ctr[b][m][j] == n )  ( +g[b][m][2c+1] if y == NULL and nbr[b][m][j] == n )
- * Floating-point accumulation order of the scatter is not fixed (atomics).
+ * `workspace` (optional, grafp_mr_aggregate_bwd_workspace_bytes(B, N, k) bytes, caller-owned scratch):
+ * when given, and the graph is the k-NN op's (ctr == NULL, y == NULL, k == 3, fp32), the backward runs
+ * in gather form over the reverse graph built into the workspace: no atomics, fixed summation order
+ * (bit-reproducible).  Without it (or outside that envelope) the scatter uses vector reductions
+ * (red.global.add) and the floating-point accumulation order is not fixed.
  */
 int grafp_mr_aggregate_fwd(const void* x, const void* y, const void* nbr_idx, const void* ctr_idx, int idx_is_i64,
                            void* out, uint8_t* argmax, int B, int N, int M, int C, int k, int dtype, void* stream);
+size_t grafp_mr_aggregate_bwd_workspace_bytes(int B, int N, int k);
 int grafp_mr_aggregate_bwd(const void* grad_out, const uint8_t* argmax, const void* nbr_idx, const void* ctr_idx,
                            int idx_is_i64, void* grad_x, void* grad_y, int B, int N, int M, int C, int k, int dtype,
-                           void* stream);
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Plain neighbour gather.  Replaces batched_index_select (torch_nn.py:79-98).

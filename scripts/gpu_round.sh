@@ -7,12 +7,12 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > g
 cp MEASURED_PEAKS.json gpurun_out/ 2>/dev/null
 timeout 300 python scripts/tc_check.py > gpurun_out/tc_check.log 2>&1; echo "tc_check rc=$?"
 tail -12 gpurun_out/tc_check.log
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 tail -5 gpurun_out/pytest_gpu.log
 timeout 300 python scripts/bench_ops.py > gpurun_out/bench_ops.log 2>&1; echo "bench_ops rc=$?"
 cat gpurun_out/bench_ops.log
 timeout 120 python scripts/measure_peaks.py > gpurun_out/peaks_self.json 2>&1; cat gpurun_out/peaks_self.json
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?"
 tail -1 gpurun_out/bench.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'knn_stream|knn_self|knn_normalize|mr_aggregate' -c 16 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'knn_stream|knn_self|knn_normalize|mr_aggregate|mr_bwd' -c 20 \
   -o gpurun_out/prof_ops -f python scripts/ncu_ops.py 512 1 > gpurun_out/ncu_ops.log 2>&1; echo "ncu rc=$?"
