@@ -503,6 +503,161 @@ mr_aggregate_bwd_fused_kernel(const T* __restrict__ g, const uint8_t* __restrict
   }
 }
 
+// K3, cluster form with TMA bulk staging (fp32): same two phases as the fused kernel above, but a CTA's
+// whole share of the segment - its rows of grad_out (contiguous, 64 KB at every encoder stage) and of the
+// argmax bytes - is pulled into shared memory by two cp.async.bulk copies issued by one thread and
+// awaited on an mbarrier.  No registers are tied up by loads in flight, three CTAs per SM keep
+// ~220 KB of reads outstanding, and phase 2 re-reads g[.., 2c+1] from the staged tile instead of a
+// separate stash.
+__device__ __forceinline__ void k3_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void k3_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void k3_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void k3_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "K3_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra K3_WAIT_DONE;\n\t"
+      "bra K3_WAIT_LOOP;\n\t"
+      "K3_WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+
+template <bool I64>
+__global__ void __launch_bounds__(kFusedThreads, 3)
+mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* __restrict__ argmax,
+                                    const void* __restrict__ nbr, float* __restrict__ grad_x, int N, int C, int k,
+                                    int rows_per_cta, int cv_shift) {
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  const int cv = 1 << cv_shift;
+  const float* gt = reinterpret_cast<const float*>(tma_smem);                                   // [rows][2C]
+  const unsigned char* at = tma_smem + (size_t)rows_per_cta * 2 * C * sizeof(float);             // [rows][C]
+  const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(tma_smem + (size_t)rows_per_cta * C * 9));
+  const unsigned csize = cluster_nctarank();
+  const long long b = blockIdx.x / csize;
+  const int row0 = static_cast<int>(cluster_ctarank()) * rows_per_cta;
+  const int nrows = max(0, min(rows_per_cta, N - row0));
+  const int items = nrows << cv_shift;
+  float* gxb = grad_x + b * (long long)N * C;
+  const long long ib = b * (long long)N * k;
+
+  if (threadIdx.x == 0) {
+    k3_mbar_init(bar, 1);
+    if (nrows > 0) {
+      const uint32_t gbytes = (uint32_t)nrows * 2 * C * 4, abytes = (uint32_t)nrows * C;
+      k3_mbar_expect_tx(bar, gbytes + abytes);
+      k3_bulk_g2s(static_cast<uint32_t>(__cvta_generic_to_shared(tma_smem)), g + (b * N + row0) * 2LL * C, gbytes, bar);
+      k3_bulk_g2s(static_cast<uint32_t>(__cvta_generic_to_shared(at)), argmax + (b * N + row0) * (long long)C, abytes, bar);
+    }
+  }
+  __syncthreads();  // the barrier is initialised before anyone waits on it
+  if (nrows > 0) k3_mbar_wait(bar, 0);
+
+  // phase 1: dense part of grad_x for this CTA's rows
+  for (int it = threadIdx.x; it < items; it += kFusedThreads) {
+    const int rl = it >> cv_shift;
+    const int n = row0 + rl;
+    const int c = (it & (cv - 1)) * 4;
+    const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
+    const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
+    const unsigned int packed = *reinterpret_cast<const unsigned int*>(at + (size_t)rl * C + c);
+    const float g0[4] = {ga.x, ga.z, gb.x, gb.z}, g1[4] = {ga.y, ga.w, gb.y, gb.w};
+    float r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int nb = load_index<I64>(nbr, ib + (long long)n * k + ((packed >> (8 * e)) & 0xff));
+      r[e] = (nb == n) ? g0[e] : g0[e] - g1[e];
+    }
+    *reinterpret_cast<float4*>(gxb + (long long)n * C + c) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+  __threadfence();
+  cluster_sync_all();
+
+  // phase 2: route g[.., 2c+1] to the winning neighbour rows of this segment (L2-resident, just written)
+  for (int it = threadIdx.x; it < items; it += kFusedThreads) {
+    const int rl = it >> cv_shift;
+    const int n = row0 + rl;
+    const int c = (it & (cv - 1)) * 4;
+    const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
+    const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
+    const unsigned int packed = *reinterpret_cast<const unsigned int*>(at + (size_t)rl * C + c);
+    const float g1[4] = {ga.y, ga.w, gb.y, gb.w};
+    int a[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) a[e] = (packed >> (8 * e)) & 0xff;
+    unsigned todo = 0xf;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (todo & (1u << e)) {
+        const int j = a[e];
+        float v[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          const bool hit = (a[f] == j);
+          v[f] = hit ? g1[f] : 0.f;
+          if (hit) todo &= ~(1u << f);
+        }
+        const int nb = load_index<I64>(nbr, ib + (long long)n * k + j);
+        if (nb != n) Pack<float, 4>::red_add(gxb + (long long)nb * C + c, v);
+      }
+    }
+  }
+}
+
+template <bool I64>
+int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void* nbr, float* grad_x, int B, int N, int C,
+                              int k, cudaStream_t s, bool* launched) {
+  *launched = false;
+  const int cv = C / 4;
+  if ((cv & (cv - 1)) != 0 || C % 16 != 0 || !aligned16(g) || !aligned16(argmax) || N < 64) return GRAFP_OK;
+  int cv_shift = 0;
+  while ((1 << cv_shift) < cv) ++cv_shift;
+  // smallest cluster whose per-CTA share (8 B + 1 B per element) fits 74 KB: three CTAs per SM
+  int cl = 0;
+  for (int cand : {1, 2, 4, 8}) {
+    const long long rows = (N + cand - 1) / cand;
+    if (rows * C * 9 + 16 <= 74 * 1024) { cl = cand; break; }
+  }
+  if (cl == 0 || (long long)B * cl > 0x7fffffffLL) return GRAFP_OK;
+  const int rows_per_cta = (N + cl - 1) / cl;
+  const size_t smem = (size_t)rows_per_cta * C * 9 + 16;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_bwd_cluster_tma): %s", cudaGetErrorString(e)); return (int)e; }
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * cl));
+  cfg.blockDim = dim3(kFusedThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mr_aggregate_bwd_cluster_tma_kernel<I64>, g, argmax, nbr, grad_x, N, C, k,
+                                     rows_per_cta, cv_shift);
+  if (e != cudaSuccess) { set_error("mr_aggregate_bwd_cluster_tma launch: %s", cudaGetErrorString(e)); return (int)e; }
+  *launched = true;
+  return check_launch("mr_aggregate_bwd_cluster_tma");
+}
+
 template <typename T, bool I64, int U>
 int launch_mr_bwd_fused(const T* g, const uint8_t* argmax, const void* nbr, T* grad_x, int B, int N, int C, int k,
                         cudaStream_t s, bool* launched) {
@@ -914,7 +1069,8 @@ namespace {
 
 // development switches: GRAFP_MR_FWD_VARIANT = 0 generic kernel, 1 / 2 / 4 fast kernel with that many items in
 // flight per thread, 8 (default) the cp.async-pipelined persistent kernel where it applies; GRAFP_MR_BWD_VARIANT = 0 two-kernel form, 1 / 2 / 4 fused cluster form,
-// 8 (default) the gather form over the reverse graph when a workspace is given
+// 8 the deterministic gather form over the reverse graph (needs the workspace), 16 (default) the cluster form
+// with TMA bulk staging
 // (read on every call - a getenv is nanoseconds next to a launch - so tests can switch kernels in-process)
 int fwd_variant() {
   const char* e = getenv("GRAFP_MR_FWD_VARIANT");
@@ -922,7 +1078,7 @@ int fwd_variant() {
 }
 int bwd_variant() {
   const char* e = getenv("GRAFP_MR_BWD_VARIANT");
-  return e ? atoi(e) : 8;
+  return e ? atoi(e) : 16;
 }
 
 template <typename F>
@@ -1035,7 +1191,7 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
       const int cv = C / 4;
       const long long items_per_seg = (long long)N * cv;
       const long long ips = items_per_seg / kThreads;
-      if (self_skip && bwd_variant() >= 8 && k == 3 && workspace != nullptr &&
+      if (self_skip && bwd_variant() == 8 && k == 3 && workspace != nullptr &&
           workspace_bytes >= mr_bwd_workspace_bytes(B, N, k) && (cv & (cv - 1)) == 0 && cv <= kThreads &&
           items_per_seg % kThreads == 0 && (ips & (ips - 1)) == 0 && ips >= 1 && (long long)B * ips < 0x7fffffffLL &&
           N <= 8192 && aligned32(g)) {
@@ -1063,6 +1219,14 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
             reinterpret_cast<const float*>(gs), argmax, nbr, rev_off, rev_src, reinterpret_cast<float*>(gx), N, C, cv_shift,
             ips_shift, total);
         return check_launch("mr_aggregate_bwd_gather");
+      }
+    }
+    if constexpr (VEC == 4 && std::is_same<T, float>::value) {
+      if (self_skip && bwd_variant() >= 8) {  // default: cluster form with TMA bulk staging
+        bool launched = false;
+        const int rc = launch_mr_bwd_cluster_tma<I64>(reinterpret_cast<const float*>(gs), argmax, nbr,
+                                                      reinterpret_cast<float*>(gx), B, N, C, k, s, &launched);
+        if (rc != GRAFP_OK || launched) return rc;
       }
     }
     if constexpr (VEC == 4) {

@@ -39,9 +39,10 @@ constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemLimit = 232448;       // 227 KB opt-in maximum per CTA
 constexpr float kPlaneScale = 4096.f;         // planes hold x_hat * 2^12 (see knn_normalize, mode 3)
 
-// instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = 128
+// instruction descriptor: D = f32, A = B = f16, both K-major, M = 128, N = BN
+template <int BN>
 __device__ __forceinline__ constexpr uint32_t make_idesc_f16() {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(BM >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
@@ -86,14 +87,16 @@ struct TopK {
     d[0] = c[0] ? v : d[0];
     id[0] = c[0] ? key : id[0];
   }
-  // 32 accumulator columns (acc = s * 2^24); ys_addr: shared address of |y|^2 of column 0.
+  // 8 accumulator columns (acc = s * 2^24); ys_addr: shared address of |y|^2 of column 0.
   // The votes of a group of kVoteGroup columns are taken up front against the threshold as of the group
   // start (a stale threshold is only looser, the exact test is redone in `insert`), so the
-  // FSETP -> VOTE -> BRA latency chain is paid once per group instead of once per column.
+  // FSETP -> VOTE -> BRA latency chain is paid once per group instead of once per column.  The
+  // callers keep this in a rolled loop (8 columns per tcgen05.ld): the unrolled 32-column form was
+  // 13 KB of code per tile pass and starved the instruction cache.
   static constexpr int kVoteGroup = 4;
-  __device__ __forceinline__ void scan32(const uint32_t (&v)[32], uint32_t ys_addr, int key0) {
+  __device__ __forceinline__ void scan8(const uint32_t (&v)[8], uint32_t ys_addr, int key0) {
 #pragma unroll
-    for (int j0 = 0; j0 < 32; j0 += kVoteGroup) {
+    for (int j0 = 0; j0 < 8; j0 += kVoteGroup) {
       bool cand[kVoteGroup];
       const float t = thr;
 #pragma unroll
@@ -111,6 +114,12 @@ struct TopK {
   }
 };
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+
 template <int KREG>
 __device__ __forceinline__ void emit(const TopK<KREG>& top, long long* nn_idx, int* nn_idx32, long long o, int k_out, int stride) {
 #pragma unroll
@@ -122,14 +131,16 @@ __device__ __forceinline__ void emit(const TopK<KREG>& top, long long* nn_idx, i
   }
 }
 
-// three MMAs per 16-channel step over one 64-channel block pair
+// three MMAs per 16-channel step over one 64-channel block pair (A block: 128 rows, B block: BN rows)
+template <int BN>
 __device__ __forceinline__ void mma_block(uint32_t acc, uint32_t a_blk, uint32_t b_blk, bool first) {
-  constexpr uint32_t idesc = make_idesc_f16();
+  constexpr uint32_t idesc = make_idesc_f16<BN>();
+  constexpr uint32_t kBPlane = BN * BK * 2;
 #pragma unroll
   for (int kk = 0; kk < BK / UMMA_K; ++kk) {
     const uint32_t off = kk * UMMA_K * 2;
     const uint64_t a_hi = make_smem_desc(a_blk + off), a_lo = make_smem_desc(a_blk + kPlaneBytes + off);
-    const uint64_t b_hi = make_smem_desc(b_blk + off), b_lo = make_smem_desc(b_blk + kPlaneBytes + off);
+    const uint64_t b_hi = make_smem_desc(b_blk + off), b_lo = make_smem_desc(b_blk + kBPlane + off);
     umma_f16(acc, a_lo, b_hi, idesc, (first && kk == 0) ? 0u : 1u);
     umma_f16(acc, a_hi, b_lo, idesc, 1u);
     umma_f16(acc, a_hi, b_hi, idesc, 1u);
@@ -147,7 +158,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
 // ---------------------------------------------------------------------------------------------
 // resident queries, streamed keys
 // ---------------------------------------------------------------------------------------------
-template <int NH, int KREG>
+template <int NH, int BN, int KREG>
 __global__ void __launch_bounds__((4 * NH + 2) * 32, 1)
 knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                   const __grid_constant__ CUtensorMap tm_y_hi, const __grid_constant__ CUtensorMap tm_y_lo,
@@ -155,15 +166,17 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
                   int* __restrict__ nn_idx32, int N, int M, int C, int k_out, int stride, int stages) {
   constexpr int kEpilogueThreads = 128 * NH;
   constexpr int kProducerWarp = 4 * NH, kMmaWarp = 4 * NH + 1;
-  constexpr uint32_t kTmemCols = 2 * NH * BM;  // two accumulator sets of NH tiles
+  constexpr uint32_t kTmemCols = 2 * NH * BN;  // two accumulator sets of NH tiles, BN keys wide
+  constexpr uint32_t kKeyBlockBytes = 2 * BN * BK * 2;  // hi + lo plane of BN keys x 64 channels
+  constexpr int kStageWarps = BN / 32;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int num_kc = (C + BK - 1) / BK;
-  const int num_tiles = (M + BM - 1) / BM;
+  const int num_tiles = (M + BN - 1) / BN;
   unsigned char* q_base = smem;                                    // [NH][num_kc] blocks
   unsigned char* ring = q_base + (size_t)NH * num_kc * kBlockBytes; // [stages] blocks
-  float* ysq_s = reinterpret_cast<float*>(ring + (size_t)stages * kBlockBytes);  // [2][BM]
-  float* ymin_s = ysq_s + 2 * BM;                                                // [2][4] per-warp minima of |y|^2
+  float* ysq_s = reinterpret_cast<float*>(ring + (size_t)stages * kKeyBlockBytes);  // [2][BN]
+  float* ymin_s = ysq_s + 2 * BN;                                                // [2][4] per-warp minima of |y|^2
   uint64_t* bars = reinterpret_cast<uint64_t*>(ymin_s + 8);
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;
@@ -206,10 +219,10 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
         for (int c = 0; c < num_kc; ++c) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const uint32_t full = bar_full + 8 * s;
-          mbar_arrive_expect_tx(full, kBlockBytes);
-          const uint32_t dst = smem_u32(ring + (size_t)s * kBlockBytes);
-          tma_load_3d(dst, &tm_y_hi, full, c * BK, t * BM, b);
-          tma_load_3d(dst + kPlaneBytes, &tm_y_lo, full, c * BK, t * BM, b);
+          mbar_arrive_expect_tx(full, kKeyBlockBytes);
+          const uint32_t dst = smem_u32(ring + (size_t)s * kKeyBlockBytes);
+          tma_load_3d(dst, &tm_y_hi, full, c * BK, t * BN, b);
+          tma_load_3d(dst + kKeyBlockBytes / 2, &tm_y_lo, full, c * BK, t * BN, b);
           if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
@@ -227,11 +240,11 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
         for (int c = 0; c < num_kc; ++c) {
           mbar_wait(bar_full + 8 * s, ph);
           tcgen05_fence_after();
-          const uint32_t b_blk = smem_u32(ring + (size_t)s * kBlockBytes);
+          const uint32_t b_blk = smem_u32(ring + (size_t)s * kKeyBlockBytes);
 #pragma unroll
           for (int h = 0; h < NH; ++h) {
             const uint32_t a_blk = smem_u32(q_base + (size_t)(h * num_kc + c) * kBlockBytes);
-            mma_block(tmem_base + (as * NH + h) * BM, a_blk, b_blk, c == 0);
+            mma_block<BN>(tmem_base + (as * NH + h) * BN, a_blk, b_blk, c == 0);
           }
           tcgen05_commit(bar_empty + 8 * s);  // frees the ring slot when these MMAs retire
           if (++s == stages) { s = 0; ph ^= 1; }
@@ -250,13 +263,13 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     TopK<KREG> top;
     top.init(sq_i);
     // |y|^2 of the next key tile is fetched one tile ahead so its global-load latency hides behind the scan
-    float yv_next = (threadIdx.x < BM && (int)threadIdx.x < M) ? ysq_b[threadIdx.x] : INFINITY;
+    float yv_next = (threadIdx.x < BN && (int)threadIdx.x < M) ? ysq_b[threadIdx.x] : INFINITY;
     for (int t = 0; t < num_tiles; ++t) {
       const int as = t & 1;
-      float* ys = ysq_s + as * BM;
-      if (threadIdx.x < BM) {
+      float* ys = ysq_s + as * BN;
+      if (threadIdx.x < BN) {
         const float yv = yv_next;  // keys past the end are +inf and can never be selected
-        const int key_next = (t + 1) * BM + threadIdx.x;
+        const int key_next = (t + 1) * BN + threadIdx.x;
         yv_next = (key_next < M) ? ysq_b[key_next] : INFINITY;
         ys[threadIdx.x] = yv;
         float mn = yv;
@@ -266,18 +279,21 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
       {
-        const float4 m4 = *reinterpret_cast<const float4*>(ymin_s + as * 4);
-        top.set_tile(fminf(fminf(m4.x, m4.y), fminf(m4.z, m4.w)));
+        float mn = ymin_s[as * 4];
+#pragma unroll
+        for (int w = 1; w < kStageWarps; ++w) mn = fminf(mn, ymin_s[as * 4 + w]);
+        top.set_tile(mn);
       }
       mbar_wait(bar_tfull + 8 * as, (t >> 1) & 1);
       tcgen05_fence_after();
-      const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * NH + h) * BM;
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * NH + h) * BN;
+      const uint32_t ys_addr = smem_u32(ys);
 #pragma unroll 1
-      for (int cc = 0; cc < BM / 32; ++cc) {
-        uint32_t v[32];
-        tmem_ld32(trow + cc * 32, v);
+      for (int cc = 0; cc < BN / 8; ++cc) {
+        uint32_t v[8];
+        tmem_ld8(trow + cc * 8, v);
         tmem_ld_wait();
-        top.scan32(v, smem_u32(ys + cc * 32), t * BM + cc * 32);
+        top.scan8(v, ys_addr + cc * 32, t * BN + cc * 8);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -362,7 +378,7 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
         for (int h = 0; h < NH; ++h) {
 #pragma unroll
           for (int t = 0; t < NH; ++t) {
-            mma_block(tmem_base + (h * NH + t) * BM, stage + h * kBlockBytes, stage + t * kBlockBytes, c == 0);
+            mma_block<BM>(tmem_base + (h * NH + t) * BM, stage + h * kBlockBytes, stage + t * kBlockBytes, c == 0);
           }
         }
         tcgen05_commit(bar_empty + 8 * s);
@@ -397,12 +413,13 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
     mbar_wait(bar_tfull, 0);
     tcgen05_fence_after();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (h * NH) * BM;
+    const uint32_t ys_addr = smem_u32(ysq_s);
 #pragma unroll 1
-    for (int cc = 0; cc < NH * BM / 32; ++cc) {
-      uint32_t v[32];
-      tmem_ld32(trow + cc * 32, v);
+    for (int cc = 0; cc < NH * BM / 8; ++cc) {
+      uint32_t v[8];
+      tmem_ld8(trow + cc * 8, v);
       tmem_ld_wait();
-      top.scan32(v, smem_u32(ysq_s + cc * 32), cc * 32);
+      top.scan8(v, ys_addr + cc * 32, cc * 8);
     }
     if (q < N) emit<KREG>(top, nn_idx, nn_idx32, ((long long)b * N + q) * k_out, k_out, stride);
   }
@@ -419,12 +436,12 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
 // host side
 // ---------------------------------------------------------------------------------------------
 // (rows x C) fp16 matrix per segment, box = 128 rows x 64 channels, 128B swizzle, zero fill out of bounds
-static bool make_map_f16(CUtensorMap* map, const void* base, int B, int rows, int C) {
+static bool make_map_f16(CUtensorMap* map, const void* base, int B, int rows, int C, int box_rows = BM) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)B};
   const cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)rows * C * 2};
-  const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -443,16 +460,16 @@ static int set_smem(Kernel kernel, bool* configured, const char* what) {
   return GRAFP_OK;
 }
 
-template <int NH, int KREG>
+template <int NH, int BN, int KREG>
 static int launch_stream(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& yh, const CUtensorMap& yl,
                          const float* xsq, const float* ysq, long long* nn_idx, int* nn_idx32, int B, int N, int M, int C,
                          int k_out, int stride, int stages, cudaStream_t s) {
   static bool configured = false;
-  if (int rc = set_smem(knn_stream_kernel<NH, KREG>, &configured, "knn_stream")) return rc;
+  if (int rc = set_smem(knn_stream_kernel<NH, BN, KREG>, &configured, "knn_stream")) return rc;
   const int num_kc = (C + BK - 1) / BK;
-  const size_t smem = (size_t)(NH * num_kc + stages) * kBlockBytes + kMiscBytes;
+  const size_t smem = (size_t)(NH * num_kc) * kBlockBytes + (size_t)stages * (2 * BN * BK * 2) + kMiscBytes;
   dim3 grid((N + BM * NH - 1) / (BM * NH), B);
-  knn_stream_kernel<NH, KREG><<<grid, (4 * NH + 2) * 32, smem, s>>>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, N, M, C,
+  knn_stream_kernel<NH, BN, KREG><<<grid, (4 * NH + 2) * 32, smem, s>>>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, N, M, C,
                                                                    k_out, stride, stages);
   return check_launch("knn_stream");
 }
@@ -467,7 +484,7 @@ static int launch_self(const CUtensorMap& xh, const CUtensorMap& xl, const float
   return check_launch("knn_self");
 }
 
-// plan: 0 = unsupported, 1 = self NH=1, 2 = self NH=2, 3 = stream NH=1, 4 = stream NH=2
+// plan: 0 = unsupported, 1 = self NH=1, 2 = self NH=2, 3 = stream NH=1, 4 = stream NH=2, 5 = stream NH=4 (64-key tiles)
 static int plan(int N, int M, int C, int K, int dtype, bool self, int* stages) {
   if (dtype != GRAFP_F32 || C % 8 != 0 || C < BK || N < BM || M < BM || K < 1 || K > 8) return 0;
   const int num_kc = (C + BK - 1) / BK;
@@ -482,6 +499,14 @@ static int plan(int N, int M, int C, int K, int dtype, bool self, int* stages) {
     if (st < 1) return 0;
     *stages = st;
     return nh;
+  }
+  // 512 resident queries, 64-key tiles (TMEM: 2 sets x 4 tiles x 64 columns), 16 epilogue warps: the selection
+  // is issue/latency bound, so the extra warps matter more than the tile width.  Needs the 4 query blocks
+  // per channel chunk to fit: C <= 64.
+  static const bool no_nh4 = getenv("GRAFP_KNN_NO_NH4") != nullptr;  // development switch (A/B timing)
+  if (!no_nh4 && N >= 4 * BM && (uint32_t)(4 * num_kc) * kBlockBytes + 4 * (kBlockBytes / 2) <= budget) {
+    *stages = 4;
+    return 5;
   }
   for (int nh = (N > BM ? 2 : 1); nh >= 1; --nh) {
     const uint32_t resident = (uint32_t)(nh * num_kc) * kBlockBytes;
@@ -511,23 +536,27 @@ int launch_knn_tc2(const void* xhi, const void* xlo, const float* xsq, const voi
     set_error("knn_tc2: unsupported configuration");
     return GRAFP_EUNSUPPORTED;
   }
+  const int key_rows = (p == 5) ? 64 : BM;
   CUtensorMap xh, xl, yh, yl;
-  if (!make_map_f16(&xh, xhi, B, N, C) || !make_map_f16(&xl, xlo, B, N, C) || !make_map_f16(&yh, yhi, B, M, C) ||
-      !make_map_f16(&yl, ylo, B, M, C)) {
+  if (!make_map_f16(&xh, xhi, B, N, C) || !make_map_f16(&xl, xlo, B, N, C) || !make_map_f16(&yh, yhi, B, M, C, key_rows) ||
+      !make_map_f16(&yl, ylo, B, M, C, key_rows)) {
     set_error("knn_tc2: cuTensorMapEncodeTiled failed (driver entry point unavailable or bad shape)");
     return GRAFP_EUNSUPPORTED;
   }
   const bool k3 = K <= 3;
+#define GRAFP_STREAM(NH_, BN_)                                                                                          \
+  (k3 ? launch_stream<NH_, BN_, 3>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, stages, s)    \
+      : launch_stream<NH_, BN_, 8>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, stages, s))
   switch (p) {
     case 1: return k3 ? launch_self<1, 3>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, stages, s)
                       : launch_self<1, 8>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, stages, s);
     case 2: return k3 ? launch_self<2, 3>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, stages, s)
                       : launch_self<2, 8>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, stages, s);
-    case 3: return k3 ? launch_stream<1, 3>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, stages, s)
-                      : launch_stream<1, 8>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, stages, s);
-    default: return k3 ? launch_stream<2, 3>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, stages, s)
-                       : launch_stream<2, 8>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, stages, s);
+    case 3: return GRAFP_STREAM(1, 128);
+    case 4: return GRAFP_STREAM(2, 128);
+    default: return GRAFP_STREAM(4, 64);
   }
+#undef GRAFP_STREAM
 }
 
 }  // namespace grafp

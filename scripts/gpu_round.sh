@@ -11,6 +11,7 @@ timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; 
 tail -5 gpurun_out/pytest_gpu.log
 timeout 300 python scripts/bench_ops.py > gpurun_out/bench_ops.log 2>&1; echo "bench_ops rc=$?"
 cat gpurun_out/bench_ops.log
+GRAFP_KNN_NO_NH4=1 ALL_VARIANTS=0 timeout 300 python scripts/bench_ops.py > gpurun_out/bench_ops_nh2.log 2>&1; grep "N= 1024" gpurun_out/bench_ops_nh2.log
 timeout 120 python scripts/measure_peaks.py > gpurun_out/peaks_self.json 2>&1; cat gpurun_out/peaks_self.json
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?"
 tail -1 gpurun_out/bench.log
