@@ -504,11 +504,11 @@ mr_aggregate_bwd_fused_kernel(const T* __restrict__ g, const uint8_t* __restrict
 }
 
 // K3, cluster form with TMA bulk staging (fp32): same two phases as the fused kernel above, but a CTA's
-// whole share of the segment - its rows of grad_out (contiguous, 64 KB at every encoder stage) and of the
-// argmax bytes - is pulled into shared memory by two cp.async.bulk copies issued by one thread and
-// awaited on an mbarrier.  No registers are tied up by loads in flight, three CTAs per SM keep
-// ~220 KB of reads outstanding, and phase 2 re-reads g[.., 2c+1] from the staged tile instead of a
-// separate stash.
+// whole share of the segment - its rows of grad_out (contiguous, 64 KB at every encoder stage) and their
+// neighbour ids - is pulled into shared memory by two cp.async.bulk copies issued by one thread and
+// awaited on an mbarrier, while the argmax words stream into registers.  No dependent global load is
+// left in either phase, three CTAs per SM keep ~200 KB of reads outstanding, and phase 2 re-reads
+// g[.., 2c+1] from the staged tile instead of a separate stash.
 __device__ __forceinline__ void k3_mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -539,77 +539,96 @@ __global__ void __launch_bounds__(kFusedThreads, 3)
 mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* __restrict__ argmax,
                                     const void* __restrict__ nbr, float* __restrict__ grad_x, int N, int C, int k,
                                     int rows_per_cta, int cv_shift) {
+  using idx_t = typename std::conditional<I64, long long, int>::type;
+  constexpr int kItems = 8;  // (row, 4-channel) items per thread: the host caps a CTA's share at 8 * 256 items
   extern __shared__ __align__(128) unsigned char tma_smem[];
   const int cv = 1 << cv_shift;
-  const float* gt = reinterpret_cast<const float*>(tma_smem);                                   // [rows][2C]
-  const unsigned char* at = tma_smem + (size_t)rows_per_cta * 2 * C * sizeof(float);             // [rows][C]
-  const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(tma_smem + (size_t)rows_per_cta * C * 9));
+  const float* gt = reinterpret_cast<const float*>(tma_smem);                                    // [rows][2C] grad_out
+  const idx_t* ids = reinterpret_cast<const idx_t*>(tma_smem + (size_t)rows_per_cta * 2 * C * 4); // [rows][k] neighbour ids
+  const uint32_t bar = static_cast<uint32_t>(
+      __cvta_generic_to_shared(tma_smem + (size_t)rows_per_cta * (2 * C * 4 + k * sizeof(idx_t))));
   const unsigned csize = cluster_nctarank();
   const long long b = blockIdx.x / csize;
   const int row0 = static_cast<int>(cluster_ctarank()) * rows_per_cta;
   const int nrows = max(0, min(rows_per_cta, N - row0));
   const int items = nrows << cv_shift;
   float* gxb = grad_x + b * (long long)N * C;
-  const long long ib = b * (long long)N * k;
 
   if (threadIdx.x == 0) {
     k3_mbar_init(bar, 1);
     if (nrows > 0) {
-      const uint32_t gbytes = (uint32_t)nrows * 2 * C * 4, abytes = (uint32_t)nrows * C;
-      k3_mbar_expect_tx(bar, gbytes + abytes);
+      const uint32_t gbytes = (uint32_t)nrows * 2 * C * 4, ibytes = (uint32_t)(nrows * k * sizeof(idx_t));
+      k3_mbar_expect_tx(bar, gbytes + ibytes);
       k3_bulk_g2s(static_cast<uint32_t>(__cvta_generic_to_shared(tma_smem)), g + (b * N + row0) * 2LL * C, gbytes, bar);
-      k3_bulk_g2s(static_cast<uint32_t>(__cvta_generic_to_shared(at)), argmax + (b * N + row0) * (long long)C, abytes, bar);
+      k3_bulk_g2s(static_cast<uint32_t>(__cvta_generic_to_shared(ids)),
+                  static_cast<const idx_t*>(nbr) + (b * N + row0) * (long long)k, ibytes, bar);
     }
+  }
+  // the argmax words stream straight into registers while the bulk copies are in flight
+  unsigned int am[kItems];
+#pragma unroll
+  for (int u = 0; u < kItems; ++u) {
+    const int it = threadIdx.x + u * kFusedThreads;
+    am[u] = (it < items)
+                ? __ldg(reinterpret_cast<const unsigned int*>(argmax + (b * N + row0 + (it >> cv_shift)) * (long long)C +
+                                                              (it & (cv - 1)) * 4))
+                : 0u;
   }
   __syncthreads();  // the barrier is initialised before anyone waits on it
   if (nrows > 0) k3_mbar_wait(bar, 0);
 
-  // phase 1: dense part of grad_x for this CTA's rows
-  for (int it = threadIdx.x; it < items; it += kFusedThreads) {
-    const int rl = it >> cv_shift;
-    const int n = row0 + rl;
-    const int c = (it & (cv - 1)) * 4;
-    const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
-    const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
-    const unsigned int packed = *reinterpret_cast<const unsigned int*>(at + (size_t)rl * C + c);
-    const float g0[4] = {ga.x, ga.z, gb.x, gb.z}, g1[4] = {ga.y, ga.w, gb.y, gb.w};
-    float r[4];
+  // phase 1: dense part of grad_x for this CTA's rows (everything it needs is in shared memory or registers)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int nb = load_index<I64>(nbr, ib + (long long)n * k + ((packed >> (8 * e)) & 0xff));
-      r[e] = (nb == n) ? g0[e] : g0[e] - g1[e];
+  for (int u = 0; u < kItems; ++u) {
+    const int it = threadIdx.x + u * kFusedThreads;
+    if (it < items) {
+      const int rl = it >> cv_shift;
+      const int n = row0 + rl;
+      const int c = (it & (cv - 1)) * 4;
+      const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
+      const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
+      const float g0[4] = {ga.x, ga.z, gb.x, gb.z}, g1[4] = {ga.y, ga.w, gb.y, gb.w};
+      float r[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int nb = static_cast<int>(ids[rl * k + ((am[u] >> (8 * e)) & 0xff)]);
+        r[e] = (nb == n) ? g0[e] : g0[e] - g1[e];
+      }
+      *reinterpret_cast<float4*>(gxb + (long long)n * C + c) = make_float4(r[0], r[1], r[2], r[3]);
     }
-    *reinterpret_cast<float4*>(gxb + (long long)n * C + c) = make_float4(r[0], r[1], r[2], r[3]);
   }
   __threadfence();
   cluster_sync_all();
 
   // phase 2: route g[.., 2c+1] to the winning neighbour rows of this segment (L2-resident, just written)
-  for (int it = threadIdx.x; it < items; it += kFusedThreads) {
-    const int rl = it >> cv_shift;
-    const int n = row0 + rl;
-    const int c = (it & (cv - 1)) * 4;
-    const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
-    const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
-    const unsigned int packed = *reinterpret_cast<const unsigned int*>(at + (size_t)rl * C + c);
-    const float g1[4] = {ga.y, ga.w, gb.y, gb.w};
-    int a[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) a[e] = (packed >> (8 * e)) & 0xff;
-    unsigned todo = 0xf;
+  for (int u = 0; u < kItems; ++u) {
+    const int it = threadIdx.x + u * kFusedThreads;
+    if (it < items) {
+      const int rl = it >> cv_shift;
+      const int n = row0 + rl;
+      const int c = (it & (cv - 1)) * 4;
+      const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
+      const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
+      const float g1[4] = {ga.y, ga.w, gb.y, gb.w};
+      int a[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (todo & (1u << e)) {
-        const int j = a[e];
-        float v[4];
+      for (int e = 0; e < 4; ++e) a[e] = (am[u] >> (8 * e)) & 0xff;
+      unsigned todo = 0xf;
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-          const bool hit = (a[f] == j);
-          v[f] = hit ? g1[f] : 0.f;
-          if (hit) todo &= ~(1u << f);
+      for (int e = 0; e < 4; ++e) {
+        if (todo & (1u << e)) {
+          const int j = a[e];
+          float v[4];
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const bool hit = (a[f] == j);
+            v[f] = hit ? g1[f] : 0.f;
+            if (hit) todo &= ~(1u << f);
+          }
+          const int nb = static_cast<int>(ids[rl * k + j]);
+          if (nb != n) Pack<float, 4>::red_add(gxb + (long long)nb * C + c, v);
         }
-        const int nb = load_index<I64>(nbr, ib + (long long)n * k + j);
-        if (nb != n) Pack<float, 4>::red_add(gxb + (long long)nb * C + c, v);
       }
     }
   }
@@ -620,22 +639,29 @@ int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void*
                               int k, cudaStream_t s, bool* launched) {
   *launched = false;
   const int cv = C / 4;
-  if ((cv & (cv - 1)) != 0 || C % 16 != 0 || !aligned16(g) || !aligned16(argmax) || N < 64) return GRAFP_OK;
+  const size_t idsz = I64 ? 8 : 4;
+  if ((cv & (cv - 1)) != 0 || !aligned16(g) || !aligned16(nbr) || (((uintptr_t)argmax) & 3) != 0 || N < 64) return GRAFP_OK;
   int cv_shift = 0;
   while ((1 << cv_shift) < cv) ++cv_shift;
-  // smallest cluster whose per-CTA share (8 B + 1 B per element) fits 74 KB: three CTAs per SM
+  // smallest cluster whose per-CTA share fits 8 items per thread and ~68 KB of shared memory (three CTAs per SM);
+  // bulk copies need 16-byte multiples and 16-byte aligned sources for every CTA of the cluster
   int cl = 0;
   for (int cand : {1, 2, 4, 8}) {
     const long long rows = (N + cand - 1) / cand;
-    if (rows * C * 9 + 16 <= 74 * 1024) { cl = cand; break; }
+    if (rows * cv <= 8 * kFusedThreads && rows * (2 * C * 4 + k * idsz) + 16 <= 68 * 1024 &&
+        (rows * k * idsz) % 16 == 0 && ((long long)N * k * idsz) % 16 == 0) {
+      cl = cand;
+      break;
+    }
   }
   if (cl == 0 || (long long)B * cl > 0x7fffffffLL) return GRAFP_OK;
   const int rows_per_cta = (N + cl - 1) / cl;
-  const size_t smem = (size_t)rows_per_cta * C * 9 + 16;
+  if (N % rows_per_cta != 0 && ((N % rows_per_cta) * k * idsz) % 16 != 0) return GRAFP_OK;  // ragged last share
+  const size_t smem = (size_t)rows_per_cta * (2 * C * 4 + k * idsz) + 16;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 68 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_bwd_cluster_tma): %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }

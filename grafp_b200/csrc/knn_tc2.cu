@@ -11,13 +11,14 @@
 // Two kernels, one data layout.  A "block" is 128 node rows x 64 channels, hi plane then lo plane
 // (2 x 16 KB, each row one 128-byte swizzle line, loaded by one TMA box each).
 //
-//  * knn_stream_kernel<NH, KREG>: a CTA owns 128*NH query rows of one segment.  Their blocks stay
-//    RESIDENT in shared memory for the whole kernel; key blocks stream through a TMA ring.  Per key
-//    tile (128 keys) the MMA thread fills NH accumulators (one per query half) of a double-buffered
-//    TMEM set, so the top-K selection of tile t (4*NH epilogue warps, one accumulator row per
-//    thread) overlaps the MMAs of tile t+1.  L2->smem traffic per MMA cycle is 1/3 of the
-//    first-generation kernel (which re-streamed the query chunk with every key chunk), which is
-//    what makes the N = 1024 / 512 stages tensor-bound instead of L2-bound.
+//  * knn_stream_kernel<NH, BN, KREG>: a CTA owns 128*NH query rows of one segment.  Their blocks stay
+//    RESIDENT in shared memory for the whole kernel; key blocks (BN keys) stream through a TMA ring.
+//    Per key tile the MMA thread fills NH accumulators (one per 128-row query block) of a
+//    double-buffered TMEM set (2 * NH * BN columns), so the top-K selection of tile t (4*NH epilogue
+//    warps, one accumulator row per thread, no block-level barrier anywhere in the loop) overlaps
+//    the MMAs of tile t+1.  NH = 4 / BN = 64 (C <= 64): 512 queries, 16 epilogue warps, L2->smem key
+//    traffic 1/6 of the first-generation kernel, which re-streamed the query chunk with every key
+//    chunk; NH = 2 / BN = 128 while 2 * C * 256 B of queries fit; NH = 1 for C <= 320.
 //  * knn_self_kernel<NH, KREG>: self-graphs (keys == queries) with N <= 128*NH.  One CTA owns the
 //    whole segment; every K-chunk is loaded ONCE and used as both MMA operands, all NH*NH
 //    accumulators stay live in TMEM (512 columns at NH = 2) and are selected from once at the end.
@@ -87,14 +88,17 @@ struct TopK {
     d[0] = c[0] ? v : d[0];
     id[0] = c[0] ? key : id[0];
   }
-  // 8 accumulator columns (acc = s * 2^24); ys_addr: shared address of |y|^2 of column 0.
+  // 8 accumulator columns (acc = s * 2^24); |y|^2 of column 0 is at shared address ys_addr (YS_SHARED) or at
+  // ys_glob (read through L1 only on the rare candidate path: no staging, no per-tile barrier).
   // The votes of a group of kVoteGroup columns are taken up front against the threshold as of the group
   // start (a stale threshold is only looser, the exact test is redone in `insert`), so the
   // FSETP -> VOTE -> BRA latency chain is paid once per group instead of once per column.  The
   // callers keep this in a rolled loop (8 columns per tcgen05.ld): the unrolled 32-column form was
   // 13 KB of code per tile pass and starved the instruction cache.
   static constexpr int kVoteGroup = 4;
-  __device__ __forceinline__ void scan8(const uint32_t (&v)[8], uint32_t ys_addr, int key0) {
+  template <bool YS_SHARED>
+  __device__ __forceinline__ void scan8(const uint32_t (&v)[8], uint32_t ys_addr, const float* ys_glob, int nvalid,
+                                        int key0) {
 #pragma unroll
     for (int j0 = 0; j0 < 8; j0 += kVoteGroup) {
       bool cand[kVoteGroup];
@@ -105,7 +109,9 @@ struct TopK {
       for (int g = 0; g < kVoteGroup; ++g) {
         if (cand[g]) {
           const int j = j0 + g;
-          const float dist = __fadd_rn(fmaf(kM2, __uint_as_float(v[j]), sq_i), lds_f32(ys_addr + 4 * j));
+          // warp-uniform address; columns past the last key (TMA zero fill) are pushed to +inf
+          const float yj = YS_SHARED ? lds_f32(ys_addr + 4 * j) : (j < nvalid ? __ldg(ys_glob + j) : INFINITY);
+          const float dist = __fadd_rn(fmaf(kM2, __uint_as_float(v[j]), sq_i), yj);
           insert(dist, key0 + j);
           update_thr();
         }
@@ -164,20 +170,16 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
                   const __grid_constant__ CUtensorMap tm_y_hi, const __grid_constant__ CUtensorMap tm_y_lo,
                   const float* __restrict__ xsq, const float* __restrict__ ysq, long long* __restrict__ nn_idx,
                   int* __restrict__ nn_idx32, int N, int M, int C, int k_out, int stride, int stages) {
-  constexpr int kEpilogueThreads = 128 * NH;
   constexpr int kProducerWarp = 4 * NH, kMmaWarp = 4 * NH + 1;
   constexpr uint32_t kTmemCols = 2 * NH * BN;  // two accumulator sets of NH tiles, BN keys wide
   constexpr uint32_t kKeyBlockBytes = 2 * BN * BK * 2;  // hi + lo plane of BN keys x 64 channels
-  constexpr int kStageWarps = BN / 32;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int num_kc = (C + BK - 1) / BK;
   const int num_tiles = (M + BN - 1) / BN;
   unsigned char* q_base = smem;                                    // [NH][num_kc] blocks
   unsigned char* ring = q_base + (size_t)NH * num_kc * kBlockBytes; // [stages] blocks
-  float* ysq_s = reinterpret_cast<float*>(ring + (size_t)stages * kKeyBlockBytes);  // [2][BN]
-  float* ymin_s = ysq_s + 2 * BN;                                                // [2][4] per-warp minima of |y|^2
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ymin_s + 8);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)stages * kKeyBlockBytes);
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;
   const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;
@@ -262,38 +264,27 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     const float* ysq_b = ysq + (long long)b * M;
     TopK<KREG> top;
     top.init(sq_i);
-    // |y|^2 of the next key tile is fetched one tile ahead so its global-load latency hides behind the scan
-    float yv_next = (threadIdx.x < BN && (int)threadIdx.x < M) ? ysq_b[threadIdx.x] : INFINITY;
+    // one threshold base per segment: min over all keys of |y|^2 (1 for normalised rows, 0 for all-zero rows)
+    {
+      float mn = INFINITY;
+      for (int i = lane; i < M; i += 32) mn = fminf(mn, __ldg(ysq_b + i));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      top.set_tile(mn);
+    }
     for (int t = 0; t < num_tiles; ++t) {
       const int as = t & 1;
-      float* ys = ysq_s + as * BN;
-      if (threadIdx.x < BN) {
-        const float yv = yv_next;  // keys past the end are +inf and can never be selected
-        const int key_next = (t + 1) * BN + threadIdx.x;
-        yv_next = (key_next < M) ? ysq_b[key_next] : INFINITY;
-        ys[threadIdx.x] = yv;
-        float mn = yv;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        if (lane == 0) ymin_s[as * 4 + warp] = mn;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
-      {
-        float mn = ymin_s[as * 4];
-#pragma unroll
-        for (int w = 1; w < kStageWarps; ++w) mn = fminf(mn, ymin_s[as * 4 + w]);
-        top.set_tile(mn);
-      }
       mbar_wait(bar_tfull + 8 * as, (t >> 1) & 1);
       tcgen05_fence_after();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * NH + h) * BN;
-      const uint32_t ys_addr = smem_u32(ys);
+      // keys past M were zero-filled by TMA (acc = 0) and would read |y|^2 out of bounds: stop at M
+      const int ncols = min(BN, M - t * BN);
 #pragma unroll 1
-      for (int cc = 0; cc < BN / 8; ++cc) {
+      for (int cc = 0; cc * 8 < ncols; ++cc) {
         uint32_t v[8];
         tmem_ld8(trow + cc * 8, v);
         tmem_ld_wait();
-        top.scan8(v, ys_addr + cc * 32, t * BN + cc * 8);
+        top.template scan8<false>(v, 0u, ysq_b + t * BN + cc * 8, ncols - cc * 8, t * BN + cc * 8);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -419,7 +410,7 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
       uint32_t v[8];
       tmem_ld8(trow + cc * 8, v);
       tmem_ld_wait();
-      top.scan8(v, ys_addr + cc * 32, cc * 8);
+      top.template scan8<true>(v, ys_addr + cc * 32, nullptr, 8, cc * 8);
     }
     if (q < N) emit<KREG>(top, nn_idx, nn_idx32, ((long long)b * N + q) * k_out, k_out, stride);
   }
