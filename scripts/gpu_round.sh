@@ -17,3 +17,6 @@ timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; e
 tail -1 gpurun_out/bench.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'knn_stream|knn_self|knn_normalize|mr_aggregate|mr_bwd' -c 20 \
   -o gpurun_out/prof_ops -f python scripts/ncu_ops.py 512 1 > gpurun_out/ncu_ops.log 2>&1; echo "ncu rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches.csv \
+  python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1; echo "launchlist rc=$?"
+python scripts/ncu_summary.py gpurun_out/prof_ops.ncu-rep > gpurun_out/ncu_summary.txt 2>&1; tail -40 gpurun_out/ncu_summary.txt
