@@ -1096,7 +1096,8 @@ namespace {
 // development switches: GRAFP_MR_FWD_VARIANT = 0 generic kernel, 1 / 2 / 4 fast kernel with that many items in
 // flight per thread, 8 (default) the cp.async-pipelined persistent kernel where it applies; GRAFP_MR_BWD_VARIANT = 0 two-kernel form, 1 / 2 / 4 fused cluster form,
 // 8 the deterministic gather form over the reverse graph (needs the workspace), 16 (default) the cluster form
-// with TMA bulk staging
+// with TMA bulk staging, 32 the deterministic shared-memory slice form (aggregate_bwd_slice.cu; measured slower:
+// it is bound by the L1 / shared-memory pipe)
 // (read on every call - a getenv is nanoseconds next to a launch - so tests can switch kernels in-process)
 int fwd_variant() {
   const char* e = getenv("GRAFP_MR_FWD_VARIANT");
@@ -1213,7 +1214,15 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
     const T* gs = static_cast<const T*>(g);
     const bool self_skip = (ctr == nullptr) && (grad_y == nullptr);
     if constexpr (VEC == 4 && std::is_same<T, float>::value) {
-      // gather form over the reverse graph (default when the caller passes a workspace)
+      if (self_skip && bwd_variant() >= 32) {  // persistent (segment, channel-slice) gather out of shared memory
+        bool launched = false;
+        const int rc = launch_mr_bwd_slice<I64>(reinterpret_cast<const float*>(gs), argmax, nbr,
+                                                reinterpret_cast<float*>(gx), B, N, C, k, s, &launched);
+        if (rc != GRAFP_OK || launched) return rc;
+      }
+    }
+    if constexpr (VEC == 4 && std::is_same<T, float>::value) {
+      // gather form over the reverse graph in a workspace
       const int cv = C / 4;
       const long long items_per_seg = (long long)N * cv;
       const long long ips = items_per_seg / kThreads;
@@ -1248,7 +1257,7 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
       }
     }
     if constexpr (VEC == 4 && std::is_same<T, float>::value) {
-      if (self_skip && bwd_variant() >= 8) {  // default: cluster form with TMA bulk staging
+      if (self_skip && bwd_variant() >= 16) {  // default: cluster form with TMA bulk staging
         bool launched = false;
         const int rc = launch_mr_bwd_cluster_tma<I64>(reinterpret_cast<const float*>(gs), argmax, nbr,
                                                       reinterpret_cast<float*>(gx), B, N, C, k, s, &launched);

@@ -171,6 +171,10 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
                             void* grad_x, void* grad_y, int B, int N, int M, int C, int k, void* workspace,
                             size_t workspace_bytes, cudaStream_t s);
 size_t mr_bwd_workspace_bytes(int B, int N, int k);
+// aggregate_bwd_slice.cu: K3 as a shared-memory gather over (segment, channel-slice) units
+template <bool I64>
+int launch_mr_bwd_slice(const float* g, const uint8_t* argmax, const void* nbr, float* grad_x, int B, int N, int C, int k,
+                        cudaStream_t s, bool* launched);
 template <typename T>
 int launch_gather_fwd(const void* src, const void* idx, int idx_is_i64, void* out, int B, int N, int M, int C, int k,
                       cudaStream_t s);

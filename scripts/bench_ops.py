@@ -42,7 +42,7 @@ def run(label):
               f"mr_bwd {t_bwd*1e3:6.1f} us {b_bwd/t_bwd/1e6:6.0f} GB/s ({b_bwd/t_bwd/1e6/PEAK*100:4.1f}%)", flush=True)
 
 
-run("defaults (pipelined forward, gather-form backward)")
+run("defaults (pipelined forward, TMA-staged cluster backward)")
 if os.environ.get("ALL_VARIANTS", "1") == "1":
     os.environ["GRAFP_MR_FWD_VARIANT"] = "4"; os.environ["GRAFP_MR_BWD_VARIANT"] = "2"
     run("register-prefetch forward, cluster-fused atomic backward")

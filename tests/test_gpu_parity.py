@@ -316,8 +316,8 @@ def test_mr_aggregate_full_batch_properties():
 @pytest.mark.parametrize("N,C", STAGES)
 def test_mr_aggregate_kernel_variants_agree(N, C, monkeypatch):
     """The pipelined forward / TMA-staged cluster backward (defaults) against the register-prefetch forward, the
-    earlier cluster-fused, the two-kernel atomic and the deterministic gather-form backwards on the same inputs,
-    incl. a hub node with a huge in-degree."""
+    earlier cluster-fused, the two-kernel atomic, the deterministic gather-form and the deterministic shared-memory
+    slice backwards on the same inputs, incl. a hub node with a huge in-degree."""
     B, k = 5, 3
     x = synth.synth_point_cloud(B, C, N, 900 + N, relu=True)
     x[0, :, 5] = 0          # a zero node is everybody's near neighbour after ReLU: in-degree ~ N
@@ -328,7 +328,7 @@ def test_mr_aggregate_kernel_variants_agree(N, C, monkeypatch):
     up = up.contiguous(memory_format=torch.channels_last)
     results = {}
     for name, fv, bv in [("default", None, None), ("regs+cluster", "4", "2"), ("regs1+two-kernel", "1", "0"),
-                         ("generic+cluster4", "0", "4"), ("regs2+gather", "2", "8")]:
+                         ("generic+cluster4", "0", "4"), ("regs2+gather", "2", "8"), ("pipe+slice", "8", "32")]:
         for var, val in (("GRAFP_MR_FWD_VARIANT", fv), ("GRAFP_MR_BWD_VARIANT", bv)):
             if val is None:
                 monkeypatch.delenv(var, raising=False)
@@ -353,6 +353,38 @@ def test_mr_aggregate_kernel_variants_agree(N, C, monkeypatch):
     xg = xd.clone().requires_grad_(True)
     (gx2,) = torch.autograd.grad(ops.mr_aggregate(xg, nbr32), xg, up)
     assert torch.equal(gx2, results["regs2+gather"][1])
+    # so has the slice form (sorted in-edge lists in shared memory)
+    monkeypatch.setenv("GRAFP_MR_BWD_VARIANT", "32")
+    xg = xd.clone().requires_grad_(True)
+    (gx3,) = torch.autograd.grad(ops.mr_aggregate(xg, nbr32), xg, up)
+    assert torch.equal(gx3, results["pipe+slice"][1])
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 1024, 16), (2, 72, 300, 5), (4, 8, 50, 2), (2, 512, 128, 3), (1, 64, 2048, 3),
+                                   (2, 48, 1000, 32)])
+@pytest.mark.parametrize("variant", ["16", "32"])
+def test_mr_aggregate_bwd_slice_shapes(shape, variant, monkeypatch):
+    """The cluster (default) and slice backwards over their whole envelope (wide k, ragged N, tiny and odd channel counts, N too large for
+    shared memory -> cluster fallback), arbitrary graphs with duplicate ids and self edges, int64 ids."""
+    B, C, N, k = shape
+    monkeypatch.setenv("GRAFP_MR_BWD_VARIANT", variant)
+    g = torch.Generator().manual_seed(N * 7 + k)
+    x = torch.randn(B, C, N, 1, generator=g)
+    nbr = torch.randint(0, N, (B, N, k), generator=g)
+    nbr[:, :, 0] = torch.arange(N)               # self edge in slot 0 like the k-NN graphs
+    nbr[:, 3, :] = 3                             # a row whose every slot is itself
+    nbr[0, :, k - 1] = 7                         # a hub: every row of segment 0 points at node 7
+    edge = torch.stack([nbr, torch.arange(N)[None, :, None].expand(B, N, k)])
+    up = torch.randn(B, 2 * C, N, 1, generator=g)
+    xo = x.clone().requires_grad_(True)
+    ref = O.max_relative_features(xo, edge)
+    ref.backward(up)
+    for idx in (nbr.to(DEV), nbr.to(DEV).int()):
+        xg = x.to(DEV).requires_grad_(True)
+        out = ops.mr_aggregate(xg, idx)
+        assert torch.equal(out.cpu(), ref.detach())
+        out.backward(up.to(DEV))
+        assert gio.rel_err(xg.grad.cpu(), xo.grad) < REL_TOL
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 64, 4), (3, 128, 100, 9), (2, 6, 33, 5)])
