@@ -179,6 +179,10 @@ def algorithmic_work(name, m):
     if name == "knn_fwd":
         M, K = m["M"], m["K"]
         return {"flops": 2.0 * B * N * M * C, "bytes": B * (N * C * e + (M * C * e if M != N else 0) + N * K * 12)}
+    if name == "bn_train_fwd":  # statistics pass + apply pass (+ residual read)
+        return {"bytes": B * N * C * e * (3 + m.get("res", 0))}
+    if name == "bn_train_bwd":  # reduction pass (dy, x) + apply pass (dy, x -> dx)
+        return {"bytes": B * N * C * e * 5}
     k = m["k"]
     idx_b = 8 if m.get("i64") else 4
     if name == "mr_aggregate_fwd":
@@ -307,12 +311,15 @@ def run_ours(args):
             kt = kernels[top]
             if top == "knn_fwd":
                 tc = ops.knn_last_algo() == "tcgen05"
-                peak = pk["bf16_tflops_sustained"] / 2.0  # dense TF32 is half the bf16 rate
-                roofline = {"kernel": f"knn_fwd ({ops.knn_last_algo()}; normalise + Gram/top-k launches)",
+                f16 = ops.knn_last_variant() == "f16x3"
+                # kind::f16 issues at the bf16 rate, kind::tf32 at half of it
+                peak = pk["bf16_tflops_sustained"] / (1.0 if f16 else 2.0)
+                roofline = {"kernel": f"knn_fwd ({ops.knn_last_algo()} {ops.knn_last_variant()}; normalise + Gram/top-k launches)",
                             "bound": "tensor", "achieved": kt["tflops"], "peak": peak, "unit": "TFLOP/s",
                             "frac": kt["tflops"] / peak, "traffic": None,
-                            "peak_source": f"{pk['source']} bf16 sustained / 2 (TF32)",
-                            "note": "algorithmic 2*N*M*C flops; the 3xTF32 split issues 3x that" if tc else
+                            "peak_source": f"{pk['source']} bf16 sustained" + ("" if f16 else " / 2 (TF32)"),
+                            "note": "algorithmic 2*N*M*C flops; the hi/lo split issues 3 MMAs per algorithmic one, "
+                                    "so 1/3 is the ceiling of this fraction" if tc else
                                     "CUDA-core fp32 path, reported against the tensor peak"}
             else:
                 peak = pk["hbm_gbs"]

@@ -32,9 +32,12 @@ SIGNATURES = {
     "grafp_edge_gather_bwd": (_i, [_vp] * 3 + [_i] + [_vp] * 2 + [_i] * 6 + [_vp]),
     "grafp_max_over_k_fwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
     "grafp_max_over_k_bwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
+    "grafp_bn_workspace_bytes": (_sz, [_i]),
+    "grafp_bn_train_fwd": (_i, [_vp] * 9 + [_c.c_longlong, _i, _c.c_float, _c.c_float, _i, _vp, _sz, _vp]),
+    "grafp_bn_train_bwd": (_i, [_vp] * 9 + [_c.c_longlong, _i, _i, _vp, _sz, _vp]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 KNN_AUTO, KNN_SIMT, KNN_TC, KNN_TC_TF32 = 0, 1, 2, 3
 KNN_MAX_K = 64
 

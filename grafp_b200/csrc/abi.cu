@@ -274,3 +274,43 @@ int grafp_max_over_k_bwd(const void* grad_out, const uint8_t* argmax, void* grad
 }
 
 }  // extern "C"
+
+extern "C" {
+
+size_t grafp_bn_workspace_bytes(int C) { return C > 0 ? bn_workspace_bytes(C) : 0; }
+
+int grafp_bn_train_fwd(const float* x, const float* residual, const float* weight, const float* bias, float* running_mean,
+                       float* running_var, float* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
+                       float momentum, int relu, void* workspace, size_t workspace_bytes, void* stream) {
+  clear_error();
+  GRAFP_REQUIRE(R > 1 && C > 0, GRAFP_EINVAL, "grafp_bn_train_fwd: needs at least two rows and C > 0");
+  GRAFP_REQUIRE(x && weight && bias && out && save_mean && save_invstd && workspace, GRAFP_EINVAL,
+                "grafp_bn_train_fwd: x, weight, bias, out, save_mean, save_invstd and workspace must be non-null");
+  GRAFP_REQUIRE(aligned16(x) && aligned16(out) && aligned16(weight) && aligned16(bias) && aligned16(save_mean) &&
+                    aligned16(save_invstd) && (residual == nullptr || aligned16(residual)),
+                GRAFP_EINVAL, "grafp_bn_train_fwd: pointers must be 16-byte aligned");
+  GRAFP_REQUIRE(workspace_bytes >= bn_workspace_bytes(C), GRAFP_EWORKSPACE, "grafp_bn_train_fwd: workspace too small");
+  { int rc = require_device("grafp_bn_train_fwd"); if (rc != GRAFP_OK) return rc; }
+  { int rc = require_device_ptr("grafp_bn_train_fwd", "x", x); if (rc) return rc; }
+  return launch_bn_train_fwd(x, residual, weight, bias, running_mean, running_var, out, save_mean, save_invstd, R, C, eps,
+                             momentum, relu, workspace, static_cast<cudaStream_t>(stream));
+}
+
+int grafp_bn_train_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* save_mean,
+                       const float* save_invstd, float* dx, float* dweight, float* dbias, long long R, int C, int relu,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  clear_error();
+  GRAFP_REQUIRE(R > 1 && C > 0, GRAFP_EINVAL, "grafp_bn_train_bwd: needs at least two rows and C > 0");
+  GRAFP_REQUIRE(dy && x && weight && bias && save_mean && save_invstd && dx && dweight && dbias && workspace, GRAFP_EINVAL,
+                "grafp_bn_train_bwd: all pointers must be non-null");
+  GRAFP_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(weight) && aligned16(bias) &&
+                    aligned16(save_mean) && aligned16(save_invstd) && aligned16(dweight) && aligned16(dbias),
+                GRAFP_EINVAL, "grafp_bn_train_bwd: pointers must be 16-byte aligned");
+  GRAFP_REQUIRE(workspace_bytes >= bn_workspace_bytes(C), GRAFP_EWORKSPACE, "grafp_bn_train_bwd: workspace too small");
+  { int rc = require_device("grafp_bn_train_bwd"); if (rc != GRAFP_OK) return rc; }
+  { int rc = require_device_ptr("grafp_bn_train_bwd", "dy", dy); if (rc) return rc; }
+  return launch_bn_train_bwd(dy, x, weight, bias, save_mean, save_invstd, dx, dweight, dbias, R, C, relu, workspace,
+                             static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

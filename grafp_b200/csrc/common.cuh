@@ -193,4 +193,14 @@ template <typename T>
 int launch_max_over_k_bwd(const void* g, const uint8_t* argmax, void* grad_h, int B, int N, int C, int k,
                           cudaStream_t s);
 
+// ---- bn_fused.cu ----
+size_t bn_workspace_bytes(int C);
+bool bn_supported(long long R, int C);
+int launch_bn_train_fwd(const float* x, const float* res, const float* weight, const float* bias, float* running_mean,
+                        float* running_var, float* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
+                        float momentum, int relu, void* workspace, cudaStream_t s);
+int launch_bn_train_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* save_mean,
+                        const float* save_invstd, float* dx, float* dweight, float* dbias, long long R, int C, int relu,
+                        void* workspace, cudaStream_t s);
+
 }  // namespace grafp

@@ -39,6 +39,14 @@ def _split_edge_index(edge_index):
     return edge_index[0], edge_index[1]
 
 
+def _basic_conv(seq, x):
+    """Run a BasicConv stack; a trailing [Conv2d, BatchNorm2d, ReLU] goes through the fused BatchNorm + ReLU op."""
+    if len(seq) == 3 and isinstance(seq[0], nn.Conv2d) and isinstance(seq[1], nn.BatchNorm2d) \
+            and isinstance(seq[2], nn.ReLU):
+        return ops.batch_norm_act(seq[0](x), seq[1], relu=True)
+    return seq(x)
+
+
 class MRConv2d(nn.Module):
     """Max-relative graph convolution (reference: torch_vertex.py:11-34)."""
 
@@ -48,7 +56,7 @@ class MRConv2d(nn.Module):
 
     def forward(self, x, edge_index, y=None):
         nbr, ctr = _split_edge_index(edge_index)
-        return self.nn(ops.mr_aggregate(x, nbr, y, ctr))
+        return _basic_conv(self.nn, ops.mr_aggregate(x, nbr, y, ctr))
 
 
 class EdgeConv2d(nn.Module):
@@ -169,7 +177,9 @@ class Grapher(nn.Module):
 
     def forward(self, x):
         shortcut = x
-        x = self.fc1(x)
+        x = ops.batch_norm_act(self.fc1[0](x), self.fc1[1])
         x = self.graph_conv(x, relative_pos=None)
+        if isinstance(self.drop_path, nn.Identity):
+            return ops.batch_norm_act(self.fc2[0](x), self.fc2[1], residual=shortcut)  # BatchNorm + residual fused
         x = self.fc2(x)
         return self.drop_path(x) + shortcut

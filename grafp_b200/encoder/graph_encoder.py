@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 from torch.nn import Sequential as Seq
 
+from .. import ops
 from .gcn_lib.torch_vertex import Grapher, DropPath
 from .gcn_lib.torch_nn import act_layer, norm_layer, MLP, BasicConv  # noqa: F401  (re-exported like the reference)
 
@@ -61,6 +62,10 @@ class FFN(nn.Module):
                        nn.BatchNorm2d(out_features))
 
     def forward(self, x):
+        if isinstance(self.drop_path, nn.Identity) and isinstance(self.act, nn.ReLU):
+            # BatchNorm + ReLU and BatchNorm + residual as fused ops (train mode; eval falls through to PyTorch)
+            h = ops.batch_norm_act(self.fc1[0](x), self.fc1[1], relu=True)
+            return ops.batch_norm_act(self.fc2[0](h), self.fc2[1], residual=x)
         return self.drop_path(self.fc2(self.act(self.fc1(x)))) + x
 
 

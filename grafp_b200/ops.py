@@ -7,6 +7,7 @@ Logical tensor shapes follow the reference (node features (B, C, N, 1), edge fea
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -361,3 +362,85 @@ def max_over_k(h: torch.Tensor) -> torch.Tensor:
     if h.dim() != 4:
         raise RuntimeError("grafp_b200.max_over_k: expected a (B, C, N, k) tensor")
     return _MaxOverK.apply(h)
+
+
+# --------------------------------------------------------------------------------------
+# train-mode BatchNorm fused with the ReLU / residual add that follows it
+# --------------------------------------------------------------------------------------
+
+def _is_rows(t: torch.Tensor) -> bool:
+    """(B, C, N, 1) tensor whose memory is (B*N, C) rows."""
+    if t.dim() != 4 or t.shape[3] != 1:
+        return False
+    B, C, N, _ = t.shape
+    s = t.stride()
+    return (C == 1 or s[1] == 1) and (N == 1 or s[2] == C) and (B == 1 or s[0] == N * C)
+
+
+class _BatchNormTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, eps, momentum, relu):
+        lib = _native.load()
+        B, C, N, _ = x.shape
+        R = B * N
+        out = _new_rows(B, C, N, x)
+        save_mean = torch.empty(C, dtype=torch.float32, device=x.device)
+        save_invstd = torch.empty(C, dtype=torch.float32, device=x.device)
+        ws_bytes = lib.grafp_bn_workspace_bytes(C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        _call("bn_train_fwd", 3, dict(B=B, N=N, C=C, relu=int(relu), res=int(residual is not None)),
+              lib.grafp_bn_train_fwd, x.data_ptr(), residual.data_ptr() if residual is not None else None,
+              weight.data_ptr(), bias.data_ptr(),
+              running_mean.data_ptr() if running_mean is not None else None,
+              running_var.data_ptr() if running_var is not None else None,
+              out.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(), R, C, float(eps), float(momentum),
+              int(relu), ws.data_ptr(), ws_bytes, _stream())
+        ctx.save_for_backward(x, weight, bias, save_mean, save_invstd)
+        ctx.relu = bool(relu)
+        ctx.has_res = residual is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _native.load()
+        x, weight, bias, save_mean, save_invstd = ctx.saved_tensors
+        B, C, N, _ = x.shape
+        g = as_rows(grad_out)
+        dx = _new_rows(B, C, N, x)
+        dweight = torch.empty_like(weight)
+        dbias = torch.empty_like(bias)
+        ws_bytes = lib.grafp_bn_workspace_bytes(C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        _call("bn_train_bwd", 3, dict(B=B, N=N, C=C, relu=int(ctx.relu)), lib.grafp_bn_train_bwd,
+              g.data_ptr(), x.data_ptr(), weight.data_ptr(), bias.data_ptr(), save_mean.data_ptr(),
+              save_invstd.data_ptr(), dx.data_ptr(), dweight.data_ptr(), dbias.data_ptr(), B * N, C, int(ctx.relu),
+              ws.data_ptr(), ws_bytes, _stream())
+        return dx, (grad_out if ctx.has_res else None), dweight, dbias, None, None, None, None, None
+
+
+def batch_norm_act(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = False,
+                   residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``relu(bn(x))`` / ``bn(x) + residual`` / ``bn(x)`` for node rows (B, C, N, 1).
+
+    In training mode on a CUDA fp32 channels-last tensor this is one fused pair of kernels (statistics +
+    apply; the backward recomputes the ReLU mask, so no intermediate is kept); the module's running
+    statistics and ``num_batches_tracked`` are updated exactly like ``nn.BatchNorm2d`` does.  Anything else
+    (eval mode, other dtypes / layouts / channel counts, or GRAFP_FUSED_BN=0 - an A/B switch) runs the module
+    and the PyTorch ops unchanged.
+    """
+    fused = (os.environ.get("GRAFP_FUSED_BN", "1") != "0" and bn.training and x.is_cuda and x.dtype == torch.float32 and _is_rows(x) and bn.affine
+             and bn.momentum is not None and not (relu and residual is not None)
+             and x.shape[1] % 4 == 0 and ((x.shape[1] // 4) & (x.shape[1] // 4 - 1)) == 0
+             and x.shape[0] * x.shape[2] > 1
+             and (residual is None or (residual.shape == x.shape and residual.dtype == x.dtype and _is_rows(residual)))
+             and bn.weight.dtype == torch.float32)
+    if not fused:
+        y = bn(x)
+        if residual is not None:
+            y = y + residual
+        return torch.relu(y) if relu else y
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    return _BatchNormTrain.apply(x, residual, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, relu)

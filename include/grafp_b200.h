@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GRAFP_ABI_VERSION 2
+#define GRAFP_ABI_VERSION 3
 
 #define GRAFP_OK 0
 #define GRAFP_EINVAL (-1)       /* null / misaligned pointer, non-positive size, k > M ... */
@@ -138,6 +138,32 @@ int grafp_edge_gather_bwd(const void* grad_out, const void* nbr_idx, const void*
 int grafp_max_over_k_fwd(const void* h, void* out, uint8_t* argmax, int B, int N, int C, int k, int dtype, void* stream);
 int grafp_max_over_k_bwd(const void* grad_out, const uint8_t* argmax, void* grad_h, int B, int N, int C, int k, int dtype,
                          void* stream);
+
+/*
+ * Train-mode BatchNorm over node rows fused with what follows it in the Grapher / FFN blocks
+ * (SURVEY 8f row 2).  Replaces nn.BatchNorm2d (training) + nn.ReLU of BasicConv
+ * (encoder/gcn_lib/torch_nn.py:52-64) and of FFN.fc1 + act (encoder/graph_encoder.py:56-66), and
+ * nn.BatchNorm2d + the residual add of Grapher.fc2 / FFN.fc2 (torch_vertex.py:158-162,194;
+ * graph_encoder.py:60-66).  fp32 only; x, residual, out, dy, dx are (R, C) rows, R = B * N,
+ * C % 4 == 0 and C / 4 a power of two (else GRAFP_EUNSUPPORTED).
+ *
+ *  forward : mean / biased variance over the R rows per channel (saved as save_mean, save_invstd =
+ *            1 / sqrt(var + eps)); running_mean / running_var (may be NULL) are updated with `momentum`
+ *            and the unbiased variance, like torch.nn.functional.batch_norm(training=True);
+ *            out = (x - mean) * invstd * weight + bias  [+ residual]  [ReLU when relu != 0]
+ *            (relu together with a residual is not implemented).
+ *  backward: dz = dy masked by the ReLU (recomputed from x, no output is kept); dbias = sum dz,
+ *            dweight = sum dz * xhat, dx = weight * invstd * (dz - dbias / R - xhat * dweight / R).
+ *            The gradient of the residual input is dy itself and is not written here.
+ *  workspace: grafp_bn_workspace_bytes(C) bytes of caller-owned scratch (block partials).
+ */
+size_t grafp_bn_workspace_bytes(int C);
+int grafp_bn_train_fwd(const float* x, const float* residual, const float* weight, const float* bias, float* running_mean,
+                       float* running_var, float* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
+                       float momentum, int relu, void* workspace, size_t workspace_bytes, void* stream);
+int grafp_bn_train_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* save_mean,
+                       const float* save_invstd, float* dx, float* dweight, float* dbias, long long R, int C, int relu,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
