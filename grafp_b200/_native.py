@@ -34,7 +34,7 @@ SIGNATURES = {
     "grafp_max_over_k_bwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
     "grafp_bn_workspace_bytes": (_sz, [_i]),
     "grafp_bn_train_fwd": (_i, [_vp] * 9 + [_c.c_longlong, _i, _c.c_float, _c.c_float, _i, _vp, _sz, _vp]),
-    "grafp_bn_train_bwd": (_i, [_vp] * 9 + [_c.c_longlong, _i, _i, _vp, _sz, _vp]),
+    "grafp_bn_train_bwd": (_i, [_vp] * 10 + [_c.c_longlong, _i, _i, _vp, _sz, _vp]),
 }
 
 ABI_VERSION = 3

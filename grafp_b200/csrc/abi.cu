@@ -297,8 +297,8 @@ int grafp_bn_train_fwd(const float* x, const float* residual, const float* weigh
 }
 
 int grafp_bn_train_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* save_mean,
-                       const float* save_invstd, float* dx, float* dweight, float* dbias, long long R, int C, int relu,
-                       void* workspace, size_t workspace_bytes, void* stream) {
+                       const float* save_invstd, float* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
+                       int relu, void* workspace, size_t workspace_bytes, void* stream) {
   clear_error();
   GRAFP_REQUIRE(R > 1 && C > 0, GRAFP_EINVAL, "grafp_bn_train_bwd: needs at least two rows and C > 0");
   GRAFP_REQUIRE(dy && x && weight && bias && save_mean && save_invstd && dx && dweight && dbias && workspace, GRAFP_EINVAL,
@@ -309,7 +309,7 @@ int grafp_bn_train_bwd(const float* dy, const float* x, const float* weight, con
   GRAFP_REQUIRE(workspace_bytes >= bn_workspace_bytes(C), GRAFP_EWORKSPACE, "grafp_bn_train_bwd: workspace too small");
   { int rc = require_device("grafp_bn_train_bwd"); if (rc != GRAFP_OK) return rc; }
   { int rc = require_device_ptr("grafp_bn_train_bwd", "dy", dy); if (rc) return rc; }
-  return launch_bn_train_bwd(dy, x, weight, bias, save_mean, save_invstd, dx, dweight, dbias, R, C, relu, workspace,
+  return launch_bn_train_bwd(dy, x, weight, bias, save_mean, save_invstd, dx, dweight, dbias, dx_colsum, R, C, relu, workspace,
                              static_cast<cudaStream_t>(stream));
 }
 

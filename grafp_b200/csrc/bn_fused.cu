@@ -280,12 +280,12 @@ bn_bwd_finalize_kernel(const float2* __restrict__ partial, int parts, int C, flo
 }
 
 // ---- backward apply: dx = weight * invstd * (dz - s1 / R - xhat * s2 / R) ----
-template <bool RELU>
+template <bool RELU, bool COLSUM>
 __global__ void __launch_bounds__(kBnThreads)
 bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ weight,
                     const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ dweight, const float* __restrict__ dbias, float* __restrict__ dx,
-                    long long total4, int cv, float inv_rows) {
+                    float* __restrict__ colsum_partial, long long total4, int cv, float inv_rows) {
   const long long T = (long long)gridDim.x * kBnThreads;
   const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
   const int c = (int)(i0 % cv) * 4;
@@ -313,15 +313,61 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
     r.w = a.w * (g.w - c1.w - v.w * is.w * c2.w);
     return r;
   };
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of dx over this thread's rows (COLSUM)
   long long i = i0;
   for (; i + 3 * T < total4; i += 4 * T) {
     float4 v[4], g[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) { v[u] = __ldg(xp + i + u * T); g[u] = __ldg(gp + i + u * T); }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) op[i + u * T] = one(v[u], g[u]);
+    for (int u = 0; u < 4; ++u) {
+      const float4 r = one(v[u], g[u]);
+      op[i + u * T] = r;
+      if (COLSUM) { cs.x += r.x; cs.y += r.y; cs.z += r.z; cs.w += r.w; }
+    }
   }
-  for (; i < total4; i += T) op[i] = one(__ldg(xp + i), __ldg(gp + i));
+  for (; i < total4; i += T) {
+    const float4 r = one(__ldg(xp + i), __ldg(gp + i));
+    op[i] = r;
+    if (COLSUM) { cs.x += r.x; cs.y += r.y; cs.z += r.z; cs.w += r.w; }
+  }
+  if (COLSUM) {
+    // block partial per channel: threads tid, tid + cv, ... of a block share a channel pack (cv <= 256), or own it (cv > 256)
+    __shared__ float4 s_cs[kBnThreads];
+    s_cs[threadIdx.x] = cs;
+    __syncthreads();
+    const int span = cv < kBnThreads ? cv : kBnThreads;
+    if ((int)threadIdx.x < span) {
+      float4 t = cs;
+      for (int o = threadIdx.x + span; o < kBnThreads; o += span) {
+        const float4 q = s_cs[o];
+        t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+      }
+      // channel pack of thread tid in this block: (blockIdx.x * 256 + tid) % cv
+      *reinterpret_cast<float4*>(colsum_partial + (long long)blockIdx.x * (4LL * span) + 4 * threadIdx.x) = t;
+    }
+  }
+}
+
+// column sums of dx: sum the block partials of bn_bwd_apply_kernel (block b, slot t holds channel pack (b * 256 + t) % cv)
+__global__ void __launch_bounds__(256)
+bn_colsum_finalize_kernel(const float* __restrict__ colsum_partial, int blocks, int cv, float* __restrict__ colsum) {
+  __shared__ double sm[8][33];
+  const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
+  const int C = cv * 4;
+  const int c = min(blockIdx.x * 32 + cl, C - 1);
+  const int c4 = c >> 2, e = c & 3;
+  const int span = cv < kBnThreads ? cv : kBnThreads;
+  double acc = 0.0;
+  if (cv <= kBnThreads) {  // every block holds every channel pack once, at slot c4
+    for (int b = pg; b < blocks; b += 8) acc += (double)colsum_partial[(long long)b * (4LL * span) + 4 * c4 + e];
+  } else {                 // block b holds packs (b * 256 + t) % cv: pack c4 lives in blocks with (b * 256) % cv == c4 - t
+    const int per = cv / kBnThreads;  // blocks per full sweep of the channel packs
+    const int t = c4 % kBnThreads, first = c4 / kBnThreads;
+    for (int b = first + pg * per; b < blocks; b += 8 * per) acc += (double)colsum_partial[(long long)b * (4LL * span) + 4 * t + e];
+  }
+  const double tot = group_sum(acc, sm, cl, pg);
+  if (pg == 0 && blockIdx.x * 32 + cl < C) colsum[c] = (float)tot;
 }
 
 int apply_grid(long long total4, int cv) {
@@ -338,7 +384,11 @@ int shift_of(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 
 }  // namespace
 
-size_t bn_workspace_bytes(int C) { return (size_t)kBnMaxPartials * (size_t)C * sizeof(float2) + kBnMaxPartials * sizeof(int) + 256; }
+size_t bn_workspace_bytes(int C) {
+  const size_t partials = (size_t)kBnMaxPartials * (size_t)C * sizeof(float2) + kBnMaxPartials * sizeof(int);
+  const size_t colsums = (size_t)(num_sms() * 8 + 8) * 4 * kBnThreads * sizeof(float);  // one float4 per thread of the apply grid
+  return (partials > colsums ? partials : colsums) + 256;
+}
 
 bool bn_supported(long long R, int C) {
   BnGeom g;
@@ -366,8 +416,8 @@ int launch_bn_train_fwd(const float* x, const float* res, const float* weight, c
 }
 
 int launch_bn_train_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* save_mean,
-                        const float* save_invstd, float* dx, float* dweight, float* dbias, long long R, int C, int relu,
-                        void* workspace, cudaStream_t s) {
+                        const float* save_invstd, float* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
+                        int relu, void* workspace, cudaStream_t s) {
   BnGeom g;
   if (!bn_geometry(R, C, &g)) { set_error("bn_train_bwd: needs C %% 4 == 0, C/4 a power of two and at least 2 rows"); return GRAFP_EUNSUPPORTED; }
   char* wb = reinterpret_cast<char*>(((uintptr_t)workspace + 255) / 256 * 256);
@@ -379,8 +429,15 @@ int launch_bn_train_bwd(const float* dy, const float* x, const float* weight, co
   const long long total4 = R * g.cv;
   const int grid = apply_grid(total4, g.cv);
   const float inv_rows = (float)(1.0 / (double)R);
-  if (relu) bn_bwd_apply_kernel<true><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, total4, g.cv, inv_rows);
-  else bn_bwd_apply_kernel<false><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, total4, g.cv, inv_rows);
+  float* csp = reinterpret_cast<float*>(wb);  // the reduction partials are consumed by now (stream order)
+  if (dx_colsum != nullptr) {
+    if (relu) bn_bwd_apply_kernel<true, true><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, csp, total4, g.cv, inv_rows);
+    else bn_bwd_apply_kernel<false, true><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, csp, total4, g.cv, inv_rows);
+    bn_colsum_finalize_kernel<<<(C + 31) / 32, 256, 0, s>>>(csp, grid, g.cv, dx_colsum);
+  } else {
+    if (relu) bn_bwd_apply_kernel<true, false><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, nullptr, total4, g.cv, inv_rows);
+    else bn_bwd_apply_kernel<false, false><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, nullptr, total4, g.cv, inv_rows);
+  }
   return check_launch("bn_train_bwd");
 }
 

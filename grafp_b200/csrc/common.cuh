@@ -200,7 +200,7 @@ int launch_bn_train_fwd(const float* x, const float* res, const float* weight, c
                         float* running_var, float* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
                         float momentum, int relu, void* workspace, cudaStream_t s);
 int launch_bn_train_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* save_mean,
-                        const float* save_invstd, float* dx, float* dweight, float* dbias, long long R, int C, int relu,
-                        void* workspace, cudaStream_t s);
+                        const float* save_invstd, float* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
+                        int relu, void* workspace, cudaStream_t s);
 
 }  // namespace grafp

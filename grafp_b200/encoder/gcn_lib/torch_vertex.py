@@ -43,7 +43,7 @@ def _basic_conv(seq, x):
     """Run a BasicConv stack; a trailing [Conv2d, BatchNorm2d, ReLU] goes through the fused BatchNorm + ReLU op."""
     if len(seq) == 3 and isinstance(seq[0], nn.Conv2d) and isinstance(seq[1], nn.BatchNorm2d) \
             and isinstance(seq[2], nn.ReLU):
-        return ops.batch_norm_act(seq[0](x), seq[1], relu=True)
+        return ops.conv_batch_norm_act(x, seq[0], seq[1], relu=True)
     return seq(x)
 
 
@@ -177,9 +177,9 @@ class Grapher(nn.Module):
 
     def forward(self, x):
         shortcut = x
-        x = ops.batch_norm_act(self.fc1[0](x), self.fc1[1])
+        x = ops.conv_batch_norm_act(x, self.fc1[0], self.fc1[1])
         x = self.graph_conv(x, relative_pos=None)
         if isinstance(self.drop_path, nn.Identity):
-            return ops.batch_norm_act(self.fc2[0](x), self.fc2[1], residual=shortcut)  # BatchNorm + residual fused
+            return ops.conv_batch_norm_act(x, self.fc2[0], self.fc2[1], residual=shortcut)  # BatchNorm + residual fused
         x = self.fc2(x)
         return self.drop_path(x) + shortcut

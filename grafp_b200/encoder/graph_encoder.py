@@ -64,8 +64,8 @@ class FFN(nn.Module):
     def forward(self, x):
         if isinstance(self.drop_path, nn.Identity) and isinstance(self.act, nn.ReLU):
             # BatchNorm + ReLU and BatchNorm + residual as fused ops (train mode; eval falls through to PyTorch)
-            h = ops.batch_norm_act(self.fc1[0](x), self.fc1[1], relu=True)
-            return ops.batch_norm_act(self.fc2[0](h), self.fc2[1], residual=x)
+            h = ops.conv_batch_norm_act(x, self.fc1[0], self.fc1[1], relu=True)
+            return ops.conv_batch_norm_act(h, self.fc2[0], self.fc2[1], residual=x)
         return self.drop_path(self.fc2(self.act(self.fc1(x)))) + x
 
 

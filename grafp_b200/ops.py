@@ -413,7 +413,7 @@ class _BatchNormTrain(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         _call("bn_train_bwd", 3, dict(B=B, N=N, C=C, relu=int(ctx.relu)), lib.grafp_bn_train_bwd,
               g.data_ptr(), x.data_ptr(), weight.data_ptr(), bias.data_ptr(), save_mean.data_ptr(),
-              save_invstd.data_ptr(), dx.data_ptr(), dweight.data_ptr(), dbias.data_ptr(), B * N, C, int(ctx.relu),
+              save_invstd.data_ptr(), dx.data_ptr(), dweight.data_ptr(), dbias.data_ptr(), None, B * N, C, int(ctx.relu),
               ws.data_ptr(), ws_bytes, _stream())
         return dx, (grad_out if ctx.has_res else None), dweight, dbias, None, None, None, None, None
 
@@ -444,3 +444,85 @@ def batch_norm_act(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = False
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
     return _BatchNormTrain.apply(x, residual, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, relu)
+
+
+class _ConvBatchNormTrain(torch.autograd.Function):
+    """Conv2d(1x1, bias) -> train-mode BatchNorm [-> ReLU | + residual] as one autograd node: the convolution stays
+    cuDNN, the BatchNorm is the fused kernel pair, and the convolution's bias gradient - the per-channel sum of the
+    BatchNorm's input gradient - is accumulated while that gradient is written instead of by a separate reduction
+    pass over it (aten::convolution_backward is asked for the input and weight gradients only)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, cw, cb, weight, bias, running_mean, running_var, eps, momentum, relu, conv_args):
+        lib = _native.load()
+        stride, padding, dilation, groups = conv_args
+        h = torch.nn.functional.conv2d(x, cw, cb, stride, padding, dilation, groups)
+        if not _is_rows(h):
+            h = as_rows(h)
+        B, C, N, _ = h.shape
+        out = _new_rows(B, C, N, h)
+        save_mean = torch.empty(C, dtype=torch.float32, device=h.device)
+        save_invstd = torch.empty(C, dtype=torch.float32, device=h.device)
+        ws_bytes = lib.grafp_bn_workspace_bytes(C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=h.device)
+        _call("bn_train_fwd", 3, dict(B=B, N=N, C=C, relu=int(relu), res=int(residual is not None)),
+              lib.grafp_bn_train_fwd, h.data_ptr(), residual.data_ptr() if residual is not None else None,
+              weight.data_ptr(), bias.data_ptr(),
+              running_mean.data_ptr() if running_mean is not None else None,
+              running_var.data_ptr() if running_var is not None else None,
+              out.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(), B * N, C, float(eps), float(momentum),
+              int(relu), ws.data_ptr(), ws_bytes, _stream())
+        ctx.save_for_backward(x, cw, h, weight, bias, save_mean, save_invstd)
+        ctx.relu = bool(relu)
+        ctx.has_res = residual is not None
+        ctx.conv_args = conv_args
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _native.load()
+        x, cw, h, weight, bias, save_mean, save_invstd = ctx.saved_tensors
+        stride, padding, dilation, groups = ctx.conv_args
+        B, C, N, _ = h.shape
+        g = as_rows(grad_out)
+        dh = _new_rows(B, C, N, h)
+        dweight = torch.empty_like(weight)
+        dbias = torch.empty_like(bias)
+        dcb = torch.empty(C, dtype=torch.float32, device=h.device)
+        ws_bytes = lib.grafp_bn_workspace_bytes(C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=h.device)
+        _call("bn_train_bwd", 4, dict(B=B, N=N, C=C, relu=int(ctx.relu)), lib.grafp_bn_train_bwd,
+              g.data_ptr(), h.data_ptr(), weight.data_ptr(), bias.data_ptr(), save_mean.data_ptr(),
+              save_invstd.data_ptr(), dh.data_ptr(), dweight.data_ptr(), dbias.data_ptr(), dcb.data_ptr(), B * N, C,
+              int(ctx.relu), ws.data_ptr(), ws_bytes, _stream())
+        dx, dcw, _ = torch.ops.aten.convolution_backward(
+            dh, x, cw, None, list(stride), list(padding), list(dilation), False, [0, 0], groups,
+            [ctx.needs_input_grad[0], ctx.needs_input_grad[2], False])
+        return (dx, (grad_out if ctx.has_res else None), dcw, dcb, dweight, dbias, None, None, None, None, None, None)
+
+
+def conv_batch_norm_act(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu: bool = False,
+                        residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``relu(bn(conv(x)))`` / ``bn(conv(x)) + residual`` / ``bn(conv(x))`` for node rows (B, C, N, 1).
+
+    With a biased 1x1 convolution in training mode (CUDA, fp32, channels-last) the three layers are one autograd
+    node (see _ConvBatchNormTrain); otherwise the convolution runs as the module and the rest goes through
+    :func:`batch_norm_act`, which applies its own envelope checks.
+    """
+    C = conv.out_channels
+    fused = (os.environ.get("GRAFP_FUSED_BN", "1") != "0" and bn.training and x.is_cuda and x.dtype == torch.float32
+             and _is_rows(x) and conv.bias is not None and conv.kernel_size == (1, 1) and conv.padding_mode == "zeros"
+             and isinstance(conv.padding, tuple) and not conv.transposed
+             and bn.affine and bn.momentum is not None and not (relu and residual is not None)
+             and C % 4 == 0 and ((C // 4) & (C // 4 - 1)) == 0 and x.shape[0] * x.shape[2] > 1
+             and (residual is None or (residual.dtype == x.dtype and _is_rows(residual) and residual.shape[1] == C))
+             and conv.weight.dtype == torch.float32 and bn.weight.dtype == torch.float32
+             and torch.is_grad_enabled())
+    if not fused:
+        return batch_norm_act(conv(x), bn, relu=relu, residual=residual)
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    return _ConvBatchNormTrain.apply(x, residual, conv.weight, conv.bias, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum,
+                                     relu, (conv.stride, conv.padding, conv.dilation, conv.groups))

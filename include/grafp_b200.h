@@ -155,6 +155,9 @@ int grafp_max_over_k_bwd(const void* grad_out, const uint8_t* argmax, void* grad
  *  backward: dz = dy masked by the ReLU (recomputed from x, no output is kept); dbias = sum dz,
  *            dweight = sum dz * xhat, dx = weight * invstd * (dz - dbias / R - xhat * dweight / R).
  *            The gradient of the residual input is dy itself and is not written here.
+ *            dx_colsum (C floats, may be NULL): per-channel sum of dx over the rows, accumulated while dx is
+ *            written - the bias gradient of the 1x1 convolution that produced x (Conv2d(bias=True) + BatchNorm2d
+ *            in Grapher.fc1 / fc2 and BasicConv), so its backward needs no separate reduction pass over dx.
  *  workspace: grafp_bn_workspace_bytes(C) bytes of caller-owned scratch (block partials).
  */
 size_t grafp_bn_workspace_bytes(int C);
@@ -162,8 +165,8 @@ int grafp_bn_train_fwd(const float* x, const float* residual, const float* weigh
                        float* running_var, float* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
                        float momentum, int relu, void* workspace, size_t workspace_bytes, void* stream);
 int grafp_bn_train_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* save_mean,
-                       const float* save_invstd, float* dx, float* dweight, float* dbias, long long R, int C, int relu,
-                       void* workspace, size_t workspace_bytes, void* stream);
+                       const float* save_invstd, float* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
+                       int relu, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

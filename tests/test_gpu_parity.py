@@ -728,3 +728,56 @@ def test_fused_batch_norm_falls_back_outside_its_envelope():
     for train in (True, False):
         bn.train(train)
         assert torch.allclose(ops.batch_norm_act(x, bn, relu=True), torch.relu(bn(x)), atol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 128, 500, 1), (2, 128, 128, 256, 4), (2, 1024, 512, 64, 1)])
+@pytest.mark.parametrize("mode", ["plain", "relu", "residual"])
+def test_fused_conv_batch_norm_matches_torch(shape, mode):
+    """ops.conv_batch_norm_act (one autograd node: cuDNN 1x1 convolution + fused BatchNorm, convolution bias
+    gradient taken from the BatchNorm backward) against the PyTorch module sequence in fp64."""
+    B, Cin, Cout, N, groups = shape
+    g = torch.Generator().manual_seed(Cin + Cout + N)
+    conv_ref = torch.nn.Conv2d(Cin, Cout, 1, groups=groups).double()
+    bn_ref = torch.nn.BatchNorm2d(Cout).double()
+    with torch.no_grad():
+        bn_ref.weight.copy_(torch.randn(Cout, generator=g).double())
+        bn_ref.bias.copy_(torch.randn(Cout, generator=g).double())
+        conv_ref.bias.copy_(torch.randn(Cout, generator=g).double())
+    conv, bn = torch.nn.Conv2d(Cin, Cout, 1, groups=groups), torch.nn.BatchNorm2d(Cout)
+    conv.load_state_dict({k: v.float() for k, v in conv_ref.state_dict().items()})
+    bn.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in bn_ref.state_dict().items()})
+    conv.to(DEV); bn.to(DEV).train(); bn_ref.train()
+    x = torch.randn(B, Cin, N, 1, generator=g)
+    res = torch.randn(B, Cout, N, 1, generator=g)
+    up = torch.randn(B, Cout, N, 1, generator=g)
+
+    def cl(t):
+        return t.to(DEV).contiguous(memory_format=torch.channels_last)
+
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        xg, rg = cl(x).requires_grad_(True), cl(res).requires_grad_(True)
+        xr, rr = x.double().requires_grad_(True), res.double().requires_grad_(True)
+        if mode == "plain":
+            got, ref = ops.conv_batch_norm_act(xg, conv, bn), bn_ref(conv_ref(xr))
+        elif mode == "relu":
+            got, ref = ops.conv_batch_norm_act(xg, conv, bn, relu=True), torch.relu(bn_ref(conv_ref(xr)))
+        else:
+            got, ref = ops.conv_batch_norm_act(xg, conv, bn, residual=rg), bn_ref(conv_ref(xr)) + rr
+        assert gio.rel_err(got.detach().cpu().double(), ref.detach()) < 2e-5
+        got.backward(cl(up)); ref.backward(up.double())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    tol = 1e-3 if mode == "relu" else 1e-4
+    assert gio.rel_err(xg.grad.cpu().double(), xr.grad) < tol
+    assert gio.rel_err(conv.weight.grad.cpu().double(), conv_ref.weight.grad) < tol
+    assert gio.rel_err(bn.weight.grad.cpu().double(), bn_ref.weight.grad) < 1e-4
+    assert gio.rel_err(bn.bias.grad.cpu().double(), bn_ref.bias.grad) < 1e-4
+    # a bias in front of a train-mode BatchNorm has a mathematically zero gradient: both are rounding noise
+    noise = 1e-4 * float(up.double().norm())
+    assert float(conv.bias.grad.double().norm()) < noise and float(conv_ref.bias.grad.norm()) < noise
+    assert gio.rel_err(bn.running_var.cpu().double(), bn_ref.running_var) < 1e-5
+    if mode == "residual":
+        assert gio.rel_err(rg.grad.cpu().double(), rr.grad) < 1e-6
