@@ -509,20 +509,57 @@ def conv_batch_norm_act(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.nn.Bat
     node (see _ConvBatchNormTrain); otherwise the convolution runs as the module and the rest goes through
     :func:`batch_norm_act`, which applies its own envelope checks.
     """
-    C = conv.out_channels
+    ok = (conv.bias is not None and conv.kernel_size == (1, 1) and conv.padding_mode == "zeros"
+          and isinstance(conv.padding, tuple) and not conv.transposed)
+    if not ok:
+        return batch_norm_act(conv(x), bn, relu=relu, residual=residual)
+    return pointwise_conv_batch_norm_act(x, conv.weight, conv.bias, bn, relu, residual,
+                                         (conv.stride, conv.padding, conv.dilation, conv.groups))
+
+
+def pointwise_conv_batch_norm_act(x, cw, cb, bn, relu=False, residual=None, conv_args=((1, 1), (0, 0), (1, 1), 1)):
+    """:func:`conv_batch_norm_act` on explicit 1x1 convolution weights ``cw`` (Cout, Cin / groups, 1, 1) and bias."""
+    C = cw.shape[0]
     fused = (os.environ.get("GRAFP_FUSED_BN", "1") != "0" and bn.training and x.is_cuda and x.dtype == torch.float32
-             and _is_rows(x) and conv.bias is not None and conv.kernel_size == (1, 1) and conv.padding_mode == "zeros"
-             and isinstance(conv.padding, tuple) and not conv.transposed
+             and _is_rows(x) and cb is not None
              and bn.affine and bn.momentum is not None and not (relu and residual is not None)
              and C % 4 == 0 and ((C // 4) & (C // 4 - 1)) == 0 and x.shape[0] * x.shape[2] > 1
              and (residual is None or (residual.dtype == x.dtype and _is_rows(residual) and residual.shape[1] == C))
-             and conv.weight.dtype == torch.float32 and bn.weight.dtype == torch.float32
+             and cw.dtype == torch.float32 and bn.weight.dtype == torch.float32
              and torch.is_grad_enabled())
     if not fused:
-        return batch_norm_act(conv(x), bn, relu=relu, residual=residual)
+        stride, padding, dilation, groups = conv_args
+        return batch_norm_act(torch.nn.functional.conv2d(x, cw, cb, stride, padding, dilation, groups), bn, relu=relu,
+                              residual=residual)
     if bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
-    return _ConvBatchNormTrain.apply(x, residual, conv.weight, conv.bias, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum,
-                                     relu, (conv.stride, conv.padding, conv.dilation, conv.groups))
+    return _ConvBatchNormTrain.apply(x, residual, cw, cb, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, relu, conv_args)
+
+
+def downsample_rows(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d) -> Optional[torch.Tensor]:
+    """``bn(conv(x))`` for the Downsample block (graph_encoder.py:16-28: Conv2d(3x3, stride 2, padding 1) over a
+    (B, C, N, 1) node list), or None when the shape is not that case.
+
+    The image is one pixel wide, so only the middle column of the 3x3 kernel ever meets data: the layer is a 3-tap,
+    stride-2 convolution along the node axis, out[n'] = sum_t W[:, :, t, 1] x[2n' + t - 1].  cuDNN's strided 3x3
+    data-gradient kernels run it at a few % of the hardware; here the three input rows of every output row are
+    laid side by side (one copy, 1.5x the input) and the layer becomes a 1x1 convolution with 3C input channels -
+    the same cuDNN GEMM kernels (and TF32 policy) as every other 1x1 convolution of the encoder - followed by the
+    fused BatchNorm.  The other six kernel taps multiply zero padding in the reference too: their weight gradients
+    are exactly zero in both.
+    """
+    if not (x.dim() == 4 and x.shape[3] == 1 and x.shape[2] % 2 == 0 and x.shape[2] >= 2 and _is_rows(x)
+            and conv.kernel_size == (3, 3) and conv.stride == (2, 2) and conv.padding == (1, 1)
+            and conv.dilation == (1, 1) and conv.groups == 1 and conv.padding_mode == "zeros"
+            and os.environ.get("GRAFP_FUSED_BN", "1") != "0"):
+        return None
+    B, C, N, _ = x.shape
+    rows = x.permute(0, 2, 3, 1).reshape(B, N // 2, 2 * C)           # [x[2n'], x[2n'+1]] per output row: a view
+    prev = torch.nn.functional.pad(rows[:, :-1, C:], (0, 0, 1, 0))   # x[2n'-1], zero row in front of every segment
+    taps = torch.cat([prev, rows], dim=2)                            # (B, N/2, 3C)
+    a = taps.view(B, N // 2, 1, 3 * C).permute(0, 3, 1, 2)           # logical (B, 3C, N/2, 1), rows in memory
+    w = conv.weight[:, :, :, 1]                                      # (Cout, Cin, 3): the middle kernel column
+    cw = torch.cat([w[:, :, 0], w[:, :, 1], w[:, :, 2]], dim=1).reshape(conv.out_channels, 3 * C, 1, 1)
+    return pointwise_conv_batch_norm_act(a, cw, conv.bias, bn)

@@ -646,7 +646,7 @@ def test_simclr_step_and_retrieval_match_reference_golden():
     with torch.no_grad():
         _, _, db_ref, _ = O.simclr_forward(p, db_specs, db_specs, True, graph_fn=replay)
         _, _, q_ref, _ = O.simclr_forward(p, q_specs[:16], q_specs[:16], True, graph_fn=replay)
-    assert replay.hard == 0
+    assert replay.hard == 0, replay.hard_gaps
     assert gio.rel_err(db.cpu(), db_ref) < REL_TOL
     assert torch.equal(ours_top1, O.top1_retrieval(db_ref, q_ref)), "identical top-1 retrieval hits"
     # (b) against the hits stored from the upstream reference: a query may only differ if its two best
