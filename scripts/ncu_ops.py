@@ -10,10 +10,12 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 for (N, C) in [(1024, 64), (512, 128), (256, 256), (128, 512)]:
     x = torch.relu(torch.randn(B, C, N, 1, device=dev)).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(2 * C).to(dev).train()
     for _ in range(reps):
         nbr, nbr32 = ops.knn_graph(x, 3)
         out = ops.mr_aggregate(x, nbr32)
-        g = torch.randn_like(out)
-        (gx,) = torch.autograd.grad(out, x, g)
+        y = ops.batch_norm_act(out, bn, relu=True)           # fused train-mode BatchNorm + ReLU on the (B, N, 2C) rows
+        g = torch.randn_like(y)
+        (gx,) = torch.autograd.grad(y, x, g)
     torch.cuda.synchronize()
 print("done", ops.knn_last_algo())
