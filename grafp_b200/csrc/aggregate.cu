@@ -534,7 +534,10 @@ __device__ __forceinline__ void k3_mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-template <bool I64>
+// JORDER: phase 2 walks the neighbour slots j = 0..k-1 in a fixed order instead of the winners of the item's four
+// channels, so the lanes that share a source row issue their red.v4 to the SAME target row in the same instruction
+// (contiguous 256-byte runs that the LSU / L2 merge per sector) and an item issues at most k-1 of them.
+template <bool I64, bool JORDER>
 __global__ void __launch_bounds__(kFusedThreads, 3)
 mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* __restrict__ argmax,
                                     const void* __restrict__ nbr, float* __restrict__ grad_x, int N, int C, int k,
@@ -614,6 +617,21 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
       int a[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) a[e] = (am[u] >> (8 * e)) & 0xff;
+      if constexpr (JORDER) {
+        for (int j = 0; j < k; ++j) {
+          float v[4];
+          bool any = false;
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const bool hit = (a[f] == j);
+            v[f] = hit ? g1[f] : 0.f;
+            any |= hit;
+          }
+          const int nb = static_cast<int>(ids[rl * k + j]);
+          if (any && nb != n) Pack<float, 4>::red_add(gxb + (long long)nb * C + c, v);
+        }
+        continue;
+      }
       unsigned todo = 0xf;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -634,7 +652,11 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
   }
 }
 
-template <bool I64>
+namespace {
+int bwd_variant();  // development switch, defined with the dispatchers below
+}
+
+template <bool I64, bool JORDER>
 int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void* nbr, float* grad_x, int B, int N, int C,
                               int k, cudaStream_t s, bool* launched) {
   *launched = false;
@@ -646,7 +668,12 @@ int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void*
   // smallest cluster whose per-CTA share fits 8 items per thread and ~68 KB of shared memory (three CTAs per SM);
   // bulk copies need 16-byte multiples and 16-byte aligned sources for every CTA of the cluster
   int cl = 0;
+  // GRAFP_MR_BWD_VARIANT=18 (development): 16-CTA clusters (non-portable size) - half the share per CTA, twice the
+  // CTAs resident per SM, so more loads in flight next to the reduction phase of the neighbours
+  const bool big = bwd_variant() == 18 && N % 16 == 0 && ((N / 16) * k * idsz) % 16 == 0 && N / 16 >= 8;
+  if (big) cl = 16;
   for (int cand : {1, 2, 4, 8}) {
+    if (big) break;
     const long long rows = (N + cand - 1) / cand;
     if (rows * cv <= 8 * kFusedThreads && rows * (2 * C * 4 + k * idsz) + 16 <= 68 * 1024 &&
         (rows * k * idsz) % 16 == 0 && ((long long)N * k * idsz) % 16 == 0) {
@@ -660,8 +687,10 @@ int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void*
   const size_t smem = (size_t)rows_per_cta * (2 * C * 4 + k * idsz) + 16;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64>,
+    cudaError_t e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 68 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER>,
+                                                   cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_bwd_cluster_tma): %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
@@ -677,7 +706,7 @@ int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, mr_aggregate_bwd_cluster_tma_kernel<I64>, g, argmax, nbr, grad_x, N, C, k,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER>, g, argmax, nbr, grad_x, N, C, k,
                                      rows_per_cta, cv_shift);
   if (e != cudaSuccess) { set_error("mr_aggregate_bwd_cluster_tma launch: %s", cudaGetErrorString(e)); return (int)e; }
   *launched = true;
@@ -1259,8 +1288,11 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
     if constexpr (VEC == 4 && std::is_same<T, float>::value) {
       if (self_skip && bwd_variant() >= 16) {  // default: cluster form with TMA bulk staging
         bool launched = false;
-        const int rc = launch_mr_bwd_cluster_tma<I64>(reinterpret_cast<const float*>(gs), argmax, nbr,
-                                                      reinterpret_cast<float*>(gx), B, N, C, k, s, &launched);
+        const int rc = (bwd_variant() == 17 || bwd_variant() == 18)
+                           ? launch_mr_bwd_cluster_tma<I64, true>(reinterpret_cast<const float*>(gs), argmax, nbr,
+                                                                  reinterpret_cast<float*>(gx), B, N, C, k, s, &launched)
+                           : launch_mr_bwd_cluster_tma<I64, false>(reinterpret_cast<const float*>(gs), argmax, nbr,
+                                                                   reinterpret_cast<float*>(gx), B, N, C, k, s, &launched);
         if (rc != GRAFP_OK || launched) return rc;
       }
     }

@@ -119,36 +119,60 @@ bn_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, int* 
   }
 }
 
-// 32 channels x 8 partial-groups per block (coalesced reads of the partials): merge the block partials in double
-// (two division-free passes: the global mean, then M2 = sum [M2_p + n_p (mean_p - mean)^2]), emit mean / invstd,
-// update the running statistics
+// 32 channels x 32 partial-groups per block (coalesced 256-byte reads of the partials, <= 19 partials per thread
+// with four loads in flight: these kernels are pure latency, 20 - 34 us each with 8 groups and a serial loop):
+// merge the block partials in double (two division-free passes: the global mean, then
+// M2 = sum [M2_p + n_p (mean_p - mean)^2]), emit mean / invstd, update the running statistics
+constexpr int kFinGroups = 32;
+constexpr int kFinThreads = 32 * kFinGroups;
+
 __device__ __forceinline__ double group_sum(double v, double (*sm)[33], int cl, int pg) {
   __syncthreads();
   sm[pg][cl] = v;
   __syncthreads();
-  double t = 0.0;
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) t += sm[i][cl];
-  return t;
+  for (int i = 0; i < kFinGroups; i += 4) { t0 += sm[i][cl]; t1 += sm[i + 1][cl]; t2 += sm[i + 2][cl]; t3 += sm[i + 3][cl]; }
+  return (t0 + t1) + (t2 + t3);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinThreads)
 bn_stats_finalize_kernel(const float2* __restrict__ partial, const int* __restrict__ pcount, int parts, int C, long long R,
                          float eps, float momentum, float* __restrict__ save_mean, float* __restrict__ save_invstd,
                          float* running_mean, float* running_var) {
-  __shared__ double sm[8][33];
+  __shared__ double sm[kFinGroups][33];
   const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
   const int c = min(blockIdx.x * 32 + cl, C - 1);
-  double acc = 0.0;
-  for (int p = pg; p < parts; p += 8) acc += (double)pcount[p] * (double)partial[(long long)p * C + c].x;
-  const double mean = group_sum(acc, sm, cl, pg) / (double)R;
-  double m2 = 0.0;
-  for (int p = pg; p < parts; p += 8) {
-    const float2 v = partial[(long long)p * C + c];
-    const double d = (double)v.x - mean;
-    m2 += (double)v.y + (double)pcount[p] * d * d;
+  const float2* pc = partial + c;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int p = pg;
+  for (; p + 3 * kFinGroups < parts; p += 4 * kFinGroups) {
+    const float m0 = pc[(long long)p * C].x, m1 = pc[(long long)(p + kFinGroups) * C].x;
+    const float m2_ = pc[(long long)(p + 2 * kFinGroups) * C].x, m3 = pc[(long long)(p + 3 * kFinGroups) * C].x;
+    a0 += (double)pcount[p] * (double)m0;
+    a1 += (double)pcount[p + kFinGroups] * (double)m1;
+    a2 += (double)pcount[p + 2 * kFinGroups] * (double)m2_;
+    a3 += (double)pcount[p + 3 * kFinGroups] * (double)m3;
   }
-  m2 = group_sum(m2, sm, cl, pg);
+  for (; p < parts; p += kFinGroups) a0 += (double)pcount[p] * (double)pc[(long long)p * C].x;
+  const double mean = group_sum((a0 + a1) + (a2 + a3), sm, cl, pg) / (double)R;
+  a0 = a1 = a2 = a3 = 0.0;
+  p = pg;
+  for (; p + 3 * kFinGroups < parts; p += 4 * kFinGroups) {
+    const float2 v0 = pc[(long long)p * C], v1 = pc[(long long)(p + kFinGroups) * C];
+    const float2 v2 = pc[(long long)(p + 2 * kFinGroups) * C], v3 = pc[(long long)(p + 3 * kFinGroups) * C];
+    const double d0 = (double)v0.x - mean, d1 = (double)v1.x - mean, d2 = (double)v2.x - mean, d3 = (double)v3.x - mean;
+    a0 += (double)v0.y + (double)pcount[p] * d0 * d0;
+    a1 += (double)v1.y + (double)pcount[p + kFinGroups] * d1 * d1;
+    a2 += (double)v2.y + (double)pcount[p + 2 * kFinGroups] * d2 * d2;
+    a3 += (double)v3.y + (double)pcount[p + 3 * kFinGroups] * d3 * d3;
+  }
+  for (; p < parts; p += kFinGroups) {
+    const float2 v = pc[(long long)p * C];
+    const double d = (double)v.x - mean;
+    a0 += (double)v.y + (double)pcount[p] * d * d;
+  }
+  const double m2 = group_sum((a0 + a1) + (a2 + a3), sm, cl, pg);
   if (pg != 0 || blockIdx.x * 32 + cl >= C) return;
   const double var = m2 / (double)R;
   save_mean[c] = (float)mean;
@@ -262,21 +286,30 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinThreads)
 bn_bwd_finalize_kernel(const float2* __restrict__ partial, int parts, int C, float* __restrict__ dweight,
                        float* __restrict__ dbias) {
-  __shared__ double sm[8][33];
+  __shared__ double sm[kFinGroups][33];
   const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
   const int c = min(blockIdx.x * 32 + cl, C - 1);
-  double s1 = 0.0, s2 = 0.0;
-  for (int p = pg; p < parts; p += 8) {
-    const float2 v = partial[(long long)p * C + c];
-    s1 += (double)v.x;
-    s2 += (double)v.y;
+  const float2* pc = partial + c;
+  double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+  int p = pg;
+  for (; p + 3 * kFinGroups < parts; p += 4 * kFinGroups) {
+    float2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = pc[(long long)(p + u * kFinGroups) * C];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { s1[u] += (double)v[u].x; s2[u] += (double)v[u].y; }
   }
-  s1 = group_sum(s1, sm, cl, pg);
-  s2 = group_sum(s2, sm, cl, pg);
-  if (pg == 0 && blockIdx.x * 32 + cl < C) { dbias[c] = (float)s1; dweight[c] = (float)s2; }
+  for (; p < parts; p += kFinGroups) {
+    const float2 v = pc[(long long)p * C];
+    s1[0] += (double)v.x;
+    s2[0] += (double)v.y;
+  }
+  const double t1 = group_sum((s1[0] + s1[1]) + (s1[2] + s1[3]), sm, cl, pg);
+  const double t2 = group_sum((s2[0] + s2[1]) + (s2[2] + s2[3]), sm, cl, pg);
+  if (pg == 0 && blockIdx.x * 32 + cl < C) { dbias[c] = (float)t1; dweight[c] = (float)t2; }
 }
 
 // ---- backward apply: dx = weight * invstd * (dz - s1 / R - xhat * s2 / R) ----
@@ -350,23 +383,33 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, c
 }
 
 // column sums of dx: sum the block partials of bn_bwd_apply_kernel (block b, slot t holds channel pack (b * 256 + t) % cv)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinThreads)
 bn_colsum_finalize_kernel(const float* __restrict__ colsum_partial, int blocks, int cv, float* __restrict__ colsum) {
-  __shared__ double sm[8][33];
+  __shared__ double sm[kFinGroups][33];
   const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
   const int C = cv * 4;
   const int c = min(blockIdx.x * 32 + cl, C - 1);
   const int c4 = c >> 2, e = c & 3;
   const int span = cv < kBnThreads ? cv : kBnThreads;
-  double acc = 0.0;
-  if (cv <= kBnThreads) {  // every block holds every channel pack once, at slot c4
-    for (int b = pg; b < blocks; b += 8) acc += (double)colsum_partial[(long long)b * (4LL * span) + 4 * c4 + e];
-  } else {                 // block b holds packs (b * 256 + t) % cv: pack c4 lives in blocks with (b * 256) % cv == c4 - t
-    const int per = cv / kBnThreads;  // blocks per full sweep of the channel packs
-    const int t = c4 % kBnThreads, first = c4 / kBnThreads;
-    for (int b = first + pg * per; b < blocks; b += 8 * per) acc += (double)colsum_partial[(long long)b * (4LL * span) + 4 * t + e];
+  // cv <= 256: every block holds every channel pack once, at slot c4; else block b holds packs (b * 256 + t) % cv,
+  // i.e. pack c4 lives in the blocks first, first + per, ... at slot t
+  const int per = cv <= kBnThreads ? 1 : cv / kBnThreads;
+  const int first = cv <= kBnThreads ? 0 : c4 / kBnThreads;
+  const int slot = cv <= kBnThreads ? c4 : c4 % kBnThreads;
+  const float* src = colsum_partial + 4 * slot + e;
+  const long long bstride = 4LL * span;
+  const int step = kFinGroups * per;
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  int b = first + pg * per;
+  for (; b + 3 * step < blocks; b += 4 * step) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = src[(long long)(b + u * step) * bstride];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] += (double)v[u];
   }
-  const double tot = group_sum(acc, sm, cl, pg);
+  for (; b < blocks; b += step) a[0] += (double)src[(long long)b * bstride];
+  const double tot = group_sum((a[0] + a[1]) + (a[2] + a[3]), sm, cl, pg);
   if (pg == 0 && blockIdx.x * 32 + cl < C) colsum[c] = (float)tot;
 }
 
@@ -405,7 +448,7 @@ int launch_bn_train_fwd(const float* x, const float* res, const float* weight, c
   float2* partial = reinterpret_cast<float2*>(wb);
   int* pcount = reinterpret_cast<int*>(wb + (size_t)kBnMaxPartials * C * sizeof(float2));
   bn_stats_kernel<<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(x, partial, pcount, R, C, shift_of(g.tpr));
-  bn_stats_finalize_kernel<<<(C + 31) / 32, 256, 0, s>>>(partial, pcount, g.gx, C, R, eps, momentum, save_mean, save_invstd,
+  bn_stats_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, s>>>(partial, pcount, g.gx, C, R, eps, momentum, save_mean, save_invstd,
                                                            running_mean, running_var);
   const long long total4 = R * g.cv;
   const int grid = apply_grid(total4, g.cv);
@@ -425,7 +468,7 @@ int launch_bn_train_bwd(const float* dy, const float* x, const float* weight, co
   const int tsh = shift_of(g.tpr);
   if (relu) bn_bwd_reduce_kernel<true><<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, partial, R, C, tsh);
   else bn_bwd_reduce_kernel<false><<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, partial, R, C, tsh);
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, s>>>(partial, g.gx, C, dweight, dbias);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, s>>>(partial, g.gx, C, dweight, dbias);
   const long long total4 = R * g.cv;
   const int grid = apply_grid(total4, g.cv);
   const float inv_rows = (float)(1.0 / (double)R);
@@ -433,7 +476,7 @@ int launch_bn_train_bwd(const float* dy, const float* x, const float* weight, co
   if (dx_colsum != nullptr) {
     if (relu) bn_bwd_apply_kernel<true, true><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, csp, total4, g.cv, inv_rows);
     else bn_bwd_apply_kernel<false, true><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, csp, total4, g.cv, inv_rows);
-    bn_colsum_finalize_kernel<<<(C + 31) / 32, 256, 0, s>>>(csp, grid, g.cv, dx_colsum);
+    bn_colsum_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, s>>>(csp, grid, g.cv, dx_colsum);
   } else {
     if (relu) bn_bwd_apply_kernel<true, false><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, nullptr, total4, g.cv, inv_rows);
     else bn_bwd_apply_kernel<false, false><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, nullptr, total4, g.cv, inv_rows);

@@ -27,6 +27,9 @@
 
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+#include <cstring>
+
 namespace grafp {
 namespace tc2 {
 using namespace tcptx;
@@ -118,12 +121,105 @@ struct TopK {
       }
     }
   }
+
+  // ---- decoupled selection: per-lane candidate queue in shared memory ------------------------------------
+  // The vote-gated scan above makes the whole warp pay the insertion path whenever ANY of its 32 rows has a
+  // candidate, which is most columns (a row's list changes ~K ln(M/K) times, times 32 rows).  Here the scan is
+  // branch-free: per quad of columns, max3/max + one FSETP against the row's (slightly stale) threshold and three
+  // predicated instructions that park the four raw accumulators in the lane's own queue (slot s of lane l at
+  // q0 + 512 s, q0 = warp base + 16 l: 128-bit accesses of a warp never conflict, whatever the lanes' fill
+  // levels) and mark the quad in a per-tile bit mask.  The queue is drained lane-parallel - every lane walks its
+  // own entries in push order, so ties still keep the lower key id - at the end of a tile, or earlier when
+  // some lane is 4 slots from full.  With thr = -inf at the start everything is pushed, the first 16 columns
+  // trigger a drain, and the thresholds tighten from there on their own.
+  uint32_t q0, qa, qlim, qmask;
+  static constexpr uint32_t kSlotStride = 512;
+  __device__ __forceinline__ void queue_init(uint32_t warp_queue, int lane, int slots) {
+    q0 = warp_queue + 16u * lane;
+    qa = q0;
+    qlim = q0 + (uint32_t)(slots - 4) * kSlotStride;
+    qmask = 0u;
+  }
+  __device__ __forceinline__ void push4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t bit) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .f32 m;\n\t"
+        "max.f32 m, %2, %3, %4;\n\t"
+        "max.f32 m, m, %5;\n\t"
+        "setp.gt.f32 p, m, %6;\n\t"
+        "@p st.shared.v4.f32 [%0], {%2, %3, %4, %5};\n\t"
+        "@p add.u32 %0, %0, 512;\n\t"
+        "@p or.b32 %1, %1, %7;\n\t"
+        "}"
+        : "+r"(qa), "+r"(qmask)
+        : "f"(__uint_as_float(a)), "f"(__uint_as_float(b)), "f"(__uint_as_float(c)), "f"(__uint_as_float(d)), "f"(thr),
+          "r"(bit)
+        : "memory");
+  }
+  // key0 = key id of the tile's column 0; keys >= M (TMA zero fill) are skipped
+  template <bool YS_SHARED>
+  __device__ __forceinline__ void drain(int key0, uint32_t ys_addr, const float* ys_glob, int M) {
+    uint32_t rd = q0;
+    while (__any_sync(0xffffffffu, rd < qa)) {
+      if (rd < qa) {
+        float v0, v1, v2, v3;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3) : "r"(rd));
+        rd += kSlotStride;
+        const int quad = __ffs(qmask) - 1;  // lowest marked quad = oldest entry
+        qmask &= qmask - 1u;
+        const int key = key0 + 4 * quad;
+        uint32_t em = (v0 > thr ? 1u : 0u) | (v1 > thr ? 2u : 0u) | (v2 > thr ? 4u : 0u) | (v3 > thr ? 8u : 0u);
+        while (em != 0u) {  // lane-local, in column order; usually one element
+          const int e = __ffs(em) - 1;
+          em &= em - 1u;
+          const float lo2 = (e & 1) ? v1 : v0, hi2 = (e & 1) ? v3 : v2;
+          const float s = (e & 2) ? hi2 : lo2;
+          const int kj = key + e;
+          if (kj < M) {
+            const float yj = YS_SHARED ? lds_f32(ys_addr + 4u * kj) : __ldg(ys_glob + kj);
+            insert(__fadd_rn(fmaf(kM2, s, sq_i), yj), kj);
+            update_thr();
+          }
+        }
+      }
+    }
+    qa = q0;
+  }
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr));
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
+// One tile (<= 128 accumulator columns, ncols of them backed by keys) of this thread's row through the
+// candidate queue: 16 columns per tcgen05.ld, four predicated quad pushes, one vote for the early drain.
+template <int KREG, bool YS_SHARED>
+__device__ __forceinline__ void scan_tile_queued(TopK<KREG>& top, uint32_t trow, int key0, int ncols, uint32_t ys_addr,
+                                                 const float* ys_glob, int M) {
+  uint32_t bq = 1u;
+#pragma unroll 1
+  for (int c0 = 0; c0 < ncols; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(trow + c0, v);
+    tmem_ld_wait();
+    top.push4(v[0], v[1], v[2], v[3], bq);
+    top.push4(v[4], v[5], v[6], v[7], bq << 1);
+    top.push4(v[8], v[9], v[10], v[11], bq << 2);
+    top.push4(v[12], v[13], v[14], v[15], bq << 3);
+    bq <<= 4;
+    if (c0 + 16 >= ncols || __any_sync(0xffffffffu, top.qa >= top.qlim)) top.template drain<YS_SHARED>(key0, ys_addr, ys_glob, M);
+  }
 }
 
 template <int KREG>
@@ -164,7 +260,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
 // ---------------------------------------------------------------------------------------------
 // resident queries, streamed keys
 // ---------------------------------------------------------------------------------------------
-template <int NH, int BN, int KREG>
+template <int NH, int BN, int KREG, int QS>
 __global__ void __launch_bounds__((4 * NH + 2) * 32, 1)
 knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                   const __grid_constant__ CUtensorMap tm_y_hi, const __grid_constant__ CUtensorMap tm_y_lo,
@@ -179,7 +275,8 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
   const int num_tiles = (M + BN - 1) / BN;
   unsigned char* q_base = smem;                                    // [NH][num_kc] blocks
   unsigned char* ring = q_base + (size_t)NH * num_kc * kBlockBytes; // [stages] blocks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)stages * kKeyBlockBytes);
+  unsigned char* queue = ring + (size_t)stages * kKeyBlockBytes;      // [4 NH warps][QS slots][32 lanes] x 16 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(queue + (size_t)(4 * NH) * QS * 512);
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;
   const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;
@@ -264,6 +361,7 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     const float* ysq_b = ysq + (long long)b * M;
     TopK<KREG> top;
     top.init(sq_i);
+    if constexpr (QS > 0) top.queue_init(smem_u32(queue) + (uint32_t)warp * (QS * 512), lane, QS);
     // one threshold base per segment: min over all keys of |y|^2 (1 for normalised rows, 0 for all-zero rows)
     {
       float mn = INFINITY;
@@ -279,12 +377,16 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * NH + h) * BN;
       // keys past M were zero-filled by TMA (acc = 0) and would read |y|^2 out of bounds: stop at M
       const int ncols = min(BN, M - t * BN);
+      if constexpr (QS > 0) {
+        scan_tile_queued<KREG, false>(top, trow, t * BN, ncols, 0u, ysq_b, M);
+      } else {
 #pragma unroll 1
-      for (int cc = 0; cc * 8 < ncols; ++cc) {
-        uint32_t v[8];
-        tmem_ld8(trow + cc * 8, v);
-        tmem_ld_wait();
-        top.template scan8<false>(v, 0u, ysq_b + t * BN + cc * 8, ncols - cc * 8, t * BN + cc * 8);
+        for (int cc = 0; cc * 8 < ncols; ++cc) {
+          uint32_t v[8];
+          tmem_ld8(trow + cc * 8, v);
+          tmem_ld_wait();
+          top.template scan8<false>(v, 0u, ysq_b + t * BN + cc * 8, ncols - cc * 8, t * BN + cc * 8);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -304,7 +406,7 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
 // ---------------------------------------------------------------------------------------------
 // self-graph of a whole segment per CTA: every chunk loaded once, used as both operands
 // ---------------------------------------------------------------------------------------------
-template <int NH, int KREG>
+template <int NH, int KREG, int QS>
 __global__ void __launch_bounds__((4 * NH + 2) * 32, (NH == 1) ? 2 : 1)
 knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                 const float* __restrict__ xsq, long long* __restrict__ nn_idx, int* __restrict__ nn_idx32, int N, int C,
@@ -317,7 +419,8 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int num_kc = (C + BK - 1) / BK;
   unsigned char* ring = smem;
-  float* ysq_s = reinterpret_cast<float*>(ring + (size_t)stages * kStageBytes);  // [NH * BM]
+  unsigned char* queue = ring + (size_t)stages * kStageBytes;                     // [4 NH warps][QS][32] x 16 B
+  float* ysq_s = reinterpret_cast<float*>(queue + (size_t)(4 * NH) * QS * 512);  // [NH * BM]
   float* ymin_s = ysq_s + NH * BM;                                               // [4 * NH]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ymin_s + 8);
   const uint32_t bar_full = smem_u32(bars);
@@ -405,12 +508,21 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
     tcgen05_fence_after();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (h * NH) * BM;
     const uint32_t ys_addr = smem_u32(ysq_s);
+    if constexpr (QS > 0) {
+      top.queue_init(smem_u32(queue) + (uint32_t)warp * (QS * 512), lane, QS);
 #pragma unroll 1
-    for (int cc = 0; cc < NH * BM / 8; ++cc) {
-      uint32_t v[8];
-      tmem_ld8(trow + cc * 8, v);
-      tmem_ld_wait();
-      top.template scan8<true>(v, ys_addr + cc * 32, nullptr, 8, cc * 8);
+      for (int t = 0; t < NH; ++t) {
+        const int ncols = min(BM, N - t * BM);
+        if (ncols > 0) scan_tile_queued<KREG, true>(top, trow + t * BM, t * BM, ncols, ys_addr, nullptr, N);
+      }
+    } else {
+#pragma unroll 1
+      for (int cc = 0; cc < NH * BM / 8; ++cc) {
+        uint32_t v[8];
+        tmem_ld8(trow + cc * 8, v);
+        tmem_ld_wait();
+        top.template scan8<true>(v, ys_addr + cc * 32, nullptr, 8, cc * 8);
+      }
     }
     if (q < N) emit<KREG>(top, nn_idx, nn_idx32, ((long long)b * N + q) * k_out, k_out, stride);
   }
@@ -451,103 +563,123 @@ static int set_smem(Kernel kernel, bool* configured, const char* what) {
   return GRAFP_OK;
 }
 
-template <int NH, int BN, int KREG>
+constexpr int kQueueSlots = 6;  // candidate-queue depth per epilogue thread (16-byte quads); 0 selects the vote-gated scan
+
+template <int NH, int BN, int KREG, int QS>
 static int launch_stream(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& yh, const CUtensorMap& yl,
                          const float* xsq, const float* ysq, long long* nn_idx, int* nn_idx32, int B, int N, int M, int C,
                          int k_out, int stride, int stages, cudaStream_t s) {
   static bool configured = false;
-  if (int rc = set_smem(knn_stream_kernel<NH, BN, KREG>, &configured, "knn_stream")) return rc;
+  if (int rc = set_smem(knn_stream_kernel<NH, BN, KREG, QS>, &configured, "knn_stream")) return rc;
   const int num_kc = (C + BK - 1) / BK;
-  const size_t smem = (size_t)(NH * num_kc) * kBlockBytes + (size_t)stages * (2 * BN * BK * 2) + kMiscBytes;
+  const size_t smem = (size_t)(NH * num_kc) * kBlockBytes + (size_t)stages * (2 * BN * BK * 2) + (size_t)(4 * NH) * QS * 512 + kMiscBytes;
   dim3 grid((N + BM * NH - 1) / (BM * NH), B);
-  knn_stream_kernel<NH, BN, KREG><<<grid, (4 * NH + 2) * 32, smem, s>>>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, N, M, C,
-                                                                   k_out, stride, stages);
+  knn_stream_kernel<NH, BN, KREG, QS><<<grid, (4 * NH + 2) * 32, smem, s>>>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, N, M,
+                                                                       C, k_out, stride, stages);
   return check_launch("knn_stream");
 }
 
-template <int NH, int KREG>
+template <int NH, int KREG, int QS>
 static int launch_self(const CUtensorMap& xh, const CUtensorMap& xl, const float* xsq, long long* nn_idx, int* nn_idx32,
                        int B, int N, int C, int k_out, int stride, int stages, cudaStream_t s) {
   static bool configured = false;
-  if (int rc = set_smem(knn_self_kernel<NH, KREG>, &configured, "knn_self")) return rc;
-  const size_t smem = (size_t)stages * NH * kBlockBytes + kMiscBytes;
-  knn_self_kernel<NH, KREG><<<B, (4 * NH + 2) * 32, smem, s>>>(xh, xl, xsq, nn_idx, nn_idx32, N, C, k_out, stride, stages);
+  if (int rc = set_smem(knn_self_kernel<NH, KREG, QS>, &configured, "knn_self")) return rc;
+  const size_t smem = (size_t)stages * NH * kBlockBytes + (size_t)(4 * NH) * QS * 512 + kMiscBytes;
+  knn_self_kernel<NH, KREG, QS><<<B, (4 * NH + 2) * 32, smem, s>>>(xh, xl, xsq, nn_idx, nn_idx32, N, C, k_out, stride, stages);
   return check_launch("knn_self");
 }
 
-// plan: 0 = unsupported, 1 = self NH=1, 2 = self NH=2, 3 = stream NH=1, 4 = stream NH=2, 5 = stream NH=4 (64-key tiles)
-static int plan(int N, int M, int C, int K, int dtype, bool self, int* stages) {
-  if (dtype != GRAFP_F32 || C % 8 != 0 || C < BK || N < BM || M < BM || K < 1 || K > 8) return 0;
+// Kernel configuration for one shape.  kind: 0 unsupported, 1 self, 2 stream.
+struct Plan {
+  int kind = 0, nh = 0, bn = 0, stages = 0, qs = 0;
+};
+
+static Plan plan(int N, int M, int C, int K, int dtype, bool self) {
+  Plan p;
+  if (dtype != GRAFP_F32 || C % 8 != 0 || C < BK || N < BM || M < BM || K < 1 || K > 8) return p;
+  // development switches (A/B timing): GRAFP_KNN_EPI=vote keeps the vote-gated scan, GRAFP_KNN_NO_NH4 /
+  // GRAFP_KNN_BN128 pick the older tile shapes
+  static const bool vote = getenv("GRAFP_KNN_EPI") != nullptr && strcmp(getenv("GRAFP_KNN_EPI"), "vote") == 0;
+  static const bool no_nh4 = getenv("GRAFP_KNN_NO_NH4") != nullptr;
+  static const bool bn128 = getenv("GRAFP_KNN_BN128") != nullptr;
+  p.qs = vote ? 0 : kQueueSlots;
   const int num_kc = (C + BK - 1) / BK;
   const uint32_t budget = kSmemLimit - kMiscBytes;
+  auto queue_bytes = [&](int nh) { return (uint32_t)(4 * nh) * p.qs * 512u; };
   if (self && N <= 2 * BM) {
     const int nh = (N > BM) ? 2 : 1;
     // NH = 1: two CTAs per SM (<= 113 KB each); NH = 2: one CTA owns the SM
-    const uint32_t cap = (nh == 1) ? (113u * 1024 - kMiscBytes) : budget;
+    const uint32_t cap = ((nh == 1) ? (113u * 1024 - kMiscBytes) : budget) - queue_bytes(nh);
     int st = (int)(cap / (nh * kBlockBytes));
     if (st > num_kc) st = num_kc;
     if (st > kMaxStages) st = kMaxStages;
-    if (st < 1) return 0;
-    *stages = st;
-    return nh;
+    if (st < 1) return p;
+    p.kind = 1; p.nh = nh; p.bn = BM; p.stages = st;
+    return p;
   }
-  // 512 resident queries, 64-key tiles (TMEM: 2 sets x 4 tiles x 64 columns), 16 epilogue warps: the selection
-  // is issue/latency bound, so the extra warps matter more than the tile width.  Needs the 4 query blocks
-  // per channel chunk to fit: C <= 64.
-  static const bool no_nh4 = getenv("GRAFP_KNN_NO_NH4") != nullptr;  // development switch (A/B timing)
-  if (!no_nh4 && N >= 4 * BM && (uint32_t)(4 * num_kc) * kBlockBytes + 4 * (kBlockBytes / 2) <= budget) {
-    *stages = 4;
-    return 5;
+  // 512 resident queries, 64-key tiles (TMEM: 2 sets x 4 tiles x 64 columns), 16 epilogue warps.  Needs the 4 query
+  // blocks per channel chunk to fit next to the queue and >= 3 key stages: C <= 64.
+  if (!no_nh4 && N >= 4 * BM) {
+    const uint32_t resident = (uint32_t)(4 * num_kc) * kBlockBytes + queue_bytes(4);
+    if (resident + 3 * (kBlockBytes / 2) <= budget) {
+      int st = (int)((budget - resident) / (kBlockBytes / 2));
+      p.kind = 2; p.nh = 4; p.bn = 64; p.stages = st > 4 ? 4 : st;
+      return p;
+    }
   }
   for (int nh = (N > BM ? 2 : 1); nh >= 1; --nh) {
-    const uint32_t resident = (uint32_t)(nh * num_kc) * kBlockBytes;
+    const uint32_t resident = (uint32_t)(nh * num_kc) * kBlockBytes + queue_bytes(nh);
+    // 64-key tiles keep four ring stages where 128-key tiles would leave two
+    if (!bn128 && p.qs > 0 && resident + 2 * kBlockBytes <= budget && resident + 3 * kBlockBytes > budget) {
+      int st = (int)((budget - resident) / (kBlockBytes / 2));
+      p.kind = 2; p.nh = nh; p.bn = 64; p.stages = st > 6 ? 6 : st;
+      return p;
+    }
     if (resident + 2 * kBlockBytes > budget) continue;
     int st = (int)((budget - resident) / kBlockBytes);
-    if (st > 4) st = 4;
-    *stages = st;
-    return 2 + nh;
+    p.kind = 2; p.nh = nh; p.bn = BM; p.stages = st > 4 ? 4 : st;
+    return p;
   }
-  return 0;
+  return p;
 }
 
 }  // namespace tc2
 
-bool knn_tc2_supported(int N, int M, int C, int K, int dtype, bool self) {
-  int stages = 0;
-  return tc2::plan(N, M, C, K, dtype, self, &stages) != 0;
-}
+bool knn_tc2_supported(int N, int M, int C, int K, int dtype, bool self) { return tc2::plan(N, M, C, K, dtype, self).kind != 0; }
 
 int launch_knn_tc2(const void* xhi, const void* xlo, const float* xsq, const void* yhi, const void* ylo,
                    const float* ysq, long long* nn_idx, int* nn_idx32, int B, int N, int M, int C, int K, int k_out,
                    int stride, int dtype, bool self, cudaStream_t s) {
   using namespace tc2;
-  int stages = 0;
-  const int p = plan(N, M, C, K, dtype, self, &stages);
-  if (p == 0) {
+  const Plan p = plan(N, M, C, K, dtype, self);
+  if (p.kind == 0) {
     set_error("knn_tc2: unsupported configuration");
     return GRAFP_EUNSUPPORTED;
   }
-  const int key_rows = (p == 5) ? 64 : BM;
   CUtensorMap xh, xl, yh, yl;
-  if (!make_map_f16(&xh, xhi, B, N, C) || !make_map_f16(&xl, xlo, B, N, C) || !make_map_f16(&yh, yhi, B, M, C, key_rows) ||
-      !make_map_f16(&yl, ylo, B, M, C, key_rows)) {
+  if (!make_map_f16(&xh, xhi, B, N, C) || !make_map_f16(&xl, xlo, B, N, C) || !make_map_f16(&yh, yhi, B, M, C, p.bn) ||
+      !make_map_f16(&yl, ylo, B, M, C, p.bn)) {
     set_error("knn_tc2: cuTensorMapEncodeTiled failed (driver entry point unavailable or bad shape)");
     return GRAFP_EUNSUPPORTED;
   }
   const bool k3 = K <= 3;
-#define GRAFP_STREAM(NH_, BN_)                                                                                          \
-  (k3 ? launch_stream<NH_, BN_, 3>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, stages, s)    \
-      : launch_stream<NH_, BN_, 8>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, stages, s))
-  switch (p) {
-    case 1: return k3 ? launch_self<1, 3>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, stages, s)
-                      : launch_self<1, 8>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, stages, s);
-    case 2: return k3 ? launch_self<2, 3>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, stages, s)
-                      : launch_self<2, 8>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, stages, s);
-    case 3: return GRAFP_STREAM(1, 128);
-    case 4: return GRAFP_STREAM(2, 128);
-    default: return GRAFP_STREAM(4, 64);
-  }
+  const bool q = p.qs > 0;
+#define GRAFP_SELF_(NH_, KR_, QS_) launch_self<NH_, KR_, QS_>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, p.stages, s)
+#define GRAFP_STREAM_(NH_, BN_, KR_, QS_) \
+  launch_stream<NH_, BN_, KR_, QS_>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, p.stages, s)
+#define GRAFP_SELF(NH_) \
+  (q ? (k3 ? GRAFP_SELF_(NH_, 3, kQueueSlots) : GRAFP_SELF_(NH_, 8, kQueueSlots)) : (k3 ? GRAFP_SELF_(NH_, 3, 0) : GRAFP_SELF_(NH_, 8, 0)))
+#define GRAFP_STREAM(NH_, BN_)                                                                              \
+  (q ? (k3 ? GRAFP_STREAM_(NH_, BN_, 3, kQueueSlots) : GRAFP_STREAM_(NH_, BN_, 8, kQueueSlots))             \
+     : (k3 ? GRAFP_STREAM_(NH_, BN_, 3, 0) : GRAFP_STREAM_(NH_, BN_, 8, 0)))
+  if (p.kind == 1) return p.nh == 1 ? GRAFP_SELF(1) : GRAFP_SELF(2);
+  if (p.nh == 4) return GRAFP_STREAM(4, 64);
+  if (p.bn == 64) return p.nh == 2 ? GRAFP_STREAM(2, 64) : GRAFP_STREAM(1, 64);
+  return p.nh == 2 ? GRAFP_STREAM(2, 128) : GRAFP_STREAM(1, 128);
 #undef GRAFP_STREAM
+#undef GRAFP_SELF
+#undef GRAFP_STREAM_
+#undef GRAFP_SELF_
 }
 
 }  // namespace grafp
