@@ -1124,8 +1124,8 @@ namespace {
 
 // development switches: GRAFP_MR_FWD_VARIANT = 0 generic kernel, 1 / 2 / 4 fast kernel with that many items in
 // flight per thread, 8 (default) the cp.async-pipelined persistent kernel where it applies; GRAFP_MR_BWD_VARIANT = 0 two-kernel form, 1 / 2 / 4 fused cluster form,
-// 8 the deterministic gather form over the reverse graph (needs the workspace), 16 (default) the cluster form
-// with TMA bulk staging, 32 the deterministic shared-memory slice form (aggregate_bwd_slice.cu; measured slower:
+// 8 the deterministic gather form over the reverse graph (needs the workspace), 16 the cluster form with TMA bulk
+// staging, 17 (default) the same with the reductions issued in neighbour-slot order, 18 that with 16-CTA clusters, 32 the deterministic shared-memory slice form (aggregate_bwd_slice.cu; measured slower:
 // it is bound by the L1 / shared-memory pipe)
 // (read on every call - a getenv is nanoseconds next to a launch - so tests can switch kernels in-process)
 int fwd_variant() {
@@ -1134,7 +1134,7 @@ int fwd_variant() {
 }
 int bwd_variant() {
   const char* e = getenv("GRAFP_MR_BWD_VARIANT");
-  return e ? atoi(e) : 16;
+  return e ? atoi(e) : 17;
 }
 
 template <typename F>

@@ -157,8 +157,10 @@ struct TopK {
           "r"(bit)
         : "memory");
   }
-  // key0 = key id of the tile's column 0; keys >= M (TMA zero fill) are skipped
-  template <bool YS_SHARED>
+  // key0 = key id of the tile's column 0; keys >= M (TMA zero fill) are skipped.  YS_VEC: the four key norms of a
+  // quad are fetched with one 128-bit load next to the queue entry (the key set's norms are 16-byte aligned,
+  // M % 4 == 0), so the per-element path has no dependent global load.
+  template <bool YS_SHARED, bool YS_VEC>
   __device__ __forceinline__ void drain(int key0, uint32_t ys_addr, const float* ys_glob, int M) {
     uint32_t rd = q0;
     while (__any_sync(0xffffffffu, rd < qa)) {
@@ -169,6 +171,13 @@ struct TopK {
         const int quad = __ffs(qmask) - 1;  // lowest marked quad = oldest entry
         qmask &= qmask - 1u;
         const int key = key0 + 4 * quad;
+        float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+        if constexpr (YS_SHARED) {
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y0), "=f"(y1), "=f"(y2), "=f"(y3) : "r"(ys_addr + 4u * key));
+        } else if constexpr (YS_VEC) {  // key % 4 == 0 and M % 4 == 0: key < M implies key + 3 < M; clamped past the end
+          const float4 yv = __ldg(reinterpret_cast<const float4*>(ys_glob + min(key, M - 4)));
+          y0 = yv.x; y1 = yv.y; y2 = yv.z; y3 = yv.w;
+        }
         uint32_t em = (v0 > thr ? 1u : 0u) | (v1 > thr ? 2u : 0u) | (v2 > thr ? 4u : 0u) | (v3 > thr ? 8u : 0u);
         while (em != 0u) {  // lane-local, in column order; usually one element
           const int e = __ffs(em) - 1;
@@ -177,7 +186,13 @@ struct TopK {
           const float s = (e & 2) ? hi2 : lo2;
           const int kj = key + e;
           if (kj < M) {
-            const float yj = YS_SHARED ? lds_f32(ys_addr + 4u * kj) : __ldg(ys_glob + kj);
+            float yj;
+            if constexpr (YS_SHARED || YS_VEC) {
+              const float ylo = (e & 1) ? y1 : y0, yhi = (e & 1) ? y3 : y2;
+              yj = (e & 2) ? yhi : ylo;
+            } else {
+              yj = __ldg(ys_glob + kj);
+            }
             insert(__fadd_rn(fmaf(kM2, s, sq_i), yj), kj);
             update_thr();
           }
@@ -204,7 +219,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 
 // One tile (<= 128 accumulator columns, ncols of them backed by keys) of this thread's row through the
 // candidate queue: 16 columns per tcgen05.ld, four predicated quad pushes, one vote for the early drain.
-template <int KREG, bool YS_SHARED>
+template <int KREG, bool YS_SHARED, bool YS_VEC>
 __device__ __forceinline__ void scan_tile_queued(TopK<KREG>& top, uint32_t trow, int key0, int ncols, uint32_t ys_addr,
                                                  const float* ys_glob, int M) {
   uint32_t bq = 1u;
@@ -218,7 +233,7 @@ __device__ __forceinline__ void scan_tile_queued(TopK<KREG>& top, uint32_t trow,
     top.push4(v[8], v[9], v[10], v[11], bq << 2);
     top.push4(v[12], v[13], v[14], v[15], bq << 3);
     bq <<= 4;
-    if (c0 + 16 >= ncols || __any_sync(0xffffffffu, top.qa >= top.qlim)) top.template drain<YS_SHARED>(key0, ys_addr, ys_glob, M);
+    if (c0 + 16 >= ncols || __any_sync(0xffffffffu, top.qa >= top.qlim)) top.template drain<YS_SHARED, YS_VEC>(key0, ys_addr, ys_glob, M);
   }
 }
 
@@ -359,6 +374,7 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     const int q = m0 + h * BM + r;
     const float sq_i = (q < N) ? xsq[(long long)b * N + q] : 0.f;
     const float* ysq_b = ysq + (long long)b * M;
+    const bool ys_vec = (M & 3) == 0 && (reinterpret_cast<uintptr_t>(ysq) & 15) == 0;
     TopK<KREG> top;
     top.init(sq_i);
     if constexpr (QS > 0) top.queue_init(smem_u32(queue) + (uint32_t)warp * (QS * 512), lane, QS);
@@ -378,7 +394,8 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       // keys past M were zero-filled by TMA (acc = 0) and would read |y|^2 out of bounds: stop at M
       const int ncols = min(BN, M - t * BN);
       if constexpr (QS > 0) {
-        scan_tile_queued<KREG, false>(top, trow, t * BN, ncols, 0u, ysq_b, M);
+        if (ys_vec) scan_tile_queued<KREG, false, true>(top, trow, t * BN, ncols, 0u, ysq_b, M);
+        else scan_tile_queued<KREG, false, false>(top, trow, t * BN, ncols, 0u, ysq_b, M);
       } else {
 #pragma unroll 1
         for (int cc = 0; cc * 8 < ncols; ++cc) {
@@ -513,7 +530,7 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
 #pragma unroll 1
       for (int t = 0; t < NH; ++t) {
         const int ncols = min(BM, N - t * BM);
-        if (ncols > 0) scan_tile_queued<KREG, true>(top, trow + t * BM, t * BM, ncols, ys_addr, nullptr, N);
+        if (ncols > 0) scan_tile_queued<KREG, true, false>(top, trow + t * BM, t * BM, ncols, ys_addr, nullptr, N);
       }
     } else {
 #pragma unroll 1
@@ -602,7 +619,11 @@ static Plan plan(int N, int M, int C, int K, int dtype, bool self) {
   static const bool vote = getenv("GRAFP_KNN_EPI") != nullptr && strcmp(getenv("GRAFP_KNN_EPI"), "vote") == 0;
   static const bool no_nh4 = getenv("GRAFP_KNN_NO_NH4") != nullptr;
   static const bool bn128 = getenv("GRAFP_KNN_BN128") != nullptr;
-  p.qs = vote ? 0 : kQueueSlots;
+  // the whole-segment self kernels select once, after the MMAs: measured 83 / 39 us with the vote-gated scan against
+  // 96 / 47 us with the queue (N <= 256 keys leave the thresholds no time to tighten), so they keep the former
+  static const bool self_queue = getenv("GRAFP_KNN_SELF_QUEUE") != nullptr;
+  const bool self_kernel = self && N <= 2 * BM;
+  p.qs = (vote || (self_kernel && !self_queue)) ? 0 : kQueueSlots;
   const int num_kc = (C + BK - 1) / BK;
   const uint32_t budget = kSmemLimit - kMiscBytes;
   auto queue_bytes = [&](int nh) { return (uint32_t)(4 * nh) * p.qs * 512u; };
@@ -629,8 +650,8 @@ static Plan plan(int N, int M, int C, int K, int dtype, bool self) {
   }
   for (int nh = (N > BM ? 2 : 1); nh >= 1; --nh) {
     const uint32_t resident = (uint32_t)(nh * num_kc) * kBlockBytes + queue_bytes(nh);
-    // 64-key tiles keep four ring stages where 128-key tiles would leave two
-    if (!bn128 && p.qs > 0 && resident + 2 * kBlockBytes <= budget && resident + 3 * kBlockBytes > budget) {
+    // 64-key tiles (16 KB stages) where fewer than three 128-key stages would fit next to the queue
+    if (!bn128 && p.qs > 0 && resident + 2 * (kBlockBytes / 2) <= budget && resident + 3 * kBlockBytes > budget) {
       int st = (int)((budget - resident) / (kBlockBytes / 2));
       p.kind = 2; p.nh = nh; p.bn = 64; p.stages = st > 6 ? 6 : st;
       return p;
