@@ -103,7 +103,8 @@ size_t grafp_knn_workspace_bytes(int B, int N, int M, int C, int K, int dtype) {
   const size_t qy = align_up((size_t)B * M * C * sizeof(float), 1024);
   const size_t sx = align_up((size_t)B * N * sizeof(float), 1024);
   const size_t sy = align_up((size_t)B * M * sizeof(float), 1024);
-  return 2 * (qx + qy) + sx + sy + 1024;  // hi+lo (or x_hat) for queries and keys, squared norms, base alignment
+  // hi+lo (or x_hat) for queries and keys, squared norms, round hand-over bounds (K > 16), base alignment
+  return 2 * (qx + qy) + sx + sy + 2 * sx + 1024;
 }
 
 int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn_idx, int32_t* nn_idx32, int B, int N,
@@ -124,7 +125,7 @@ int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn
   { int rc = require_device_ptr("grafp_knn_fwd", "nn_idx", nn_idx); if (rc) return rc; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
-  // tensor-core kernels: f16x3 (knn_tc2.cu, K <= 8) preferred, tf32x3 (knn_tc.cu) for the rest of the envelope
+  // tensor-core kernels: f16x3 (knn_tc2.cu, K <= 64) preferred, tf32x3 (knn_tc.cu) for the rest of the envelope
   // (f16x3 needs |x| <= 1, i.e. the normalised features DenseDilatedKnnGraph always passes)
   const bool tc2_ok = relpos == nullptr && normalize != 0 && knn_tc2_supported(N, M, C, (int)K, dtype, y == nullptr);
   const bool tc1_ok = relpos == nullptr && knn_tc_supported(N, M, C, (int)K, dtype);
@@ -146,6 +147,7 @@ int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn
   float* y_lo = reinterpret_cast<float*>(base + 2 * qx + qy);
   float* x_sq = reinterpret_cast<float*>(base + 2 * qx + 2 * qy);
   float* y_sq = reinterpret_cast<float*>(base + 2 * qx + 2 * qy + sx);
+  void* bounds = base + 2 * qx + 2 * qy + sx + align_up((size_t)B * M * sizeof(float), 1024);
 
   const int mode = use_tc2 ? 3 : (use_tc ? (dtype == GRAFP_F32 ? 1 : 2) : 0);
   int rc;
@@ -165,7 +167,7 @@ int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn
     g_knn_algo = "tcgen05";
     g_knn_variant = "f16x3";
     return launch_knn_tc2(x_hi, x_lo, x_sq, y_hi, y_lo, y_sq, reinterpret_cast<long long*>(nn_idx), nn_idx32, B, N, M, C,
-                          (int)K, k_out, stride, dtype, y == nullptr, s);
+                          (int)K, k_out, stride, dtype, y == nullptr, bounds, s);
   }
   if (use_tc) {
     g_knn_algo = "tcgen05";

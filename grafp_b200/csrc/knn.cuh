@@ -23,11 +23,12 @@ int launch_knn_tc(const void* xhi, const void* xlo, const float* xsq, const void
                   const float* ysq, const float* relpos, long long* nn_idx, int* nn_idx32, int B, int N, int M, int C,
                   int K, int k_out, int stride, int dtype, cudaStream_t s);
 
-// second-generation tensor-core path (knn_tc2.cu): fp16 hi/lo planes, kind::f16, K <= 8.
+// second-generation tensor-core path (knn_tc2.cu): fp16 hi/lo planes, kind::f16, K <= 64 (K > 16 in rounds of 16
+// ranks; `bounds` = B * N * 8 bytes of scratch for the hand-over between rounds).
 // `self`: the keys are the queries (y == NULL).
 bool knn_tc2_supported(int N, int M, int C, int K, int dtype, bool self);
 int launch_knn_tc2(const void* xhi, const void* xlo, const float* xsq, const void* yhi, const void* ylo,
                    const float* ysq, long long* nn_idx, int* nn_idx32, int B, int N, int M, int C, int K, int k_out,
-                   int stride, int dtype, bool self, cudaStream_t s);
+                   int stride, int dtype, bool self, void* bounds, cudaStream_t s);
 
 }  // namespace grafp

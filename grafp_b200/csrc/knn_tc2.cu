@@ -66,6 +66,8 @@ struct TopK {
   float d[KREG];
   int id[KREG];
   float sq_i;  // |x_i|^2
+  float lo_d;  // K > 16 runs in rounds of 16 ranks: only keys with (dist, id) > (lo_d, lo_id), the last entry of the
+  int lo_id;   // previous round, may enter the list (-inf / -1: no bound)
   float base;  // (sq_i + a lower bound of |y_j|^2 over the current key tile - slack) * 2^23
   float thr;   // candidate iff acc > thr
   static constexpr float kHalfScale2 = 0.5f * kPlaneScale * kPlaneScale;
@@ -73,7 +75,7 @@ struct TopK {
   __device__ __forceinline__ void init(float sq) {
 #pragma unroll
     for (int p = 0; p < KREG; ++p) { d[p] = INFINITY; id[p] = 0; }
-    sq_i = sq; base = 0.f; thr = -INFINITY;
+    sq_i = sq; base = 0.f; thr = -INFINITY; lo_d = -INFINITY; lo_id = -1;
   }
   // dist < d[K-1] implies sq_i + kM2*acc + ymin < d[K-1] + 1e-6 (fp32 evaluation error of dist is < 5e-7 for
   // normalised features); 4e-6 also covers the rounding of this expression itself.
@@ -115,8 +117,10 @@ struct TopK {
           // warp-uniform address; columns past the last key (TMA zero fill) are pushed to +inf
           const float yj = YS_SHARED ? lds_f32(ys_addr + 4 * j) : (j < nvalid ? __ldg(ys_glob + j) : INFINITY);
           const float dist = __fadd_rn(fmaf(kM2, __uint_as_float(v[j]), sq_i), yj);
-          insert(dist, key0 + j);
-          update_thr();
+          if (dist > lo_d || (dist == lo_d && key0 + j > lo_id)) {
+            insert(dist, key0 + j);
+            update_thr();
+          }
         }
       }
     }
@@ -193,8 +197,11 @@ struct TopK {
             } else {
               yj = __ldg(ys_glob + kj);
             }
-            insert(__fadd_rn(fmaf(kM2, s, sq_i), yj), kj);
-            update_thr();
+            const float dist = __fadd_rn(fmaf(kM2, s, sq_i), yj);
+            if (dist > lo_d || (dist == lo_d && kj > lo_id)) {
+              insert(dist, kj);
+              update_thr();
+            }
           }
         }
       }
@@ -237,15 +244,33 @@ __device__ __forceinline__ void scan_tile_queued(TopK<KREG>& top, uint32_t trow,
   }
 }
 
+// ranks rank0 .. rank0 + KREG - 1 of the row's list; every `stride`-th global rank is written (dilation fused)
 template <int KREG>
-__device__ __forceinline__ void emit(const TopK<KREG>& top, long long* nn_idx, int* nn_idx32, long long o, int k_out, int stride) {
+__device__ __forceinline__ void emit(const TopK<KREG>& top, long long* nn_idx, int* nn_idx32, long long o, int k_out, int stride,
+                                     int rank0) {
 #pragma unroll
   for (int p = 0; p < KREG; ++p) {
-    if (p % stride == 0 && p / stride < k_out) {
-      nn_idx[o + p / stride] = top.id[p];
-      if (nn_idx32 != nullptr) nn_idx32[o + p / stride] = top.id[p];
+    const int g = rank0 + p;
+    const int slot = g / stride;
+    if (g - slot * stride == 0 && slot < k_out) {
+      nn_idx[o + slot] = top.id[p];
+      if (nn_idx32 != nullptr) nn_idx32[o + slot] = top.id[p];
     }
   }
+}
+
+// round hand-over: the last list entry of round r is the exclusive lower bound of round r + 1
+template <int KREG>
+__device__ __forceinline__ void load_bound(TopK<KREG>& top, const float2* bounds, long long row, int rank0) {
+  if (bounds != nullptr && rank0 > 0) {
+    const float2 v = bounds[row];
+    top.lo_d = v.x;
+    top.lo_id = __float_as_int(v.y);
+  }
+}
+template <int KREG>
+__device__ __forceinline__ void store_bound(const TopK<KREG>& top, float2* bounds, long long row, int more_rounds) {
+  if (bounds != nullptr && more_rounds) bounds[row] = make_float2(top.d[KREG - 1], __int_as_float(top.id[KREG - 1]));
 }
 
 // three MMAs per 16-channel step over one 64-channel block pair (A block: 128 rows, B block: BN rows)
@@ -280,7 +305,8 @@ __global__ void __launch_bounds__((4 * NH + 2) * 32, 1)
 knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                   const __grid_constant__ CUtensorMap tm_y_hi, const __grid_constant__ CUtensorMap tm_y_lo,
                   const float* __restrict__ xsq, const float* __restrict__ ysq, long long* __restrict__ nn_idx,
-                  int* __restrict__ nn_idx32, int N, int M, int C, int k_out, int stride, int stages) {
+                  int* __restrict__ nn_idx32, int N, int M, int C, int k_out, int stride, int stages,
+                  float2* bounds, int rank0, int more_rounds) {
   constexpr int kProducerWarp = 4 * NH, kMmaWarp = 4 * NH + 1;
   constexpr uint32_t kTmemCols = 2 * NH * BN;  // two accumulator sets of NH tiles, BN keys wide
   constexpr uint32_t kKeyBlockBytes = 2 * BN * BK * 2;  // hi + lo plane of BN keys x 64 channels
@@ -377,6 +403,7 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     const bool ys_vec = (M & 3) == 0 && (reinterpret_cast<uintptr_t>(ysq) & 15) == 0;
     TopK<KREG> top;
     top.init(sq_i);
+    if (q < N) load_bound<KREG>(top, bounds, (long long)b * N + q, rank0);
     if constexpr (QS > 0) top.queue_init(smem_u32(queue) + (uint32_t)warp * (QS * 512), lane, QS);
     // one threshold base per segment: min over all keys of |y|^2 (1 for normalised rows, 0 for all-zero rows)
     {
@@ -409,7 +436,10 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
     }
-    if (q < N) emit<KREG>(top, nn_idx, nn_idx32, ((long long)b * N + q) * k_out, k_out, stride);
+    if (q < N) {
+      emit<KREG>(top, nn_idx, nn_idx32, ((long long)b * N + q) * k_out, k_out, stride, rank0);
+      store_bound<KREG>(top, bounds, (long long)b * N + q, more_rounds);
+    }
   }
 
   tcgen05_fence_before();
@@ -427,7 +457,7 @@ template <int NH, int KREG, int QS>
 __global__ void __launch_bounds__((4 * NH + 2) * 32, (NH == 1) ? 2 : 1)
 knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
                 const float* __restrict__ xsq, long long* __restrict__ nn_idx, int* __restrict__ nn_idx32, int N, int C,
-                int k_out, int stride, int stages) {
+                int k_out, int stride, int stages, float2* bounds, int rank0, int more_rounds) {
   constexpr int kEpilogueThreads = 128 * NH;
   constexpr int kProducerWarp = 4 * NH, kMmaWarp = 4 * NH + 1;
   constexpr uint32_t kTmemCols = NH * NH * BM;
@@ -515,6 +545,7 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
     asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
     TopK<KREG> top;
     top.init(sq_i);
+    if (q < N) load_bound<KREG>(top, bounds, (long long)b * N + q, rank0);
     {
       float mn = ymin_s[0];
 #pragma unroll
@@ -541,7 +572,10 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
         top.template scan8<true>(v, ys_addr + cc * 32, nullptr, 8, cc * 8);
       }
     }
-    if (q < N) emit<KREG>(top, nn_idx, nn_idx32, ((long long)b * N + q) * k_out, k_out, stride);
+    if (q < N) {
+      emit<KREG>(top, nn_idx, nn_idx32, ((long long)b * N + q) * k_out, k_out, stride, rank0);
+      store_bound<KREG>(top, bounds, (long long)b * N + q, more_rounds);
+    }
   }
 
   tcgen05_fence_before();
@@ -582,27 +616,33 @@ static int set_smem(Kernel kernel, bool* configured, const char* what) {
 
 constexpr int kQueueSlots = 6;  // candidate-queue depth per epilogue thread (16-byte quads); 0 selects the vote-gated scan
 
+struct Round {
+  float2* bounds;
+  int rank0, more;
+};
+
 template <int NH, int BN, int KREG, int QS>
 static int launch_stream(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& yh, const CUtensorMap& yl,
                          const float* xsq, const float* ysq, long long* nn_idx, int* nn_idx32, int B, int N, int M, int C,
-                         int k_out, int stride, int stages, cudaStream_t s) {
+                         int k_out, int stride, int stages, Round r, cudaStream_t s) {
   static bool configured = false;
   if (int rc = set_smem(knn_stream_kernel<NH, BN, KREG, QS>, &configured, "knn_stream")) return rc;
   const int num_kc = (C + BK - 1) / BK;
   const size_t smem = (size_t)(NH * num_kc) * kBlockBytes + (size_t)stages * (2 * BN * BK * 2) + (size_t)(4 * NH) * QS * 512 + kMiscBytes;
   dim3 grid((N + BM * NH - 1) / (BM * NH), B);
   knn_stream_kernel<NH, BN, KREG, QS><<<grid, (4 * NH + 2) * 32, smem, s>>>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, N, M,
-                                                                       C, k_out, stride, stages);
+                                                                       C, k_out, stride, stages, r.bounds, r.rank0, r.more);
   return check_launch("knn_stream");
 }
 
 template <int NH, int KREG, int QS>
 static int launch_self(const CUtensorMap& xh, const CUtensorMap& xl, const float* xsq, long long* nn_idx, int* nn_idx32,
-                       int B, int N, int C, int k_out, int stride, int stages, cudaStream_t s) {
+                       int B, int N, int C, int k_out, int stride, int stages, Round r, cudaStream_t s) {
   static bool configured = false;
   if (int rc = set_smem(knn_self_kernel<NH, KREG, QS>, &configured, "knn_self")) return rc;
   const size_t smem = (size_t)stages * NH * kBlockBytes + (size_t)(4 * NH) * QS * 512 + kMiscBytes;
-  knn_self_kernel<NH, KREG, QS><<<B, (4 * NH + 2) * 32, smem, s>>>(xh, xl, xsq, nn_idx, nn_idx32, N, C, k_out, stride, stages);
+  knn_self_kernel<NH, KREG, QS><<<B, (4 * NH + 2) * 32, smem, s>>>(xh, xl, xsq, nn_idx, nn_idx32, N, C, k_out, stride, stages,
+                                                               r.bounds, r.rank0, r.more);
   return check_launch("knn_self");
 }
 
@@ -613,7 +653,7 @@ struct Plan {
 
 static Plan plan(int N, int M, int C, int K, int dtype, bool self) {
   Plan p;
-  if (dtype != GRAFP_F32 || C % 8 != 0 || C < BK || N < BM || M < BM || K < 1 || K > 8) return p;
+  if (dtype != GRAFP_F32 || C % 8 != 0 || C < BK || N < BM || M < BM || K < 1 || K > 64) return p;
   // development switches (A/B timing): GRAFP_KNN_EPI=vote keeps the vote-gated scan, GRAFP_KNN_NO_NH4 /
   // GRAFP_KNN_BN128 pick the older tile shapes
   static const bool vote = getenv("GRAFP_KNN_EPI") != nullptr && strcmp(getenv("GRAFP_KNN_EPI"), "vote") == 0;
@@ -623,7 +663,7 @@ static Plan plan(int N, int M, int C, int K, int dtype, bool self) {
   // 96 / 47 us with the queue (N <= 256 keys leave the thresholds no time to tighten), so they keep the former
   static const bool self_queue = getenv("GRAFP_KNN_SELF_QUEUE") != nullptr;
   const bool self_kernel = self && N <= 2 * BM;
-  p.qs = (vote || (self_kernel && !self_queue)) ? 0 : kQueueSlots;
+  p.qs = (K <= 8 && (vote || (self_kernel && !self_queue))) ? 0 : kQueueSlots;  // K > 8 (16-entry lists) is queue-only
   const int num_kc = (C + BK - 1) / BK;
   const uint32_t budget = kSmemLimit - kMiscBytes;
   auto queue_bytes = [&](int nh) { return (uint32_t)(4 * nh) * p.qs * 512u; };
@@ -668,9 +708,37 @@ static Plan plan(int N, int M, int C, int K, int dtype, bool self) {
 
 bool knn_tc2_supported(int N, int M, int C, int K, int dtype, bool self) { return tc2::plan(N, M, C, K, dtype, self).kind != 0; }
 
+namespace tc2 {
+
+struct Args {
+  const CUtensorMap *xh, *xl, *yh, *yl;
+  const float *xsq, *ysq;
+  long long* nn_idx;
+  int* nn_idx32;
+  int B, N, M, C, k_out, stride;
+  cudaStream_t s;
+};
+
+template <int KR, int QS>
+static int launch_planned(const Plan& p, const Args& a, Round r) {
+#define GRAFP_SELF(NH_) launch_self<NH_, KR, QS>(*a.xh, *a.xl, a.xsq, a.nn_idx, a.nn_idx32, a.B, a.N, a.C, a.k_out, a.stride, p.stages, r, a.s)
+#define GRAFP_STREAM(NH_, BN_)                                                                                          \
+  launch_stream<NH_, BN_, KR, QS>(*a.xh, *a.xl, *a.yh, *a.yl, a.xsq, a.ysq, a.nn_idx, a.nn_idx32, a.B, a.N, a.M, a.C, a.k_out, \
+                                  a.stride, p.stages, r, a.s)
+  if (p.kind == 1) return p.nh == 1 ? GRAFP_SELF(1) : GRAFP_SELF(2);
+  if (p.nh == 4) return GRAFP_STREAM(4, 64);
+  if (p.bn == 64) return p.nh == 2 ? GRAFP_STREAM(2, 64) : GRAFP_STREAM(1, 64);
+  return p.nh == 2 ? GRAFP_STREAM(2, 128) : GRAFP_STREAM(1, 128);
+#undef GRAFP_STREAM
+#undef GRAFP_SELF
+}
+
+}  // namespace tc2
+
+// `bounds`: B * N float2 of scratch, used when K > 16 (rounds of 16 ranks hand their last entry to the next round)
 int launch_knn_tc2(const void* xhi, const void* xlo, const float* xsq, const void* yhi, const void* ylo,
                    const float* ysq, long long* nn_idx, int* nn_idx32, int B, int N, int M, int C, int K, int k_out,
-                   int stride, int dtype, bool self, cudaStream_t s) {
+                   int stride, int dtype, bool self, void* bounds, cudaStream_t s) {
   using namespace tc2;
   const Plan p = plan(N, M, C, K, dtype, self);
   if (p.kind == 0) {
@@ -683,24 +751,22 @@ int launch_knn_tc2(const void* xhi, const void* xlo, const float* xsq, const voi
     set_error("knn_tc2: cuTensorMapEncodeTiled failed (driver entry point unavailable or bad shape)");
     return GRAFP_EUNSUPPORTED;
   }
-  const bool k3 = K <= 3;
-  const bool q = p.qs > 0;
-#define GRAFP_SELF_(NH_, KR_, QS_) launch_self<NH_, KR_, QS_>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, p.stages, s)
-#define GRAFP_STREAM_(NH_, BN_, KR_, QS_) \
-  launch_stream<NH_, BN_, KR_, QS_>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, p.stages, s)
-#define GRAFP_SELF(NH_) \
-  (q ? (k3 ? GRAFP_SELF_(NH_, 3, kQueueSlots) : GRAFP_SELF_(NH_, 8, kQueueSlots)) : (k3 ? GRAFP_SELF_(NH_, 3, 0) : GRAFP_SELF_(NH_, 8, 0)))
-#define GRAFP_STREAM(NH_, BN_)                                                                              \
-  (q ? (k3 ? GRAFP_STREAM_(NH_, BN_, 3, kQueueSlots) : GRAFP_STREAM_(NH_, BN_, 8, kQueueSlots))             \
-     : (k3 ? GRAFP_STREAM_(NH_, BN_, 3, 0) : GRAFP_STREAM_(NH_, BN_, 8, 0)))
-  if (p.kind == 1) return p.nh == 1 ? GRAFP_SELF(1) : GRAFP_SELF(2);
-  if (p.nh == 4) return GRAFP_STREAM(4, 64);
-  if (p.bn == 64) return p.nh == 2 ? GRAFP_STREAM(2, 64) : GRAFP_STREAM(1, 64);
-  return p.nh == 2 ? GRAFP_STREAM(2, 128) : GRAFP_STREAM(1, 128);
-#undef GRAFP_STREAM
-#undef GRAFP_SELF
-#undef GRAFP_STREAM_
-#undef GRAFP_SELF_
+  const Args a = {&xh, &xl, &yh, &yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, s};
+  const Round one = {nullptr, 0, 0};
+  if (K <= 3) return p.qs > 0 ? launch_planned<3, kQueueSlots>(p, a, one) : launch_planned<3, 0>(p, a, one);
+  if (K <= 8) return p.qs > 0 ? launch_planned<8, kQueueSlots>(p, a, one) : launch_planned<8, 0>(p, a, one);
+  // 16-entry register lists; K = 17..64 takes ceil(K / 16) passes over the keys (the Gram tiles are recomputed: the
+  // tensor pipe is far from busy, the selection is what costs), each pass bounded below by the previous one's last entry
+  const int rounds = (K + 15) / 16;
+  if (rounds > 1 && bounds == nullptr) {
+    set_error("knn_tc2: K > 16 needs the bounds scratch");
+    return GRAFP_EWORKSPACE;
+  }
+  for (int r = 0; r < rounds; ++r) {
+    const Round rd = {static_cast<float2*>(bounds), 16 * r, r + 1 < rounds ? 1 : 0};
+    if (int rc = launch_planned<16, kQueueSlots>(p, a, rd)) return rc;
+  }
+  return GRAFP_OK;
 }
 
 }  // namespace grafp

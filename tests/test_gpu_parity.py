@@ -128,6 +128,13 @@ TC_CASES = [
     (2, 72, 640, 0, 4, 2),      # channel tail inside the second 64-wide chunk
     (2, 64, 512, 300, 4, 1),    # separate key set with a ragged last key tile
     (2, 320, 256, 256, 3, 1),   # separate key set, 5 resident channel chunks
+    (2, 64, 1024, 0, 16, 1),    # K = 16: one pass with 16-entry register lists (configs[3] stress shape)
+    (2, 64, 1024, 0, 16, 4),    # K = 64: four bounded rounds of 16 ranks, dilation 4
+    (2, 128, 512, 0, 9, 2),     # K = 18: two rounds, the second only needs two ranks
+    (2, 64, 512, 300, 16, 2),   # K = 32 against a separate, ragged key set
+    (2, 256, 256, 0, 16, 1),    # whole-segment self kernel (two halves) with 16-entry lists
+    (2, 512, 128, 0, 12, 2),    # whole-segment self kernel (one half), K = 24
+    (2, 256, 1024, 0, 16, 3),   # K = 48, one resident query block, 4 channel chunks
 ]
 
 
@@ -140,7 +147,7 @@ def test_knn_tensor_core_path_vs_oracle(B, C, N, M, k, d, algo):
     assert ops.knn_last_algo() == "tcgen05"
     if algo == _native.KNN_TC_TF32:
         assert ops.knn_last_variant() == "tf32x3"
-    elif k * d <= 8 and C >= 64 and C % 8 == 0 and N >= 128 and (M == 0 or M >= 128):
+    elif k * d <= 64 and C >= 64 and C % 8 == 0 and N >= 128 and (M == 0 or M >= 128):
         assert ops.knn_last_variant() == "f16x3", (B, C, N, M, k, d)
     assert_knn_ok(x, nn_idx, k, d, y, what=f"tc N={N} M={M} C={C} k={k} d={d} {ops.knn_last_variant()}")
 
