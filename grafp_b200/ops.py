@@ -501,6 +501,33 @@ class _ConvBatchNormTrain(torch.autograd.Function):
         return (dx, (grad_out if ctx.has_res else None), dcw, dcb, dweight, dbias, None, None, None, None, None, None)
 
 
+def _fold_eval_ok(x: torch.Tensor, bn: torch.nn.BatchNorm2d) -> bool:
+    return (os.environ.get("GRAFP_FOLD_BN", "1") != "0" and not bn.training and not torch.is_grad_enabled()
+            and x.is_cuda and x.dtype == torch.float32 and bn.track_running_stats and bn.running_var is not None
+            and bn.affine)
+
+
+def _folded_conv_bn_eval(x, cw, cb, bn, relu, residual, conv_args):
+    """Inference form of conv -> BatchNorm(eval) [-> ReLU | + residual] (generate.py's path):
+    the BatchNorm's affine map is folded into the convolution's weight and bias (w' = w * g / sqrt(var + eps),
+    b' = (b - mean) * g / sqrt(var + eps) + beta), so the layer is one cuDNN convolution - with the ReLU in its
+    epilogue where cuDNN offers that - instead of three passes over the activations."""
+    stride, padding, dilation, groups = conv_args
+    scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+    w = cw * scale.view(-1, 1, 1, 1)
+    b = bn.bias - bn.running_mean * scale if cb is None else (cb - bn.running_mean) * scale + bn.bias
+    if relu and residual is None and os.environ.get("GRAFP_FOLD_BN", "1") != "2":
+        try:
+            y = torch.cudnn_convolution_relu(x, w, b, list(stride), list(padding), list(dilation), groups)
+            return y if _is_rows(y) else as_rows(y)
+        except RuntimeError:
+            pass
+    y = torch.nn.functional.conv2d(x, w, b, stride, padding, dilation, groups)
+    if residual is not None:
+        y = y.add_(residual)
+    return y.relu_() if relu else y
+
+
 def conv_batch_norm_act(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu: bool = False,
                         residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``relu(bn(conv(x)))`` / ``bn(conv(x)) + residual`` / ``bn(conv(x))`` for node rows (B, C, N, 1).
@@ -509,6 +536,10 @@ def conv_batch_norm_act(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.nn.Bat
     node (see _ConvBatchNormTrain); otherwise the convolution runs as the module and the rest goes through
     :func:`batch_norm_act`, which applies its own envelope checks.
     """
+    if (_fold_eval_ok(x, bn) and conv.padding_mode == "zeros" and isinstance(conv.padding, tuple) and not conv.transposed
+            and conv.weight.dtype == torch.float32):
+        return _folded_conv_bn_eval(x, conv.weight, conv.bias, bn, relu, residual,
+                                    (conv.stride, conv.padding, conv.dilation, conv.groups))
     ok = (conv.bias is not None and conv.kernel_size == (1, 1) and conv.padding_mode == "zeros"
           and isinstance(conv.padding, tuple) and not conv.transposed)
     if not ok:
@@ -520,6 +551,8 @@ def conv_batch_norm_act(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.nn.Bat
 def pointwise_conv_batch_norm_act(x, cw, cb, bn, relu=False, residual=None, conv_args=((1, 1), (0, 0), (1, 1), 1)):
     """:func:`conv_batch_norm_act` on explicit 1x1 convolution weights ``cw`` (Cout, Cin / groups, 1, 1) and bias."""
     C = cw.shape[0]
+    if _fold_eval_ok(x, bn) and cw.dtype == torch.float32:
+        return _folded_conv_bn_eval(x, cw, cb, bn, relu, residual, conv_args)
     fused = (os.environ.get("GRAFP_FUSED_BN", "1") != "0" and bn.training and x.is_cuda and x.dtype == torch.float32
              and _is_rows(x) and cb is not None
              and bn.affine and bn.momentum is not None and not (relu and residual is not None)

@@ -155,5 +155,9 @@ if __name__ == "__main__":
         edge_rows()
     if "stress" in what:
         stress()
+    if "stress1" in what:   # one launch set for ncu captures
+        x = torch.randn(256, 64, 1024, 1, device=dev).contiguous(memory_format=torch.channels_last)
+        ops.knn_graph(x, 16, 1)
+        torch.cuda.synchronize()
     if "fp" in what:
         fingerprints()
