@@ -537,7 +537,11 @@ __device__ __forceinline__ void k3_mbar_wait(uint32_t bar, uint32_t parity) {
 // JORDER: phase 2 walks the neighbour slots j = 0..k-1 in a fixed order instead of the winners of the item's four
 // channels, so the lanes that share a source row issue their red.v4 to the SAME target row in the same instruction
 // (contiguous 256-byte runs that the LSU / L2 merge per sector) and an item issues at most k-1 of them.
-template <bool I64, bool JORDER>
+// LEAN: the routed half of grad_out (g[.., 2c+1]) stays in registers between the phases instead of being read from
+// shared memory twice, and the device-wide fence in front of the cluster barrier is dropped (barrier.cluster
+// arrive.release / wait.acquire already orders the phase-1 stores of every CTA of the cluster before the
+// phase-2 reductions of every other one).
+template <bool I64, bool JORDER, bool LEAN>
 __global__ void __launch_bounds__(kFusedThreads, 3)
 mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* __restrict__ argmax,
                                     const void* __restrict__ nbr, float* __restrict__ grad_x, int N, int C, int k,
@@ -581,6 +585,7 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
   if (nrows > 0) k3_mbar_wait(bar, 0);
 
   // phase 1: dense part of grad_x for this CTA's rows (everything it needs is in shared memory or registers)
+  float keep[LEAN ? kItems : 1][4];
 #pragma unroll
   for (int u = 0; u < kItems; ++u) {
     const int it = threadIdx.x + u * kFusedThreads;
@@ -591,6 +596,7 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
       const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
       const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
       const float g0[4] = {ga.x, ga.z, gb.x, gb.z}, g1[4] = {ga.y, ga.w, gb.y, gb.w};
+      if constexpr (LEAN) { keep[u][0] = g1[0]; keep[u][1] = g1[1]; keep[u][2] = g1[2]; keep[u][3] = g1[3]; }
       float r[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -600,7 +606,7 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
       *reinterpret_cast<float4*>(gxb + (long long)n * C + c) = make_float4(r[0], r[1], r[2], r[3]);
     }
   }
-  __threadfence();
+  if constexpr (!LEAN) __threadfence();
   cluster_sync_all();
 
   // phase 2: route g[.., 2c+1] to the winning neighbour rows of this segment (L2-resident, just written)
@@ -611,9 +617,14 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
       const int rl = it >> cv_shift;
       const int n = row0 + rl;
       const int c = (it & (cv - 1)) * 4;
-      const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
-      const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
-      const float g1[4] = {ga.y, ga.w, gb.y, gb.w};
+      float g1[4];
+      if constexpr (LEAN) {
+        g1[0] = keep[u][0]; g1[1] = keep[u][1]; g1[2] = keep[u][2]; g1[3] = keep[u][3];
+      } else {
+        const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
+        const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
+        g1[0] = ga.y; g1[1] = ga.w; g1[2] = gb.y; g1[3] = gb.w;
+      }
       int a[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) a[e] = (am[u] >> (8 * e)) & 0xff;
@@ -656,7 +667,7 @@ namespace {
 int bwd_variant();  // development switch, defined with the dispatchers below
 }
 
-template <bool I64, bool JORDER>
+template <bool I64, bool JORDER, bool LEAN>
 int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void* nbr, float* grad_x, int B, int N, int C,
                               int k, cudaStream_t s, bool* launched) {
   *launched = false;
@@ -687,9 +698,9 @@ int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void*
   const size_t smem = (size_t)rows_per_cta * (2 * C * 4 + k * idsz) + 16;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER>,
+    cudaError_t e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, LEAN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 68 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER>,
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, LEAN>,
                                                    cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_bwd_cluster_tma): %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
@@ -706,7 +717,7 @@ int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER>, g, argmax, nbr, grad_x, N, C, k,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, LEAN>, g, argmax, nbr, grad_x, N, C, k,
                                      rows_per_cta, cv_shift);
   if (e != cudaSuccess) { set_error("mr_aggregate_bwd_cluster_tma launch: %s", cudaGetErrorString(e)); return (int)e; }
   *launched = true;
@@ -1125,7 +1136,8 @@ namespace {
 // development switches: GRAFP_MR_FWD_VARIANT = 0 generic kernel, 1 / 2 / 4 fast kernel with that many items in
 // flight per thread, 8 (default) the cp.async-pipelined persistent kernel where it applies; GRAFP_MR_BWD_VARIANT = 0 two-kernel form, 1 / 2 / 4 fused cluster form,
 // 8 the deterministic gather form over the reverse graph (needs the workspace), 16 the cluster form with TMA bulk
-// staging, 17 (default) the same with the reductions issued in neighbour-slot order, 18 that with 16-CTA clusters, 32 the deterministic shared-memory slice form (aggregate_bwd_slice.cu; measured slower:
+// staging, 17 (default) the same with the reductions issued in neighbour-slot order, 18 that with 16-CTA clusters,
+// 19 = 17 without the device-wide fence and with the routed half kept in registers between the phases, 32 the deterministic shared-memory slice form (aggregate_bwd_slice.cu; measured slower:
 // it is bound by the L1 / shared-memory pipe)
 // (read on every call - a getenv is nanoseconds next to a launch - so tests can switch kernels in-process)
 int fwd_variant() {
@@ -1288,11 +1300,12 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
     if constexpr (VEC == 4 && std::is_same<T, float>::value) {
       if (self_skip && bwd_variant() >= 16) {  // default: cluster form with TMA bulk staging
         bool launched = false;
-        const int rc = (bwd_variant() == 17 || bwd_variant() == 18)
-                           ? launch_mr_bwd_cluster_tma<I64, true>(reinterpret_cast<const float*>(gs), argmax, nbr,
-                                                                  reinterpret_cast<float*>(gx), B, N, C, k, s, &launched)
-                           : launch_mr_bwd_cluster_tma<I64, false>(reinterpret_cast<const float*>(gs), argmax, nbr,
-                                                                   reinterpret_cast<float*>(gx), B, N, C, k, s, &launched);
+        const float* gf = reinterpret_cast<const float*>(gs);
+        float* gxf = reinterpret_cast<float*>(gx);
+        const int bv = bwd_variant();
+        const int rc = (bv == 19)               ? launch_mr_bwd_cluster_tma<I64, true, true>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
+                       : (bv == 17 || bv == 18) ? launch_mr_bwd_cluster_tma<I64, true, false>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
+                                                : launch_mr_bwd_cluster_tma<I64, false, false>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched);
         if (rc != GRAFP_OK || launched) return rc;
       }
     }
