@@ -1136,8 +1136,7 @@ namespace {
 // development switches: GRAFP_MR_FWD_VARIANT = 0 generic kernel, 1 / 2 / 4 fast kernel with that many items in
 // flight per thread, 8 (default) the cp.async-pipelined persistent kernel where it applies; GRAFP_MR_BWD_VARIANT = 0 two-kernel form, 1 / 2 / 4 fused cluster form,
 // 8 the deterministic gather form over the reverse graph (needs the workspace), 16 the cluster form with TMA bulk
-// staging, 17 (default) the same with the reductions issued in neighbour-slot order, 18 that with 16-CTA clusters,
-// 19 = 17 without the device-wide fence and with the routed half kept in registers between the phases, 32 the deterministic shared-memory slice form (aggregate_bwd_slice.cu; measured slower:
+// staging, 17 (default) the same with the reductions issued in neighbour-slot order, 18 that with 16-CTA clusters, 32 the deterministic shared-memory slice form (aggregate_bwd_slice.cu; measured slower:
 // it is bound by the L1 / shared-memory pipe)
 // (read on every call - a getenv is nanoseconds next to a launch - so tests can switch kernels in-process)
 int fwd_variant() {
@@ -1303,9 +1302,10 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
         const float* gf = reinterpret_cast<const float*>(gs);
         float* gxf = reinterpret_cast<float*>(gx);
         const int bv = bwd_variant();
-        const int rc = (bv == 19)               ? launch_mr_bwd_cluster_tma<I64, true, true>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
-                       : (bv == 17 || bv == 18) ? launch_mr_bwd_cluster_tma<I64, true, false>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
-                                                : launch_mr_bwd_cluster_tma<I64, false, false>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched);
+        // (a LEAN form - routed half kept in registers between the phases, no device-wide fence - exists as a template
+        // flag; measured 136 - 145 us against 125 us: 80 registers per thread cost more occupancy than the re-read)
+        const int rc = (bv == 17 || bv == 18) ? launch_mr_bwd_cluster_tma<I64, true, false>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
+                                              : launch_mr_bwd_cluster_tma<I64, false, false>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched);
         if (rc != GRAFP_OK || launched) return rc;
       }
     }

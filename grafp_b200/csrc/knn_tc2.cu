@@ -117,10 +117,8 @@ struct TopK {
           // warp-uniform address; columns past the last key (TMA zero fill) are pushed to +inf
           const float yj = YS_SHARED ? lds_f32(ys_addr + 4 * j) : (j < nvalid ? __ldg(ys_glob + j) : INFINITY);
           const float dist = __fadd_rn(fmaf(kM2, __uint_as_float(v[j]), sq_i), yj);
-          if (dist > lo_d || (dist == lo_d && key0 + j > lo_id)) {
-            insert(dist, key0 + j);
-            update_thr();
-          }
+          insert(dist, key0 + j);  // (the round bounds lo_d / lo_id only exist for K > 16: queue path)
+          update_thr();
         }
       }
     }
@@ -225,50 +223,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 
 // One tile (<= 128 accumulator columns, ncols of them backed by keys) of this thread's row through the
-// candidate queue: 16 columns per tcgen05.ld, four predicated quad pushes, one vote for the early drain.  The
-// loads are software-pipelined over two register sets: the next 16 columns are in flight while the current ones
-// are filtered (tcgen05.wait::ld waits for every outstanding load, so there is never more than one).
-template <int KREG>
-__device__ __forceinline__ void push16(TopK<KREG>& top, const uint32_t (&v)[16], uint32_t bq) {
-  top.push4(v[0], v[1], v[2], v[3], bq);
-  top.push4(v[4], v[5], v[6], v[7], bq << 1);
-  top.push4(v[8], v[9], v[10], v[11], bq << 2);
-  top.push4(v[12], v[13], v[14], v[15], bq << 3);
-}
-
+// candidate queue: 16 columns per tcgen05.ld, four predicated quad pushes, one vote for the early drain.
+// (Software-pipelining the loads over two register sets was measured: 378 -> 390 us at stage 0, the extra 16
+// registers cost more than the exposed TMEM latency.)
 template <int KREG, bool YS_SHARED, bool YS_VEC>
 __device__ __forceinline__ void scan_tile_queued(TopK<KREG>& top, uint32_t trow, int key0, int ncols, uint32_t ys_addr,
                                                  const float* ys_glob, int M) {
   uint32_t bq = 1u;
-  if constexpr (KREG > 8) {  // 16-entry lists leave no room for the second register set: one load at a time
 #pragma unroll 1
-    for (int c0 = 0; c0 < ncols; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(trow + c0, v);
-      tmem_ld_wait();
-      push16<KREG>(top, v, bq);
-      bq <<= 4;
-      if (c0 + 16 >= ncols || __any_sync(0xffffffffu, top.qa >= top.qlim)) top.template drain<YS_SHARED, YS_VEC>(key0, ys_addr, ys_glob, M);
-    }
-    return;
-  }
-  uint32_t va[16], vb[16];
-  tmem_ld16(trow, va);
-#pragma unroll 1
-  for (int c0 = 0; c0 < ncols; c0 += 32) {
+  for (int c0 = 0; c0 < ncols; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(trow + c0, v);
     tmem_ld_wait();
-    const bool more_b = c0 + 16 < ncols;
-    if (more_b) tmem_ld16(trow + c0 + 16, vb);
-    push16<KREG>(top, va, bq);
+    top.push4(v[0], v[1], v[2], v[3], bq);
+    top.push4(v[4], v[5], v[6], v[7], bq << 1);
+    top.push4(v[8], v[9], v[10], v[11], bq << 2);
+    top.push4(v[12], v[13], v[14], v[15], bq << 3);
     bq <<= 4;
-    if (!more_b || __any_sync(0xffffffffu, top.qa >= top.qlim)) top.template drain<YS_SHARED, YS_VEC>(key0, ys_addr, ys_glob, M);
-    if (!more_b) break;
-    tmem_ld_wait();
-    const bool more_a = c0 + 32 < ncols;
-    if (more_a) tmem_ld16(trow + c0 + 32, va);
-    push16<KREG>(top, vb, bq);
-    bq <<= 4;
-    if (!more_a || __any_sync(0xffffffffu, top.qa >= top.qlim)) top.template drain<YS_SHARED, YS_VEC>(key0, ys_addr, ys_glob, M);
+    if (c0 + 16 >= ncols || __any_sync(0xffffffffu, top.qa >= top.qlim)) top.template drain<YS_SHARED, YS_VEC>(key0, ys_addr, ys_glob, M);
   }
 }
 
