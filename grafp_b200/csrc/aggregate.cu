@@ -537,17 +537,18 @@ __device__ __forceinline__ void k3_mbar_wait(uint32_t bar, uint32_t parity) {
 // JORDER: phase 2 walks the neighbour slots j = 0..k-1 in a fixed order instead of the winners of the item's four
 // channels, so the lanes that share a source row issue their red.v4 to the SAME target row in the same instruction
 // (contiguous 256-byte runs that the LSU / L2 merge per sector) and an item issues at most k-1 of them.
+// THREADS: 256 (8 items per thread) or 512 (4 items per thread, twice the warps per SM at the same shared memory).
 // LEAN: the routed half of grad_out (g[.., 2c+1]) stays in registers between the phases instead of being read from
 // shared memory twice, and the device-wide fence in front of the cluster barrier is dropped (barrier.cluster
 // arrive.release / wait.acquire already orders the phase-1 stores of every CTA of the cluster before the
 // phase-2 reductions of every other one).
-template <bool I64, bool JORDER, bool LEAN>
-__global__ void __launch_bounds__(kFusedThreads, 3)
+template <bool I64, bool JORDER, bool LEAN, int THREADS>
+__global__ void __launch_bounds__(THREADS, 3)
 mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* __restrict__ argmax,
                                     const void* __restrict__ nbr, float* __restrict__ grad_x, int N, int C, int k,
                                     int rows_per_cta, int cv_shift) {
   using idx_t = typename std::conditional<I64, long long, int>::type;
-  constexpr int kItems = 8;  // (row, 4-channel) items per thread: the host caps a CTA's share at 8 * 256 items
+  constexpr int kItems = 2048 / THREADS;  // (row, 4-channel) items per thread: the host caps a CTA's share at 2048 items
   extern __shared__ __align__(128) unsigned char tma_smem[];
   const int cv = 1 << cv_shift;
   const float* gt = reinterpret_cast<const float*>(tma_smem);                                    // [rows][2C] grad_out
@@ -575,7 +576,7 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
   unsigned int am[kItems];
 #pragma unroll
   for (int u = 0; u < kItems; ++u) {
-    const int it = threadIdx.x + u * kFusedThreads;
+    const int it = threadIdx.x + u * THREADS;
     am[u] = (it < items)
                 ? __ldg(reinterpret_cast<const unsigned int*>(argmax + (b * N + row0 + (it >> cv_shift)) * (long long)C +
                                                               (it & (cv - 1)) * 4))
@@ -588,7 +589,7 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
   float keep[LEAN ? kItems : 1][4];
 #pragma unroll
   for (int u = 0; u < kItems; ++u) {
-    const int it = threadIdx.x + u * kFusedThreads;
+    const int it = threadIdx.x + u * THREADS;
     if (it < items) {
       const int rl = it >> cv_shift;
       const int n = row0 + rl;
@@ -612,7 +613,7 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
   // phase 2: route g[.., 2c+1] to the winning neighbour rows of this segment (L2-resident, just written)
 #pragma unroll
   for (int u = 0; u < kItems; ++u) {
-    const int it = threadIdx.x + u * kFusedThreads;
+    const int it = threadIdx.x + u * THREADS;
     if (it < items) {
       const int rl = it >> cv_shift;
       const int n = row0 + rl;
@@ -667,7 +668,7 @@ namespace {
 int bwd_variant();  // development switch, defined with the dispatchers below
 }
 
-template <bool I64, bool JORDER, bool LEAN>
+template <bool I64, bool JORDER, bool LEAN, int THREADS = kFusedThreads>
 int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void* nbr, float* grad_x, int B, int N, int C,
                               int k, cudaStream_t s, bool* launched) {
   *launched = false;
@@ -698,16 +699,16 @@ int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void*
   const size_t smem = (size_t)rows_per_cta * (2 * C * 4 + k * idsz) + 16;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, LEAN>,
+    cudaError_t e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, LEAN, THREADS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 68 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, LEAN>,
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, LEAN, THREADS>,
                                                    cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_bwd_cluster_tma): %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * cl));
-  cfg.blockDim = dim3(kFusedThreads);
+  cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -717,7 +718,7 @@ int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, LEAN>, g, argmax, nbr, grad_x, N, C, k,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, LEAN, THREADS>, g, argmax, nbr, grad_x, N, C, k,
                                      rows_per_cta, cv_shift);
   if (e != cudaSuccess) { set_error("mr_aggregate_bwd_cluster_tma launch: %s", cudaGetErrorString(e)); return (int)e; }
   *launched = true;
@@ -1136,7 +1137,7 @@ namespace {
 // development switches: GRAFP_MR_FWD_VARIANT = 0 generic kernel, 1 / 2 / 4 fast kernel with that many items in
 // flight per thread, 8 (default) the cp.async-pipelined persistent kernel where it applies; GRAFP_MR_BWD_VARIANT = 0 two-kernel form, 1 / 2 / 4 fused cluster form,
 // 8 the deterministic gather form over the reverse graph (needs the workspace), 16 the cluster form with TMA bulk
-// staging, 17 (default) the same with the reductions issued in neighbour-slot order, 18 that with 16-CTA clusters, 32 the deterministic shared-memory slice form (aggregate_bwd_slice.cu; measured slower:
+// staging, 17 (default) the same with the reductions issued in neighbour-slot order, 18 that with 16-CTA clusters, 20 = 17 with 512-thread CTAs, 32 the deterministic shared-memory slice form (aggregate_bwd_slice.cu; measured slower:
 // it is bound by the L1 / shared-memory pipe)
 // (read on every call - a getenv is nanoseconds next to a launch - so tests can switch kernels in-process)
 int fwd_variant() {
@@ -1304,7 +1305,8 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
         const int bv = bwd_variant();
         // (a LEAN form - routed half kept in registers between the phases, no device-wide fence - exists as a template
         // flag; measured 136 - 145 us against 125 us: 80 registers per thread cost more occupancy than the re-read)
-        const int rc = (bv == 17 || bv == 18) ? launch_mr_bwd_cluster_tma<I64, true, false>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
+        const int rc = (bv == 20)             ? launch_mr_bwd_cluster_tma<I64, true, false, 512>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
+                       : (bv == 17 || bv == 18) ? launch_mr_bwd_cluster_tma<I64, true, false>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
                                               : launch_mr_bwd_cluster_tma<I64, false, false>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched);
         if (rc != GRAFP_OK || launched) return rc;
       }

@@ -147,6 +147,18 @@ def fingerprints(total=10000):
             e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         print(f"chunk {chunk:5d}: {n_chunks * chunk / ms * 1e3:9.0f} segments/s ({ms / n_chunks:.2f} ms per chunk)", flush=True)
+        from grafp_b200.inference import GraphedEncoder
+        runner = GraphedEncoder(lambda s: F.normalize(enc(pe(s)), dim=1), xs)
+        with torch.no_grad():
+            same = torch.equal(runner(xs), F.normalize(enc(pe(xs)), dim=1))
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n_chunks):
+            fp = runner(xs)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print(f"chunk {chunk:5d}: {n_chunks * chunk / ms * 1e3:9.0f} segments/s ({ms / n_chunks:.2f} ms per chunk)  CUDA-graph replay, "
+              f"output identical to eager: {same}", flush=True)
 
 
 if __name__ == "__main__":

@@ -789,3 +789,20 @@ def test_fused_conv_batch_norm_matches_torch(shape, mode):
     assert gio.rel_err(bn.running_var.cpu().double(), bn_ref.running_var) < 1e-5
     if mode == "residual":
         assert gio.rel_err(rg.grad.cpu().double(), rr.grad) < 1e-6
+
+
+def test_graphed_encoder_replays_the_eager_forward():
+    """Fingerprint generation through one CUDA graph per chunk shape: bit-identical to the eager eval-mode forward,
+    on fresh inputs too (nothing of the first input may be baked into the graph), ragged tail handled eagerly."""
+    from grafp_b200.inference import GraphedEncoder, generate_fingerprints
+    cfg = dict(synth.DEFAULT_CFG)
+    torch.manual_seed(3)
+    enc = GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3).to(DEV).eval()
+    g = torch.Generator().manual_seed(11)
+    pts = torch.rand(20, cfg["n_filters"], 1024, generator=g).to(DEV)
+    runner = GraphedEncoder(enc, pts[:8])
+    with torch.no_grad():
+        for lo in (0, 8):
+            assert torch.equal(runner(pts[lo:lo + 8]), enc(pts[lo:lo + 8]))
+        want = torch.cat([enc(pts[0:8]), enc(pts[8:16]), enc(pts[16:20])])
+    assert torch.equal(generate_fingerprints(enc, pts, chunk=8), want)
