@@ -1015,6 +1015,91 @@ edge_gather_fwd_kernel(const T* __restrict__ x, const T* __restrict__ src, const
   }
 }
 
+// Row form of the EdgeConv features for graphs whose centre is the row itself (the DenseDilatedKnnGraph case) and a
+// compile-time k: a thread owns U (row, 4-channel) items per iteration, reads each centre slice once (the edge form
+// above re-reads it for every neighbour), and has the U * KN neighbour ids and then the U * (KN + 1) 16-byte loads in
+// flight before the first store - the same latency-hiding recipe that took K2 from 61 % to 80 % of the HBM rate.
+// 32-bit index arithmetic (the host checks the item count).
+template <typename T, int VEC, bool I64, int KN, int U>
+__global__ void __launch_bounds__(kThreads)
+edge_gather_fwd_row_kernel(const T* __restrict__ x, const T* __restrict__ src, const void* __restrict__ nbr,
+                           T* __restrict__ out, unsigned rows, unsigned cv, int N, int M, int C) {
+  const unsigned items = rows * cv;
+  const unsigned step = gridDim.x * kThreads;
+  for (unsigned it0 = blockIdx.x * kThreads + threadIdx.x; it0 < items; it0 += step * U) {
+    unsigned row[U], c[U];
+    int nb[U][KN];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned it = it0 + u * step;
+      ok[u] = it < items;
+      const unsigned itc = ok[u] ? it : items - 1;
+      row[u] = itc / cv;
+      c[u] = (itc - row[u] * cv) * VEC;
+#pragma unroll
+      for (int j = 0; j < KN; ++j) nb[u][j] = load_index<I64>(nbr, (long long)row[u] * KN + j);
+    }
+    float xi[U][VEC], xj[U][KN][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long seg = (long long)(row[u] / (unsigned)N) * M;
+      Pack<T, VEC>::load(x + (long long)row[u] * C + c[u], xi[u]);
+#pragma unroll
+      for (int j = 0; j < KN; ++j) Pack<T, VEC>::load(src + (seg + nb[u][j]) * (long long)C + c[u], xj[u][j]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+#pragma unroll
+      for (int j = 0; j < KN; ++j) {
+        float d[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) d[e] = xj[u][j][e] - xi[u][e];
+        T* o = out + ((long long)row[u] * KN + j) * 2 * C + c[u];
+        Pack<T, VEC>::store(o, xi[u]);
+        Pack<T, VEC>::store(o + C, d);
+      }
+    }
+  }
+}
+
+// One-pass backward of the same case: a thread owns a (row, 4-channel) item, reads its 2 * KN slices of grad_out once,
+// keeps the dense part sum_j (ga - gb) in registers and routes every gb slice to its neighbour row with red.v4 -
+// including the dense part itself, into a grad_x that the host zero-fills first (one extra write pass of N * C,
+// against the second read pass of k * N * C that the dense + scatter pair of kernels needs).
+template <typename T, int VEC, bool I64, int KN>
+__global__ void __launch_bounds__(kThreads)
+edge_gather_bwd_row_kernel(const T* __restrict__ g, const void* __restrict__ nbr, T* __restrict__ grad_x, unsigned rows,
+                           unsigned cv, int N, int C) {
+  const unsigned items = rows * cv;
+  for (unsigned it = blockIdx.x * kThreads + threadIdx.x; it < items; it += gridDim.x * kThreads) {
+    const unsigned row = it / cv;
+    const unsigned c = (it - row * cv) * VEC;
+    const long long seg = (long long)(row / (unsigned)N) * N;
+    int nb[KN];
+#pragma unroll
+    for (int j = 0; j < KN; ++j) nb[j] = load_index<I64>(nbr, (long long)row * KN + j);
+    float ga[KN][VEC], gb[KN][VEC];
+#pragma unroll
+    for (int j = 0; j < KN; ++j) {
+      const T* p = g + ((long long)row * KN + j) * 2 * C + c;
+      Pack<T, VEC>::load(p, ga[j]);
+      Pack<T, VEC>::load(p + C, gb[j]);
+    }
+    float acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < KN; ++j) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[e] += ga[j][e] - gb[j][e];
+      Pack<T, VEC>::red_add(grad_x + (seg + nb[j]) * (long long)C + c, gb[j]);
+    }
+    Pack<T, VEC>::red_add(grad_x + (long long)row * C + c, acc);
+  }
+}
+
 // dense part (centre == row): grad_x[row][c] = sum_j (ga[row][j][c] - gb[row][j][c]); plain store
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
@@ -1101,6 +1186,53 @@ max_over_k_fwd_kernel(const T* __restrict__ h, T* __restrict__ out, uint8_t* __r
             make_uchar4((unsigned char)arg[0], (unsigned char)arg[1], (unsigned char)arg[2], (unsigned char)arg[3]);
       } else {
         argmax[row * C + c] = (uint8_t)arg[0];
+      }
+    }
+  }
+}
+
+// compile-time k, U items per thread and iteration: all U * KN loads are issued before the first compare
+template <typename T, int KN, int U>
+__global__ void __launch_bounds__(kThreads)
+max_over_k_fwd_row_kernel(const T* __restrict__ h, T* __restrict__ out, uint8_t* __restrict__ argmax, unsigned rows,
+                          unsigned cv, int C) {
+  constexpr int VEC = 4;
+  const unsigned items = rows * cv;
+  const unsigned step = gridDim.x * kThreads;
+  for (unsigned it0 = blockIdx.x * kThreads + threadIdx.x; it0 < items; it0 += step * U) {
+    float v[U][KN][VEC];
+    unsigned row[U], c[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned it = it0 + u * step;
+      ok[u] = it < items;
+      const unsigned itc = ok[u] ? it : items - 1;
+      row[u] = itc / cv;
+      c[u] = (itc - row[u] * cv) * VEC;
+#pragma unroll
+      for (int j = 0; j < KN; ++j) Pack<T, VEC>::load(h + ((long long)row[u] * KN + j) * C + c[u], v[u][j]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      float best[VEC];
+      int arg[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { best[e] = -INFINITY; arg[e] = 0; }
+#pragma unroll
+      for (int j = 0; j < KN; ++j) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          if (v[u][j][e] > best[e] || v[u][j][e] != v[u][j][e]) {
+            if (!(best[e] != best[e])) { best[e] = v[u][j][e]; arg[e] = j; }
+          }
+        }
+      }
+      Pack<T, VEC>::store(out + (long long)row[u] * C + c[u], best);
+      if (argmax != nullptr) {
+        *reinterpret_cast<uchar4*>(argmax + (long long)row[u] * C + c[u]) =
+            make_uchar4((unsigned char)arg[0], (unsigned char)arg[1], (unsigned char)arg[2], (unsigned char)arg[3]);
       }
     }
   }
@@ -1378,6 +1510,18 @@ int launch_edge_gather_fwd(const void* x, const void* y, const void* nbr, const 
     constexpr int VEC = decltype(vec)::value;
     constexpr bool I64 = decltype(i64)::value;
     const int grid = grid_for(edges * (C / VEC), kThreads, 8);
+    if constexpr (VEC == 4) {
+      const long long rows = (long long)B * N;
+      const bool row_form = getenv("GRAFP_EDGE_ROW_FORM") == nullptr || atoi(getenv("GRAFP_EDGE_ROW_FORM")) != 0;
+      if (!ctr && row_form && k >= 2 && k <= 4 && rows * (C / VEC) < 0x7fffffffLL) {
+        const unsigned cv = C / VEC;
+        const int g2 = grid_for((rows * cv + 1) / 2, kThreads, 8);
+#define GRAFP_EDGE_ROW(KN_) edge_gather_fwd_row_kernel<T, VEC, I64, KN_, 2><<<g2, kThreads, 0, s>>>(xs, src, nbr, static_cast<T*>(out), (unsigned)rows, cv, N, M, C)
+        if (k == 2) GRAFP_EDGE_ROW(2); else if (k == 3) GRAFP_EDGE_ROW(3); else GRAFP_EDGE_ROW(4);
+#undef GRAFP_EDGE_ROW
+        return check_launch("edge_gather_fwd_row");
+      }
+    }
     if (ctr) {
       edge_gather_fwd_kernel<T, VEC, I64, true><<<grid, kThreads, 0, s>>>(xs, src, nbr, ctr, static_cast<T*>(out), edges,
                                                                            N, M, C, k);
@@ -1404,6 +1548,20 @@ int launch_edge_gather_bwd(const void* g, const void* nbr, const void* ctr, int 
     constexpr int VEC = decltype(vec)::value;
     constexpr bool I64 = decltype(i64)::value;
     const T* gs = static_cast<const T*>(g);
+    if constexpr (VEC == 4) {
+      // one-pass form (development switch GRAFP_EDGE_BWD_ROW=1; default is the dense + scatter pair until measured)
+      const bool row_form = getenv("GRAFP_EDGE_BWD_ROW") != nullptr && atoi(getenv("GRAFP_EDGE_BWD_ROW")) != 0;
+      if (!ctr && !grad_y && row_form && k >= 2 && k <= 4 && rows * (C / VEC) < 0x7fffffffLL) {
+        cudaError_t e2 = cudaMemsetAsync(grad_x, 0, (size_t)B * N * C * sizeof(T), s);
+        if (e2 != cudaSuccess) { set_error("cudaMemsetAsync(edge grad_x): %s", cudaGetErrorString(e2)); return (int)e2; }
+        const unsigned cv = C / VEC;
+        const int g1 = grid_for(rows * cv, kThreads, 8);
+#define GRAFP_EDGE_BWD_ROW(KN_) edge_gather_bwd_row_kernel<T, VEC, I64, KN_><<<g1, kThreads, 0, s>>>(gs, nbr, gx, (unsigned)rows, cv, N, C)
+        if (k == 2) GRAFP_EDGE_BWD_ROW(2); else if (k == 3) GRAFP_EDGE_BWD_ROW(3); else GRAFP_EDGE_BWD_ROW(4);
+#undef GRAFP_EDGE_BWD_ROW
+        return check_launch("edge_gather_bwd_row");
+      }
+    }
     if (ctr) {
       const int grid = grid_for(edges * (C / VEC), kThreads, 8);
       edge_gather_bwd_scatter_kernel<T, VEC, I64, true><<<grid, kThreads, 0, s>>>(gs, nbr, ctr, gx, gsrc, edges, N, M, C, k);
@@ -1421,6 +1579,15 @@ template <typename T>
 int launch_max_over_k_fwd(const void* h, void* out, uint8_t* argmax, int B, int N, int C, int k, cudaStream_t s) {
   const long long rows = (long long)B * N;
   const bool vec4 = (C % 4 == 0) && aligned16(h) && aligned16(out) && (argmax == nullptr || ((uintptr_t)argmax & 3) == 0);
+  const bool row_form = getenv("GRAFP_MAXK_ROW_FORM") == nullptr || atoi(getenv("GRAFP_MAXK_ROW_FORM")) != 0;
+  if (vec4 && row_form && k >= 2 && k <= 4 && rows * (C / 4) < 0x7fffffffLL) {
+    const unsigned cv = C / 4;
+    const int g2 = grid_for((rows * cv + 1) / 2, kThreads, 8);
+#define GRAFP_MAXK_ROW(KN_) max_over_k_fwd_row_kernel<T, KN_, 2><<<g2, kThreads, 0, s>>>(static_cast<const T*>(h), static_cast<T*>(out), argmax, (unsigned)rows, cv, C)
+    if (k == 2) GRAFP_MAXK_ROW(2); else if (k == 3) GRAFP_MAXK_ROW(3); else GRAFP_MAXK_ROW(4);
+#undef GRAFP_MAXK_ROW
+    return check_launch("max_over_k_fwd_row");
+  }
   if (vec4) {
     max_over_k_fwd_kernel<T, 4><<<grid_for(rows * (C / 4), kThreads, 8), kThreads, 0, s>>>(
         static_cast<const T*>(h), static_cast<T*>(out), argmax, rows, C, k);

@@ -395,8 +395,13 @@ def test_mr_aggregate_bwd_slice_shapes(shape, variant, monkeypatch):
         assert gio.rel_err(xg.grad.cpu(), xo.grad) < REL_TOL
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 64, 4), (3, 128, 100, 9), (2, 6, 33, 5)])
-def test_gather_edge_maxk_vs_oracle(shape):
+@pytest.mark.parametrize("edge_bwd_row", ["0", "1"])
+@pytest.mark.parametrize("shape", [(2, 16, 64, 4), (3, 128, 100, 9), (2, 6, 33, 5), (3, 64, 301, 3), (1, 32, 50, 2),
+                                   (2, 256, 256, 3)])
+def test_gather_edge_maxk_vs_oracle(shape, edge_bwd_row, monkeypatch):
+    """(k = 2..4 with C % 4 == 0 take the row-form kernels, the rest the edge-form ones; GRAFP_EDGE_BWD_ROW switches
+    the EdgeConv backward between the dense + scatter pair and the one-pass form.)"""
+    monkeypatch.setenv("GRAFP_EDGE_BWD_ROW", edge_bwd_row)
     B, C, N, k = shape
     x = synth.synth_point_cloud(B, C, N, 400 + N)
     edge = O.dilated_knn_graph(x, k)
