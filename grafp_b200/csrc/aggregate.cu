@@ -968,6 +968,43 @@ gather_fwd_kernel(const T* __restrict__ src, const void* __restrict__ idx, T* __
   }
 }
 
+// row form with compile-time k: U (row, 4-channel) items per thread and iteration, all ids then all gathers in flight
+template <typename T, int VEC, bool I64, int KN, int U>
+__global__ void __launch_bounds__(kThreads)
+gather_fwd_row_kernel(const T* __restrict__ src, const void* __restrict__ idx, T* __restrict__ out, unsigned rows,
+                      unsigned cv, int N, int M, int C) {
+  const unsigned items = rows * cv;
+  const unsigned step = gridDim.x * kThreads;
+  for (unsigned it0 = blockIdx.x * kThreads + threadIdx.x; it0 < items; it0 += step * U) {
+    unsigned row[U], c[U];
+    int nb[U][KN];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned it = it0 + u * step;
+      ok[u] = it < items;
+      const unsigned itc = ok[u] ? it : items - 1;
+      row[u] = itc / cv;
+      c[u] = (itc - row[u] * cv) * VEC;
+#pragma unroll
+      for (int j = 0; j < KN; ++j) nb[u][j] = load_index<I64>(idx, (long long)row[u] * KN + j);
+    }
+    float v[U][KN][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long seg = (long long)(row[u] / (unsigned)N) * M;
+#pragma unroll
+      for (int j = 0; j < KN; ++j) Pack<T, VEC>::load(src + (seg + nb[u][j]) * (long long)C + c[u], v[u][j]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+#pragma unroll
+      for (int j = 0; j < KN; ++j) Pack<T, VEC>::store(out + ((long long)row[u] * KN + j) * C + c[u], v[u][j]);
+    }
+  }
+}
+
 template <typename T, int VEC, bool I64>
 __global__ void __launch_bounds__(kThreads)
 gather_bwd_kernel(const T* __restrict__ g, const void* __restrict__ idx, T* __restrict__ grad_src, long long edges,
@@ -1478,6 +1515,18 @@ int launch_gather_fwd(const void* src, const void* idx, int idx_is_i64, void* ou
     constexpr int VEC = decltype(vec)::value;
     constexpr bool I64 = decltype(i64)::value;
     const int grid = grid_for(edges * (C / VEC), kThreads, 8);
+    if constexpr (VEC == 4) {
+      const long long rows = (long long)B * N;
+      const bool row_form = getenv("GRAFP_GATHER_ROW_FORM") == nullptr || atoi(getenv("GRAFP_GATHER_ROW_FORM")) != 0;
+      if (row_form && k >= 2 && k <= 4 && rows * (C / VEC) < 0x7fffffffLL) {
+        const unsigned cv = C / VEC;
+        const int g2 = grid_for((rows * cv + 1) / 2, kThreads, 8);
+#define GRAFP_GATHER_ROW(KN_) gather_fwd_row_kernel<T, VEC, I64, KN_, 2><<<g2, kThreads, 0, s>>>(static_cast<const T*>(src), idx, static_cast<T*>(out), (unsigned)rows, cv, N, M, C)
+        if (k == 2) GRAFP_GATHER_ROW(2); else if (k == 3) GRAFP_GATHER_ROW(3); else GRAFP_GATHER_ROW(4);
+#undef GRAFP_GATHER_ROW
+        return check_launch("gather_fwd_row");
+      }
+    }
     gather_fwd_kernel<T, VEC, I64><<<grid, kThreads, 0, s>>>(static_cast<const T*>(src), idx, static_cast<T*>(out),
                                                              edges, N, M, C, k);
     return check_launch("gather_fwd");
@@ -1549,8 +1598,8 @@ int launch_edge_gather_bwd(const void* g, const void* nbr, const void* ctr, int 
     constexpr bool I64 = decltype(i64)::value;
     const T* gs = static_cast<const T*>(g);
     if constexpr (VEC == 4) {
-      // one-pass form (development switch GRAFP_EDGE_BWD_ROW=1; default is the dense + scatter pair until measured)
-      const bool row_form = getenv("GRAFP_EDGE_BWD_ROW") != nullptr && atoi(getenv("GRAFP_EDGE_BWD_ROW")) != 0;
+      // one-pass form (default; GRAFP_EDGE_BWD_ROW=0 selects the dense + scatter pair): 229-241 us against 280-290 us
+      const bool row_form = getenv("GRAFP_EDGE_BWD_ROW") == nullptr || atoi(getenv("GRAFP_EDGE_BWD_ROW")) != 0;
       if (!ctr && !grad_y && row_form && k >= 2 && k <= 4 && rows * (C / VEC) < 0x7fffffffLL) {
         cudaError_t e2 = cudaMemsetAsync(grad_x, 0, (size_t)B * N * C * sizeof(T), s);
         if (e2 != cudaSuccess) { set_error("cudaMemsetAsync(edge grad_x): %s", cudaGetErrorString(e2)); return (int)e2; }
