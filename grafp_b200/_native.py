@@ -28,6 +28,8 @@ SIGNATURES = {
     "grafp_mr_aggregate_bwd": (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 6 + [_vp, _sz, _vp]),
     "grafp_gather_fwd": (_i, [_vp] * 2 + [_i] + [_vp] + [_i] * 6 + [_vp]),
     "grafp_gather_bwd": (_i, [_vp] * 2 + [_i] + [_vp] + [_i] * 6 + [_vp]),
+    "grafp_neighbor_sum_fwd": (_i, [_vp] * 2 + [_i] + [_vp] + [_i] * 6 + [_vp]),
+    "grafp_neighbor_sum_bwd": (_i, [_vp] * 2 + [_i] + [_vp] + [_i] * 6 + [_vp]),
     "grafp_edge_gather_fwd": (_i, [_vp] * 4 + [_i] + [_vp] + [_i] * 6 + [_vp]),
     "grafp_edge_gather_bwd": (_i, [_vp] * 3 + [_i] + [_vp] * 2 + [_i] * 6 + [_vp]),
     "grafp_max_over_k_fwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
@@ -37,7 +39,7 @@ SIGNATURES = {
     "grafp_bn_train_bwd": (_i, [_vp] * 10 + [_c.c_longlong, _i, _i, _vp, _sz, _vp]),
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 KNN_AUTO, KNN_SIMT, KNN_TC, KNN_TC_TF32 = 0, 1, 2, 3
 KNN_MAX_K = 64
 

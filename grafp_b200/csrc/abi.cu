@@ -232,6 +232,26 @@ int grafp_gather_bwd(const void* grad_out, const void* idx, int idx_is_i64, void
                         launch_gather_bwd<__nv_bfloat16>(grad_out, idx, idx_is_i64, grad_src, B, N, M, C, k, s));
 }
 
+int grafp_neighbor_sum_fwd(const void* src, const void* idx, int idx_is_i64, void* out, int B, int N, int M, int C, int k,
+                           int dtype, void* stream) {
+  COMMON_SHAPE_CHECKS("grafp_neighbor_sum_fwd");
+  GRAFP_REQUIRE(src && idx && out, GRAFP_EINVAL, "grafp_neighbor_sum_fwd: src, idx and out must be non-null");
+  { int rc = require_device_ptr("grafp_neighbor_sum_fwd", "src", src); if (rc) return rc; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return DISPATCH_DTYPE(launch_neighbor_sum_fwd<float>(src, idx, idx_is_i64, out, B, N, M, C, k, s),
+                        launch_neighbor_sum_fwd<__nv_bfloat16>(src, idx, idx_is_i64, out, B, N, M, C, k, s));
+}
+
+int grafp_neighbor_sum_bwd(const void* grad_out, const void* idx, int idx_is_i64, void* grad_src, int B, int N, int M,
+                           int C, int k, int dtype, void* stream) {
+  COMMON_SHAPE_CHECKS("grafp_neighbor_sum_bwd");
+  GRAFP_REQUIRE(grad_out && idx && grad_src, GRAFP_EINVAL, "grafp_neighbor_sum_bwd: grad_out, idx and grad_src must be non-null");
+  { int rc = require_device_ptr("grafp_neighbor_sum_bwd", "grad_out", grad_out); if (rc) return rc; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return DISPATCH_DTYPE(launch_neighbor_sum_bwd<float>(grad_out, idx, idx_is_i64, grad_src, B, N, M, C, k, s),
+                        launch_neighbor_sum_bwd<__nv_bfloat16>(grad_out, idx, idx_is_i64, grad_src, B, N, M, C, k, s));
+}
+
 int grafp_edge_gather_fwd(const void* x, const void* y, const void* nbr_idx, const void* ctr_idx, int idx_is_i64,
                           void* out, int B, int N, int M, int C, int k, int dtype, void* stream) {
   COMMON_SHAPE_CHECKS("grafp_edge_gather_fwd");

@@ -1024,6 +1024,83 @@ gather_bwd_kernel(const T* __restrict__ g, const void* __restrict__ idx, T* __re
 }
 
 // ------------------------------------------------------------------------------------
+// neighbour sum: out[b][n][c] = sum_j src[b][idx[b][n][j]][c]  (GINConv2d: batched_index_select + torch.sum over
+// the neighbour axis, torch_vertex.py:84-88) without the (B, C, N, k) intermediate; backward routes grad_out[b][n]
+// to its k neighbour rows with red.v4 into a zero-filled grad_src.  Summation order j = 0..k-1.
+// ------------------------------------------------------------------------------------
+template <typename T, int VEC, bool I64, int U>
+__global__ void __launch_bounds__(kThreads)
+neighbor_sum_fwd_kernel(const T* __restrict__ src, const void* __restrict__ idx, T* __restrict__ out, long long rows,
+                        int N, int M, int C, int k) {
+  const long long cv = C / VEC;
+  const long long items = rows * cv;
+  const long long step = (long long)gridDim.x * kThreads;
+  for (long long it0 = blockIdx.x * (long long)kThreads + threadIdx.x; it0 < items; it0 += step * U) {
+    long long row[U];
+    int c[U];
+    bool ok[U];
+    float acc[U][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long it = it0 + u * step;
+      ok[u] = it < items;
+      const long long itc = ok[u] ? it : items - 1;
+      row[u] = itc / cv;
+      c[u] = static_cast<int>(itc - row[u] * cv) * VEC;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[u][e] = 0.f;
+    }
+    for (int j0 = 0; j0 < k; j0 += 4) {  // four neighbours x U items in flight
+      float v[U][4][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long seg = (row[u] / N) * M;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = min(j0 + jj, k - 1);
+          const int nb = load_index<I64>(idx, row[u] * k + j);
+          Pack<T, VEC>::load(src + (seg + nb) * (long long)C + c[u], v[u][jj]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          if (j0 + jj < k) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[u][e] += v[u][jj][e];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (ok[u]) Pack<T, VEC>::store(out + row[u] * C + c[u], acc[u]);
+    }
+  }
+}
+
+template <typename T, int VEC, bool I64>
+__global__ void __launch_bounds__(kThreads)
+neighbor_sum_bwd_kernel(const T* __restrict__ g, const void* __restrict__ idx, T* __restrict__ grad_src, long long rows,
+                        int N, int M, int C, int k) {
+  const long long cv = C / VEC;
+  const long long items = rows * cv;
+  for (long long it = blockIdx.x * (long long)kThreads + threadIdx.x; it < items;
+       it += (long long)gridDim.x * kThreads) {
+    const long long row = it / cv;
+    const int c = static_cast<int>(it - row * cv) * VEC;
+    const long long seg = (row / N) * M;
+    float gv[VEC];
+    Pack<T, VEC>::load(g + row * C + c, gv);
+    for (int j = 0; j < k; ++j) {
+      const int nb = load_index<I64>(idx, row * k + j);
+      Pack<T, VEC>::red_add(grad_src + (seg + nb) * (long long)C + c, gv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // EdgeConv features [x_i | x_j - x_i] (torch_vertex.py:46-51) and backward
 // ------------------------------------------------------------------------------------
 template <typename T, int VEC, bool I64, bool HAS_CTR>
@@ -1550,6 +1627,36 @@ int launch_gather_bwd(const void* g, const void* idx, int idx_is_i64, void* grad
 }
 
 template <typename T>
+int launch_neighbor_sum_fwd(const void* src, const void* idx, int idx_is_i64, void* out, int B, int N, int M, int C, int k,
+                            cudaStream_t s) {
+  const long long rows = (long long)B * N;
+  return dispatch_vec_idx(C, aligned16(src) && aligned16(out), idx_is_i64, [&](auto vec, auto i64) {
+    constexpr int VEC = decltype(vec)::value;
+    constexpr bool I64 = decltype(i64)::value;
+    const int grid = grid_for((rows * (C / VEC) + 1) / 2, kThreads, 8);
+    neighbor_sum_fwd_kernel<T, VEC, I64, 2><<<grid, kThreads, 0, s>>>(static_cast<const T*>(src), idx, static_cast<T*>(out),
+                                                                      rows, N, M, C, k);
+    return check_launch("neighbor_sum_fwd");
+  });
+}
+
+template <typename T>
+int launch_neighbor_sum_bwd(const void* g, const void* idx, int idx_is_i64, void* grad_src, int B, int N, int M, int C,
+                            int k, cudaStream_t s) {
+  const long long rows = (long long)B * N;
+  cudaError_t e = cudaMemsetAsync(grad_src, 0, (size_t)B * M * C * sizeof(T), s);
+  if (e != cudaSuccess) { set_error("cudaMemsetAsync(grad_src): %s", cudaGetErrorString(e)); return (int)e; }
+  return dispatch_vec_idx(C, aligned16(g) && aligned16(grad_src), idx_is_i64, [&](auto vec, auto i64) {
+    constexpr int VEC = decltype(vec)::value;
+    constexpr bool I64 = decltype(i64)::value;
+    const int grid = grid_for(rows * (C / VEC), kThreads, 8);
+    neighbor_sum_bwd_kernel<T, VEC, I64><<<grid, kThreads, 0, s>>>(static_cast<const T*>(g), idx, static_cast<T*>(grad_src),
+                                                                   rows, N, M, C, k);
+    return check_launch("neighbor_sum_bwd");
+  });
+}
+
+template <typename T>
 int launch_edge_gather_fwd(const void* x, const void* y, const void* nbr, const void* ctr, int idx_is_i64, void* out,
                            int B, int N, int M, int C, int k, cudaStream_t s) {
   const long long edges = (long long)B * N * k;
@@ -1669,6 +1776,8 @@ int launch_max_over_k_bwd(const void* g, const uint8_t* argmax, void* grad_h, in
                                           int, int, int, int, int, void*, size_t, cudaStream_t);                     \
   template int launch_gather_fwd<T>(const void*, const void*, int, void*, int, int, int, int, int, cudaStream_t);    \
   template int launch_gather_bwd<T>(const void*, const void*, int, void*, int, int, int, int, int, cudaStream_t);    \
+  template int launch_neighbor_sum_fwd<T>(const void*, const void*, int, void*, int, int, int, int, int, cudaStream_t); \
+  template int launch_neighbor_sum_bwd<T>(const void*, const void*, int, void*, int, int, int, int, int, cudaStream_t); \
   template int launch_edge_gather_fwd<T>(const void*, const void*, const void*, const void*, int, void*, int, int,   \
                                          int, int, int, cudaStream_t);                                               \
   template int launch_edge_gather_bwd<T>(const void*, const void*, const void*, int, void*, void*, int, int, int,    \

@@ -182,6 +182,12 @@ template <typename T>
 int launch_gather_bwd(const void* g, const void* idx, int idx_is_i64, void* grad_src, int B, int N, int M, int C, int k,
                       cudaStream_t s);
 template <typename T>
+int launch_neighbor_sum_fwd(const void* src, const void* idx, int idx_is_i64, void* out, int B, int N, int M, int C, int k,
+                            cudaStream_t s);
+template <typename T>
+int launch_neighbor_sum_bwd(const void* g, const void* idx, int idx_is_i64, void* grad_src, int B, int N, int M, int C,
+                            int k, cudaStream_t s);
+template <typename T>
 int launch_edge_gather_fwd(const void* x, const void* y, const void* nbr, const void* ctr, int idx_is_i64, void* out,
                            int B, int N, int M, int C, int k, cudaStream_t s);
 template <typename T>

@@ -96,8 +96,7 @@ class GINConv2d(nn.Module):
 
     def forward(self, x, edge_index, y=None):
         nbr, _ = _split_edge_index(edge_index)
-        x_j = batched_index_select(x if y is None else y, nbr)
-        x_j = torch.sum(x_j, -1, keepdim=True)
+        x_j = ops.neighbor_sum(x if y is None else y, nbr)   # gather + sum over the neighbour axis, fused
         return self.nn((1 + self.eps) * x + x_j)
 
 

@@ -284,6 +284,43 @@ def gather_neighbors(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return _Gather.apply(src, idx)
 
 
+class _NeighborSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, idx):
+        lib = _native.load()
+        sr = as_rows(src)
+        B, C, M, _ = sr.shape
+        idx_c, i64 = _index_arg(idx)
+        _, N, k = idx_c.shape
+        out = _new_rows(B, C, N, sr)
+        _call("neighbor_sum_fwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_neighbor_sum_fwd, sr.data_ptr(),
+              idx_c.data_ptr(), i64, out.data_ptr(), B, N, M, C, k, _dtype_code(sr), _stream())
+        ctx.save_for_backward(idx_c)
+        ctx.dims = (B, N, M, C, k, i64, _dtype_code(sr))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _native.load()
+        (idx_c,) = ctx.saved_tensors
+        B, N, M, C, k, i64, dt = ctx.dims
+        g = as_rows(grad_out)
+        grad_src = _new_rows(B, C, M, g)
+        _call("neighbor_sum_bwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_neighbor_sum_bwd, g.data_ptr(),
+              idx_c.data_ptr(), i64, grad_src.data_ptr(), B, N, M, C, k, dt, _stream())
+        return grad_src, None
+
+
+def neighbor_sum(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """out[b, c, n, 0] = sum_j src[b, c, idx[b, n, j]] as a (B, C, N, 1) tensor: ``batched_index_select`` followed by
+    ``torch.sum(x_j, -1, keepdim=True)`` (reference: torch_vertex.py:84-88, GINConv2d) without the (B, C, N, k)
+    intermediate."""
+    _require_cuda(src, idx)
+    if idx.dim() != 3 or idx.shape[0] != src.shape[0]:
+        raise RuntimeError("grafp_b200.neighbor_sum: idx must be (B, N, k)")
+    return _NeighborSum.apply(src, idx)
+
+
 # --------------------------------------------------------------------------------------
 # EdgeConv features and max over k
 # --------------------------------------------------------------------------------------

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GRAFP_ABI_VERSION 3
+#define GRAFP_ABI_VERSION 4
 
 #define GRAFP_OK 0
 #define GRAFP_EINVAL (-1)       /* null / misaligned pointer, non-positive size, k > M ... */
@@ -116,6 +116,18 @@ int grafp_gather_fwd(const void* src, const void* idx, int idx_is_i64, void* out
                      int dtype, void* stream);
 int grafp_gather_bwd(const void* grad_out, const void* idx, int idx_is_i64, void* grad_src, int B, int N, int M, int C,
                      int k, int dtype, void* stream);
+
+/*
+ * Neighbour sum.  Replaces batched_index_select + torch.sum(x_j, -1, keepdim=True) of GINConv2d.forward
+ * (torch_vertex.py:84-88) without the (B, C, N, k) intermediate.
+ *  out[b][n][c] = sum_j src[b][idx[b][n][j]][c]        out is (B, N, C), summed in the order j = 0 .. k-1
+ * Backward overwrites grad_src (B, M, C):  grad_src[b][m][c] = sum over edges (n, j) with idx[b][n][j] = m of
+ * grad_out[b][n][c].
+ */
+int grafp_neighbor_sum_fwd(const void* src, const void* idx, int idx_is_i64, void* out, int B, int N, int M, int C, int k,
+                           int dtype, void* stream);
+int grafp_neighbor_sum_bwd(const void* grad_out, const void* idx, int idx_is_i64, void* grad_src, int B, int N, int M,
+                           int C, int k, int dtype, void* stream);
 
 /*
  * EdgeConv feature construction.  Replaces cat([x_i, x_j - x_i], dim=1) of

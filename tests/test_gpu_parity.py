@@ -811,3 +811,28 @@ def test_graphed_encoder_replays_the_eager_forward():
             assert torch.equal(runner(pts[lo:lo + 8]), enc(pts[lo:lo + 8]))
         want = torch.cat([enc(pts[0:8]), enc(pts[8:16]), enc(pts[16:20])])
     assert torch.equal(generate_fingerprints(enc, pts, chunk=8), want)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 64, 4), (3, 128, 100, 9), (2, 6, 33, 5), (3, 64, 301, 3), (2, 64, 1024, 16)])
+def test_neighbor_sum_vs_reference_ops(shape):
+    """GIN aggregation: gather + sum over the neighbour axis (torch_vertex.py:84-88) as one kernel, fwd and bwd,
+    int64 and int32 ids, a separate key set, against the reference's two ops evaluated in fp64."""
+    B, C, N, k = shape
+    g = torch.Generator().manual_seed(N + k)
+    x = torch.randn(B, C, N, 1, generator=g)
+    y = torch.randn(B, C, N // 2 + 3, 1, generator=g)
+    up = torch.randn(B, C, N, 1, generator=g)
+    for src in (x, y):
+        M = src.shape[2]
+        idx = torch.randint(0, M, (B, N, k), generator=g)
+        idx[0, :, 0] = 1                                   # a hub
+        s64 = src.double().requires_grad_(True)
+        ref = O.gather_neighbors(s64, idx).sum(-1, keepdim=True)
+        ref.backward(up.double())
+        for ids in (idx.to(DEV), idx.to(DEV).int()):
+            sg = src.to(DEV).requires_grad_(True)
+            out = ops.neighbor_sum(sg, ids)
+            assert out.shape == (B, C, N, 1)
+            assert gio.rel_err(out.detach().cpu().double(), ref.detach()) < 1e-6
+            out.backward(up.to(DEV))
+            assert gio.rel_err(sg.grad.cpu().double(), s64.grad) < 1e-5
