@@ -180,25 +180,40 @@ struct TopK {
           const float4 yv = __ldg(reinterpret_cast<const float4*>(ys_glob + min(key, M - 4)));
           y0 = yv.x; y1 = yv.y; y2 = yv.z; y3 = yv.w;
         }
-        uint32_t em = (v0 > thr ? 1u : 0u) | (v1 > thr ? 2u : 0u) | (v2 > thr ? 4u : 0u) | (v3 > thr ? 8u : 0u);
-        while (em != 0u) {  // lane-local, in column order; usually one element
-          const int e = __ffs(em) - 1;
-          em &= em - 1u;
-          const float lo2 = (e & 1) ? v1 : v0, hi2 = (e & 1) ? v3 : v2;
-          const float s = (e & 2) ? hi2 : lo2;
-          const int kj = key + e;
-          if (kj < M) {
-            float yj;
-            if constexpr (YS_SHARED || YS_VEC) {
-              const float ylo = (e & 1) ? y1 : y0, yhi = (e & 1) ? y3 : y2;
-              yj = (e & 2) ? yhi : ylo;
-            } else {
-              yj = __ldg(ys_glob + kj);
-            }
-            const float dist = __fadd_rn(fmaf(kM2, s, sq_i), yj);
-            if (dist > lo_d || (dist == lo_d && kj > lo_id)) {
+        if constexpr (YS_SHARED || YS_VEC) {
+          // exact distances of the whole quad up front (2 instructions each) and the exact, strict test against the
+          // current K-th entry: keys that only TIE with it (duplicate nodes - frequent in real point clouds, where
+          // they made this path slower than the vote-gated one) are dropped here instead of walking the insertion
+          // path one by one.  An insertion inside the quad only tightens d[K-1]; `insert` re-tests exactly.
+          const float e0 = __fadd_rn(fmaf(kM2, v0, sq_i), y0), e1 = __fadd_rn(fmaf(kM2, v1, sq_i), y1);
+          const float e2 = __fadd_rn(fmaf(kM2, v2, sq_i), y2), e3 = __fadd_rn(fmaf(kM2, v3, sq_i), y3);
+          const float dk = d[KREG - 1];
+          uint32_t em = (e0 < dk ? 1u : 0u) | (e1 < dk ? 2u : 0u) | (e2 < dk ? 4u : 0u) | (e3 < dk ? 8u : 0u);
+          while (em != 0u) {  // lane-local, in column order; usually one element
+            const int e = __ffs(em) - 1;
+            em &= em - 1u;
+            const float lo2 = (e & 1) ? e1 : e0, hi2 = (e & 1) ? e3 : e2;
+            const float dist = (e & 2) ? hi2 : lo2;
+            const int kj = key + e;
+            if (kj < M && (dist > lo_d || (dist == lo_d && kj > lo_id))) {
               insert(dist, kj);
               update_thr();
+            }
+          }
+        } else {
+          uint32_t em = (v0 > thr ? 1u : 0u) | (v1 > thr ? 2u : 0u) | (v2 > thr ? 4u : 0u) | (v3 > thr ? 8u : 0u);
+          while (em != 0u) {
+            const int e = __ffs(em) - 1;
+            em &= em - 1u;
+            const float lo2 = (e & 1) ? v1 : v0, hi2 = (e & 1) ? v3 : v2;
+            const float s = (e & 2) ? hi2 : lo2;
+            const int kj = key + e;
+            if (kj < M) {
+              const float dist = __fadd_rn(fmaf(kM2, s, sq_i), __ldg(ys_glob + kj));
+              if (dist > lo_d || (dist == lo_d && kj > lo_id)) {
+                insert(dist, kj);
+                update_thr();
+              }
             }
           }
         }
