@@ -669,16 +669,19 @@ struct Plan {
 static Plan plan(int N, int M, int C, int K, int dtype, bool self) {
   Plan p;
   if (dtype != GRAFP_F32 || C % 8 != 0 || C < BK || N < BM || M < BM || K < 1 || K > 64) return p;
-  // development switches (A/B timing): GRAFP_KNN_EPI=vote keeps the vote-gated scan, GRAFP_KNN_NO_NH4 /
-  // GRAFP_KNN_BN128 pick the older tile shapes
-  static const bool vote = getenv("GRAFP_KNN_EPI") != nullptr && strcmp(getenv("GRAFP_KNN_EPI"), "vote") == 0;
+  // Which selection epilogue.  K > 8 (16-entry lists, rounds) exists in the candidate-queue form only.  For K <= 8 both
+  // exist and neither dominates: on features with independent rows (random point clouds: scripts/bench_ops.py, the
+  // configs[3] stress) the queue form is faster (stage 0: 385 vs 429 us) because some lane of a warp has a candidate
+  // in most column groups and the vote-gated form then pays its insertion path for the whole warp; inside the
+  // training step - where, as far as we can tell, the 32 consecutive rows of a warp are neighbouring spectrogram peaks
+  // whose candidates sit in the SAME few key columns, so the vote-gated form skips almost everything - it wins (k-NN 5.1-5.5 vs 5.6-5.9 ms per
+  // step, A/B on the same box).  The default follows the headline workload; GRAFP_KNN_EPI=queue / =vote force one.
+  // GRAFP_KNN_NO_NH4 / GRAFP_KNN_BN128 pick the older tile shapes (A/B timing).
+  const char* epi = getenv("GRAFP_KNN_EPI");
+  const bool force_queue = epi != nullptr && strcmp(epi, "queue") == 0;
   static const bool no_nh4 = getenv("GRAFP_KNN_NO_NH4") != nullptr;
   static const bool bn128 = getenv("GRAFP_KNN_BN128") != nullptr;
-  // the whole-segment self kernels select once, after the MMAs: measured 83 / 39 us with the vote-gated scan against
-  // 96 / 47 us with the queue (N <= 256 keys leave the thresholds no time to tighten), so they keep the former
-  static const bool self_queue = getenv("GRAFP_KNN_SELF_QUEUE") != nullptr;
-  const bool self_kernel = self && N <= 2 * BM;
-  p.qs = (K <= 8 && (vote || (self_kernel && !self_queue))) ? 0 : kQueueSlots;  // K > 8 (16-entry lists) is queue-only
+  p.qs = (K <= 8 && !force_queue) ? 0 : kQueueSlots;
   const int num_kc = (C + BK - 1) / BK;
   const uint32_t budget = kSmemLimit - kMiscBytes;
   auto queue_bytes = [&](int nh) { return (uint32_t)(4 * nh) * p.qs * 512u; };

@@ -139,8 +139,12 @@ TC_CASES = [
 
 
 @pytest.mark.parametrize("B,C,N,M,k,d", TC_CASES)
-@pytest.mark.parametrize("algo", [_native.KNN_TC, _native.KNN_TC_TF32])
-def test_knn_tensor_core_path_vs_oracle(B, C, N, M, k, d, algo):
+@pytest.mark.parametrize("algo", [_native.KNN_TC, _native.KNN_TC_TF32, "queue"])
+def test_knn_tensor_core_path_vs_oracle(B, C, N, M, k, d, algo, monkeypatch):
+    """("queue": the f16x3 kernels with the candidate-queue selection forced for K <= 8 too; K > 8 always uses it.)"""
+    if algo == "queue":
+        monkeypatch.setenv("GRAFP_KNN_EPI", "queue")
+        algo = _native.KNN_TC
     x = synth.synth_point_cloud(B, C, N, 3000 + N + C)
     y = synth.synth_point_cloud(B, C, M, 4000 + M) if M else None
     nn_idx, _ = ops.knn_graph(x.to(DEV), k, d, None if y is None else y.to(DEV), algo=algo)
