@@ -538,11 +538,9 @@ __device__ __forceinline__ void k3_mbar_wait(uint32_t bar, uint32_t parity) {
 // channels, so the lanes that share a source row issue their red.v4 to the SAME target row in the same instruction
 // (contiguous 256-byte runs that the LSU / L2 merge per sector) and an item issues at most k-1 of them.
 // THREADS: 256 (8 items per thread) or 512 (4 items per thread, twice the warps per SM at the same shared memory).
-// LEAN: the routed half of grad_out (g[.., 2c+1]) stays in registers between the phases instead of being read from
-// shared memory twice, and the device-wide fence in front of the cluster barrier is dropped (barrier.cluster
-// arrive.release / wait.acquire already orders the phase-1 stores of every CTA of the cluster before the
-// phase-2 reductions of every other one).
-template <bool I64, bool JORDER, bool LEAN, int THREADS>
+// (Measured and dropped: keeping the routed half of grad_out in registers between the phases and omitting the
+// device-wide fence in front of the cluster barrier - 80 registers per thread, 136-145 us against 125 us.)
+template <bool I64, bool JORDER, int THREADS>
 __global__ void __launch_bounds__(THREADS, 3)
 mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* __restrict__ argmax,
                                     const void* __restrict__ nbr, float* __restrict__ grad_x, int N, int C, int k,
@@ -586,7 +584,6 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
   if (nrows > 0) k3_mbar_wait(bar, 0);
 
   // phase 1: dense part of grad_x for this CTA's rows (everything it needs is in shared memory or registers)
-  float keep[LEAN ? kItems : 1][4];
 #pragma unroll
   for (int u = 0; u < kItems; ++u) {
     const int it = threadIdx.x + u * THREADS;
@@ -597,7 +594,6 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
       const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
       const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
       const float g0[4] = {ga.x, ga.z, gb.x, gb.z}, g1[4] = {ga.y, ga.w, gb.y, gb.w};
-      if constexpr (LEAN) { keep[u][0] = g1[0]; keep[u][1] = g1[1]; keep[u][2] = g1[2]; keep[u][3] = g1[3]; }
       float r[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -607,7 +603,7 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
       *reinterpret_cast<float4*>(gxb + (long long)n * C + c) = make_float4(r[0], r[1], r[2], r[3]);
     }
   }
-  if constexpr (!LEAN) __threadfence();
+  __threadfence();
   cluster_sync_all();
 
   // phase 2: route g[.., 2c+1] to the winning neighbour rows of this segment (L2-resident, just written)
@@ -618,14 +614,9 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
       const int rl = it >> cv_shift;
       const int n = row0 + rl;
       const int c = (it & (cv - 1)) * 4;
-      float g1[4];
-      if constexpr (LEAN) {
-        g1[0] = keep[u][0]; g1[1] = keep[u][1]; g1[2] = keep[u][2]; g1[3] = keep[u][3];
-      } else {
-        const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
-        const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
-        g1[0] = ga.y; g1[1] = ga.w; g1[2] = gb.y; g1[3] = gb.w;
-      }
+      const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
+      const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
+      const float g1[4] = {ga.y, ga.w, gb.y, gb.w};
       int a[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) a[e] = (am[u] >> (8 * e)) & 0xff;
@@ -668,7 +659,7 @@ namespace {
 int bwd_variant();  // development switch, defined with the dispatchers below
 }
 
-template <bool I64, bool JORDER, bool LEAN, int THREADS = kFusedThreads>
+template <bool I64, bool JORDER, int THREADS = kFusedThreads>
 int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void* nbr, float* grad_x, int B, int N, int C,
                               int k, cudaStream_t s, bool* launched) {
   *launched = false;
@@ -699,9 +690,9 @@ int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void*
   const size_t smem = (size_t)rows_per_cta * (2 * C * 4 + k * idsz) + 16;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, LEAN, THREADS>,
+    cudaError_t e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, THREADS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 68 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, LEAN, THREADS>,
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, THREADS>,
                                                    cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_bwd_cluster_tma): %s", cudaGetErrorString(e)); return (int)e; }
     configured = true;
@@ -718,7 +709,7 @@ int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, LEAN, THREADS>, g, argmax, nbr, grad_x, N, C, k,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, THREADS>, g, argmax, nbr, grad_x, N, C, k,
                                      rows_per_cta, cv_shift);
   if (e != cudaSuccess) { set_error("mr_aggregate_bwd_cluster_tma launch: %s", cudaGetErrorString(e)); return (int)e; }
   *launched = true;
@@ -1549,11 +1540,9 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
         const float* gf = reinterpret_cast<const float*>(gs);
         float* gxf = reinterpret_cast<float*>(gx);
         const int bv = bwd_variant();
-        // (a LEAN form - routed half kept in registers between the phases, no device-wide fence - exists as a template
-        // flag; measured 136 - 145 us against 125 us: 80 registers per thread cost more occupancy than the re-read)
-        const int rc = (bv == 20)             ? launch_mr_bwd_cluster_tma<I64, true, false, 512>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
-                       : (bv == 17 || bv == 18) ? launch_mr_bwd_cluster_tma<I64, true, false>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
-                                              : launch_mr_bwd_cluster_tma<I64, false, false>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched);
+        const int rc = (bv == 20)             ? launch_mr_bwd_cluster_tma<I64, true, 512>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
+                       : (bv == 17 || bv == 18) ? launch_mr_bwd_cluster_tma<I64, true>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
+                                              : launch_mr_bwd_cluster_tma<I64, false>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched);
         if (rc != GRAFP_OK || launched) return rc;
       }
     }

@@ -142,3 +142,38 @@ def test_synth_is_deterministic():
     s1 = synth.synth_state_dict({"w.weight": (4, 3, 1, 1), "bn.running_var": (4,)}, 9)
     s2 = synth.synth_state_dict({"bn.running_var": (4,), "w.weight": (4, 3, 1, 1)}, 9)
     assert all(torch.equal(s1[k], s2[k]) for k in s1)
+
+
+@pytest.mark.parametrize("groups,bias,relu,res", [(1, True, True, False), (4, True, True, False), (1, False, False, True),
+                                                  (1, False, True, False), (1, True, False, False)])
+def test_folded_conv_batchnorm_equals_the_eval_modules(groups, bias, relu, res, monkeypatch):
+    """Inference path: conv -> BatchNorm(eval) [-> ReLU | + residual] with the BatchNorm folded into the convolution's
+    weight and bias is the same map as the three modules (fp64, CPU: the algebra, not the kernels)."""
+    monkeypatch.setenv("GRAFP_FOLD_BN", "2")     # plain conv2d form (cudnn_convolution_relu is CUDA-only)
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(16, 32, 1, groups=groups, bias=bias).double()
+    bn = torch.nn.BatchNorm2d(32).double()
+    with torch.no_grad():
+        bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0); bn.weight.normal_(); bn.bias.normal_()
+    bn.eval()
+    x = torch.randn(3, 16, 50, 1, dtype=torch.float64)
+    r = torch.randn(3, 32, 50, 1, dtype=torch.float64) if res else None
+    with torch.no_grad():
+        want = bn(conv(x))
+        want = want + r if res else want
+        want = torch.relu(want) if relu else want
+        got = ops._folded_conv_bn_eval(x, conv.weight, conv.bias, bn, relu, r.clone() if res else None,
+                                       (conv.stride, conv.padding, conv.dilation, conv.groups))
+    assert float((got - want).abs().max()) < 1e-12
+
+
+def test_fold_and_graph_paths_are_gated_to_cuda_inference():
+    """The folded path is taken only in eval mode under no_grad on CUDA tensors; GraphedEncoder refuses CPU inputs."""
+    from grafp_b200.inference import GraphedEncoder
+    bn = torch.nn.BatchNorm2d(8)
+    x = torch.randn(2, 8, 4, 1)
+    with torch.no_grad():
+        assert not ops._fold_eval_ok(x, bn.eval())          # CPU tensor
+    assert not ops._fold_eval_ok(x, bn.train())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GraphedEncoder(lambda t: t, x)
