@@ -63,3 +63,88 @@ def generate_fingerprints(module: Callable[[torch.Tensor], torch.Tensor], segmen
             else:
                 outs.append(module(x))
     return torch.cat(outs, dim=0)
+
+
+class FingerprintWriter:
+    """Streams fingerprints into the reference's on-disk database format (test_fp.py:108-125, read back by
+    eval.py:126-170 ``load_memmap_data``): ``<dir>/<name>.mm`` - a raw float32 (n, d) array written through
+    ``np.memmap`` - next to ``<dir>/<name>_shape.npy`` holding ``(n, d)``.
+
+    The reference concatenates every batch on the host and copies the result once more into the memmap; here each
+    chunk goes device -> pinned staging buffer (asynchronously, so the copy overlaps the next chunk's kernels) ->
+    its rows of the memmap.  ``n`` must be known up front, as the memmap is created at its final size.
+    """
+
+    def __init__(self, output_root_dir: str, name: str, n: int, d: int):
+        import os
+
+        import numpy as np
+        self._np = np
+        os.makedirs(output_root_dir, exist_ok=True)
+        self.shape = (int(n), int(d))
+        self.path = os.path.join(output_root_dir, f"{name}.mm")
+        self.shape_path = os.path.join(output_root_dir, f"{name}_shape.npy")
+        self._mm = np.memmap(self.path, dtype="float32", mode="w+", shape=self.shape)
+        self._row = 0
+        self._pending = None      # (event, staging tensor, first row, rows)
+        self._staging = [None, None]
+        self._flip = 0
+
+    def _retire(self):
+        if self._pending is not None:
+            ev, buf, row, rows = self._pending
+            if ev is not None:
+                ev.synchronize()
+            self._mm[row:row + rows] = buf[:rows].numpy()
+            self._pending = None
+
+    def append(self, z: torch.Tensor) -> None:
+        """z: (rows, d) float tensor on any device; rows are written in call order."""
+        rows = int(z.shape[0])
+        if z.dim() != 2 or z.shape[1] != self.shape[1] or self._row + rows > self.shape[0]:
+            raise ValueError(f"FingerprintWriter.append: got {tuple(z.shape)} at row {self._row} of {self.shape}")
+        z = z.detach().to(torch.float32)
+        if not z.is_cuda:
+            self._retire()
+            self._mm[self._row:self._row + rows] = z.contiguous().numpy()
+            self._row += rows
+            return
+        slot = self._flip
+        self._flip ^= 1
+        buf = self._staging[slot]
+        if buf is None or buf.shape[0] < rows:
+            buf = torch.empty((max(rows, 1), self.shape[1]), dtype=torch.float32).pin_memory()
+            self._staging[slot] = buf
+        buf[:rows].copy_(z, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(z.device))
+        self._retire()            # the previous chunk's copy has had a whole chunk of kernels to finish
+        self._pending = (ev, buf, self._row, rows)
+        self._row += rows
+
+    def close(self) -> tuple:
+        self._retire()
+        if self._row != self.shape[0]:
+            raise ValueError(f"FingerprintWriter.close: {self._row} of {self.shape[0]} rows written")
+        self._mm.flush()
+        del self._mm
+        self._np.save(self.shape_path, self.shape)
+        return self.shape
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is None:
+            self.close()
+        return False
+
+
+def load_fingerprint_db(source_dir: str, name: str):
+    """(memmap, shape) of a database written by :class:`FingerprintWriter` or by the reference
+    (same reader as eval.py:126-170 ``load_memmap_data``, read-only)."""
+    import os
+
+    import numpy as np
+    shape = tuple(int(v) for v in np.load(os.path.join(source_dir, name + "_shape.npy")))
+    return np.memmap(os.path.join(source_dir, name + ".mm"), dtype="float32", mode="r", shape=shape), shape

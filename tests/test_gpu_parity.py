@@ -840,3 +840,20 @@ def test_neighbor_sum_vs_reference_ops(shape):
             assert gio.rel_err(out.detach().cpu().double(), ref.detach()) < 1e-6
             out.backward(up.to(DEV))
             assert gio.rel_err(sg.grad.cpu().double(), s64.grad) < 1e-5
+
+
+def test_fingerprint_writer_streams_from_the_device(tmp_path):
+    """generate.py / test_fp.py path end to end: graphed chunks -> pinned staging -> db.mm + db_shape.npy."""
+    from grafp_b200.inference import FingerprintWriter, GraphedEncoder, load_fingerprint_db
+    cfg = dict(synth.DEFAULT_CFG)
+    torch.manual_seed(5)
+    enc = GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3).to(DEV).eval()
+    pts = torch.rand(20, cfg["n_filters"], 1024, generator=torch.Generator().manual_seed(12)).to(DEV)
+    runner = GraphedEncoder(enc, pts[:8])
+    with torch.no_grad():
+        want = torch.cat([enc(pts[0:8]), enc(pts[8:16]), enc(pts[16:20])]).cpu().numpy()
+    with FingerprintWriter(str(tmp_path), "db", 20, want.shape[1]) as w:
+        for lo in (0, 8, 16):
+            w.append(runner(pts[lo:lo + 8]))      # the last chunk is ragged: eager path
+    data, shape = load_fingerprint_db(str(tmp_path), "db")
+    assert shape == want.shape and np.array_equal(np.asarray(data), want)

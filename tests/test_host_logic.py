@@ -177,3 +177,25 @@ def test_fold_and_graph_paths_are_gated_to_cuda_inference():
     assert not ops._fold_eval_ok(x, bn.train())
     with pytest.raises(RuntimeError, match="CUDA"):
         GraphedEncoder(lambda t: t, x)
+
+
+def test_fingerprint_writer_matches_the_reference_memmap_format(tmp_path):
+    """db.mm / db_shape.npy exactly as test_fp.py:108-125 writes them: raw float32 (n, d) + the shape tuple."""
+    from grafp_b200.inference import FingerprintWriter, load_fingerprint_db
+    g = torch.Generator().manual_seed(5)
+    chunks = [torch.randn(n, 128, generator=g) for n in (128, 128, 37)]
+    want = torch.cat(chunks).numpy()
+    with FingerprintWriter(str(tmp_path), "db", want.shape[0], 128) as w:
+        for c in chunks:
+            w.append(c)
+    # the reference's own way of writing / reading the same data
+    ref = np.memmap(tmp_path / "ref.mm", dtype="float32", mode="w+", shape=want.shape)
+    ref[:] = want[:]
+    ref.flush(); del ref
+    assert (tmp_path / "db.mm").read_bytes() == (tmp_path / "ref.mm").read_bytes()
+    assert tuple(np.load(tmp_path / "db_shape.npy")) == want.shape
+    data, shape = load_fingerprint_db(str(tmp_path), "db")
+    assert shape == want.shape and np.array_equal(np.asarray(data), want)
+    with pytest.raises(ValueError):
+        with FingerprintWriter(str(tmp_path), "short", 10, 128) as w:
+            w.append(torch.zeros(4, 128))
