@@ -487,13 +487,18 @@ class _ConvBatchNormTrain(torch.autograd.Function):
     """Conv2d(1x1, bias) -> train-mode BatchNorm [-> ReLU | + residual] as one autograd node: the convolution stays
     cuDNN, the BatchNorm is the fused kernel pair, and the convolution's bias gradient - the per-channel sum of the
     BatchNorm's input gradient - is accumulated while that gradient is written instead of by a separate reduction
-    pass over it (aten::convolution_backward is asked for the input and weight gradients only)."""
+    pass over it (aten::convolution_backward is asked for the input and weight gradients only).
+
+    The convolution itself runs WITHOUT its bias: a per-channel constant in front of a train-mode BatchNorm cancels in
+    (h - mean(h)), so adding it is a full read + write pass over the activations (cuDNN does not fuse it: ~105
+    broadcast-add launches, ~10 ms of the 120 ms step in the ncu launch list) that changes nothing but rounding.  The
+    statistics are taken of the bias-free output and the bias is added back where it is visible: the running mean."""
 
     @staticmethod
     def forward(ctx, x, residual, cw, cb, weight, bias, running_mean, running_var, eps, momentum, relu, conv_args):
         lib = _native.load()
         stride, padding, dilation, groups = conv_args
-        h = torch.nn.functional.conv2d(x, cw, cb, stride, padding, dilation, groups)
+        h = torch.nn.functional.conv2d(x, cw, None, stride, padding, dilation, groups)   # bias: see the class docstring
         if not _is_rows(h):
             h = as_rows(h)
         B, C, N, _ = h.shape
@@ -509,6 +514,9 @@ class _ConvBatchNormTrain(torch.autograd.Function):
               running_var.data_ptr() if running_var is not None else None,
               out.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(), B * N, C, float(eps), float(momentum),
               int(relu), ws.data_ptr(), ws_bytes, _stream())
+        if running_mean is not None:
+            # running_mean <- (1 - m) running_mean + m (mean(h) + cb): the kernel did the first two terms
+            running_mean.add_(cb.detach().to(running_mean.dtype), alpha=float(momentum))
         ctx.save_for_backward(x, cw, h, weight, bias, save_mean, save_invstd)
         ctx.relu = bool(relu)
         ctx.has_res = residual is not None
