@@ -483,6 +483,54 @@ def batch_norm_act(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = False
     return _BatchNormTrain.apply(x, residual, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, relu)
 
 
+def _gemm_form(conv_args, cw: torch.Tensor) -> bool:
+    """Experimental (round-2 A/B, off by default): GRAFP_CONV_AS_GEMM=1 runs the dense 1x1 convolutions of the fused
+    conv + BatchNorm node as plain GEMMs on the node rows (out = X W^T, dX = dOut W, dW = dOut^T X) through
+    cuBLASLt instead of cuDNN's implicit-GEMM convolution kernels, with the same TF32 policy as the convolutions."""
+    stride, padding, dilation, groups = conv_args
+    return (os.environ.get("GRAFP_CONV_AS_GEMM", "0") == "1" and groups == 1 and tuple(cw.shape[2:]) == (1, 1)
+            and tuple(stride) == (1, 1) and tuple(padding) == (0, 0) and tuple(dilation) == (1, 1))
+
+
+class _conv_tf32_policy:
+    """matmul under the TF32 policy the convolutions use (torch.backends.cudnn.allow_tf32)."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(torch.backends.cudnn.allow_tf32)
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
+
+def _rows2d(t: torch.Tensor) -> torch.Tensor:
+    """(B, C, N, 1) node rows -> the (B * N, C) matrix they are in memory (a view)."""
+    B, C, N, _ = t.shape
+    return t.permute(0, 2, 3, 1).reshape(B * N, C)
+
+
+def _conv1x1_rows_fwd(x: torch.Tensor, cw: torch.Tensor) -> torch.Tensor:
+    B, _, N, _ = x.shape
+    Cout = cw.shape[0]
+    with _conv_tf32_policy():
+        h2 = _rows2d(x) @ cw.reshape(Cout, -1).t()
+    return h2.view(B, N, 1, Cout).permute(0, 3, 1, 2)        # logical (B, Cout, N, 1), rows in memory
+
+
+def _conv1x1_rows_bwd(dh: torch.Tensor, x: torch.Tensor, cw: torch.Tensor, need_dx: bool, need_dw: bool):
+    B, Cin, N, _ = x.shape
+    Cout = cw.shape[0]
+    dx = dcw = None
+    with _conv_tf32_policy():
+        d2 = _rows2d(dh)
+        if need_dx:
+            dx = (d2 @ cw.reshape(Cout, Cin)).view(B, N, 1, Cin).permute(0, 3, 1, 2)
+        if need_dw:
+            dcw = (d2.t() @ _rows2d(x)).reshape(cw.shape)
+    return dx, dcw
+
+
 class _ConvBatchNormTrain(torch.autograd.Function):
     """Conv2d(1x1, bias) -> train-mode BatchNorm [-> ReLU | + residual] as one autograd node: the convolution stays
     cuDNN, the BatchNorm is the fused kernel pair, and the convolution's bias gradient - the per-channel sum of the
@@ -498,7 +546,10 @@ class _ConvBatchNormTrain(torch.autograd.Function):
     def forward(ctx, x, residual, cw, cb, weight, bias, running_mean, running_var, eps, momentum, relu, conv_args):
         lib = _native.load()
         stride, padding, dilation, groups = conv_args
-        h = torch.nn.functional.conv2d(x, cw, None, stride, padding, dilation, groups)   # bias: see the class docstring
+        if _gemm_form(conv_args, cw) and _is_rows(x):
+            h = _conv1x1_rows_fwd(x, cw)
+        else:
+            h = torch.nn.functional.conv2d(x, cw, None, stride, padding, dilation, groups)   # bias: see the class docstring
         if not _is_rows(h):
             h = as_rows(h)
         B, C, N, _ = h.shape
@@ -540,9 +591,12 @@ class _ConvBatchNormTrain(torch.autograd.Function):
               g.data_ptr(), h.data_ptr(), weight.data_ptr(), bias.data_ptr(), save_mean.data_ptr(),
               save_invstd.data_ptr(), dh.data_ptr(), dweight.data_ptr(), dbias.data_ptr(), dcb.data_ptr(), B * N, C,
               int(ctx.relu), ws.data_ptr(), ws_bytes, _stream())
-        dx, dcw, _ = torch.ops.aten.convolution_backward(
-            dh, x, cw, None, list(stride), list(padding), list(dilation), False, [0, 0], groups,
-            [ctx.needs_input_grad[0], ctx.needs_input_grad[2], False])
+        if _gemm_form(ctx.conv_args, cw) and _is_rows(x):
+            dx, dcw = _conv1x1_rows_bwd(dh, x, cw, ctx.needs_input_grad[0], ctx.needs_input_grad[2])
+        else:
+            dx, dcw, _ = torch.ops.aten.convolution_backward(
+                dh, x, cw, None, list(stride), list(padding), list(dilation), False, [0, 0], groups,
+                [ctx.needs_input_grad[0], ctx.needs_input_grad[2], False])
         return (dx, (grad_out if ctx.has_res else None), dcw, dcb, dweight, dbias, None, None, None, None, None, None)
 
 
