@@ -2,11 +2,12 @@
 """Benchmark: segments/s of a GraphEncoder forward+backward NT-Xent training step.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+    python bench.py --impl reference --steps K --warmup W    # the reference's own PyTorch code on the host CPU
 
 Workload (BASELINE.json configs[1]): SimCLR(GraphEncoder(k=3)) on synthetic log-mel segments,
 batch 512 pairs per GPU (= 1024 segments per step), fp32, Adam.  One step = zero_grad, both
-views forward, NT-Xent, backward, optimizer step.  Prints ONE JSON line (see DESIGN.md, section
+views forward, NT-Xent, backward, optimizer step.  ``--dtype bf16`` runs configs[2]'s arithmetic
+(torch.autocast bf16 activations, fp32 parameters).  Prints ONE JSON line (see DESIGN.md, section
 "Measurement", for every key).
 """
 import argparse
@@ -37,8 +38,11 @@ def parse_args():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=512, help="pairs per GPU per step (2 segments each)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="pairs per step of the CPU reference sample")
+    ap.add_argument("--dtype", choices=["fp32", "bf16"], default="fp32",
+                    help="fp32 = configs[1]; bf16 = torch.autocast(bfloat16) activations with fp32 parameters (configs[2])")
     ap.add_argument("--knn-algo", choices=["auto", "simt", "tc"], default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-eager-on-this-GPU baseline")
     return ap.parse_args()
 
 
@@ -50,6 +54,16 @@ def peaks():
         return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
                 "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def dram_traffic():
+    """Per-launch DRAM bytes of our kernels from the committed ncu --set full capture (profiles/dram_traffic.json,
+    written by scripts/ncu_summary.py), keyed by op name; {} when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
 
 
 # ------------------------------------------------------------------------------------------
@@ -107,18 +121,32 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# CPU reference arm: the oracle's restatement of the reference algorithm on the host cores
+# the reference's training step (its own modules from baseline/_ref; the oracle port when that copy is absent)
 # ------------------------------------------------------------------------------------------
-def cpu_reference_steps(pairs, steps, warmup, seed=1234):
-    """Time `steps` SimCLR training steps of the reference algorithm on the CPU (all host threads)."""
-    from grafp_b200 import synth
+def reference_model(cfg, device):
+    """-> (kind, step_fn(spec_i, spec_j) -> loss tensor).  kind "reference": the unmodified upstream SimCLR / GraphEncoder /
+    ntxent_loss; "port": the oracle's restatement of the same algorithm (CPU only)."""
+    from oracle import reference_arm as RA
+    if RA.available():
+        ref = RA.load()
+        torch.manual_seed(0)
+        model = ref.SimCLR(cfg, ref.GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3)).to(device).train()
+        opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"])
+
+        def step(s_i, s_j):
+            opt.zero_grad(set_to_none=True)
+            _, _, z_i, z_j = model(s_i, s_j)
+            loss = ref.ntxent_loss(z_i, z_j, cfg)
+            loss.backward()
+            opt.step()
+            return loss
+
+        return "reference", step
+    if device.type != "cpu":
+        raise RuntimeError("no staged reference (baseline/_ref): the GPU-eager baseline needs the upstream modules")
     from grafp_b200.encoder.graph_encoder import GraphEncoder
     from grafp_b200.simclr.simclr import SimCLR
     from oracle import grafp_oracle as O
-
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cfg = dict(synth.DEFAULT_CFG)
     torch.manual_seed(0)
     shapes_model = SimCLR(cfg, GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3))  # parameter container only
     params = {k: v.detach().clone() for k, v in shapes_model.state_dict().items() if not k.endswith("relative_pos")}
@@ -126,20 +154,74 @@ def cpu_reference_steps(pairs, steps, warmup, seed=1234):
     for n in trainable:
         params[n].requires_grad_(True)
     opt = torch.optim.Adam([params[n] for n in trainable], lr=cfg["lr"])
-    s_i, s_j = synth.synth_spec(pairs, seed)
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
+
+    def step(s_i, s_j):
         opt.zero_grad(set_to_none=True)
         _, _, z_i, z_j = O.simclr_forward(params, s_i, s_j, True, k=3)
         loss = O.ntxent_loss(z_i, z_j, cfg["tau"])
         loss.backward()
         opt.step()
-        loss.item()
+        return loss
+
+    return "port", step
+
+
+def cpu_reference_steps(pairs, steps, warmup, seed=1234):
+    """Time `steps` SimCLR training steps of the reference on the CPU (all host threads)."""
+    from grafp_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = dict(synth.DEFAULT_CFG)
+    cfg["bsz_train"] = pairs
+    kind, step = reference_model(cfg, torch.device("cpu"))
+    s_i, s_j = synth.synth_spec(pairs, seed)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        step(s_i, s_j).item()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    return {"value": 2 * pairs * steps / total, "seconds": total, "cores": cores, "pairs": pairs, "steps": steps}
+    return {"value": 2 * pairs * steps / total, "seconds": total, "cores": cores, "pairs": pairs, "steps": steps,
+            "kind": kind}
+
+
+def gpu_eager_reference(dev, pairs, steps=3, warmup=1, seed=1234):
+    """The unmodified reference run eager on this GPU: same step, same inputs, PyTorch-default math, at the largest
+    batch <= `pairs` that fits (its (B, N, N) distance matrices and (B, C, N, k) gathers are materialised)."""
+    from grafp_b200 import synth
+    cfg = dict(synth.DEFAULT_CFG)
+    tried = []
+    B = pairs
+    while B >= 8:
+        cfg["bsz_train"] = B
+        step = None
+        try:
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats(dev)
+            kind, step = reference_model(cfg, dev)
+            s_i, s_j = (t.to(dev) for t in synth.synth_spec(B, seed))
+            for _ in range(warmup):
+                step(s_i, s_j)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step(s_i, s_j).item()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1)
+            return {"value": 2 * B * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "pairs_per_gpu": B,
+                    "segments_per_step": 2 * B, "steps": steps, "warmup": warmup,
+                    "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2**30, "kind": kind,
+                    "did_not_fit": tried,
+                    "what": "unmodified upstream SimCLR(GraphEncoder) + ntxent_loss + Adam from baseline/_ref, PyTorch eager "
+                            "on this GPU (cuBLAS bmm, ATen topk / index / index_put_, cuDNN), fp32, PyTorch-default TF32 policy"}
+        except torch.cuda.OutOfMemoryError:
+            tried.append(B)
+            del step
+            B //= 2
+    return {"unavailable": f"out of memory down to {B} pairs", "did_not_fit": tried}
 
 
 def run_reference(args):
@@ -147,14 +229,21 @@ def run_reference(args):
     if rank != 0:
         return
     r = cpu_reference_steps(args.cpu_batch, args.steps, args.warmup)
-    sample = (f"{args.steps} steps x {args.cpu_batch} pairs ({2 * args.cpu_batch} segments/step) of the same SimCLR step, "
-              f"oracle port of the reference on {r['cores']} host threads")
+    what = ("the unmodified upstream modules (baseline/_ref)" if r["kind"] == "reference"
+            else "oracle port of the reference (baseline/_ref not staged)")
+    sample = (f"{args.steps} steps x {args.cpu_batch} pairs ({2 * args.cpu_batch} segments/step) of the same SimCLR training step, "
+              f"{what} on {r['cores']} host threads")
+    cfg = workload_config(args, 1)
+    # this arm's step is a bounded sample: say so where the config is read, not only in the sample string
+    cfg.update({"pairs_per_gpu": args.cpu_batch, "segments_per_step": 2 * args.cpu_batch,
+                "sample": f"bounded CPU sample of that workload: the same training step at {args.cpu_batch} pairs per step "
+                          f"instead of {args.batch} (a 512-pair step of the reference takes minutes on the host cores)"})
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -162,10 +251,16 @@ def run_reference(args):
 
 
 def workload_config(args, world):
-    return {"workload": "configs[1]: GraphEncoder fwd+bwd NT-Xent training step, batch 512 pairs/GPU, fp32",
+    if args.dtype == "bf16":
+        name = ("configs[2] arithmetic: GraphEncoder fwd+bwd NT-Xent training step, batch 512 pairs/GPU, "
+                "torch.autocast(bfloat16) activations, fp32 parameters")
+    else:
+        name = "configs[1]: GraphEncoder fwd+bwd NT-Xent training step, batch 512 pairs/GPU, fp32"
+    return {"workload": name,
             "pairs_per_gpu": args.batch, "segments_per_step": 2 * args.batch * world, "k": 3, "nodes": 1024,
             "encoder": "GraphEncoder size t (12 Grapher+FFN blocks)", "optimizer": "Adam",
-            "parallelism": f"dp{world}", "conv_math": "PyTorch default (cuDNN conv TF32 allowed, matmul fp32)",
+            "parallelism": f"dp{world}", "conv_math": "PyTorch default (cuDNN conv TF32 allowed, matmul fp32)"
+            if args.dtype == "fp32" else "cuDNN bf16 convolutions under autocast",
             "l2": "no explicit flush: one step touches ~70 GB of activations, far above the 126 MB L2"}
 
 
@@ -183,6 +278,10 @@ def algorithmic_work(name, m):
         return {"bytes": B * N * C * e * (3 + m.get("res", 0))}
     if name == "bn_train_bwd":  # reduction pass (dy, x) + apply pass (dy, x -> dx)
         return {"bytes": B * N * C * e * 5}
+    if name in ("ntxent_fwd", "ntxent_bwd"):
+        return {"flops": (2.0 if name == "ntxent_fwd" else 4.0) * m["N"] * m["N"] * m["C"], "bytes": 0}
+    if "k" not in m:
+        return {"bytes": 0}
     k = m["k"]
     idx_b = 8 if m.get("i64") else 4
     if name == "mr_aggregate_fwd":
@@ -190,6 +289,36 @@ def algorithmic_work(name, m):
     if name == "mr_aggregate_bwd":
         return {"bytes": B * (2 * N * C * e + N * C + N * k * idx_b + N * C * e)}
     return {"bytes": 0}
+
+
+_ROOFLINE_NAMES = {
+    "knn_fwd": "K1 dilated k-NN graph (normalise + tcgen05 Gram / top-k)",
+    "mr_aggregate_fwd": "K2 gather + max-relative + interleave",
+    "mr_aggregate_bwd": "K3 argmax-routed scatter backward",
+    "bn_train_fwd": "K5 train-mode BatchNorm (+ReLU / +residual) forward",
+    "bn_train_bwd": "K5 backward",
+}
+
+
+def roofline_entry(name, kt, pk, ops, traffic):
+    if name == "knn_fwd":
+        tc = ops.knn_last_algo() == "tcgen05"
+        f16 = ops.knn_last_variant() == "f16x3"
+        # kind::f16 issues at the bf16 rate, kind::tf32 at half of it
+        peak = pk["bf16_tflops_sustained"] / (1.0 if f16 else 2.0)
+        ach = kt["tflops"]
+        return {"kernel": f"{_ROOFLINE_NAMES[name]} [{ops.knn_last_algo()} {ops.knn_last_variant()}]",
+                "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak if ach else None, "issued_frac": 3 * ach / peak if (ach and f16) else None,
+                "traffic": traffic.get(name), "ms_per_step": kt["ms_per_step"],
+                "peak_source": f"{pk['source']} bf16 sustained" + ("" if f16 else " / 2 (TF32)"),
+                "note": "achieved = algorithmic 2*N*M*C flops / time of the whole op (normalise launch included); the "
+                        "fp16 hi/lo split issues 3 MMAs per algorithmic one (issued_frac); ncu tensor-pipe % per stage "
+                        "is in profiles/" if tc else "CUDA-core fp32 path, reported against the tensor peak"}
+    peak = pk["hbm_gbs"]
+    return {"kernel": _ROOFLINE_NAMES.get(name, name), "bound": "hbm", "achieved": kt["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": kt["gbs"] / peak if kt["gbs"] else None, "traffic": traffic.get(name),
+            "ms_per_step": kt["ms_per_step"], "peak_source": pk["source"]}
 
 
 def run_ours(args):
@@ -224,20 +353,19 @@ def run_ours(args):
     if algo != _native.KNN_AUTO:
         _orig = ops.knn_graph
         ops.knn_graph = lambda *a, **kw: _orig(*a, **{**kw, "algo": algo})
+    bf16 = args.dtype == "bf16"
 
     s_i, s_j = synth.synth_spec(args.batch, 1234 + rank)
     host_i, host_j = s_i.pin_memory(), s_j.pin_memory()
     dev_i, dev_j = host_i.to(dev), host_j.to(dev)
     h2d_bytes = host_i.numel() * 4 + host_j.numel() * 4
 
-    def loss_fn(z_i, z_j):
-        # global-batch negatives like the reference's DataParallel gather (train.py:69-71)
-        return global_ntxent_loss(z_i, z_j, cfg)
-
     def step(x_i, x_j):
         opt.zero_grad(set_to_none=True)
-        _, _, z_i, z_j = net(x_i, x_j)
-        loss = loss_fn(z_i, z_j)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+            _, _, z_i, z_j = net(x_i, x_j)
+        # global-batch negatives like the reference's DataParallel gather (train.py:69-71); the loss runs in fp32
+        loss = global_ntxent_loss(z_i.float(), z_j.float(), cfg)
         loss.backward()
         opt.step()
         return loss
@@ -292,6 +420,7 @@ def run_ours(args):
 
     if rank == 0:
         pk = peaks()
+        traffic = dram_traffic()
         kernels = {}
         for name, rec in ksum.items():
             work = {"bytes": 0.0, "flops": 0.0}
@@ -301,49 +430,51 @@ def run_ours(args):
                 work["flops"] += w.get("flops", 0.0) * sh["calls"]
             sec = rec["ms_total"] / 1e3
             kernels[name] = {"calls": rec["calls"], "ms_total": rec["ms_total"],
+                             "ms_per_step": rec["ms_total"] / args.steps,
                              "share_of_step": rec["ms_total"] / ms_resident,
-                             "gbs": work["bytes"] / sec / 1e9 if sec > 0 else None,
-                             "tflops": work["flops"] / sec / 1e12 if sec > 0 and work["flops"] else None,
-                             "_bytes": work["bytes"], "_flops": work["flops"]}
+                             "gbs": work["bytes"] / sec / 1e9 if sec > 0 and work["bytes"] else None,
+                             "tflops": work["flops"] / sec / 1e12 if sec > 0 and work["flops"] else None}
+        # `roofline`: the costliest of our kernels (the contract's "dominant kernel"); `rooflines`: every hot-path kernel,
+        # K1 against the tensor peak, K2 / K3 / K5 against the HBM peak
         roofline = None
+        rooflines = [roofline_entry(n, kernels[n], pk, ops, traffic) for n in _ROOFLINE_NAMES if n in kernels]
         if kernels:
-            top = max(kernels, key=lambda n: kernels[n]["ms_total"])
-            kt = kernels[top]
-            if top == "knn_fwd":
-                tc = ops.knn_last_algo() == "tcgen05"
-                f16 = ops.knn_last_variant() == "f16x3"
-                # kind::f16 issues at the bf16 rate, kind::tf32 at half of it
-                peak = pk["bf16_tflops_sustained"] / (1.0 if f16 else 2.0)
-                roofline = {"kernel": f"knn_fwd ({ops.knn_last_algo()} {ops.knn_last_variant()}; normalise + Gram/top-k launches)",
-                            "bound": "tensor", "achieved": kt["tflops"], "peak": peak, "unit": "TFLOP/s",
-                            "frac": kt["tflops"] / peak, "traffic": None,
-                            "peak_source": f"{pk['source']} bf16 sustained" + ("" if f16 else " / 2 (TF32)"),
-                            "note": "algorithmic 2*N*M*C flops; the hi/lo split issues 3 MMAs per algorithmic one, "
-                                    "so 1/3 is the ceiling of this fraction" if tc else
-                                    "CUDA-core fp32 path, reported against the tensor peak"}
-            else:
-                peak = pk["hbm_gbs"]
-                roofline = {"kernel": top, "bound": "hbm", "achieved": kt["gbs"], "peak": peak, "unit": "GB/s",
-                            "frac": kt["gbs"] / peak, "traffic": None, "peak_source": pk["source"]}
-        for kt in kernels.values():
-            kt.pop("_bytes"); kt.pop("_flops")
+            top = max((n for n in kernels if n in _ROOFLINE_NAMES), key=lambda n: kernels[n]["ms_total"], default=None)
+            if top is not None:
+                roofline = roofline_entry(top, kernels[top], pk, ops, traffic)
 
-        cpu_baseline = None
-        if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_steps(args.cpu_batch, 3, 1)
-            cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                            "sample": f"3 steps x {args.cpu_batch} pairs of the same SimCLR training step (oracle port "
-                                      f"of the reference algorithm), {r['seconds']:.1f} s on {r['cores']} host threads"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "dtype": "f32" if not bf16 else "bf16", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
             "gpu_launches": timer.launches, "knn_algo": ops.knn_last_algo(),
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "roofline": roofline, "rooflines": rooflines, "kernels": kernels, "clocks": clocks,
             "loss_last": losses[-1] if losses else None, "pairs_per_s": value / 2,
         }
+        # ---- baselines (rank 0, one GPU only): the reference eager on this GPU, then on the host cores ----
+        if world == 1:
+            del opt, net, model
+            torch.cuda.empty_cache()
+            if not args.no_gpu_eager:
+                try:
+                    g = gpu_eager_reference(dev, args.batch)
+                except Exception as exc:  # a missing baseline/_ref must not cost the bench line
+                    g = {"unavailable": f"{type(exc).__name__}: {exc}"}
+                if "value" in g:
+                    g["speedup_resident"] = value / g["value"]
+                    g["speedup_e2e"] = e2e_value / g["value"]
+                line["gpu_eager_baseline"] = g
+            if not args.no_cpu_baseline:
+                r = cpu_reference_steps(args.cpu_batch, 3, 1)
+                line["cpu_baseline"] = {
+                    "value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                    "sample": f"3 steps x {args.cpu_batch} pairs of the same SimCLR training step ("
+                              + ("the unmodified upstream modules from baseline/_ref" if r["kind"] == "reference"
+                                 else "oracle port of the reference algorithm")
+                              + f"), {r['seconds']:.1f} s on {r['cores']} host threads"}
+        line.setdefault("cpu_baseline", None)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -19,6 +19,9 @@ _vp, _i, _sz = _c.c_void_p, _c.c_int, _c.c_size_t
 SIGNATURES = {
     "grafp_abi_version": (_i, []),
     "grafp_last_error": (_c.c_char_p, []),
+    "grafp_set_option": (_i, [_c.c_char_p, _i]),
+    "grafp_get_option": (_i, [_c.c_char_p]),
+    "grafp_check_index": (_i, [_vp, _i, _c.c_longlong, _i, _vp, _vp]),
     "grafp_knn_last_algo": (_c.c_char_p, []),
     "grafp_knn_last_variant": (_c.c_char_p, []),
     "grafp_knn_workspace_bytes": (_sz, [_i] * 6),
@@ -35,11 +38,11 @@ SIGNATURES = {
     "grafp_max_over_k_fwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
     "grafp_max_over_k_bwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
     "grafp_bn_workspace_bytes": (_sz, [_i]),
-    "grafp_bn_train_fwd": (_i, [_vp] * 9 + [_c.c_longlong, _i, _c.c_float, _c.c_float, _i, _vp, _sz, _vp]),
-    "grafp_bn_train_bwd": (_i, [_vp] * 10 + [_c.c_longlong, _i, _i, _vp, _sz, _vp]),
+    "grafp_bn_train_fwd": (_i, [_vp] * 9 + [_c.c_longlong, _i, _c.c_float, _c.c_float, _i, _i, _vp, _sz, _vp]),
+    "grafp_bn_train_bwd": (_i, [_vp] * 10 + [_c.c_longlong, _i, _i, _i, _vp, _sz, _vp]),
 }
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 KNN_AUTO, KNN_SIMT, KNN_TC, KNN_TC_TF32 = 0, 1, 2, 3
 KNN_MAX_K = 64
 

@@ -1,4 +1,7 @@
 // extern "C" entry points of libgrafp_b200.so: argument validation + dispatch.
+#include <atomic>
+#include <cctype>
+#include <cstring>
 #include <mutex>
 #include <string>
 
@@ -29,6 +32,45 @@ int check_launch(const char* what) {
     return static_cast<int>(e);
   }
   return GRAFP_OK;
+}
+
+int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return dev;
+}
+
+// ---- run-time options: defaults, overridden once at load by GRAFP_<NAME>, then by grafp_set_option ----
+namespace {
+struct OptionSpec { const char* name; int def; };
+const OptionSpec kOptionSpecs[OPT_COUNT] = {
+    {"mr_fwd_form", 2}, {"mr_bwd_form", 2}, {"knn_epilogue", 0}, {"edge_bwd_row", 1}, {"gather_row", 1},
+    {"edge_row", 1},    {"maxk_row", 1},    {"bn_reverse", 1},   {"check_index", 0},
+};
+std::atomic<int> g_options[OPT_COUNT];
+std::once_flag g_options_once;
+void init_options() {
+  for (int i = 0; i < OPT_COUNT; ++i) {
+    int v = kOptionSpecs[i].def;
+    char env[64] = "GRAFP_";
+    size_t n = strlen(env);
+    for (const char* c = kOptionSpecs[i].name; *c && n + 1 < sizeof(env); ++c) env[n++] = (char)toupper((unsigned char)*c);
+    env[n] = 0;
+    if (const char* e = getenv(env)) v = atoi(e);
+    g_options[i].store(v, std::memory_order_relaxed);
+  }
+}
+int option_index(const char* name) {
+  if (name == nullptr) return -1;
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(name, kOptionSpecs[i].name) == 0) return i;
+  return -1;
+}
+}  // namespace
+
+int option(Option o) {
+  std::call_once(g_options_once, init_options);
+  return g_options[o].load(std::memory_order_relaxed);
 }
 
 int num_sms() {
@@ -92,6 +134,29 @@ using namespace grafp;
 extern "C" {
 
 int grafp_abi_version(void) { return GRAFP_ABI_VERSION; }
+
+int grafp_set_option(const char* name, int value) {
+  clear_error();
+  const int i = option_index(name);
+  GRAFP_REQUIRE(i >= 0, GRAFP_EINVAL, "grafp_set_option: unknown option '%s'", name ? name : "(null)");
+  std::call_once(g_options_once, init_options);
+  g_options[i].store(value, std::memory_order_relaxed);
+  return GRAFP_OK;
+}
+
+int grafp_check_index(const void* idx, int idx_is_i64, long long count, int limit, int* bad_count, void* stream) {
+  clear_error();
+  GRAFP_REQUIRE(idx && bad_count && count > 0 && limit > 0, GRAFP_EINVAL, "grafp_check_index: idx, bad_count must be non-null, count and limit positive");
+  { int rc = require_device("grafp_check_index"); if (rc != GRAFP_OK) return rc; }
+  { int rc = require_device_ptr("grafp_check_index", "idx", idx); if (rc) return rc; }
+  return launch_check_index(idx, idx_is_i64, count, limit, bad_count, static_cast<cudaStream_t>(stream));
+}
+
+int grafp_get_option(const char* name) {
+  const int i = option_index(name);
+  if (i < 0) return GRAFP_EINVAL;
+  return option(static_cast<Option>(i));
+}
 const char* grafp_last_error(void) { return g_error.c_str(); }
 const char* grafp_knn_last_algo(void) { return g_knn_algo; }
 const char* grafp_knn_last_variant(void) { return g_knn_variant; }
@@ -149,7 +214,7 @@ int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn
   float* y_sq = reinterpret_cast<float*>(base + 2 * qx + 2 * qy + sx);
   void* bounds = base + 2 * qx + 2 * qy + sx + align_up((size_t)B * M * sizeof(float), 1024);
 
-  const int mode = use_tc2 ? 3 : (use_tc ? (dtype == GRAFP_F32 ? 1 : 2) : 0);
+  const int mode = use_tc2 ? 3 : (use_tc ? 1 : 0);  // fp16 hi/lo planes, tf32 hi/lo planes, or plain fp32 x_hat
   int rc;
   if (dtype == GRAFP_F32) {
     rc = launch_knn_normalize<float>(x, x_hi, x_lo, x_sq, (long long)B * N, C, mode, normalize != 0, s);
@@ -301,38 +366,38 @@ extern "C" {
 
 size_t grafp_bn_workspace_bytes(int C) { return C > 0 ? bn_workspace_bytes(C) : 0; }
 
-int grafp_bn_train_fwd(const float* x, const float* residual, const float* weight, const float* bias, float* running_mean,
-                       float* running_var, float* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
-                       float momentum, int relu, void* workspace, size_t workspace_bytes, void* stream) {
+int grafp_bn_train_fwd(const void* x, const void* residual, const float* weight, const float* bias, float* running_mean,
+                       float* running_var, void* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
+                       float momentum, int relu, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
   clear_error();
   GRAFP_REQUIRE(R > 1 && C > 0, GRAFP_EINVAL, "grafp_bn_train_fwd: needs at least two rows and C > 0");
+  GRAFP_REQUIRE(dtype == GRAFP_F32 || dtype == GRAFP_BF16, GRAFP_EUNSUPPORTED, "grafp_bn_train_fwd: dtype %d not supported", dtype);
   GRAFP_REQUIRE(x && weight && bias && out && save_mean && save_invstd && workspace, GRAFP_EINVAL,
                 "grafp_bn_train_fwd: x, weight, bias, out, save_mean, save_invstd and workspace must be non-null");
-  GRAFP_REQUIRE(aligned16(x) && aligned16(out) && aligned16(weight) && aligned16(bias) && aligned16(save_mean) &&
-                    aligned16(save_invstd) && (residual == nullptr || aligned16(residual)),
-                GRAFP_EINVAL, "grafp_bn_train_fwd: pointers must be 16-byte aligned");
+  GRAFP_REQUIRE(aligned16(x) && aligned16(out) && (residual == nullptr || aligned16(residual)),
+                GRAFP_EINVAL, "grafp_bn_train_fwd: x, out and residual must be 16-byte aligned");
   GRAFP_REQUIRE(workspace_bytes >= bn_workspace_bytes(C), GRAFP_EWORKSPACE, "grafp_bn_train_fwd: workspace too small");
   { int rc = require_device("grafp_bn_train_fwd"); if (rc != GRAFP_OK) return rc; }
   { int rc = require_device_ptr("grafp_bn_train_fwd", "x", x); if (rc) return rc; }
   return launch_bn_train_fwd(x, residual, weight, bias, running_mean, running_var, out, save_mean, save_invstd, R, C, eps,
-                             momentum, relu, workspace, static_cast<cudaStream_t>(stream));
+                             momentum, relu, dtype, workspace, static_cast<cudaStream_t>(stream));
 }
 
-int grafp_bn_train_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* save_mean,
-                       const float* save_invstd, float* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
-                       int relu, void* workspace, size_t workspace_bytes, void* stream) {
+int grafp_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,
+                       const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
+                       int relu, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
   clear_error();
   GRAFP_REQUIRE(R > 1 && C > 0, GRAFP_EINVAL, "grafp_bn_train_bwd: needs at least two rows and C > 0");
+  GRAFP_REQUIRE(dtype == GRAFP_F32 || dtype == GRAFP_BF16, GRAFP_EUNSUPPORTED, "grafp_bn_train_bwd: dtype %d not supported", dtype);
   GRAFP_REQUIRE(dy && x && weight && bias && save_mean && save_invstd && dx && dweight && dbias && workspace, GRAFP_EINVAL,
                 "grafp_bn_train_bwd: all pointers must be non-null");
-  GRAFP_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(weight) && aligned16(bias) &&
-                    aligned16(save_mean) && aligned16(save_invstd) && aligned16(dweight) && aligned16(dbias),
-                GRAFP_EINVAL, "grafp_bn_train_bwd: pointers must be 16-byte aligned");
+  GRAFP_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx), GRAFP_EINVAL,
+                "grafp_bn_train_bwd: dy, x and dx must be 16-byte aligned");
   GRAFP_REQUIRE(workspace_bytes >= bn_workspace_bytes(C), GRAFP_EWORKSPACE, "grafp_bn_train_bwd: workspace too small");
   { int rc = require_device("grafp_bn_train_bwd"); if (rc != GRAFP_OK) return rc; }
   { int rc = require_device_ptr("grafp_bn_train_bwd", "dy", dy); if (rc) return rc; }
-  return launch_bn_train_bwd(dy, x, weight, bias, save_mean, save_invstd, dx, dweight, dbias, dx_colsum, R, C, relu, workspace,
-                             static_cast<cudaStream_t>(stream));
+  return launch_bn_train_bwd(dy, x, weight, bias, save_mean, save_invstd, dx, dweight, dbias, dx_colsum, R, C, relu, dtype,
+                             workspace, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -164,8 +164,8 @@ mr_aggregate_fwd_fast_kernel(const T* __restrict__ x, const T* __restrict__ src,
 }
 
 // ------------------------------------------------------------------------------------
-// K2, pipelined form (fp32, k = KN neighbours, centre == row, C/4 a power of two): persistent CTAs,
-// one (row, 4-channel) item per thread and iteration.  The item's own 16 bytes and its KN
+// K2, pipelined form (k = KN neighbours, centre == row): persistent CTAs, one item = (row, 16 bytes of
+// channels: 4 fp32 / 8 bf16) per thread and iteration.  The item's own 16 bytes and its KN
 // neighbour slices are fetched with cp.async into a per-thread shared-memory slot D iterations
 // ahead, so D * (KN + 1) * 16 bytes per thread are in flight without holding registers, and the
 // neighbour ids (the dependent load in front of the gathers) are read one iteration earlier
@@ -179,17 +179,93 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N_>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
-template <bool I64, int KN, int D>
+// 16 bytes of node features as fp32 registers, and the matching output / argmax / gradient forms
+template <typename T>
+struct Item16;
+
+template <>
+struct Item16<float> {
+  static constexpr int V = 4;
+  static __device__ __forceinline__ void unpack(const uint4& q, float (&v)[4]) {
+    v[0] = __uint_as_float(q.x); v[1] = __uint_as_float(q.y); v[2] = __uint_as_float(q.z); v[3] = __uint_as_float(q.w);
+  }
+  static __device__ __forceinline__ float round_like_t(float d) { return d; }
+  // [x_0, m_0, x_1, m_1, ...]: 2 V values = 32 bytes, one 256-bit store
+  static __device__ __forceinline__ void store_interleaved(float* p, const float (&x)[4], const float (&m)[4]) {
+    const float il[8] = {x[0], m[0], x[1], m[1], x[2], m[2], x[3], m[3]};
+    Pack8<float>::store(p, il);
+  }
+  static __device__ __forceinline__ void store_argmax(uint8_t* p, const int (&a)[4]) {
+    *reinterpret_cast<unsigned int*>(p) = (unsigned)a[0] | ((unsigned)a[1] << 8) | ((unsigned)a[2] << 16) | ((unsigned)a[3] << 24);
+  }
+  // 32 bytes of interleaved gradient [g0_0, g1_0, g0_1, g1_1, ...] -> the two planes
+  static __device__ __forceinline__ void unpack_pairs(const uint4& a, const uint4& b, float (&g0)[4], float (&g1)[4]) {
+    g0[0] = __uint_as_float(a.x); g1[0] = __uint_as_float(a.y); g0[1] = __uint_as_float(a.z); g1[1] = __uint_as_float(a.w);
+    g0[2] = __uint_as_float(b.x); g1[2] = __uint_as_float(b.y); g0[3] = __uint_as_float(b.z); g1[3] = __uint_as_float(b.w);
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  static __device__ __forceinline__ void red_add(float* p, const float (&v)[4]) { Pack<float, 4>::red_add(p, v); }
+};
+
+template <>
+struct Item16<__nv_bfloat16> {
+  static constexpr int V = 8;
+  static __device__ __forceinline__ float lo(uint32_t w) { return __uint_as_float(w << 16); }
+  static __device__ __forceinline__ float hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ void unpack(const uint4& q, float (&v)[8]) {
+    v[0] = lo(q.x); v[1] = hi(q.x); v[2] = lo(q.y); v[3] = hi(q.y);
+    v[4] = lo(q.z); v[5] = hi(q.z); v[6] = lo(q.w); v[7] = hi(q.w);
+  }
+  // the reference subtracts in bf16: round the difference before it is compared
+  static __device__ __forceinline__ float round_like_t(float d) { return __bfloat162float(__float2bfloat16_rn(d)); }
+  static __device__ __forceinline__ void store_interleaved(__nv_bfloat16* p, const float (&x)[8], const float (&m)[8]) {
+    uint32_t w[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[e] = pack2(x[e], m[e]);
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+  }
+  static __device__ __forceinline__ void store_argmax(uint8_t* p, const int (&a)[8]) {
+    uint2 t;
+    t.x = (unsigned)a[0] | ((unsigned)a[1] << 8) | ((unsigned)a[2] << 16) | ((unsigned)a[3] << 24);
+    t.y = (unsigned)a[4] | ((unsigned)a[5] << 8) | ((unsigned)a[6] << 16) | ((unsigned)a[7] << 24);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+  static __device__ __forceinline__ void unpack_pairs(const uint4& a, const uint4& b, float (&g0)[8], float (&g1)[8]) {
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { g0[e] = lo(w[e]); g1[e] = hi(w[e]); }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+  }
+  static __device__ __forceinline__ void red_add(__nv_bfloat16* p, const float (&v)[8]) {
+    asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(pack2(v[0], v[1])),
+                 "r"(pack2(v[2], v[3])), "r"(pack2(v[4], v[5])), "r"(pack2(v[6], v[7]))
+                 : "memory");
+  }
+};
+
+template <typename T, bool I64, int KN, int D>
 __global__ void __launch_bounds__(kThreads)
-mr_aggregate_fwd_pipe_kernel(const float* __restrict__ x, const float* __restrict__ src, const void* __restrict__ nbr,
-                             float* __restrict__ out, uint8_t* __restrict__ argmax, int N, int M, int C, int cv_shift,
+mr_aggregate_fwd_pipe_kernel(const T* __restrict__ x, const T* __restrict__ src, const void* __restrict__ nbr,
+                             T* __restrict__ out, uint8_t* __restrict__ argmax, int N, int M, int C, int cv_shift,
                              int ips_shift, int total_iters) {
+  using It = Item16<T>;
+  constexpr int V = It::V;
   extern __shared__ __align__(16) unsigned char pipe_smem[];
   // slot (stage s, operand o, thread t) -> 16 bytes; consecutive threads are consecutive: conflict-free
   const uint32_t slot0 = static_cast<uint32_t>(__cvta_generic_to_shared(pipe_smem)) + threadIdx.x * 16;
   auto slot = [&](int s, int o) { return slot0 + (uint32_t)((s * (KN + 1) + o) * kThreads * 16); };
   const int cmask = (1 << cv_shift) - 1;
-  const int c = (threadIdx.x & cmask) * 4;  // 256 % cv == 0: the channel pack of a thread never changes
+  const int c = (threadIdx.x & cmask) * V;  // 256 % cv == 0: the channel pack of a thread never changes
 
   // work item w = (segment b, chunk of 256 items): b = w >> ips_shift
   auto row_of = [&](int w, long long& rowg, int& b) {
@@ -208,7 +284,7 @@ mr_aggregate_fwd_pipe_kernel(const float* __restrict__ x, const float* __restric
     long long rowg; int b;
     row_of(w, rowg, b);
     cp_async16(slot(s, 0), x + rowg * C + c);
-    const float* sb = src + (long long)b * M * C + c;
+    const T* sb = src + (long long)b * M * C + c;
 #pragma unroll
     for (int j = 0; j < KN; ++j) cp_async16(slot(s, 1 + j), sb + (long long)ids[j] * C);
   };
@@ -226,23 +302,21 @@ mr_aggregate_fwd_pipe_kernel(const float* __restrict__ x, const float* __restric
   int s = 0;
   for (int w = w0; w < total_iters; w += stride) {
     cp_async_wait<D - 1>();
-    float self[4], best[4];
-    int arg[4];
-    {
-      const float4 v = *reinterpret_cast<const float4*>(pipe_smem + (slot(s, 0) - (slot0 - threadIdx.x * 16)));
-      self[0] = v.x; self[1] = v.y; self[2] = v.z; self[3] = v.w;
-    }
+    float self[V], best[V];
+    int arg[V];
+    It::unpack(*reinterpret_cast<const uint4*>(pipe_smem + (slot(s, 0) - (slot0 - threadIdx.x * 16))), self);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { best[e] = -INFINITY; arg[e] = 0; }
-    float xj[KN][4];
+    for (int e = 0; e < V; ++e) { best[e] = -INFINITY; arg[e] = 0; }
+    float dj[KN][V];
     float poison = 0.f;
 #pragma unroll
     for (int j = 0; j < KN; ++j) {
-      const float4 v = *reinterpret_cast<const float4*>(pipe_smem + (slot(s, 1 + j) - (slot0 - threadIdx.x * 16)));
-      xj[j][0] = v.x; xj[j][1] = v.y; xj[j][2] = v.z; xj[j][3] = v.w;
+      float xj[V];
+      It::unpack(*reinterpret_cast<const uint4*>(pipe_smem + (slot(s, 1 + j) - (slot0 - threadIdx.x * 16))), xj);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float d = xj[j][e] - self[e];
+      for (int e = 0; e < V; ++e) {
+        const float d = It::round_like_t(xj[e] - self[e]);
+        dj[j][e] = d;
         poison = fmaf(d, 0.f, poison);      // NaN / inf anywhere -> NaN
         const bool gt = d > best[e];        // strict: the first maximiser wins (torch.max)
         best[e] = gt ? d : best[e];
@@ -251,12 +325,12 @@ mr_aggregate_fwd_pipe_kernel(const float* __restrict__ x, const float* __restric
     }
     if (poison != 0.f) {  // redo with exact torch.max semantics (NaN propagates, first NaN wins)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { best[e] = -INFINITY; arg[e] = 0; }
+      for (int e = 0; e < V; ++e) { best[e] = -INFINITY; arg[e] = 0; }
 #pragma unroll
       for (int j = 0; j < KN; ++j) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float d = xj[j][e] - self[e];
+        for (int e = 0; e < V; ++e) {
+          const float d = dj[j][e];
           if (d > best[e] || d != d) {
             if (!(best[e] != best[e])) { best[e] = d; arg[e] = j; }
           }
@@ -265,12 +339,8 @@ mr_aggregate_fwd_pipe_kernel(const float* __restrict__ x, const float* __restric
     }
     long long rowg; int b;
     row_of(w, rowg, b);
-    const float il[8] = {self[0], best[0], self[1], best[1], self[2], best[2], self[3], best[3]};
-    Pack8<float>::store(out + rowg * 2 * C + 2 * c, il);
-    if (argmax != nullptr) {
-      const unsigned int packed = (unsigned)arg[0] | ((unsigned)arg[1] << 8) | ((unsigned)arg[2] << 16) | ((unsigned)arg[3] << 24);
-      *reinterpret_cast<unsigned int*>(argmax + rowg * C + c) = packed;
-    }
+    It::store_interleaved(out + rowg * 2 * C + 2 * c, self, best);
+    if (argmax != nullptr) It::store_argmax(argmax + rowg * C + c, arg);
     // refill this slot D iterations ahead (the slot's values are in registers / stored by now)
     const int wn = w + D * stride;
     if (wn < total_iters) issue(wn, s, ids);
@@ -280,7 +350,6 @@ mr_aggregate_fwd_pipe_kernel(const float* __restrict__ x, const float* __restric
   }
   cp_async_wait<0>();
 }
-
 // ------------------------------------------------------------------------------------
 // K3 (generic form): dense pass + atomic scatter pass, ordered by the stream.
 //   dense:   grad_x[row][c] = g[row][2c] (- g[row][2c+1] when the centre is the row itself)
@@ -399,13 +468,18 @@ mr_aggregate_bwd_scatter_kernel(const T* __restrict__ g, const uint8_t* __restri
 }
 
 // ------------------------------------------------------------------------------------
-// K3 (fused form, the one the k-NN graphs of the encoder use): one thread-block cluster per
-// segment.  Phase 1: every CTA streams its share of grad_out rows once, writes the dense part
-// of grad_x with plain stores and parks g[.., 2c+1] + argmax in shared memory.  A cluster
-// barrier orders all dense stores of the segment before phase 2, which routes the parked
-// values to their winning neighbour rows with vector reductions (red.global.add.v4.f32) that
-// hit the just-written, L2-resident grad_x rows.  HBM traffic = algorithmic bytes: grad_out,
-// argmax and the ids are read once, grad_x is written once.
+// K3 (cluster form, the one the k-NN graphs of the encoder use): one thread-block cluster per
+// segment.  A CTA's whole share of the segment - its rows of grad_out (contiguous) and their
+// neighbour ids - is pulled into shared memory by two cp.async.bulk copies issued by one thread and
+// awaited on an mbarrier, while the argmax bytes stream into registers.  Phase 1 writes the dense
+// part of grad_x with plain stores; a cluster barrier (release / acquire at cluster scope) orders all
+// dense stores of the segment before phase 2, which routes g[.., 2c+1] to the winning neighbour rows
+// with vector reductions (red.global.add.v4.f32 / .v4.bf16x2) that hit the just-written, L2-resident
+// grad_x rows.  HBM traffic = algorithmic bytes: grad_out, argmax and the ids are read once, grad_x
+// is written once.  Phase 2 walks the neighbour slots j = 0..k-1 in a fixed order, so the lanes that
+// share a source row issue their reduction to the SAME target row in the same instruction
+// (contiguous runs that the LSU / L2 merge per sector) and an item issues at most k-1 of them.
+// An item is (row, 16 bytes of channels): 4 fp32 or 8 bf16 channels.
 // ------------------------------------------------------------------------------------
 constexpr int kFusedThreads = 256;
 
@@ -415,100 +489,6 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-
-template <typename T, bool I64, int U>
-__global__ void __launch_bounds__(kFusedThreads, 4)
-mr_aggregate_bwd_fused_kernel(const T* __restrict__ g, const uint8_t* __restrict__ argmax, const void* __restrict__ nbr,
-                              T* __restrict__ grad_x, int N, int C, int k, int rows_per_cta, int cv_shift) {
-  extern __shared__ __align__(16) unsigned char fused_smem[];
-  const int cv = 1 << cv_shift;
-  float4* g1s = reinterpret_cast<float4*>(fused_smem);                                     // [rows_per_cta * cv]
-  unsigned int* ams = reinterpret_cast<unsigned int*>(fused_smem + (size_t)rows_per_cta * cv * 16);
-  const unsigned csize = cluster_nctarank();
-  const long long b = blockIdx.x / csize;
-  const int row0 = static_cast<int>(cluster_ctarank()) * rows_per_cta;
-  const int nrows = max(0, min(rows_per_cta, N - row0));
-  const int items = nrows << cv_shift;
-  const T* gb = g + b * (long long)N * 2 * C;
-  const uint8_t* ab = argmax + b * (long long)N * C;
-  T* gxb = grad_x + b * (long long)N * C;
-  const long long ib = b * (long long)N * k;
-
-  // phase 1: U independent items per thread in flight (loads first, then the dependent id look-ups)
-  for (int it0 = threadIdx.x; it0 < items; it0 += kFusedThreads * U) {
-    float g0[U][4], g1[U][4];
-    unsigned int packed[U];
-    int n[U], c[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int it = min(it0 + u * kFusedThreads, items - 1);
-      n[u] = row0 + (it >> cv_shift);
-      c[u] = (it & (cv - 1)) * 4;
-      {
-        float gp[8];
-        Pack8<T>::load(gb + (long long)n[u] * 2 * C + 2 * c[u], gp);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { g0[u][e] = gp[2 * e]; g1[u][e] = gp[2 * e + 1]; }
-      }
-      packed[u] = __ldg(reinterpret_cast<const unsigned int*>(ab + (long long)n[u] * C + c[u]));
-    }
-    int nb[U][4];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) nb[u][e] = load_index<I64>(nbr, ib + n[u] * k + ((packed[u] >> (8 * e)) & 0xff));
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int it = it0 + u * kFusedThreads;
-      if (it >= items) continue;
-      float r[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) r[e] = (nb[u][e] == n[u]) ? g0[u][e] : g0[u][e] - g1[u][e];
-      Pack<T, 4>::store(gxb + (long long)n[u] * C + c[u], r);
-      g1s[it] = make_float4(g1[u][0], g1[u][1], g1[u][2], g1[u][3]);
-      ams[it] = packed[u];
-    }
-  }
-  __threadfence();
-  cluster_sync_all();
-
-  // phase 2: route the parked values to the winning neighbour rows of this segment
-  for (int it = threadIdx.x; it < items; it += kFusedThreads) {
-    const int n = row0 + (it >> cv_shift);
-    const int c = (it & (cv - 1)) * 4;
-    const float4 gv = g1s[it];
-    const unsigned int packed = ams[it];
-    const float g1[4] = {gv.x, gv.y, gv.z, gv.w};
-    // One 16-byte reduction per distinct winning neighbour (channels that picked another neighbour add 0):
-    // the reduction issue rate, not the bytes, bounds this phase.
-    int a[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) a[e] = (packed >> (8 * e)) & 0xff;
-    unsigned todo = 0xf;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if (todo & (1u << e)) {
-        const int j = a[e];
-        float v[4];
-#pragma unroll
-        for (int f = 0; f < 4; ++f) {
-          const bool hit = (a[f] == j);
-          v[f] = hit ? g1[f] : 0.f;
-          if (hit) todo &= ~(1u << f);
-        }
-        const int nb = load_index<I64>(nbr, ib + n * k + j);
-        if (nb != n) Pack<T, 4>::red_add(gxb + (long long)nb * C + c, v);
-      }
-    }
-  }
-}
-
-// K3, cluster form with TMA bulk staging (fp32): same two phases as the fused kernel above, but a CTA's
-// whole share of the segment - its rows of grad_out (contiguous, 64 KB at every encoder stage) and their
-// neighbour ids - is pulled into shared memory by two cp.async.bulk copies issued by one thread and
-// awaited on an mbarrier, while the argmax words stream into registers.  No dependent global load is
-// left in either phase, three CTAs per SM keep ~200 KB of reads outstanding, and phase 2 re-reads
-// g[.., 2c+1] from the staged tile instead of a separate stash.
 __device__ __forceinline__ void k3_mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -534,51 +514,49 @@ __device__ __forceinline__ void k3_mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-// JORDER: phase 2 walks the neighbour slots j = 0..k-1 in a fixed order instead of the winners of the item's four
-// channels, so the lanes that share a source row issue their red.v4 to the SAME target row in the same instruction
-// (contiguous 256-byte runs that the LSU / L2 merge per sector) and an item issues at most k-1 of them.
-// THREADS: 256 (8 items per thread) or 512 (4 items per thread, twice the warps per SM at the same shared memory).
-// (Measured and dropped: keeping the routed half of grad_out in registers between the phases and omitting the
-// device-wide fence in front of the cluster barrier - 80 registers per thread, 136-145 us against 125 us.)
-template <bool I64, bool JORDER, int THREADS>
-__global__ void __launch_bounds__(THREADS, 3)
-mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* __restrict__ argmax,
-                                    const void* __restrict__ nbr, float* __restrict__ grad_x, int N, int C, int k,
-                                    int rows_per_cta, int cv_shift) {
+// FENCE: a device-scope fence in front of the cluster barrier (the round-1 form; the barrier's own release / acquire
+// at cluster scope already orders the dense stores before the reductions of the other CTAs of the cluster).
+template <typename T, bool I64, bool FENCE>
+__global__ void __launch_bounds__(kFusedThreads, 3)
+mr_aggregate_bwd_cluster_kernel(const T* __restrict__ g, const uint8_t* __restrict__ argmax,
+                                const void* __restrict__ nbr, T* __restrict__ grad_x, int N, int C, int k,
+                                int rows_per_cta, int cv_shift) {
+  using It = Item16<T>;
+  constexpr int V = It::V;
   using idx_t = typename std::conditional<I64, long long, int>::type;
-  constexpr int kItems = 2048 / THREADS;  // (row, 4-channel) items per thread: the host caps a CTA's share at 2048 items
+  constexpr int kItems = 2048 / kFusedThreads;  // items per thread: the host caps a CTA's share at 2048 items
   extern __shared__ __align__(128) unsigned char tma_smem[];
   const int cv = 1 << cv_shift;
-  const float* gt = reinterpret_cast<const float*>(tma_smem);                                    // [rows][2C] grad_out
-  const idx_t* ids = reinterpret_cast<const idx_t*>(tma_smem + (size_t)rows_per_cta * 2 * C * 4); // [rows][k] neighbour ids
+  const size_t row_bytes = (size_t)2 * C * sizeof(T);
+  const unsigned char* gt = tma_smem;                                                       // [rows][2C] grad_out
+  const idx_t* ids = reinterpret_cast<const idx_t*>(tma_smem + (size_t)rows_per_cta * row_bytes);  // [rows][k] neighbour ids
   const uint32_t bar = static_cast<uint32_t>(
-      __cvta_generic_to_shared(tma_smem + (size_t)rows_per_cta * (2 * C * 4 + k * sizeof(idx_t))));
+      __cvta_generic_to_shared(tma_smem + (size_t)rows_per_cta * (row_bytes + k * sizeof(idx_t))));
   const unsigned csize = cluster_nctarank();
   const long long b = blockIdx.x / csize;
   const int row0 = static_cast<int>(cluster_ctarank()) * rows_per_cta;
   const int nrows = max(0, min(rows_per_cta, N - row0));
   const int items = nrows << cv_shift;
-  float* gxb = grad_x + b * (long long)N * C;
+  T* gxb = grad_x + b * (long long)N * C;
 
   if (threadIdx.x == 0) {
     k3_mbar_init(bar, 1);
     if (nrows > 0) {
-      const uint32_t gbytes = (uint32_t)nrows * 2 * C * 4, ibytes = (uint32_t)(nrows * k * sizeof(idx_t));
+      const uint32_t gbytes = (uint32_t)(nrows * row_bytes), ibytes = (uint32_t)(nrows * k * sizeof(idx_t));
       k3_mbar_expect_tx(bar, gbytes + ibytes);
       k3_bulk_g2s(static_cast<uint32_t>(__cvta_generic_to_shared(tma_smem)), g + (b * N + row0) * 2LL * C, gbytes, bar);
       k3_bulk_g2s(static_cast<uint32_t>(__cvta_generic_to_shared(ids)),
                   static_cast<const idx_t*>(nbr) + (b * N + row0) * (long long)k, ibytes, bar);
     }
   }
-  // the argmax words stream straight into registers while the bulk copies are in flight
-  unsigned int am[kItems];
+  // the argmax bytes stream straight into registers while the bulk copies are in flight
+  unsigned int am[kItems][V / 4];
 #pragma unroll
   for (int u = 0; u < kItems; ++u) {
-    const int it = threadIdx.x + u * THREADS;
-    am[u] = (it < items)
-                ? __ldg(reinterpret_cast<const unsigned int*>(argmax + (b * N + row0 + (it >> cv_shift)) * (long long)C +
-                                                              (it & (cv - 1)) * 4))
-                : 0u;
+    const int it = threadIdx.x + u * kFusedThreads;
+    const uint8_t* ap = argmax + (b * N + row0 + (it >> cv_shift)) * (long long)C + (it & (cv - 1)) * V;
+#pragma unroll
+    for (int q = 0; q < V / 4; ++q) am[u][q] = (it < items) ? __ldg(reinterpret_cast<const unsigned int*>(ap) + q) : 0u;
   }
   __syncthreads();  // the barrier is initialised before anyone waits on it
   if (nrows > 0) k3_mbar_wait(bar, 0);
@@ -586,100 +564,73 @@ mr_aggregate_bwd_cluster_tma_kernel(const float* __restrict__ g, const uint8_t* 
   // phase 1: dense part of grad_x for this CTA's rows (everything it needs is in shared memory or registers)
 #pragma unroll
   for (int u = 0; u < kItems; ++u) {
-    const int it = threadIdx.x + u * THREADS;
+    const int it = threadIdx.x + u * kFusedThreads;
     if (it < items) {
       const int rl = it >> cv_shift;
       const int n = row0 + rl;
-      const int c = (it & (cv - 1)) * 4;
-      const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
-      const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
-      const float g0[4] = {ga.x, ga.z, gb.x, gb.z}, g1[4] = {ga.y, ga.w, gb.y, gb.w};
-      float r[4];
+      const int c = (it & (cv - 1)) * V;
+      const uint4* gp = reinterpret_cast<const uint4*>(gt + (size_t)rl * row_bytes + (size_t)2 * c * sizeof(T));
+      float g0[V], g1[V];
+      It::unpack_pairs(gp[0], gp[1], g0, g1);
+      float r[V];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int nb = static_cast<int>(ids[rl * k + ((am[u] >> (8 * e)) & 0xff)]);
+      for (int e = 0; e < V; ++e) {
+        const int nb = static_cast<int>(ids[rl * k + ((am[u][e >> 2] >> (8 * (e & 3))) & 0xff)]);
         r[e] = (nb == n) ? g0[e] : g0[e] - g1[e];
       }
-      *reinterpret_cast<float4*>(gxb + (long long)n * C + c) = make_float4(r[0], r[1], r[2], r[3]);
+      It::store(gxb + (long long)n * C + c, r);
     }
   }
-  __threadfence();
+  if constexpr (FENCE) __threadfence();
   cluster_sync_all();
 
   // phase 2: route g[.., 2c+1] to the winning neighbour rows of this segment (L2-resident, just written)
 #pragma unroll
   for (int u = 0; u < kItems; ++u) {
-    const int it = threadIdx.x + u * THREADS;
+    const int it = threadIdx.x + u * kFusedThreads;
     if (it < items) {
       const int rl = it >> cv_shift;
       const int n = row0 + rl;
-      const int c = (it & (cv - 1)) * 4;
-      const float4 ga = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c);
-      const float4 gb = *reinterpret_cast<const float4*>(gt + (size_t)rl * 2 * C + 2 * c + 4);
-      const float g1[4] = {ga.y, ga.w, gb.y, gb.w};
-      int a[4];
+      const int c = (it & (cv - 1)) * V;
+      const uint4* gp = reinterpret_cast<const uint4*>(gt + (size_t)rl * row_bytes + (size_t)2 * c * sizeof(T));
+      float g0[V], g1[V];
+      It::unpack_pairs(gp[0], gp[1], g0, g1);
+      for (int j = 0; j < k; ++j) {
+        float v[V];
+        bool any = false;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) a[e] = (am[u] >> (8 * e)) & 0xff;
-      if constexpr (JORDER) {
-        for (int j = 0; j < k; ++j) {
-          float v[4];
-          bool any = false;
-#pragma unroll
-          for (int f = 0; f < 4; ++f) {
-            const bool hit = (a[f] == j);
-            v[f] = hit ? g1[f] : 0.f;
-            any |= hit;
-          }
-          const int nb = static_cast<int>(ids[rl * k + j]);
-          if (any && nb != n) Pack<float, 4>::red_add(gxb + (long long)nb * C + c, v);
+        for (int f = 0; f < V; ++f) {
+          const bool hit = ((am[u][f >> 2] >> (8 * (f & 3))) & 0xff) == (unsigned)j;
+          v[f] = hit ? g1[f] : 0.f;
+          any |= hit;
         }
-        continue;
-      }
-      unsigned todo = 0xf;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (todo & (1u << e)) {
-          const int j = a[e];
-          float v[4];
-#pragma unroll
-          for (int f = 0; f < 4; ++f) {
-            const bool hit = (a[f] == j);
-            v[f] = hit ? g1[f] : 0.f;
-            if (hit) todo &= ~(1u << f);
-          }
-          const int nb = static_cast<int>(ids[rl * k + j]);
-          if (nb != n) Pack<float, 4>::red_add(gxb + (long long)nb * C + c, v);
-        }
+        const int nb = static_cast<int>(ids[rl * k + j]);
+        if (any && nb != n) It::red_add(gxb + (long long)nb * C + c, v);
       }
     }
   }
 }
 
-namespace {
-int bwd_variant();  // development switch, defined with the dispatchers below
-}
-
-template <bool I64, bool JORDER, int THREADS = kFusedThreads>
-int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void* nbr, float* grad_x, int B, int N, int C,
-                              int k, cudaStream_t s, bool* launched) {
+template <typename T, bool I64>
+int launch_mr_bwd_cluster(const T* g, const uint8_t* argmax, const void* nbr, T* grad_x, int B, int N, int C, int k,
+                          bool fence, cudaStream_t s, bool* launched) {
   *launched = false;
-  const int cv = C / 4;
+  constexpr int V = Item16<T>::V;
+  if (C % V != 0) return GRAFP_OK;
+  const int cv = C / V;
   const size_t idsz = I64 ? 8 : 4;
-  if ((cv & (cv - 1)) != 0 || !aligned16(g) || !aligned16(nbr) || (((uintptr_t)argmax) & 3) != 0 || N < 64) return GRAFP_OK;
+  if ((cv & (cv - 1)) != 0 || !aligned16(g) || !aligned16(grad_x) || !aligned16(nbr) || (((uintptr_t)argmax) & 3) != 0 || N < 64)
+    return GRAFP_OK;
   int cv_shift = 0;
   while ((1 << cv_shift) < cv) ++cv_shift;
+  const size_t row_bytes = (size_t)2 * C * sizeof(T);
   // smallest cluster whose per-CTA share fits 8 items per thread and ~68 KB of shared memory (three CTAs per SM);
   // bulk copies need 16-byte multiples and 16-byte aligned sources for every CTA of the cluster
   int cl = 0;
-  // GRAFP_MR_BWD_VARIANT=18 (development): 16-CTA clusters (non-portable size) - half the share per CTA, twice the
-  // CTAs resident per SM, so more loads in flight next to the reduction phase of the neighbours
-  const bool big = bwd_variant() == 18 && N % 16 == 0 && ((N / 16) * k * idsz) % 16 == 0 && N / 16 >= 8;
-  if (big) cl = 16;
   for (int cand : {1, 2, 4, 8}) {
-    if (big) break;
     const long long rows = (N + cand - 1) / cand;
-    if (rows * cv <= 8 * kFusedThreads && rows * (2 * C * 4 + k * idsz) + 16 <= 68 * 1024 &&
-        (rows * k * idsz) % 16 == 0 && ((long long)N * k * idsz) % 16 == 0) {
+    if (rows * cv <= 8 * kFusedThreads && rows * (row_bytes + k * idsz) + 16 <= 68 * 1024 &&
+        (rows * k * idsz) % 16 == 0 && ((long long)N * k * idsz) % 16 == 0 && (rows * row_bytes) % 16 == 0) {
       cl = cand;
       break;
     }
@@ -687,81 +638,33 @@ int launch_mr_bwd_cluster_tma(const float* g, const uint8_t* argmax, const void*
   if (cl == 0 || (long long)B * cl > 0x7fffffffLL) return GRAFP_OK;
   const int rows_per_cta = (N + cl - 1) / cl;
   if (N % rows_per_cta != 0 && ((N % rows_per_cta) * k * idsz) % 16 != 0) return GRAFP_OK;  // ragged last share
-  const size_t smem = (size_t)rows_per_cta * (2 * C * 4 + k * idsz) + 16;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, THREADS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 68 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, THREADS>,
-                                                   cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_bwd_cluster_tma): %s", cudaGetErrorString(e)); return (int)e; }
-    configured = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(B * cl));
-  cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cl;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, mr_aggregate_bwd_cluster_tma_kernel<I64, JORDER, THREADS>, g, argmax, nbr, grad_x, N, C, k,
-                                     rows_per_cta, cv_shift);
-  if (e != cudaSuccess) { set_error("mr_aggregate_bwd_cluster_tma launch: %s", cudaGetErrorString(e)); return (int)e; }
-  *launched = true;
-  return check_launch("mr_aggregate_bwd_cluster_tma");
-}
-
-template <typename T, bool I64, int U>
-int launch_mr_bwd_fused(const T* g, const uint8_t* argmax, const void* nbr, T* grad_x, int B, int N, int C, int k,
-                        cudaStream_t s, bool* launched) {
-  *launched = false;
-  const int cv = C / 4;
-  if ((cv & (cv - 1)) != 0 || !aligned32(g)) return GRAFP_OK;  // C/4 a power of two (shift/mask indexing), 256-bit loads
-  int cv_shift = 0;
-  while ((1 << cv_shift) < cv) ++cv_shift;
-  // cluster of 8 CTAs per segment when the per-CTA share (g1 stash 4 B + argmax 1 B per element) fits
-  // 48 KB (4 CTAs resident per SM in different phases), else the smallest cluster that fits 96 KB
-  int cl = 0;
-  if (N >= 64 && (long long)((N + 7) / 8) * C * 5 <= 48 * 1024) cl = 8;
-  else {
-    for (int cand : {2, 4, 8}) {
-      const long long rows = (N + cand - 1) / cand;
-      if (rows * C * 5 <= 96 * 1024) { cl = cand; break; }
+  const size_t smem = (size_t)rows_per_cta * (row_bytes + k * idsz) + 16;
+  auto launch = [&](auto kernel, DeviceOnce& once) -> int {
+    if (once.pending()) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 68 * 1024);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_bwd_cluster): %s", cudaGetErrorString(e)); return (int)e; }
+      once.mark();
     }
-  }
-  if (cl == 0) return GRAFP_OK;
-  if ((long long)B * cl > 0x7fffffffLL) return GRAFP_OK;
-  const int rows_per_cta = (N + cl - 1) / cl;
-  const size_t smem = (size_t)rows_per_cta * C * 5;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mr_aggregate_bwd_fused_kernel<T, I64, U>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_bwd_fused): %s", cudaGetErrorString(e)); return (int)e; }
-    configured = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(B * cl));
-  cfg.blockDim = dim3(kFusedThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cl;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, mr_aggregate_bwd_fused_kernel<T, I64, U>, g, argmax, nbr, grad_x, N, C, k,
-                                     rows_per_cta, cv_shift);
-  if (e != cudaSuccess) { set_error("mr_aggregate_bwd_fused launch: %s", cudaGetErrorString(e)); return (int)e; }
-  *launched = true;
-  return check_launch("mr_aggregate_bwd_fused");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * cl));
+    cfg.blockDim = dim3(kFusedThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, g, argmax, nbr, grad_x, N, C, k, rows_per_cta, cv_shift);
+    if (e != cudaSuccess) { set_error("mr_aggregate_bwd_cluster launch: %s", cudaGetErrorString(e)); return (int)e; }
+    *launched = true;
+    return check_launch("mr_aggregate_bwd_cluster");
+  };
+  static DeviceOnce once_fence, once_nofence;
+  if (fence) return launch(mr_aggregate_bwd_cluster_kernel<T, I64, true>, once_fence);
+  return launch(mr_aggregate_bwd_cluster_kernel<T, I64, false>, once_nofence);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1371,21 +1274,6 @@ max_over_k_bwd_kernel(const T* __restrict__ g, const uint8_t* __restrict__ argma
 // ------------------------------------------------------------------------------------
 namespace {
 
-// development switches: GRAFP_MR_FWD_VARIANT = 0 generic kernel, 1 / 2 / 4 fast kernel with that many items in
-// flight per thread, 8 (default) the cp.async-pipelined persistent kernel where it applies; GRAFP_MR_BWD_VARIANT = 0 two-kernel form, 1 / 2 / 4 fused cluster form,
-// 8 the deterministic gather form over the reverse graph (needs the workspace), 16 the cluster form with TMA bulk
-// staging, 17 (default) the same with the reductions issued in neighbour-slot order, 18 that with 16-CTA clusters, 20 = 17 with 512-thread CTAs, 32 the deterministic shared-memory slice form (aggregate_bwd_slice.cu; measured slower:
-// it is bound by the L1 / shared-memory pipe)
-// (read on every call - a getenv is nanoseconds next to a launch - so tests can switch kernels in-process)
-int fwd_variant() {
-  const char* e = getenv("GRAFP_MR_FWD_VARIANT");
-  return e ? atoi(e) : 8;
-}
-int bwd_variant() {
-  const char* e = getenv("GRAFP_MR_BWD_VARIANT");
-  return e ? atoi(e) : 17;
-}
-
 template <typename F>
 int dispatch_vec_idx(int C, bool ptrs_aligned, int idx_is_i64, F&& f) {
   const bool vec4 = (C % 4 == 0) && ptrs_aligned;
@@ -1399,6 +1287,8 @@ int dispatch_vec_idx(int C, bool ptrs_aligned, int idx_is_i64, F&& f) {
 
 }  // namespace
 
+// K2 dispatch (option OPT_MR_FWD_FORM): pipelined persistent kernel where it applies (k == 3, centre == row, whole
+// 256-item chunks), else the register-prefetch kernel (4-channel packs, C/4 a power of two), else the generic one.
 template <typename T>
 int launch_mr_aggregate_fwd(const void* x, const void* y, const void* nbr, const void* ctr, int idx_is_i64, void* out,
                             uint8_t* argmax, int B, int N, int M, int C, int k, cudaStream_t s) {
@@ -1406,53 +1296,52 @@ int launch_mr_aggregate_fwd(const void* x, const void* y, const void* nbr, const
   const T* src = y ? static_cast<const T*>(y) : xs;
   const long long rows = (long long)B * N;
   const bool al = aligned16(x) && aligned16(src) && aligned16(out) && (argmax == nullptr || ((uintptr_t)argmax & 3) == 0);
+  const int form = option(OPT_MR_FWD_FORM);
   return dispatch_vec_idx(C, al, idx_is_i64, [&](auto vec, auto i64) {
     constexpr int VEC = decltype(vec)::value;
     constexpr bool I64 = decltype(i64)::value;
     const int grid = grid_for(rows * (C / VEC), kThreads, 8);
     if constexpr (VEC == 4) {
+      // pipelined form: one item = 16 bytes of channels
+      constexpr int V = Item16<T>::V;
+      if (!ctr && form >= 2 && k == 3 && C % V == 0 && aligned32(out) && (argmax == nullptr || ((uintptr_t)argmax & 7) == 0)) {
+        const int cvp = C / V;
+        const long long items_per_seg = (long long)N * cvp;
+        const long long ips = items_per_seg / kThreads;
+        if ((cvp & (cvp - 1)) == 0 && cvp <= kThreads && items_per_seg % kThreads == 0 && (ips & (ips - 1)) == 0 && ips >= 1 &&
+            (long long)B * ips < 0x7fffffffLL) {
+          int cv_shift = 0, ips_shift = 0;
+          while ((1 << cv_shift) < cvp) ++cv_shift;
+          while ((1LL << ips_shift) < ips) ++ips_shift;
+          const int total = (int)(B * ips);
+          constexpr int D = 4;
+          const size_t smem = (size_t)D * 4 * kThreads * 16;
+          static DeviceOnce once;
+          if (once.pending()) {
+            cudaError_t e = cudaFuncSetAttribute(mr_aggregate_fwd_pipe_kernel<T, I64, 3, D>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_fwd_pipe): %s", cudaGetErrorString(e)); return (int)e; }
+            once.mark();
+          }
+          int ctas = num_sms() * 3;  // 64 KB of slots per CTA: three CTAs per SM
+          if (ctas > total) ctas = total;
+          mr_aggregate_fwd_pipe_kernel<T, I64, 3, D><<<ctas, kThreads, smem, s>>>(xs, src, nbr, static_cast<T*>(out), argmax, N, M,
+                                                                                C, cv_shift, ips_shift, total);
+          return check_launch("mr_aggregate_fwd_pipe");
+        }
+      }
       const int cv = C / 4;
-      const int variant = fwd_variant();
-      if (!ctr && variant > 0 && (cv & (cv - 1)) == 0 && cv <= kThreads && B <= 65535 && aligned32(out)) {
+      if (!ctr && form >= 1 && (cv & (cv - 1)) == 0 && cv <= kThreads && B <= 65535 && aligned32(out)) {
         int cv_shift = 0;
         while ((1 << cv_shift) < cv) ++cv_shift;
-        if constexpr (std::is_same<T, float>::value) {
-          // pipelined persistent form: k == 3 (GraFP's k), whole 256-item chunks, a power-of-two number per segment
-          const long long items_per_seg = (long long)N * cv;
-          const long long ips = items_per_seg / kThreads;
-          if (variant >= 8 && k == 3 && items_per_seg % kThreads == 0 && (ips & (ips - 1)) == 0 && ips >= 1 &&
-              (long long)B * ips < 0x7fffffffLL) {
-            int ips_shift = 0;
-            while ((1LL << ips_shift) < ips) ++ips_shift;
-            const int total = (int)(B * ips);
-            constexpr int D = 4;
-            const size_t smem = (size_t)D * 4 * kThreads * 16;
-            static bool configured = false;
-            if (!configured) {
-              cudaError_t e = cudaFuncSetAttribute(mr_aggregate_fwd_pipe_kernel<I64, 3, D>,
-                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-              if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_fwd_pipe): %s", cudaGetErrorString(e)); return (int)e; }
-              configured = true;
-            }
-            int ctas = num_sms() * 3;  // 64 KB of slots per CTA: three CTAs per SM
-            if (ctas > total) ctas = total;
-            mr_aggregate_fwd_pipe_kernel<I64, 3, D><<<ctas, kThreads, smem, s>>>(
-                reinterpret_cast<const float*>(xs), reinterpret_cast<const float*>(src), nbr, reinterpret_cast<float*>(out),
-                argmax, N, M, C, cv_shift, ips_shift, total);
-            return check_launch("mr_aggregate_fwd_pipe");
-          }
-        }
         const int rpb = kThreads >> cv_shift;
-        const int u = variant >= 8 ? 4 : variant;  // items in flight per thread: 1, 2 or 4
-        const int passes = (N + rpb * u - 1) / (rpb * u);
+        constexpr int U = 4;  // items in flight per thread
+        const int passes = (N + rpb * U - 1) / (rpb * U);
         int gx = (num_sms() * 8 + B - 1) / B;  // about 8 resident CTAs per SM across the whole batch
         if (gx > passes) gx = passes;
         if (gx < 1) gx = 1;
-        dim3 grid2(gx, B);
-        T* o = static_cast<T*>(out);
-        if (u == 1) mr_aggregate_fwd_fast_kernel<T, I64, 1><<<grid2, kThreads, 0, s>>>(xs, src, nbr, o, argmax, N, M, C, k, cv_shift);
-        else if (u == 2) mr_aggregate_fwd_fast_kernel<T, I64, 2><<<grid2, kThreads, 0, s>>>(xs, src, nbr, o, argmax, N, M, C, k, cv_shift);
-        else mr_aggregate_fwd_fast_kernel<T, I64, 4><<<grid2, kThreads, 0, s>>>(xs, src, nbr, o, argmax, N, M, C, k, cv_shift);
+        mr_aggregate_fwd_fast_kernel<T, I64, U><<<dim3(gx, B), kThreads, 0, s>>>(xs, src, nbr, static_cast<T*>(out), argmax, N, M, C,
+                                                                             k, cv_shift);
         return check_launch("mr_aggregate_fwd");
       }
     }
@@ -1473,6 +1362,9 @@ size_t mr_bwd_workspace_bytes(int B, int N, int k) {
   return off + (size_t)B * N * k * 4 + 256;
 }
 
+// K3 dispatch (option OPT_MR_BWD_FORM): 2 (default) / 1 cluster kernel without / with the device-scope fence,
+// 3 deterministic gather over the reverse graph (fp32, k == 3, needs the workspace), 0 dense + scatter pair.
+// Graphs with explicit centre ids or a separate key set always take the pair.
 template <typename T>
 int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nbr, const void* ctr, int idx_is_i64,
                             void* grad_x, void* grad_y, int B, int N, int M, int C, int k, void* workspace,
@@ -1485,6 +1377,7 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
     cudaError_t e = cudaMemsetAsync(grad_y, 0, (size_t)B * M * C * sizeof(T), s);
     if (e != cudaSuccess) { set_error("cudaMemsetAsync(grad_y): %s", cudaGetErrorString(e)); return (int)e; }
   }
+  const int form = option(OPT_MR_BWD_FORM);
   return dispatch_vec_idx(C, al, idx_is_i64, [&](auto vec, auto i64) {
     constexpr int VEC = decltype(vec)::value;
     constexpr bool I64 = decltype(i64)::value;
@@ -1492,19 +1385,11 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
     const T* gs = static_cast<const T*>(g);
     const bool self_skip = (ctr == nullptr) && (grad_y == nullptr);
     if constexpr (VEC == 4 && std::is_same<T, float>::value) {
-      if (self_skip && bwd_variant() >= 32) {  // persistent (segment, channel-slice) gather out of shared memory
-        bool launched = false;
-        const int rc = launch_mr_bwd_slice<I64>(reinterpret_cast<const float*>(gs), argmax, nbr,
-                                                reinterpret_cast<float*>(gx), B, N, C, k, s, &launched);
-        if (rc != GRAFP_OK || launched) return rc;
-      }
-    }
-    if constexpr (VEC == 4 && std::is_same<T, float>::value) {
       // gather form over the reverse graph in a workspace
       const int cv = C / 4;
       const long long items_per_seg = (long long)N * cv;
       const long long ips = items_per_seg / kThreads;
-      if (self_skip && bwd_variant() == 8 && k == 3 && workspace != nullptr &&
+      if (self_skip && form == 3 && k == 3 && workspace != nullptr &&
           workspace_bytes >= mr_bwd_workspace_bytes(B, N, k) && (cv & (cv - 1)) == 0 && cv <= kThreads &&
           items_per_seg % kThreads == 0 && (ips & (ips - 1)) == 0 && ips >= 1 && (long long)B * ips < 0x7fffffffLL &&
           N <= 8192 && aligned32(g)) {
@@ -1517,12 +1402,12 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
         const size_t smem_rev = (size_t)(2 * N + 2) * sizeof(int);
         constexpr int D = 4;
         const size_t smem_pipe = (size_t)D * kThreads * 36;
-        static bool configured = false;
-        if (!configured) {
+        static DeviceOnce once;
+        if (once.pending()) {
           cudaError_t e = cudaFuncSetAttribute(mr_bwd_build_reverse_kernel<I64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
           if (e == cudaSuccess) e = cudaFuncSetAttribute(mr_aggregate_bwd_gather_kernel<I64, 3, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
           if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(mr_bwd_gather): %s", cudaGetErrorString(e)); return (int)e; }
-          configured = true;
+          once.mark();
         }
         mr_bwd_build_reverse_kernel<I64><<<B, kThreads, smem_rev, s>>>(nbr, rev_off, rev_src, N, k);
         const int total = (int)(B * ips);
@@ -1534,25 +1419,10 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
         return check_launch("mr_aggregate_bwd_gather");
       }
     }
-    if constexpr (VEC == 4 && std::is_same<T, float>::value) {
-      if (self_skip && bwd_variant() >= 16) {  // default: cluster form with TMA bulk staging
-        bool launched = false;
-        const float* gf = reinterpret_cast<const float*>(gs);
-        float* gxf = reinterpret_cast<float*>(gx);
-        const int bv = bwd_variant();
-        const int rc = (bv == 20)             ? launch_mr_bwd_cluster_tma<I64, true, 512>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
-                       : (bv == 17 || bv == 18) ? launch_mr_bwd_cluster_tma<I64, true>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched)
-                                              : launch_mr_bwd_cluster_tma<I64, false>(gf, argmax, nbr, gxf, B, N, C, k, s, &launched);
-        if (rc != GRAFP_OK || launched) return rc;
-      }
-    }
     if constexpr (VEC == 4) {
-      const int bv = bwd_variant() >= 8 ? 2 : bwd_variant();  // 0: two-kernel form; 1 / 2 / 4: fused cluster form
-      if (self_skip && bv > 0) {
+      if (self_skip && form >= 1) {  // default: cluster form with bulk staging
         bool launched = false;
-        const int rc = bv == 1 ? launch_mr_bwd_fused<T, I64, 1>(gs, argmax, nbr, gx, B, N, C, k, s, &launched)
-                     : bv == 2 ? launch_mr_bwd_fused<T, I64, 2>(gs, argmax, nbr, gx, B, N, C, k, s, &launched)
-                               : launch_mr_bwd_fused<T, I64, 4>(gs, argmax, nbr, gx, B, N, C, k, s, &launched);
+        const int rc = launch_mr_bwd_cluster<T, I64>(gs, argmax, nbr, gx, B, N, C, k, form == 1, s, &launched);
         if (rc != GRAFP_OK || launched) return rc;
       }
     }
@@ -1583,7 +1453,7 @@ int launch_gather_fwd(const void* src, const void* idx, int idx_is_i64, void* ou
     const int grid = grid_for(edges * (C / VEC), kThreads, 8);
     if constexpr (VEC == 4) {
       const long long rows = (long long)B * N;
-      const bool row_form = getenv("GRAFP_GATHER_ROW_FORM") == nullptr || atoi(getenv("GRAFP_GATHER_ROW_FORM")) != 0;
+      const bool row_form = option(OPT_GATHER_ROW) != 0;
       if (row_form && k >= 2 && k <= 4 && rows * (C / VEC) < 0x7fffffffLL) {
         const unsigned cv = C / VEC;
         const int g2 = grid_for((rows * cv + 1) / 2, kThreads, 8);
@@ -1657,7 +1527,7 @@ int launch_edge_gather_fwd(const void* x, const void* y, const void* nbr, const 
     const int grid = grid_for(edges * (C / VEC), kThreads, 8);
     if constexpr (VEC == 4) {
       const long long rows = (long long)B * N;
-      const bool row_form = getenv("GRAFP_EDGE_ROW_FORM") == nullptr || atoi(getenv("GRAFP_EDGE_ROW_FORM")) != 0;
+      const bool row_form = option(OPT_EDGE_ROW) != 0;
       if (!ctr && row_form && k >= 2 && k <= 4 && rows * (C / VEC) < 0x7fffffffLL) {
         const unsigned cv = C / VEC;
         const int g2 = grid_for((rows * cv + 1) / 2, kThreads, 8);
@@ -1695,7 +1565,7 @@ int launch_edge_gather_bwd(const void* g, const void* nbr, const void* ctr, int 
     const T* gs = static_cast<const T*>(g);
     if constexpr (VEC == 4) {
       // one-pass form (default; GRAFP_EDGE_BWD_ROW=0 selects the dense + scatter pair): 229-241 us against 280-290 us
-      const bool row_form = getenv("GRAFP_EDGE_BWD_ROW") == nullptr || atoi(getenv("GRAFP_EDGE_BWD_ROW")) != 0;
+      const bool row_form = option(OPT_EDGE_BWD_ROW) != 0;
       if (!ctr && !grad_y && row_form && k >= 2 && k <= 4 && rows * (C / VEC) < 0x7fffffffLL) {
         cudaError_t e2 = cudaMemsetAsync(grad_x, 0, (size_t)B * N * C * sizeof(T), s);
         if (e2 != cudaSuccess) { set_error("cudaMemsetAsync(edge grad_x): %s", cudaGetErrorString(e2)); return (int)e2; }
@@ -1724,7 +1594,7 @@ template <typename T>
 int launch_max_over_k_fwd(const void* h, void* out, uint8_t* argmax, int B, int N, int C, int k, cudaStream_t s) {
   const long long rows = (long long)B * N;
   const bool vec4 = (C % 4 == 0) && aligned16(h) && aligned16(out) && (argmax == nullptr || ((uintptr_t)argmax & 3) == 0);
-  const bool row_form = getenv("GRAFP_MAXK_ROW_FORM") == nullptr || atoi(getenv("GRAFP_MAXK_ROW_FORM")) != 0;
+  const bool row_form = option(OPT_MAXK_ROW) != 0;
   if (vec4 && row_form && k >= 2 && k <= 4 && rows * (C / 4) < 0x7fffffffLL) {
     const unsigned cv = C / 4;
     const int g2 = grid_for((rows * cv + 1) / 2, kThreads, 8);
@@ -1776,5 +1646,31 @@ int launch_max_over_k_bwd(const void* g, const uint8_t* argmax, void* grad_h, in
 
 GRAFP_INSTANTIATE(float)
 GRAFP_INSTANTIATE(__nv_bfloat16)
+
+// ------------------------------------------------------------------------------------
+// index range check (the reference's advanced indexing raises for ids outside [0, M); see grafp_check_index)
+// ------------------------------------------------------------------------------------
+template <bool I64>
+__global__ void __launch_bounds__(kThreads)
+check_index_kernel(const void* __restrict__ idx, long long count, int limit, int* __restrict__ bad) {
+  int local = 0;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < count; i += (long long)gridDim.x * kThreads) {
+    long long v;
+    if constexpr (I64) v = __ldg(reinterpret_cast<const long long*>(idx) + i);
+    else v = __ldg(reinterpret_cast<const int*>(idx) + i);
+    local += (v < 0 || v >= limit) ? 1 : 0;
+  }
+  local = __reduce_add_sync(0xffffffffu, local);
+  if ((threadIdx.x & 31) == 0 && local != 0) atomicAdd(bad, local);
+}
+
+int launch_check_index(const void* idx, int idx_is_i64, long long count, int limit, int* bad_count, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(bad_count, 0, sizeof(int), s);
+  if (e != cudaSuccess) { set_error("grafp_check_index: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+  const int grid = grid_for(count, kThreads, 4);
+  if (idx_is_i64) check_index_kernel<true><<<grid, kThreads, 0, s>>>(idx, count, limit, bad_count);
+  else check_index_kernel<false><<<grid, kThreads, 0, s>>>(idx, count, limit, bad_count);
+  return check_launch("check_index");
+}
 
 }  // namespace grafp

@@ -2,420 +2,361 @@
 // in the Grapher / FFN blocks (reference: torch_vertex.py:152-162,183-194 fc1 / fc2 = Conv2d + BatchNorm2d,
 // graph_encoder.py:45-67 FFN, torch_nn.py:52-64 BasicConv = Conv2d + BatchNorm2d + ReLU).  SURVEY 8(f) row 2.
 //
-// Activations are rows (R = B*N, C) fp32, C % 4 == 0 and C/4 a power of two.  HBM-bound streaming:
+// Activations are rows (R = B*N, C), fp32 or bf16 (statistics and parameters always fp32); a thread owns 16 bytes
+// of channels (V = 4 fp32 / 8 bf16), C % V == 0 and C / V a power of two.  HBM-bound streaming, TWO launches each way:
 //   forward : statistics pass (read x) + apply pass (read x [, residual], write y)            -> 3-4 tensor passes
 //             (PyTorch: BN 3 + ReLU 2 or add 3)
 //   backward: reduction pass (read dy, x) + apply pass (read dy, x, write dx)                  -> 5 tensor passes
 //             (PyTorch: ReLU backward 3 + BN backward 5); the ReLU mask is recomputed from x, so neither the
 //             BN output nor the ReLU output is kept for backward.
-// Statistics are accumulated per thread around a shift (the first element it sees), merged with Chan's
-// formula and finalised in double precision, so they do not suffer E[x^2] - E[x]^2 cancellation.
+// There are no finalize kernels (round 1 had three of them, 9-17 us of pure latency each, 126 calls per step): every
+// block of the first pass folds its per-channel partial sums into 2C doubles with red.f64 (a few hundred
+// reductions per address), and the second pass turns those into mean / invstd (or the two gradient sums) in its
+// prologue; block-0 threads also write the saved statistics, the running statistics and dweight / dbias.
+// Statistics are accumulated around a common shift (row 0 of the tensor) so E[x^2] - E[x]^2 never cancels
+// catastrophically, in fp32 per thread and block, in double across blocks.
+// With OPT_BN_REVERSE the second pass walks the rows back to front: the first pass leaves the tail of the tensor in
+// the 126 MB L2, so the second pass starts on L2 hits instead of evicting them before it gets there.
 #include "common.cuh"
 
 namespace grafp {
 namespace {
 
 constexpr int kBnThreads = 256;
-constexpr int kBnMaxPartials = 1024;
+constexpr int kBnMaxTpr = 32;  // threads per row chunk: a block covers <= 32 * V channels, which bounds the number of
+                               // red.f64 per block (blocks * channels-per-block * 2 per pass)
+
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  static constexpr int V = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int V = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) { Pack8<__nv_bfloat16>::load(p, v); }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) { Pack8<__nv_bfloat16>::store(p, v); }
+};
 
 struct BnGeom {
-  int cv;      // float4 packs per row
-  int tpr;     // threads per row inside a block (power of two <= 256)
+  int cv;      // 16-byte packs per row
+  int tpr;     // threads per row inside a block (power of two <= kBnMaxTpr)
   int rpp;     // rows per block pass = 256 / tpr
   int ctiles;  // channel tiles (grid.y) = cv / tpr
   int gx;      // row blocks (grid.x)
 };
 
-inline bool bn_geometry(long long R, int C, BnGeom* g) {
-  if (C < 4 || C % 4 != 0 || R < 2) return false;
-  const int cv = C / 4;
+inline bool bn_geometry(long long R, int C, int V, BnGeom* g) {
+  if (C < V || C % V != 0 || R < 2) return false;
+  const int cv = C / V;
   if ((cv & (cv - 1)) != 0) return false;
   g->cv = cv;
-  g->tpr = cv < kBnThreads ? cv : kBnThreads;
+  g->tpr = cv < kBnMaxTpr ? cv : kBnMaxTpr;
   g->rpp = kBnThreads / g->tpr;
   g->ctiles = cv / g->tpr;
   long long need = (R + g->rpp - 1) / g->rpp;
   long long cap = (long long)num_sms() * 4 / g->ctiles;
   if (cap < 1) cap = 1;
-  if (cap > kBnMaxPartials) cap = kBnMaxPartials;
   g->gx = (int)(need < cap ? need : cap);
   return true;
 }
 
-__device__ __forceinline__ void chan_merge(float& na, float& ma, float& Ma, float nb, float mb, float Mb) {
-  if (nb == 0.f) return;
-  const float n = na + nb;
-  const float d = mb - ma;
-  ma = ma + d * (nb / n);
-  Ma = Ma + Mb + d * d * (na * nb / n);
-  na = n;
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_f64_cg(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
 }
 
-// ---- forward statistics: per block and channel (mean, M2) over the rows the block owns ----
+// block reduction over the row lanes that share a channel pack: thread (rl, tc) holds NV values; after the call the
+// threads with rl == 0 hold the sums.  `sm` has NV * 256 floats.
+template <int NV>
+__device__ __forceinline__ void reduce_row_lanes(float (&v)[NV], float* sm, int tpr_shift) {
+  const int rpp = kBnThreads >> tpr_shift;
+  const int rl = threadIdx.x >> tpr_shift;
+#pragma unroll
+  for (int e = 0; e < NV; ++e) sm[e * kBnThreads + threadIdx.x] = v[e];
+  __syncthreads();
+  for (int half = rpp >> 1; half >= 1; half >>= 1) {
+    if (rl < half) {
+      const int o = threadIdx.x + (half << tpr_shift);
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        v[e] += sm[e * kBnThreads + o];
+        sm[e * kBnThreads + threadIdx.x] = v[e];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- forward statistics: sums[c] += sum (x - sh_c), sums[C + c] += sum (x - sh_c)^2, sh = row 0 ----
+template <typename T>
 __global__ void __launch_bounds__(kBnThreads)
-bn_stats_kernel(const float* __restrict__ x, float2* __restrict__ partial, int* __restrict__ pcount, long long R, int C,
-                int tpr_shift) {
-  __shared__ float4 s_mean[kBnThreads];
-  __shared__ float4 s_m2[kBnThreads];
-  __shared__ float s_n[kBnThreads];
+bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long R, int C, int tpr_shift) {
+  constexpr int V = Vec16<T>::V;
+  __shared__ float sm[2 * V * kBnThreads];
   const int tpr = 1 << tpr_shift;
   const int rpp = kBnThreads >> tpr_shift;
   const int tc = threadIdx.x & (tpr - 1);
   const int rl = threadIdx.x >> tpr_shift;
-  const int c4 = blockIdx.y * tpr + tc;
-  const float4* xp = reinterpret_cast<const float4*>(x) + c4;
-  const long long cv = C >> 2;
+  const int c = (blockIdx.y * tpr + tc) * V;
+  const T* xp = x + c;
   const long long step = (long long)gridDim.x * rpp;
   long long r = (long long)blockIdx.x * rpp + rl;
-  float4 sh = make_float4(0.f, 0.f, 0.f, 0.f), s = sh, q = sh;
-  float n = 0.f;
-  if (r < R) sh = __ldg(xp + r * cv);
-  for (; r + 3 * step < R; r += 4 * step) {  // four independent rows in flight
-    float4 v[4];
+  float sh[V], acc[2 * V];
+  Vec16<T>::load(xp, sh);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = __ldg(xp + (r + u * step) * cv);
+  for (int e = 0; e < 2 * V; ++e) acc[e] = 0.f;
+  auto add = [&](const float (&v)[V]) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float dx = v[u].x - sh.x, dy = v[u].y - sh.y, dz = v[u].z - sh.z, dw = v[u].w - sh.w;
-      s.x += dx; s.y += dy; s.z += dz; s.w += dw;
-      q.x = fmaf(dx, dx, q.x); q.y = fmaf(dy, dy, q.y); q.z = fmaf(dz, dz, q.z); q.w = fmaf(dw, dw, q.w);
+    for (int e = 0; e < V; ++e) {
+      const float d = v[e] - sh[e];
+      acc[e] += d;
+      acc[V + e] = fmaf(d, d, acc[V + e]);
     }
-    n += 4.f;
+  };
+  for (; r + 3 * step < R; r += 4 * step) {  // four independent rows in flight
+    float v[4][V];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Vec16<T>::load(xp + (r + u * step) * C, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) add(v[u]);
   }
   for (; r < R; r += step) {
-    const float4 v = __ldg(xp + r * cv);
-    const float dx = v.x - sh.x, dy = v.y - sh.y, dz = v.z - sh.z, dw = v.w - sh.w;
-    s.x += dx; s.y += dy; s.z += dz; s.w += dw;
-    q.x = fmaf(dx, dx, q.x); q.y = fmaf(dy, dy, q.y); q.z = fmaf(dz, dz, q.z); q.w = fmaf(dw, dw, q.w);
-    n += 1.f;
+    float v[V];
+    Vec16<T>::load(xp + r * C, v);
+    add(v);
   }
-  const float inv = n > 0.f ? 1.f / n : 0.f;
-  float4 mean = make_float4(sh.x + s.x * inv, sh.y + s.y * inv, sh.z + s.z * inv, sh.w + s.w * inv);
-  float4 m2 = make_float4(q.x - s.x * s.x * inv, q.y - s.y * s.y * inv, q.z - s.z * s.z * inv, q.w - s.w * s.w * inv);
-  s_mean[threadIdx.x] = mean; s_m2[threadIdx.x] = m2; s_n[threadIdx.x] = n;
-  __syncthreads();
-  // tree merge over the row lanes that share a channel pack
-  for (int half = rpp >> 1; half >= 1; half >>= 1) {
-    if (rl < half) {
-      const int o = threadIdx.x + (half << tpr_shift);
-      float na = s_n[threadIdx.x];
-      const float nb = s_n[o];
-      float4 ma = s_mean[threadIdx.x], Ma = s_m2[threadIdx.x];
-      const float4 mb = s_mean[o], Mb = s_m2[o];
-      float t;
-      t = na; chan_merge(t, ma.x, Ma.x, nb, mb.x, Mb.x);
-      t = na; chan_merge(t, ma.y, Ma.y, nb, mb.y, Mb.y);
-      t = na; chan_merge(t, ma.z, Ma.z, nb, mb.z, Mb.z);
-      chan_merge(na, ma.w, Ma.w, nb, mb.w, Mb.w);
-      s_mean[threadIdx.x] = ma; s_m2[threadIdx.x] = Ma; s_n[threadIdx.x] = na;
-    }
-    __syncthreads();
-  }
+  reduce_row_lanes<2 * V>(acc, sm, tpr_shift);
   if (rl == 0) {
-    const float4 m = s_mean[threadIdx.x], M = s_m2[threadIdx.x];
-    float2* p = partial + (long long)blockIdx.x * C + c4 * 4;
-    p[0] = make_float2(m.x, M.x); p[1] = make_float2(m.y, M.y); p[2] = make_float2(m.z, M.z); p[3] = make_float2(m.w, M.w);
-    if (tc == 0 && blockIdx.y == 0) pcount[blockIdx.x] = (int)s_n[threadIdx.x];
-  }
-}
-
-// 32 channels x 32 partial-groups per block (coalesced 256-byte reads of the partials, <= 19 partials per thread
-// with four loads in flight: these kernels are pure latency, 20 - 34 us each with 8 groups and a serial loop):
-// merge the block partials in double (two division-free passes: the global mean, then
-// M2 = sum [M2_p + n_p (mean_p - mean)^2]), emit mean / invstd, update the running statistics
-constexpr int kFinGroups = 32;
-constexpr int kFinThreads = 32 * kFinGroups;
-
-__device__ __forceinline__ double group_sum(double v, double (*sm)[33], int cl, int pg) {
-  __syncthreads();
-  sm[pg][cl] = v;
-  __syncthreads();
-  double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
 #pragma unroll
-  for (int i = 0; i < kFinGroups; i += 4) { t0 += sm[i][cl]; t1 += sm[i + 1][cl]; t2 += sm[i + 2][cl]; t3 += sm[i + 3][cl]; }
-  return (t0 + t1) + (t2 + t3);
+    for (int e = 0; e < V; ++e) {
+      red_add_f64(sums + c + e, (double)acc[e]);
+      red_add_f64(sums + C + c + e, (double)acc[V + e]);
+    }
+  }
 }
 
-__global__ void __launch_bounds__(kFinThreads)
-bn_stats_finalize_kernel(const float2* __restrict__ partial, const int* __restrict__ pcount, int parts, int C, long long R,
-                         float eps, float momentum, float* __restrict__ save_mean, float* __restrict__ save_invstd,
-                         float* running_mean, float* running_var) {
-  __shared__ double sm[kFinGroups][33];
-  const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
-  const int c = min(blockIdx.x * 32 + cl, C - 1);
-  const float2* pc = partial + c;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int p = pg;
-  for (; p + 3 * kFinGroups < parts; p += 4 * kFinGroups) {
-    const float m0 = pc[(long long)p * C].x, m1 = pc[(long long)(p + kFinGroups) * C].x;
-    const float m2_ = pc[(long long)(p + 2 * kFinGroups) * C].x, m3 = pc[(long long)(p + 3 * kFinGroups) * C].x;
-    a0 += (double)pcount[p] * (double)m0;
-    a1 += (double)pcount[p + kFinGroups] * (double)m1;
-    a2 += (double)pcount[p + 2 * kFinGroups] * (double)m2_;
-    a3 += (double)pcount[p + 3 * kFinGroups] * (double)m3;
-  }
-  for (; p < parts; p += kFinGroups) a0 += (double)pcount[p] * (double)pc[(long long)p * C].x;
-  const double mean = group_sum((a0 + a1) + (a2 + a3), sm, cl, pg) / (double)R;
-  a0 = a1 = a2 = a3 = 0.0;
-  p = pg;
-  for (; p + 3 * kFinGroups < parts; p += 4 * kFinGroups) {
-    const float2 v0 = pc[(long long)p * C], v1 = pc[(long long)(p + kFinGroups) * C];
-    const float2 v2 = pc[(long long)(p + 2 * kFinGroups) * C], v3 = pc[(long long)(p + 3 * kFinGroups) * C];
-    const double d0 = (double)v0.x - mean, d1 = (double)v1.x - mean, d2 = (double)v2.x - mean, d3 = (double)v3.x - mean;
-    a0 += (double)v0.y + (double)pcount[p] * d0 * d0;
-    a1 += (double)v1.y + (double)pcount[p + kFinGroups] * d1 * d1;
-    a2 += (double)v2.y + (double)pcount[p + 2 * kFinGroups] * d2 * d2;
-    a3 += (double)v3.y + (double)pcount[p + 3 * kFinGroups] * d3 * d3;
-  }
-  for (; p < parts; p += kFinGroups) {
-    const float2 v = pc[(long long)p * C];
-    const double d = (double)v.x - mean;
-    a0 += (double)v.y + (double)pcount[p] * d * d;
-  }
-  const double m2 = group_sum((a0 + a1) + (a2 + a3), sm, cl, pg);
-  if (pg != 0 || blockIdx.x * 32 + cl >= C) return;
-  const double var = m2 / (double)R;
-  save_mean[c] = (float)mean;
-  save_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean != nullptr) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-  if (running_var != nullptr) {
-    const double unbiased = m2 / (double)(R - 1);
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+// mean / invstd of this thread's V channels from the global sums (every thread of the second pass does this once)
+template <typename T, int V>
+__device__ __forceinline__ void bn_finish_stats(const T* x, const double* sums, int C, int c, double inv_rows, float eps,
+                                                float (&mean)[V], float (&invstd)[V], double (&var_b)[V]) {
+  float sh[V];
+  Vec16<T>::load(x + c, sh);
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    const double s = ld_f64_cg(sums + c + e) * inv_rows;
+    const double q = ld_f64_cg(sums + C + c + e) * inv_rows;
+    const double var = fmax(q - s * s, 0.0);
+    mean[e] = (float)((double)sh[e] + s);
+    invstd[e] = (float)(1.0 / sqrt(var + (double)eps));
+    var_b[e] = var;
   }
 }
 
 // ---- forward apply: y = (x - mean) * a + bias (+ residual) (ReLU), a = weight * invstd ----
-template <bool RELU, bool RES>
+template <typename T, bool RELU, bool RES>
 __global__ void __launch_bounds__(kBnThreads)
-bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ weight,
-                const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ invstd,
-                float* __restrict__ out, long long total4, int cv) {
-  const long long T = (long long)gridDim.x * kBnThreads;  // a multiple of cv: a thread's channel pack never changes
+bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ weight,
+                const float* __restrict__ bias, const double* __restrict__ sums, T* __restrict__ out,
+                float* __restrict__ save_mean, float* __restrict__ save_invstd, float* running_mean, float* running_var,
+                long long R, int C, int cv, float eps, float momentum, int reverse) {
+  constexpr int V = Vec16<T>::V;
+  const long long total = R * cv;                        // 16-byte items
+  const long long T_ = (long long)gridDim.x * kBnThreads;  // a multiple of cv: a thread's channel pack never changes
   const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
-  const int c = (int)(i0 % cv) * 4;
-  const float4 w = *reinterpret_cast<const float4*>(weight + c), bb = *reinterpret_cast<const float4*>(bias + c);
-  const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
-  const float4 a = make_float4(w.x * is.x, w.y * is.y, w.z * is.z, w.w * is.w);
-  const float4* xp = reinterpret_cast<const float4*>(x);
-  const float4* rp = reinterpret_cast<const float4*>(res);
-  float4* op = reinterpret_cast<float4*>(out);
+  const int c = (int)(i0 % cv) * V;
+  float mu[V], is[V], a[V], bb[V];
+  double var_b[V];
+  bn_finish_stats<T, V>(x, sums, C, c, 1.0 / (double)R, eps, mu, is, var_b);
+#pragma unroll
+  for (int e = 0; e < V; ++e) { a[e] = __ldg(weight + c + e) * is[e]; bb[e] = __ldg(bias + c + e); }
+  if (i0 < cv) {  // one thread per channel pack: the saved and the running statistics
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      save_mean[c + e] = mu[e];
+      save_invstd[c + e] = is[e];
+      if (running_mean != nullptr) running_mean[c + e] = (1.f - momentum) * running_mean[c + e] + momentum * mu[e];
+      if (running_var != nullptr) {
+        const double unbiased = var_b[e] * ((double)R / (double)(R - 1));
+        running_var[c + e] = (1.f - momentum) * running_var[c + e] + momentum * (float)unbiased;
+      }
+    }
+  }
+  if (i0 >= total) return;
   // (x - mean) first: exact-ish difference, no cancellation against a pre-multiplied shift when |mean| >> std
-  auto one = [&](float4 v, float4 rv) {
-    float4 y = make_float4(fmaf(v.x - mu.x, a.x, bb.x), fmaf(v.y - mu.y, a.y, bb.y), fmaf(v.z - mu.z, a.z, bb.z),
-                           fmaf(v.w - mu.w, a.w, bb.w));
-    if (RES) { y.x += rv.x; y.y += rv.y; y.z += rv.z; y.w += rv.w; }
-    if (RELU) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-    return y;
+  auto one = [&](const float (&v)[V], const float (&rv)[V], T* o) {
+    float y[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      y[e] = fmaf(v[e] - mu[e], a[e], bb[e]);
+      if (RES) y[e] += rv[e];
+      if (RELU) y[e] = fmaxf(y[e], 0.f);
+    }
+    Vec16<T>::store(o, y);
   };
-  long long i = i0;
-  for (; i + 3 * T < total4; i += 4 * T) {
-    float4 v[4], rv[4];
+  const long long n = (total - i0 + T_ - 1) / T_;  // items of this thread: i0 + j * T_, j < n
+  auto at = [&](long long j) { return (i0 + (reverse ? (n - 1 - j) : j) * T_) * V; };
+  long long j = 0;
+  for (; j + 3 < n; j += 4) {
+    float v[4][V], rv[4][V];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      v[u] = __ldg(xp + i + u * T);
-      rv[u] = RES ? __ldg(rp + i + u * T) : make_float4(0.f, 0.f, 0.f, 0.f);
+      Vec16<T>::load(x + at(j + u), v[u]);
+      if (RES) Vec16<T>::load(res + at(j + u), rv[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) op[i + u * T] = one(v[u], rv[u]);
+    for (int u = 0; u < 4; ++u) one(v[u], rv[u], out + at(j + u));
   }
-  for (; i < total4; i += T) op[i] = one(__ldg(xp + i), RES ? __ldg(rp + i) : make_float4(0.f, 0.f, 0.f, 0.f));
+  for (; j < n; ++j) {
+    float v[V], rv[V];
+    Vec16<T>::load(x + at(j), v);
+    if (RES) Vec16<T>::load(res + at(j), rv);
+    one(v, rv, out + at(j));
+  }
 }
 
-// ---- backward reduction: s1 = sum dz, s2 = sum dz * xhat, dz = dy masked by the recomputed ReLU ----
-template <bool RELU>
+// ---- backward reduction: s1 = sum dz, s2 = sum dz * xhat, s3 = sum (x - mean), dz = dy masked by the recomputed ReLU ----
+template <typename T, bool RELU>
 __global__ void __launch_bounds__(kBnThreads)
-bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ weight,
+bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ weight,
                      const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ invstd,
-                     float2* __restrict__ partial, long long R, int C, int tpr_shift) {
-  __shared__ float4 s_a[kBnThreads];
-  __shared__ float4 s_b[kBnThreads];
+                     double* __restrict__ sums, long long R, int C, int tpr_shift) {
+  constexpr int V = Vec16<T>::V;
+  __shared__ float sm[3 * V * kBnThreads];
   const int tpr = 1 << tpr_shift;
   const int rpp = kBnThreads >> tpr_shift;
   const int tc = threadIdx.x & (tpr - 1);
   const int rl = threadIdx.x >> tpr_shift;
-  const int c4 = blockIdx.y * tpr + tc;
-  const int c = c4 * 4;
-  const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;  // ReLU mask: (x - mean) * a + b > 0, the forward's expression
-  if (RELU) {
-    const float4 w = *reinterpret_cast<const float4*>(weight + c);
-    b = *reinterpret_cast<const float4*>(bias + c);
-    a = make_float4(w.x * is.x, w.y * is.y, w.z * is.z, w.w * is.w);
+  const int c = (blockIdx.y * tpr + tc) * V;
+  float mu[V], is[V], a[V], b[V], acc[3 * V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    mu[e] = __ldg(mean + c + e);
+    is[e] = __ldg(invstd + c + e);
+    a[e] = RELU ? __ldg(weight + c + e) * is[e] : 0.f;  // ReLU mask: (x - mean) * a + b > 0, the forward's expression
+    b[e] = RELU ? __ldg(bias + c + e) : 0.f;
+    acc[e] = 0.f; acc[V + e] = 0.f; acc[2 * V + e] = 0.f;
   }
-  const float4* xp = reinterpret_cast<const float4*>(x) + c4;
-  const float4* gp = reinterpret_cast<const float4*>(dy) + c4;
-  const long long cv = C >> 2;
+  const T* xp = x + c;
+  const T* gp = dy + c;
   const long long step = (long long)gridDim.x * rpp;
-  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-  auto acc = [&](float4 v, float4 g) {
-    v.x -= mu.x; v.y -= mu.y; v.z -= mu.z; v.w -= mu.w;
-    if (RELU) {
-      g.x = fmaf(v.x, a.x, b.x) > 0.f ? g.x : 0.f; g.y = fmaf(v.y, a.y, b.y) > 0.f ? g.y : 0.f;
-      g.z = fmaf(v.z, a.z, b.z) > 0.f ? g.z : 0.f; g.w = fmaf(v.w, a.w, b.w) > 0.f ? g.w : 0.f;
+  auto add = [&](const float (&v)[V], const float (&g)[V]) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float d = v[e] - mu[e];
+      float gz = g[e];
+      if (RELU) gz = fmaf(d, a[e], b[e]) > 0.f ? gz : 0.f;
+      acc[e] += gz;
+      acc[V + e] = fmaf(gz, d * is[e], acc[V + e]);
+      acc[2 * V + e] += d;
     }
-    s1.x += g.x; s1.y += g.y; s1.z += g.z; s1.w += g.w;
-    s2.x = fmaf(g.x, v.x * is.x, s2.x); s2.y = fmaf(g.y, v.y * is.y, s2.y);
-    s2.z = fmaf(g.z, v.z * is.z, s2.z); s2.w = fmaf(g.w, v.w * is.w, s2.w);
   };
   long long r = (long long)blockIdx.x * rpp + rl;
   for (; r + 3 * step < R; r += 4 * step) {
-    float4 v[4], g[4];
+    float v[4][V], g[4][V];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { v[u] = __ldg(xp + (r + u * step) * cv); g[u] = __ldg(gp + (r + u * step) * cv); }
+    for (int u = 0; u < 4; ++u) { Vec16<T>::load(xp + (r + u * step) * C, v[u]); Vec16<T>::load(gp + (r + u * step) * C, g[u]); }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc(v[u], g[u]);
+    for (int u = 0; u < 4; ++u) add(v[u], g[u]);
   }
-  for (; r < R; r += step) acc(__ldg(xp + r * cv), __ldg(gp + r * cv));
-  s_a[threadIdx.x] = s1; s_b[threadIdx.x] = s2;
-  __syncthreads();
-  for (int half = rpp >> 1; half >= 1; half >>= 1) {
-    if (rl < half) {
-      const int o = threadIdx.x + (half << tpr_shift);
-      float4 p = s_a[threadIdx.x], q = s_b[threadIdx.x];
-      const float4 po = s_a[o], qo = s_b[o];
-      p.x += po.x; p.y += po.y; p.z += po.z; p.w += po.w;
-      q.x += qo.x; q.y += qo.y; q.z += qo.z; q.w += qo.w;
-      s_a[threadIdx.x] = p; s_b[threadIdx.x] = q;
-    }
-    __syncthreads();
+  for (; r < R; r += step) {
+    float v[V], g[V];
+    Vec16<T>::load(xp + r * C, v);
+    Vec16<T>::load(gp + r * C, g);
+    add(v, g);
   }
+  reduce_row_lanes<3 * V>(acc, sm, tpr_shift);
   if (rl == 0) {
-    const float4 p = s_a[threadIdx.x], q = s_b[threadIdx.x];
-    float2* o = partial + (long long)blockIdx.x * C + c;
-    o[0] = make_float2(p.x, q.x); o[1] = make_float2(p.y, q.y); o[2] = make_float2(p.z, q.z); o[3] = make_float2(p.w, q.w);
-  }
-}
-
-__global__ void __launch_bounds__(kFinThreads)
-bn_bwd_finalize_kernel(const float2* __restrict__ partial, int parts, int C, float* __restrict__ dweight,
-                       float* __restrict__ dbias) {
-  __shared__ double sm[kFinGroups][33];
-  const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
-  const int c = min(blockIdx.x * 32 + cl, C - 1);
-  const float2* pc = partial + c;
-  double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
-  int p = pg;
-  for (; p + 3 * kFinGroups < parts; p += 4 * kFinGroups) {
-    float2 v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = pc[(long long)(p + u * kFinGroups) * C];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { s1[u] += (double)v[u].x; s2[u] += (double)v[u].y; }
+    for (int e = 0; e < V; ++e) {
+      red_add_f64(sums + c + e, (double)acc[e]);
+      red_add_f64(sums + C + c + e, (double)acc[V + e]);
+      red_add_f64(sums + 2 * C + c + e, (double)acc[2 * V + e]);
+    }
   }
-  for (; p < parts; p += kFinGroups) {
-    const float2 v = pc[(long long)p * C];
-    s1[0] += (double)v.x;
-    s2[0] += (double)v.y;
-  }
-  const double t1 = group_sum((s1[0] + s1[1]) + (s1[2] + s1[3]), sm, cl, pg);
-  const double t2 = group_sum((s2[0] + s2[1]) + (s2[2] + s2[3]), sm, cl, pg);
-  if (pg == 0 && blockIdx.x * 32 + cl < C) { dbias[c] = (float)t1; dweight[c] = (float)t2; }
 }
 
 // ---- backward apply: dx = weight * invstd * (dz - s1 / R - xhat * s2 / R) ----
-template <bool RELU, bool COLSUM>
+// `colsum` (optional): the per-channel column sums of dx - the bias gradient of the convolution in front of the
+// BatchNorm.  Analytically sum_r dx = a (s1 - R c1 - invstd c2 s3) with s3 = sum_r (x - mean): exactly zero in real
+// arithmetic, and in floating point the rounding residue of c1 = fl(s1 / R) and of the mean.  That residue is what
+// the reference's separate reduction over dx measures too; here it costs one extra sum in the reduction pass.
+template <typename T, bool RELU>
 __global__ void __launch_bounds__(kBnThreads)
-bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ weight,
+bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ weight,
                     const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ dweight, const float* __restrict__ dbias, float* __restrict__ dx,
-                    float* __restrict__ colsum_partial, long long total4, int cv, float inv_rows) {
-  const long long T = (long long)gridDim.x * kBnThreads;
+                    const double* __restrict__ sums, T* __restrict__ dx, float* __restrict__ dweight,
+                    float* __restrict__ dbias, float* __restrict__ colsum, long long R, int C, int cv, int reverse) {
+  constexpr int V = Vec16<T>::V;
+  const long long total = R * cv;
+  const long long T_ = (long long)gridDim.x * kBnThreads;
   const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
-  const int c = (int)(i0 % cv) * 4;
-  const float4 w = *reinterpret_cast<const float4*>(weight + c);
-  const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
-  const float4 a = make_float4(w.x * is.x, w.y * is.y, w.z * is.z, w.w * is.w);
-  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (RELU) b = *reinterpret_cast<const float4*>(bias + c);
-  const float4 d1 = *reinterpret_cast<const float4*>(dbias + c), d2 = *reinterpret_cast<const float4*>(dweight + c);
-  const float4 c1 = make_float4(d1.x * inv_rows, d1.y * inv_rows, d1.z * inv_rows, d1.w * inv_rows);
-  const float4 c2 = make_float4(d2.x * inv_rows, d2.y * inv_rows, d2.z * inv_rows, d2.w * inv_rows);
-  const float4* xp = reinterpret_cast<const float4*>(x);
-  const float4* gp = reinterpret_cast<const float4*>(dy);
-  float4* op = reinterpret_cast<float4*>(dx);
-  auto one = [&](float4 v, float4 g) {
-    v.x -= mu.x; v.y -= mu.y; v.z -= mu.z; v.w -= mu.w;
-    if (RELU) {
-      g.x = fmaf(v.x, a.x, b.x) > 0.f ? g.x : 0.f; g.y = fmaf(v.y, a.y, b.y) > 0.f ? g.y : 0.f;
-      g.z = fmaf(v.z, a.z, b.z) > 0.f ? g.z : 0.f; g.w = fmaf(v.w, a.w, b.w) > 0.f ? g.w : 0.f;
-    }
-    float4 r;
-    r.x = a.x * (g.x - c1.x - v.x * is.x * c2.x);
-    r.y = a.y * (g.y - c1.y - v.y * is.y * c2.y);
-    r.z = a.z * (g.z - c1.z - v.z * is.z * c2.z);
-    r.w = a.w * (g.w - c1.w - v.w * is.w * c2.w);
-    return r;
-  };
-  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of dx over this thread's rows (COLSUM)
-  long long i = i0;
-  for (; i + 3 * T < total4; i += 4 * T) {
-    float4 v[4], g[4];
+  const int c = (int)(i0 % cv) * V;
+  const double inv_rows = 1.0 / (double)R;
+  float mu[V], is[V], a[V], b[V], c1[V], c2[V];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { v[u] = __ldg(xp + i + u * T); g[u] = __ldg(gp + i + u * T); }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float4 r = one(v[u], g[u]);
-      op[i + u * T] = r;
-      if (COLSUM) { cs.x += r.x; cs.y += r.y; cs.z += r.z; cs.w += r.w; }
-    }
-  }
-  for (; i < total4; i += T) {
-    const float4 r = one(__ldg(xp + i), __ldg(gp + i));
-    op[i] = r;
-    if (COLSUM) { cs.x += r.x; cs.y += r.y; cs.z += r.z; cs.w += r.w; }
-  }
-  if (COLSUM) {
-    // block partial per channel: threads tid, tid + cv, ... of a block share a channel pack (cv <= 256), or own it (cv > 256)
-    __shared__ float4 s_cs[kBnThreads];
-    s_cs[threadIdx.x] = cs;
-    __syncthreads();
-    const int span = cv < kBnThreads ? cv : kBnThreads;
-    if ((int)threadIdx.x < span) {
-      float4 t = cs;
-      for (int o = threadIdx.x + span; o < kBnThreads; o += span) {
-        const float4 q = s_cs[o];
-        t.x += q.x; t.y += q.y; t.z += q.z; t.w += q.w;
+  for (int e = 0; e < V; ++e) {
+    mu[e] = __ldg(mean + c + e);
+    is[e] = __ldg(invstd + c + e);
+    a[e] = __ldg(weight + c + e) * is[e];
+    b[e] = RELU ? __ldg(bias + c + e) : 0.f;
+    const double s1 = ld_f64_cg(sums + c + e), s2 = ld_f64_cg(sums + C + c + e);
+    c1[e] = (float)(s1 * inv_rows);
+    c2[e] = (float)(s2 * inv_rows);
+    if (i0 < cv) {
+      dbias[c + e] = (float)s1;
+      dweight[c + e] = (float)s2;
+      if (colsum != nullptr) {
+        const double s3 = ld_f64_cg(sums + 2 * C + c + e);
+        colsum[c + e] = (float)((double)a[e] * ((s1 - (double)R * (double)c1[e]) - (double)is[e] * (double)c2[e] * s3));
       }
-      // channel pack of thread tid in this block: (blockIdx.x * 256 + tid) % cv
-      *reinterpret_cast<float4*>(colsum_partial + (long long)blockIdx.x * (4LL * span) + 4 * threadIdx.x) = t;
     }
   }
-}
-
-// column sums of dx: sum the block partials of bn_bwd_apply_kernel (block b, slot t holds channel pack (b * 256 + t) % cv)
-__global__ void __launch_bounds__(kFinThreads)
-bn_colsum_finalize_kernel(const float* __restrict__ colsum_partial, int blocks, int cv, float* __restrict__ colsum) {
-  __shared__ double sm[kFinGroups][33];
-  const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
-  const int C = cv * 4;
-  const int c = min(blockIdx.x * 32 + cl, C - 1);
-  const int c4 = c >> 2, e = c & 3;
-  const int span = cv < kBnThreads ? cv : kBnThreads;
-  // cv <= 256: every block holds every channel pack once, at slot c4; else block b holds packs (b * 256 + t) % cv,
-  // i.e. pack c4 lives in the blocks first, first + per, ... at slot t
-  const int per = cv <= kBnThreads ? 1 : cv / kBnThreads;
-  const int first = cv <= kBnThreads ? 0 : c4 / kBnThreads;
-  const int slot = cv <= kBnThreads ? c4 : c4 % kBnThreads;
-  const float* src = colsum_partial + 4 * slot + e;
-  const long long bstride = 4LL * span;
-  const int step = kFinGroups * per;
-  double a[4] = {0.0, 0.0, 0.0, 0.0};
-  int b = first + pg * per;
-  for (; b + 3 * step < blocks; b += 4 * step) {
-    float v[4];
+  if (i0 >= total) return;
+  auto one = [&](const float (&v)[V], const float (&g)[V], T* o) {
+    float r[V];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = src[(long long)(b + u * step) * bstride];
+    for (int e = 0; e < V; ++e) {
+      const float d = v[e] - mu[e];
+      float gz = g[e];
+      if (RELU) gz = fmaf(d, a[e], b[e]) > 0.f ? gz : 0.f;
+      r[e] = a[e] * (gz - c1[e] - d * is[e] * c2[e]);
+    }
+    Vec16<T>::store(o, r);
+  };
+  const long long n = (total - i0 + T_ - 1) / T_;
+  auto at = [&](long long j) { return (i0 + (reverse ? (n - 1 - j) : j) * T_) * V; };
+  long long j = 0;
+  for (; j + 3 < n; j += 4) {
+    float v[4][V], g[4][V];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) a[u] += (double)v[u];
+    for (int u = 0; u < 4; ++u) { Vec16<T>::load(x + at(j + u), v[u]); Vec16<T>::load(dy + at(j + u), g[u]); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(v[u], g[u], dx + at(j + u));
   }
-  for (; b < blocks; b += step) a[0] += (double)src[(long long)b * bstride];
-  const double tot = group_sum((a[0] + a[1]) + (a[2] + a[3]), sm, cl, pg);
-  if (pg == 0 && blockIdx.x * 32 + cl < C) colsum[c] = (float)tot;
+  for (; j < n; ++j) {
+    float v[V], g[V];
+    Vec16<T>::load(x + at(j), v);
+    Vec16<T>::load(dy + at(j), g);
+    one(v, g, dx + at(j));
+  }
 }
 
-int apply_grid(long long total4, int cv) {
+int apply_grid(long long total, int cv) {
   // whole waves of 8 CTAs per SM, rounded so that grid * 256 is a multiple of cv
-  long long need = (total4 + kBnThreads - 1) / kBnThreads;
+  long long need = (total + kBnThreads - 1) / kBnThreads;
   long long g = (long long)num_sms() * 8;
   if (g > need) g = need;
   const int q = cv > kBnThreads ? cv / kBnThreads : 1;
@@ -425,63 +366,82 @@ int apply_grid(long long total4, int cv) {
 
 int shift_of(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 
-}  // namespace
-
-size_t bn_workspace_bytes(int C) {
-  const size_t partials = (size_t)kBnMaxPartials * (size_t)C * sizeof(float2) + kBnMaxPartials * sizeof(int);
-  const size_t colsums = (size_t)(num_sms() * 8 + 8) * 4 * kBnThreads * sizeof(float);  // one float4 per thread of the apply grid
-  return (partials > colsums ? partials : colsums) + 256;
-}
-
-bool bn_supported(long long R, int C) {
+template <typename T>
+int bn_fwd_t(const void* x_, const void* res_, const float* weight, const float* bias, float* running_mean, float* running_var,
+             void* out_, float* save_mean, float* save_invstd, long long R, int C, float eps, float momentum, int relu,
+             void* workspace, cudaStream_t s) {
+  constexpr int V = Vec16<T>::V;
   BnGeom g;
-  return bn_geometry(R, C, &g) && R * (long long)(C / 4) < (1LL << 40);
-}
-
-int launch_bn_train_fwd(const float* x, const float* res, const float* weight, const float* bias, float* running_mean,
-                        float* running_var, float* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
-                        float momentum, int relu, void* workspace, cudaStream_t s) {
-  BnGeom g;
-  if (!bn_geometry(R, C, &g)) { set_error("bn_train_fwd: needs C %% 4 == 0, C/4 a power of two and at least 2 rows"); return GRAFP_EUNSUPPORTED; }
-  if (relu && res != nullptr) { set_error("bn_train_fwd: ReLU together with a residual is not implemented"); return GRAFP_EUNSUPPORTED; }
-  char* wb = reinterpret_cast<char*>(((uintptr_t)workspace + 255) / 256 * 256);
-  float2* partial = reinterpret_cast<float2*>(wb);
-  int* pcount = reinterpret_cast<int*>(wb + (size_t)kBnMaxPartials * C * sizeof(float2));
-  bn_stats_kernel<<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(x, partial, pcount, R, C, shift_of(g.tpr));
-  bn_stats_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, s>>>(partial, pcount, g.gx, C, R, eps, momentum, save_mean, save_invstd,
-                                                           running_mean, running_var);
-  const long long total4 = R * g.cv;
-  const int grid = apply_grid(total4, g.cv);
-  if (relu) bn_apply_kernel<true, false><<<grid, kBnThreads, 0, s>>>(x, res, weight, bias, save_mean, save_invstd, out, total4, g.cv);
-  else if (res) bn_apply_kernel<false, true><<<grid, kBnThreads, 0, s>>>(x, res, weight, bias, save_mean, save_invstd, out, total4, g.cv);
-  else bn_apply_kernel<false, false><<<grid, kBnThreads, 0, s>>>(x, res, weight, bias, save_mean, save_invstd, out, total4, g.cv);
+  if (!bn_geometry(R, C, V, &g)) { set_error("bn_train_fwd: needs C %% %d == 0, C/%d a power of two and at least 2 rows", V, V); return GRAFP_EUNSUPPORTED; }
+  if (relu && res_ != nullptr) { set_error("bn_train_fwd: ReLU together with a residual is not implemented"); return GRAFP_EUNSUPPORTED; }
+  const T* x = static_cast<const T*>(x_);
+  const T* res = static_cast<const T*>(res_);
+  T* out = static_cast<T*>(out_);
+  double* sums = reinterpret_cast<double*>(((uintptr_t)workspace + 255) / 256 * 256);
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), s);
+  if (e != cudaSuccess) { set_error("bn_train_fwd: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+  bn_stats_kernel<T><<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(x, sums, R, C, shift_of(g.tpr));
+  const long long total = R * g.cv;
+  const int grid = apply_grid(total, g.cv);
+  const int rev = option(OPT_BN_REVERSE) != 0;
+#define GRAFP_BN_APPLY(RELU_, RES_)                                                                                        \
+  bn_apply_kernel<T, RELU_, RES_><<<grid, kBnThreads, 0, s>>>(x, res, weight, bias, sums, out, save_mean, save_invstd,      \
+                                                            running_mean, running_var, R, C, g.cv, eps, momentum, rev)
+  if (relu) GRAFP_BN_APPLY(true, false);
+  else if (res) GRAFP_BN_APPLY(false, true);
+  else GRAFP_BN_APPLY(false, false);
+#undef GRAFP_BN_APPLY
   return check_launch("bn_train_fwd");
 }
 
-int launch_bn_train_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* save_mean,
-                        const float* save_invstd, float* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
-                        int relu, void* workspace, cudaStream_t s) {
+template <typename T>
+int bn_bwd_t(const void* dy_, const void* x_, const float* weight, const float* bias, const float* save_mean,
+             const float* save_invstd, void* dx_, float* dweight, float* dbias, float* dx_colsum, long long R, int C, int relu,
+             void* workspace, cudaStream_t s) {
+  constexpr int V = Vec16<T>::V;
   BnGeom g;
-  if (!bn_geometry(R, C, &g)) { set_error("bn_train_bwd: needs C %% 4 == 0, C/4 a power of two and at least 2 rows"); return GRAFP_EUNSUPPORTED; }
-  char* wb = reinterpret_cast<char*>(((uintptr_t)workspace + 255) / 256 * 256);
-  float2* partial = reinterpret_cast<float2*>(wb);
+  if (!bn_geometry(R, C, V, &g)) { set_error("bn_train_bwd: needs C %% %d == 0, C/%d a power of two and at least 2 rows", V, V); return GRAFP_EUNSUPPORTED; }
+  const T* dy = static_cast<const T*>(dy_);
+  const T* x = static_cast<const T*>(x_);
+  T* dx = static_cast<T*>(dx_);
+  double* sums = reinterpret_cast<double*>(((uintptr_t)workspace + 255) / 256 * 256);
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)3 * C * sizeof(double), s);
+  if (e != cudaSuccess) { set_error("bn_train_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
   const int tsh = shift_of(g.tpr);
-  if (relu) bn_bwd_reduce_kernel<true><<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, partial, R, C, tsh);
-  else bn_bwd_reduce_kernel<false><<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, partial, R, C, tsh);
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, s>>>(partial, g.gx, C, dweight, dbias);
-  const long long total4 = R * g.cv;
-  const int grid = apply_grid(total4, g.cv);
-  const float inv_rows = (float)(1.0 / (double)R);
-  float* csp = reinterpret_cast<float*>(wb);  // the reduction partials are consumed by now (stream order)
-  if (dx_colsum != nullptr) {
-    if (relu) bn_bwd_apply_kernel<true, true><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, csp, total4, g.cv, inv_rows);
-    else bn_bwd_apply_kernel<false, true><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, csp, total4, g.cv, inv_rows);
-    bn_colsum_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, s>>>(csp, grid, g.cv, dx_colsum);
-  } else {
-    if (relu) bn_bwd_apply_kernel<true, false><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, nullptr, total4, g.cv, inv_rows);
-    else bn_bwd_apply_kernel<false, false><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, dweight, dbias, dx, nullptr, total4, g.cv, inv_rows);
-  }
+  if (relu) bn_bwd_reduce_kernel<T, true><<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, sums, R, C, tsh);
+  else bn_bwd_reduce_kernel<T, false><<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, sums, R, C, tsh);
+  const long long total = R * g.cv;
+  const int grid = apply_grid(total, g.cv);
+  const int rev = option(OPT_BN_REVERSE) != 0;
+  if (relu) bn_bwd_apply_kernel<T, true><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, sums, dx, dweight, dbias, dx_colsum, R, C, g.cv, rev);
+  else bn_bwd_apply_kernel<T, false><<<grid, kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, sums, dx, dweight, dbias, dx_colsum, R, C, g.cv, rev);
   return check_launch("bn_train_bwd");
+}
+
+}  // namespace
+
+size_t bn_workspace_bytes(int C) { return (size_t)3 * C * sizeof(double) + 256; }
+
+bool bn_supported(long long R, int C, int dtype) {
+  BnGeom g;
+  const int V = dtype == GRAFP_F32 ? 4 : 8;
+  return bn_geometry(R, C, V, &g) && R * (long long)(C / V) < (1LL << 40);
+}
+
+int launch_bn_train_fwd(const void* x, const void* res, const float* weight, const float* bias, float* running_mean,
+                        float* running_var, void* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
+                        float momentum, int relu, int dtype, void* workspace, cudaStream_t s) {
+  if (dtype == GRAFP_F32)
+    return bn_fwd_t<float>(x, res, weight, bias, running_mean, running_var, out, save_mean, save_invstd, R, C, eps, momentum, relu, workspace, s);
+  return bn_fwd_t<__nv_bfloat16>(x, res, weight, bias, running_mean, running_var, out, save_mean, save_invstd, R, C, eps, momentum, relu, workspace, s);
+}
+
+int launch_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,
+                        const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
+                        int relu, int dtype, void* workspace, cudaStream_t s) {
+  if (dtype == GRAFP_F32)
+    return bn_bwd_t<float>(dy, x, weight, bias, save_mean, save_invstd, dx, dweight, dbias, dx_colsum, R, C, relu, workspace, s);
+  return bn_bwd_t<__nv_bfloat16>(dy, x, weight, bias, save_mean, save_invstd, dx, dweight, dbias, dx_colsum, R, C, relu, workspace, s);
 }
 
 }  // namespace grafp

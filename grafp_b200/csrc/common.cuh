@@ -31,6 +31,30 @@ int num_sms();
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---- run-time options (grafp_set_option / grafp_get_option; defaults from GRAFP_<NAME> read once at load) ----
+enum Option {
+  OPT_MR_FWD_FORM = 0,   // K2: 0 generic, 1 register-prefetch, 2 cp.async-pipelined persistent kernel (default)
+  OPT_MR_BWD_FORM,       // K3: 0 dense + scatter pair, 1 cluster kernel with a register stash, 2 cluster kernel with bulk
+                         //     staging (default), 3 deterministic gather over the reverse graph (needs the workspace)
+  OPT_KNN_EPILOGUE,      // K1 selection: 0 auto, 1 vote-gated scan, 2 candidate queues, 3 group maxima (K <= 4)
+  OPT_EDGE_BWD_ROW,      // EdgeConv backward: 1 one-pass row form (default), 0 dense + scatter pair
+  OPT_GATHER_ROW,        // plain gather: 1 row form (default)
+  OPT_EDGE_ROW,          // EdgeConv features: 1 row form (default)
+  OPT_MAXK_ROW,          // max over k: 1 row form (default)
+  OPT_BN_REVERSE,        // K5: 1 = the second pass walks the rows backwards so it starts in what L2 still holds (default)
+  OPT_CHECK_INDEX,       // 1 = validate neighbour / centre ids against [0, M) before the aggregation kernels run
+  OPT_COUNT
+};
+int option(Option o);
+
+// One-time per-DEVICE kernel configuration (cudaFuncSetAttribute is per device, not per process).
+int current_device();
+struct DeviceOnce {
+  bool done[64] = {};
+  bool pending() const { const int d = current_device(); return d < 0 || d >= 64 || !done[d]; }
+  void mark() { const int d = current_device(); if (d >= 0 && d < 64) done[d] = true; }
+};
+
 // ---- element access: VEC consecutive channels as fp32 registers ----
 template <typename T, int VEC>
 struct Pack;
@@ -171,10 +195,6 @@ int launch_mr_aggregate_bwd(const void* g, const uint8_t* argmax, const void* nb
                             void* grad_x, void* grad_y, int B, int N, int M, int C, int k, void* workspace,
                             size_t workspace_bytes, cudaStream_t s);
 size_t mr_bwd_workspace_bytes(int B, int N, int k);
-// aggregate_bwd_slice.cu: K3 as a shared-memory gather over (segment, channel-slice) units
-template <bool I64>
-int launch_mr_bwd_slice(const float* g, const uint8_t* argmax, const void* nbr, float* grad_x, int B, int N, int C, int k,
-                        cudaStream_t s, bool* launched);
 template <typename T>
 int launch_gather_fwd(const void* src, const void* idx, int idx_is_i64, void* out, int B, int N, int M, int C, int k,
                       cudaStream_t s);
@@ -199,14 +219,16 @@ template <typename T>
 int launch_max_over_k_bwd(const void* g, const uint8_t* argmax, void* grad_h, int B, int N, int C, int k,
                           cudaStream_t s);
 
+int launch_check_index(const void* idx, int idx_is_i64, long long count, int limit, int* bad_count, cudaStream_t s);
+
 // ---- bn_fused.cu ----
 size_t bn_workspace_bytes(int C);
-bool bn_supported(long long R, int C);
-int launch_bn_train_fwd(const float* x, const float* res, const float* weight, const float* bias, float* running_mean,
-                        float* running_var, float* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
-                        float momentum, int relu, void* workspace, cudaStream_t s);
-int launch_bn_train_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* save_mean,
-                        const float* save_invstd, float* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
-                        int relu, void* workspace, cudaStream_t s);
+bool bn_supported(long long R, int C, int dtype);
+int launch_bn_train_fwd(const void* x, const void* res, const float* weight, const float* bias, float* running_mean,
+                        float* running_var, void* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
+                        float momentum, int relu, int dtype, void* workspace, cudaStream_t s);
+int launch_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,
+                        const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
+                        int relu, int dtype, void* workspace, cudaStream_t s);
 
 }  // namespace grafp

@@ -397,11 +397,11 @@ int launch_knn_simt(const float* xh, const float* xsq, const float* yh, const fl
                     long long* nn_idx, int* nn_idx32, int B, int N, int M, int C, int K, int k_out, int stride,
                     cudaStream_t s) {
   const size_t smem = sizeof(float) * (TC * TQ + TC * TK + TQ * (TK + 1)) + (sizeof(float) + sizeof(int)) * TQ * K;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(knn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(knn_simt): %s", cudaGetErrorString(e)); return (int)e; }
-    configured = true;
+    once.mark();
   }
   dim3 grid((N + TQ - 1) / TQ, B);
   knn_simt_kernel<<<grid, 256, smem, s>>>(xh, xsq, yh, ysq, relpos, nn_idx, nn_idx32, N, M, C, K, k_out, stride);

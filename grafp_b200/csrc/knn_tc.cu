@@ -297,12 +297,12 @@ static int launch_variant(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, co
                           const CUtensorMap& tb_lo, const float* xsq, const float* ysq, long long* nn_idx, int* nn_idx32,
                           int B, int N, int M, int C, int K, int k_out, int stride, cudaStream_t s) {
   using cfg = Cfg<BN, KREG>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  if (once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(knn_tc_kernel<BN, KREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)cfg::kSmemBytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(knn_tc): %s", cudaGetErrorString(e)); return (int)e; }
-    configured = true;
+    once.mark();
   }
   dim3 grid((N + BM - 1) / BM, B);
   knn_tc_kernel<BN, KREG><<<grid, kThreads, cfg::kSmemBytes, s>>>(ta_hi, ta_lo, tb_hi, tb_lo, xsq, ysq, nn_idx, nn_idx32,
@@ -329,7 +329,8 @@ EncodeTiledFn encode_tiled_fn() {
 }  // namespace tcptx
 
 bool knn_tc_supported(int N, int M, int C, int K, int dtype) {
-  return dtype == GRAFP_F32 && C % 4 == 0 && C >= 32 && N >= 128 && M >= 128 && K >= 1 && K <= GRAFP_KNN_MAX_K;
+  // (the tf32 planes live in fp32 containers whatever the input dtype: the normalise kernel reads fp32 or bf16 rows)
+  return (dtype == GRAFP_F32 || dtype == GRAFP_BF16) && C % 4 == 0 && C >= 32 && N >= 128 && M >= 128 && K >= 1 && K <= GRAFP_KNN_MAX_K;
 }
 
 int launch_knn_tc(const void* xhi, const void* xlo, const float* xsq, const void* yhi, const void* ylo,

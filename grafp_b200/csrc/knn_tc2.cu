@@ -621,11 +621,11 @@ static bool make_map_f16(CUtensorMap* map, const void* base, int B, int rows, in
 constexpr uint32_t kMiscBytes = 2 * BM * 4 + 32 + (2 * kMaxStages + 8) * 8 + 1024;  // ysq, barriers + TMEM slot, alignment slack
 
 template <typename Kernel>
-static int set_smem(Kernel kernel, bool* configured, const char* what) {
-  if (*configured) return GRAFP_OK;
+static int set_smem(Kernel kernel, DeviceOnce* once, const char* what) {
+  if (!once->pending()) return GRAFP_OK;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
   if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e)); return (int)e; }
-  *configured = true;
+  once->mark();
   return GRAFP_OK;
 }
 
@@ -640,8 +640,8 @@ template <int NH, int BN, int KREG, int QS>
 static int launch_stream(const CUtensorMap& xh, const CUtensorMap& xl, const CUtensorMap& yh, const CUtensorMap& yl,
                          const float* xsq, const float* ysq, long long* nn_idx, int* nn_idx32, int B, int N, int M, int C,
                          int k_out, int stride, int stages, Round r, cudaStream_t s) {
-  static bool configured = false;
-  if (int rc = set_smem(knn_stream_kernel<NH, BN, KREG, QS>, &configured, "knn_stream")) return rc;
+  static DeviceOnce once;
+  if (int rc = set_smem(knn_stream_kernel<NH, BN, KREG, QS>, &once, "knn_stream")) return rc;
   const int num_kc = (C + BK - 1) / BK;
   const size_t smem = (size_t)(NH * num_kc) * kBlockBytes + (size_t)stages * (2 * BN * BK * 2) + (size_t)(4 * NH) * QS * 512 + kMiscBytes;
   dim3 grid((N + BM * NH - 1) / (BM * NH), B);
@@ -653,8 +653,8 @@ static int launch_stream(const CUtensorMap& xh, const CUtensorMap& xl, const CUt
 template <int NH, int KREG, int QS>
 static int launch_self(const CUtensorMap& xh, const CUtensorMap& xl, const float* xsq, long long* nn_idx, int* nn_idx32,
                        int B, int N, int C, int k_out, int stride, int stages, Round r, cudaStream_t s) {
-  static bool configured = false;
-  if (int rc = set_smem(knn_self_kernel<NH, KREG, QS>, &configured, "knn_self")) return rc;
+  static DeviceOnce once;
+  if (int rc = set_smem(knn_self_kernel<NH, KREG, QS>, &once, "knn_self")) return rc;
   const size_t smem = (size_t)stages * NH * kBlockBytes + (size_t)(4 * NH) * QS * 512 + kMiscBytes;
   knn_self_kernel<NH, KREG, QS><<<B, (4 * NH + 2) * 32, smem, s>>>(xh, xl, xsq, nn_idx, nn_idx32, N, C, k_out, stride, stages,
                                                                r.bounds, r.rank0, r.more);
@@ -668,19 +668,17 @@ struct Plan {
 
 static Plan plan(int N, int M, int C, int K, int dtype, bool self) {
   Plan p;
-  if (dtype != GRAFP_F32 || C % 8 != 0 || C < BK || N < BM || M < BM || K < 1 || K > 64) return p;
+  // (dtype: the planes are fp16 whatever the input was - the normalise kernel reads fp32 or bf16 rows)
+  if ((dtype != GRAFP_F32 && dtype != GRAFP_BF16) || C % 8 != 0 || C < BK || N < BM || M < BM || K < 1 || K > 64) return p;
   // Which selection epilogue.  K > 8 (16-entry lists, rounds) exists in the candidate-queue form only.  For K <= 8 both
   // exist and neither dominates: on features with independent rows (random point clouds: scripts/bench_ops.py, the
   // configs[3] stress) the queue form is faster (stage 0: 385 vs 429 us) because some lane of a warp has a candidate
   // in most column groups and the vote-gated form then pays its insertion path for the whole warp; inside the
   // training step - where, as far as we can tell, the 32 consecutive rows of a warp are neighbouring spectrogram peaks
   // whose candidates sit in the SAME few key columns, so the vote-gated form skips almost everything - it wins (k-NN 5.1-5.5 vs 5.6-5.9 ms per
-  // step, A/B on the same box).  The default follows the headline workload; GRAFP_KNN_EPI=queue / =vote force one.
-  // GRAFP_KNN_NO_NH4 / GRAFP_KNN_BN128 pick the older tile shapes (A/B timing).
-  const char* epi = getenv("GRAFP_KNN_EPI");
-  const bool force_queue = epi != nullptr && strcmp(epi, "queue") == 0;
-  static const bool no_nh4 = getenv("GRAFP_KNN_NO_NH4") != nullptr;
-  static const bool bn128 = getenv("GRAFP_KNN_BN128") != nullptr;
+  // step, A/B on the same box).  The default follows the headline workload; option OPT_KNN_EPILOGUE = 2 forces the queues.
+  const bool force_queue = option(OPT_KNN_EPILOGUE) == 2;
+  const bool no_nh4 = false, bn128 = false;
   p.qs = (K <= 8 && !force_queue) ? 0 : kQueueSlots;
   const int num_kc = (C + BK - 1) / BK;
   const uint32_t budget = kSmemLimit - kMiscBytes;

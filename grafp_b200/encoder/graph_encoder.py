@@ -123,6 +123,7 @@ class GraphEncoder(nn.Module):
                 ))
         self.backbone = Seq(*layers)
         self.proj = nn.Conv2d(self.channels[-1], 1024, 1, bias=True)
+        ops.match_grad_strides(self)  # weight gradients keep the parameters' strides (DistributedDataParallel buckets)
 
     def model_init(self):
         for m in self.modules():

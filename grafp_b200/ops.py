@@ -49,22 +49,38 @@ def set_timer(timer: Optional[KernelTimer]) -> None:
     _TIMER = timer
 
 
-def _call(name: str, n_kernels: int, meta: dict, fn, *args) -> None:
-    """Invoke one C-ABI entry point, raising on a non-zero return code."""
+def _call(name: str, n_kernels: int, meta: dict, fn, dev: torch.device, *args) -> None:
+    """Invoke one C-ABI entry point with ``dev`` (the tensors' device) current, raising on a non-zero return code.
+
+    The library launches on the *current* CUDA device and configures its kernels per device, so a call for tensors
+    on another GPU of the process (nn.DataParallel replicas, a model on cuda:1) switches to it for the call."""
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            return _call(name, n_kernels, meta, fn, dev, *args)
     t = _TIMER
     if t is None:
         _native.check(fn(*args), name)
         return
     t.launches += n_kernels
     if t.timing:
+        stream = torch.cuda.current_stream(dev)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(stream)
         _native.check(fn(*args), name)
-        e1.record()
+        e1.record(stream)
         t.records.append((name, meta, e0, e1))
     else:
         _native.check(fn(*args), name)
+
+
+def set_option(name: str, value: int) -> None:
+    """Process-wide kernel-selection / diagnostic option of the library (see include/grafp_b200.h)."""
+    _native.check(_native.load().grafp_set_option(name.encode(), int(value)), "set_option")
+
+
+def get_option(name: str) -> int:
+    return int(_native.load().grafp_get_option(name.encode()))
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -80,8 +96,31 @@ def _require_cuda(*tensors: Optional[torch.Tensor]) -> None:
             raise RuntimeError("grafp_b200: expected CUDA tensors - the B200 path has no CPU fallback")
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(t: torch.Tensor) -> int:
+    """Handle of the current torch stream of the tensor's own device."""
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _same_device(first: torch.Tensor, *rest: Optional[torch.Tensor]) -> None:
+    for t in rest:
+        if t is not None and t.device != first.device:
+            raise RuntimeError(f"grafp_b200: tensors on different devices ({first.device} and {t.device})")
+
+
+def _check_index(idx: torch.Tensor, limit: int, what: str) -> None:
+    """With option check_index = 1: raise like the reference's advanced indexing (IndexError, torch_nn.py:92-96) when a
+    user-supplied graph holds an id outside [0, limit).  One small kernel + a host read, so it is off by default;
+    graphs produced by the k-NN op are in range by construction and are never checked."""
+    if get_option("check_index") == 0:
+        return
+    lib = _native.load()
+    bad = torch.empty(1, dtype=torch.int32, device=idx.device)
+    idx_c = idx.contiguous()
+    _call("check_index", 1, {}, lib.grafp_check_index, idx.device, idx_c.data_ptr(), int(idx_c.dtype == torch.int64),
+          idx_c.numel(), int(limit), bad.data_ptr(), _stream(idx_c))
+    n_bad = int(bad.item())
+    if n_bad:
+        raise IndexError(f"grafp_b200.{what}: {n_bad} index entries are outside [0, {limit})")
 
 
 def as_rows(x: torch.Tensor) -> torch.Tensor:
@@ -141,6 +180,7 @@ def knn_graph(x: torch.Tensor, k: int, dilation: int = 1, y: Optional[torch.Tens
     (e.g. ``edge_index[0]``).  Not differentiable, like the reference (no_grad + detach).
     """
     _require_cuda(x, y, relative_pos)
+    _same_device(x, y, relative_pos, out)
     lib = _native.load()
     with torch.no_grad():
         xr = as_rows(x.detach())
@@ -167,12 +207,12 @@ def knn_graph(x: torch.Tensor, k: int, dilation: int = 1, y: Optional[torch.Tens
         dt = _dtype_code(xr)
         ws_bytes = lib.grafp_knn_workspace_bytes(B, N, M, C, K, dt)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        _call("knn_fwd", 2 if yr is None else 3, dict(B=B, N=N, M=M, C=C, K=K, dtype=dt), lib.grafp_knn_fwd,
+        _call("knn_fwd", 2 if yr is None else 3, dict(B=B, N=N, M=M, C=C, K=K, dtype=dt), lib.grafp_knn_fwd, x.device,
               xr.data_ptr(), yr.data_ptr() if yr is not None else None,
               rp.data_ptr() if rp is not None else None, out.data_ptr(),
               out32.data_ptr() if out32 is not None else None,
               B, N, M, C, int(k), int(dilation), int(emit_all), int(normalize), dt, int(algo),
-              ws.data_ptr(), ws_bytes, _stream())
+              ws.data_ptr(), ws_bytes, _stream(xr))
     return out, out32
 
 
@@ -208,9 +248,9 @@ class _MRAggregate(torch.autograd.Function):
         argmax = torch.empty((B, N, C), dtype=torch.uint8, device=x.device) if need_grad else None
         _call("mr_aggregate_fwd", 1, dict(B=B, N=N, M=M, C=C, k=k, dtype=_dtype_code(xr), i64=i64,
                                           argmax=int(argmax is not None)),
-              lib.grafp_mr_aggregate_fwd, xr.data_ptr(), yr.data_ptr() if yr is not None else None, nbr_c.data_ptr(),
-              ctr_c.data_ptr() if ctr_c is not None else None, i64, out.data_ptr(),
-              argmax.data_ptr() if argmax is not None else None, B, N, M, C, k, _dtype_code(xr), _stream())
+              lib.grafp_mr_aggregate_fwd, xr.device, xr.data_ptr(), yr.data_ptr() if yr is not None else None,
+              nbr_c.data_ptr(), ctr_c.data_ptr() if ctr_c is not None else None, i64, out.data_ptr(),
+              argmax.data_ptr() if argmax is not None else None, B, N, M, C, k, _dtype_code(xr), _stream(xr))
         ctx.save_for_backward(nbr_c, ctr_c, argmax)
         ctx.dims = (B, N, M, C, k, i64, y is not None, _dtype_code(xr))
         return out
@@ -224,14 +264,15 @@ class _MRAggregate(torch.autograd.Function):
         grad_x = _new_rows(B, C, N, g)
         grad_y = _new_rows(B, C, M, g) if has_y else None
         ws, ws_bytes = None, 0
-        if ctr_c is None and not has_y:  # k-NN-op graph: gather-form backward over the reverse graph
+        if ctr_c is None and not has_y and get_option("mr_bwd_form") == 3:
+            # only the deterministic gather form reads the reverse-graph workspace
             ws_bytes = lib.grafp_mr_aggregate_bwd_workspace_bytes(B, N, k)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
-        _call("mr_aggregate_bwd", 2, dict(B=B, N=N, M=M, C=C, k=k, dtype=dt, i64=i64),
-              lib.grafp_mr_aggregate_bwd, g.data_ptr(), argmax.data_ptr(), nbr_c.data_ptr(),
+        _call("mr_aggregate_bwd", 1 if (ctr_c is None and not has_y) else 2, dict(B=B, N=N, M=M, C=C, k=k, dtype=dt, i64=i64),
+              lib.grafp_mr_aggregate_bwd, g.device, g.data_ptr(), argmax.data_ptr(), nbr_c.data_ptr(),
               ctr_c.data_ptr() if ctr_c is not None else None, i64, grad_x.data_ptr(),
               grad_y.data_ptr() if grad_y is not None else None, B, N, M, C, k, dt,
-              ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
+              ws.data_ptr() if ws is not None else None, ws_bytes, _stream(g))
         return grad_x, grad_y, None, None
 
 
@@ -242,6 +283,11 @@ def mr_aggregate(x: torch.Tensor, nbr: torch.Tensor, y: Optional[torch.Tensor] =
     nbr / ctr: (B, N, k) neighbour / centre ids; ``ctr=None`` means the centre of row n is n.
     """
     _require_cuda(x, y, nbr, ctr)
+    _same_device(x, y, nbr, ctr)
+    if ctr is not None or y is not None:  # a user-supplied graph (the k-NN op's graphs come tagged, without ctr)
+        _check_index(nbr, (y if y is not None else x).shape[2], "mr_aggregate")
+        if ctr is not None:
+            _check_index(ctr, x.shape[2], "mr_aggregate")
     return _MRAggregate.apply(x, y, nbr, ctr)
 
 
@@ -258,8 +304,8 @@ class _Gather(torch.autograd.Function):
         idx_c, i64 = _index_arg(idx)
         _, N, k = idx_c.shape
         out = _new_edge_rows(B, C, N, k, sr)
-        _call("gather_fwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_gather_fwd, sr.data_ptr(), idx_c.data_ptr(),
-              i64, out.data_ptr(), B, N, M, C, k, _dtype_code(sr), _stream())
+        _call("gather_fwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_gather_fwd, sr.device, sr.data_ptr(),
+              idx_c.data_ptr(), i64, out.data_ptr(), B, N, M, C, k, _dtype_code(sr), _stream(sr))
         ctx.save_for_backward(idx_c)
         ctx.dims = (B, N, M, C, k, i64, _dtype_code(sr))
         return out
@@ -271,8 +317,8 @@ class _Gather(torch.autograd.Function):
         B, N, M, C, k, i64, dt = ctx.dims
         g = as_edge_rows(grad_out)
         grad_src = _new_rows(B, C, M, g)
-        _call("gather_bwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_gather_bwd, g.data_ptr(), idx_c.data_ptr(), i64,
-              grad_src.data_ptr(), B, N, M, C, k, dt, _stream())
+        _call("gather_bwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_gather_bwd, g.device, g.data_ptr(),
+              idx_c.data_ptr(), i64, grad_src.data_ptr(), B, N, M, C, k, dt, _stream(g))
         return grad_src, None
 
 
@@ -281,6 +327,8 @@ def gather_neighbors(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     _require_cuda(src, idx)
     if idx.dim() != 3 or idx.shape[0] != src.shape[0]:
         raise RuntimeError("grafp_b200.gather_neighbors: idx must be (B, N, k)")
+    _same_device(src, idx)
+    _check_index(idx, src.shape[2], "gather_neighbors")
     return _Gather.apply(src, idx)
 
 
@@ -293,8 +341,8 @@ class _NeighborSum(torch.autograd.Function):
         idx_c, i64 = _index_arg(idx)
         _, N, k = idx_c.shape
         out = _new_rows(B, C, N, sr)
-        _call("neighbor_sum_fwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_neighbor_sum_fwd, sr.data_ptr(),
-              idx_c.data_ptr(), i64, out.data_ptr(), B, N, M, C, k, _dtype_code(sr), _stream())
+        _call("neighbor_sum_fwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_neighbor_sum_fwd, sr.device, sr.data_ptr(),
+              idx_c.data_ptr(), i64, out.data_ptr(), B, N, M, C, k, _dtype_code(sr), _stream(sr))
         ctx.save_for_backward(idx_c)
         ctx.dims = (B, N, M, C, k, i64, _dtype_code(sr))
         return out
@@ -306,8 +354,8 @@ class _NeighborSum(torch.autograd.Function):
         B, N, M, C, k, i64, dt = ctx.dims
         g = as_rows(grad_out)
         grad_src = _new_rows(B, C, M, g)
-        _call("neighbor_sum_bwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_neighbor_sum_bwd, g.data_ptr(),
-              idx_c.data_ptr(), i64, grad_src.data_ptr(), B, N, M, C, k, dt, _stream())
+        _call("neighbor_sum_bwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_neighbor_sum_bwd, g.device, g.data_ptr(),
+              idx_c.data_ptr(), i64, grad_src.data_ptr(), B, N, M, C, k, dt, _stream(g))
         return grad_src, None
 
 
@@ -318,6 +366,7 @@ def neighbor_sum(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     _require_cuda(src, idx)
     if idx.dim() != 3 or idx.shape[0] != src.shape[0]:
         raise RuntimeError("grafp_b200.neighbor_sum: idx must be (B, N, k)")
+    _same_device(src, idx)
     return _NeighborSum.apply(src, idx)
 
 
@@ -337,10 +386,10 @@ class _EdgeGather(torch.autograd.Function):
         ctr_c = ctr.to(nbr_c.dtype).contiguous() if ctr is not None else None
         k = nbr_c.shape[-1]
         out = _new_edge_rows(B, 2 * C, N, k, xr)
-        _call("edge_gather_fwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_edge_gather_fwd, xr.data_ptr(),
+        _call("edge_gather_fwd", 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_edge_gather_fwd, xr.device, xr.data_ptr(),
               yr.data_ptr() if yr is not None else None, nbr_c.data_ptr(),
               ctr_c.data_ptr() if ctr_c is not None else None, i64, out.data_ptr(),
-              B, N, M, C, k, _dtype_code(xr), _stream())
+              B, N, M, C, k, _dtype_code(xr), _stream(xr))
         ctx.save_for_backward(nbr_c, ctr_c)
         ctx.dims = (B, N, M, C, k, i64, y is not None, _dtype_code(xr))
         return out
@@ -354,9 +403,9 @@ class _EdgeGather(torch.autograd.Function):
         grad_x = _new_rows(B, C, N, g)
         grad_y = _new_rows(B, C, M, g) if has_y else None
         _call("edge_gather_bwd", 2 if ctr_c is None else 1, dict(B=B, N=N, M=M, C=C, k=k), lib.grafp_edge_gather_bwd,
-              g.data_ptr(), nbr_c.data_ptr(), ctr_c.data_ptr() if ctr_c is not None else None,
+              g.device, g.data_ptr(), nbr_c.data_ptr(), ctr_c.data_ptr() if ctr_c is not None else None,
               i64, grad_x.data_ptr(), grad_y.data_ptr() if grad_y is not None else None,
-              B, N, M, C, k, dt, _stream())
+              B, N, M, C, k, dt, _stream(g))
         return grad_x, grad_y, None, None
 
 
@@ -364,6 +413,11 @@ def edge_features(x: torch.Tensor, nbr: torch.Tensor, y: Optional[torch.Tensor] 
                   ctr: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(B, 2C, N, k) = cat([x_i, x_j - x_i], dim=1) (reference: torch_vertex.py:46-51)."""
     _require_cuda(x, y, nbr, ctr)
+    _same_device(x, y, nbr, ctr)
+    if ctr is not None or y is not None:
+        _check_index(nbr, (y if y is not None else x).shape[2], "edge_features")
+        if ctr is not None:
+            _check_index(ctr, x.shape[2], "edge_features")
     return _EdgeGather.apply(x, y, nbr, ctr)
 
 
@@ -375,8 +429,8 @@ class _MaxOverK(torch.autograd.Function):
         B, C, N, k = hr.shape
         out = _new_rows(B, C, N, hr)
         argmax = torch.empty((B, N, C), dtype=torch.uint8, device=h.device) if ctx.needs_input_grad[0] else None
-        _call("max_over_k_fwd", 1, dict(B=B, N=N, C=C, k=k), lib.grafp_max_over_k_fwd, hr.data_ptr(), out.data_ptr(),
-              argmax.data_ptr() if argmax is not None else None, B, N, C, k, _dtype_code(hr), _stream())
+        _call("max_over_k_fwd", 1, dict(B=B, N=N, C=C, k=k), lib.grafp_max_over_k_fwd, hr.device, hr.data_ptr(),
+              out.data_ptr(), argmax.data_ptr() if argmax is not None else None, B, N, C, k, _dtype_code(hr), _stream(hr))
         ctx.save_for_backward(argmax)
         ctx.dims = (B, N, C, k, _dtype_code(hr))
         return out
@@ -388,8 +442,8 @@ class _MaxOverK(torch.autograd.Function):
         B, N, C, k, dt = ctx.dims
         g = as_rows(grad_out)
         grad_h = _new_edge_rows(B, C, N, k, g)
-        _call("max_over_k_bwd", 1, dict(B=B, N=N, C=C, k=k), lib.grafp_max_over_k_bwd, g.data_ptr(), argmax.data_ptr(),
-              grad_h.data_ptr(), B, N, C, k, dt, _stream())
+        _call("max_over_k_bwd", 1, dict(B=B, N=N, C=C, k=k), lib.grafp_max_over_k_bwd, g.device, g.data_ptr(),
+              argmax.data_ptr(), grad_h.data_ptr(), B, N, C, k, dt, _stream(g))
         return grad_h
 
 
@@ -405,6 +459,12 @@ def max_over_k(h: torch.Tensor) -> torch.Tensor:
 # train-mode BatchNorm fused with the ReLU / residual add that follows it
 # --------------------------------------------------------------------------------------
 
+# A/B switches, read once at import: GRAFP_FUSED_BN=0 runs the PyTorch BatchNorm modules, GRAFP_FOLD_BN=0 keeps the
+# eval-mode BatchNorm unfolded (=2: folded, but without cuDNN's fused ReLU epilogue)
+_FUSED_BN = os.environ.get("GRAFP_FUSED_BN", "1") != "0"
+_FOLD_BN = os.environ.get("GRAFP_FOLD_BN", "1")
+
+
 def _is_rows(t: torch.Tensor) -> bool:
     """(B, C, N, 1) tensor whose memory is (B*N, C) rows."""
     if t.dim() != 4 or t.shape[3] != 1:
@@ -414,24 +474,57 @@ def _is_rows(t: torch.Tensor) -> bool:
     return (C == 1 or s[1] == 1) and (N == 1 or s[2] == C) and (B == 1 or s[0] == N * C)
 
 
+def _bn_kernel_ok(t: torch.Tensor, C: int) -> bool:
+    """Envelope of the fused BatchNorm kernels: fp32 or bf16 rows, 16 bytes of channels per thread (4 fp32 / 8 bf16),
+    C / that a power of two."""
+    if t.dtype == torch.float32:
+        v = 4
+    elif t.dtype == torch.bfloat16:
+        v = 8
+    else:
+        return False
+    return C % v == 0 and ((C // v) & (C // v - 1)) == 0
+
+
+def _bn_fwd_call(lib, h, residual, weight, bias, running_mean, running_var, eps, momentum, relu):
+    B, C, N, _ = h.shape
+    out = _new_rows(B, C, N, h)
+    save_mean = torch.empty(C, dtype=torch.float32, device=h.device)
+    save_invstd = torch.empty(C, dtype=torch.float32, device=h.device)
+    ws_bytes = lib.grafp_bn_workspace_bytes(C)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=h.device)
+    _call("bn_train_fwd", 2, dict(B=B, N=N, C=C, relu=int(relu), res=int(residual is not None), dtype=_dtype_code(h)),
+          lib.grafp_bn_train_fwd, h.device, h.data_ptr(), residual.data_ptr() if residual is not None else None,
+          weight.data_ptr(), bias.data_ptr(),
+          running_mean.data_ptr() if running_mean is not None else None,
+          running_var.data_ptr() if running_var is not None else None,
+          out.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(), B * N, C, float(eps), float(momentum),
+          int(relu), _dtype_code(h), ws.data_ptr(), ws_bytes, _stream(h))
+    return out, save_mean, save_invstd
+
+
+def _bn_bwd_call(lib, g, h, weight, bias, save_mean, save_invstd, relu, want_colsum):
+    B, C, N, _ = h.shape
+    dh = _new_rows(B, C, N, h)
+    dweight = torch.empty(C, dtype=torch.float32, device=h.device)
+    dbias = torch.empty(C, dtype=torch.float32, device=h.device)
+    colsum = torch.empty(C, dtype=torch.float32, device=h.device) if want_colsum else None
+    ws_bytes = lib.grafp_bn_workspace_bytes(C)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=h.device)
+    _call("bn_train_bwd", 2, dict(B=B, N=N, C=C, relu=int(relu), dtype=_dtype_code(h)), lib.grafp_bn_train_bwd, h.device,
+          g.data_ptr(), h.data_ptr(), weight.data_ptr(), bias.data_ptr(), save_mean.data_ptr(),
+          save_invstd.data_ptr(), dh.data_ptr(), dweight.data_ptr(), dbias.data_ptr(),
+          colsum.data_ptr() if colsum is not None else None, B * N, C, int(relu), _dtype_code(h),
+          ws.data_ptr(), ws_bytes, _stream(h))
+    return dh, dweight, dbias, colsum
+
+
 class _BatchNormTrain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, residual, weight, bias, running_mean, running_var, eps, momentum, relu):
         lib = _native.load()
-        B, C, N, _ = x.shape
-        R = B * N
-        out = _new_rows(B, C, N, x)
-        save_mean = torch.empty(C, dtype=torch.float32, device=x.device)
-        save_invstd = torch.empty(C, dtype=torch.float32, device=x.device)
-        ws_bytes = lib.grafp_bn_workspace_bytes(C)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        _call("bn_train_fwd", 3, dict(B=B, N=N, C=C, relu=int(relu), res=int(residual is not None)),
-              lib.grafp_bn_train_fwd, x.data_ptr(), residual.data_ptr() if residual is not None else None,
-              weight.data_ptr(), bias.data_ptr(),
-              running_mean.data_ptr() if running_mean is not None else None,
-              running_var.data_ptr() if running_var is not None else None,
-              out.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(), R, C, float(eps), float(momentum),
-              int(relu), ws.data_ptr(), ws_bytes, _stream())
+        out, save_mean, save_invstd = _bn_fwd_call(lib, x, residual, weight, bias, running_mean, running_var, eps,
+                                                   momentum, relu)
         ctx.save_for_backward(x, weight, bias, save_mean, save_invstd)
         ctx.relu = bool(relu)
         ctx.has_res = residual is not None
@@ -441,34 +534,25 @@ class _BatchNormTrain(torch.autograd.Function):
     def backward(ctx, grad_out):
         lib = _native.load()
         x, weight, bias, save_mean, save_invstd = ctx.saved_tensors
-        B, C, N, _ = x.shape
-        g = as_rows(grad_out)
-        dx = _new_rows(B, C, N, x)
-        dweight = torch.empty_like(weight)
-        dbias = torch.empty_like(bias)
-        ws_bytes = lib.grafp_bn_workspace_bytes(C)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-        _call("bn_train_bwd", 3, dict(B=B, N=N, C=C, relu=int(ctx.relu)), lib.grafp_bn_train_bwd,
-              g.data_ptr(), x.data_ptr(), weight.data_ptr(), bias.data_ptr(), save_mean.data_ptr(),
-              save_invstd.data_ptr(), dx.data_ptr(), dweight.data_ptr(), dbias.data_ptr(), None, B * N, C, int(ctx.relu),
-              ws.data_ptr(), ws_bytes, _stream())
-        return dx, (grad_out if ctx.has_res else None), dweight, dbias, None, None, None, None, None
+        g = as_rows(grad_out.to(x.dtype))
+        dx, dweight, dbias, _ = _bn_bwd_call(lib, g, x, weight, bias, save_mean, save_invstd, ctx.relu, False)
+        return (dx, (grad_out if ctx.has_res else None), dweight.to(weight.dtype), dbias.to(bias.dtype), None, None, None,
+                None, None)
 
 
 def batch_norm_act(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = False,
                    residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``relu(bn(x))`` / ``bn(x) + residual`` / ``bn(x)`` for node rows (B, C, N, 1).
 
-    In training mode on a CUDA fp32 channels-last tensor this is one fused pair of kernels (statistics +
+    In training mode on a CUDA fp32 / bf16 channels-last tensor this is one fused pair of kernels (statistics +
     apply; the backward recomputes the ReLU mask, so no intermediate is kept); the module's running
     statistics and ``num_batches_tracked`` are updated exactly like ``nn.BatchNorm2d`` does.  Anything else
     (eval mode, other dtypes / layouts / channel counts, or GRAFP_FUSED_BN=0 - an A/B switch) runs the module
     and the PyTorch ops unchanged.
     """
-    fused = (os.environ.get("GRAFP_FUSED_BN", "1") != "0" and bn.training and x.is_cuda and x.dtype == torch.float32 and _is_rows(x) and bn.affine
+    fused = (_FUSED_BN and bn.training and x.is_cuda and _is_rows(x) and bn.affine
              and bn.momentum is not None and not (relu and residual is not None)
-             and x.shape[1] % 4 == 0 and ((x.shape[1] // 4) & (x.shape[1] // 4 - 1)) == 0
-             and x.shape[0] * x.shape[2] > 1
+             and _bn_kernel_ok(x, x.shape[1]) and x.shape[0] * x.shape[2] > 1
              and (residual is None or (residual.shape == x.shape and residual.dtype == x.dtype and _is_rows(residual)))
              and bn.weight.dtype == torch.float32)
     if not fused:
@@ -483,94 +567,58 @@ def batch_norm_act(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = False
     return _BatchNormTrain.apply(x, residual, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, relu)
 
 
-def _gemm_form(conv_args, cw: torch.Tensor) -> bool:
-    """Experimental (round-2 A/B, off by default): GRAFP_CONV_AS_GEMM=1 runs the dense 1x1 convolutions of the fused
-    conv + BatchNorm node as plain GEMMs on the node rows (out = X W^T, dX = dOut W, dW = dOut^T X) through
-    cuBLASLt instead of cuDNN's implicit-GEMM convolution kernels, with the same TF32 policy as the convolutions."""
-    stride, padding, dilation, groups = conv_args
-    return (os.environ.get("GRAFP_CONV_AS_GEMM", "0") == "1" and groups == 1 and tuple(cw.shape[2:]) == (1, 1)
-            and tuple(stride) == (1, 1) and tuple(padding) == (0, 0) and tuple(dilation) == (1, 1))
+def grad_with_param_strides(grad: torch.Tensor, param: torch.Tensor) -> torch.Tensor:
+    """cuDNN returns the weight gradient of a convolution over channels-last activations with channels-last strides;
+    for a (Cout, Cin, 1, 1) weight that is the same memory as the contiguous layout, but DistributedDataParallel
+    compares strides literally ("Grad strides do not match bucket view strides") and then copies the gradient into
+    its bucket instead of aliasing it.  Re-stride (no copy) when the two layouts are the same bytes."""
+    if grad.stride() != param.stride() and grad.shape == param.shape and grad.is_contiguous() and param.is_contiguous():
+        return grad.as_strided(param.shape, param.stride())
+    return grad
 
 
-class _conv_tf32_policy:
-    """matmul under the TF32 policy the convolutions use (torch.backends.cudnn.allow_tf32)."""
-
-    def __enter__(self):
-        self.prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = bool(torch.backends.cudnn.allow_tf32)
-
-    def __exit__(self, *exc):
-        torch.backends.cuda.matmul.allow_tf32 = self.prev
-        return False
-
-
-def _rows2d(t: torch.Tensor) -> torch.Tensor:
-    """(B, C, N, 1) node rows -> the (B * N, C) matrix they are in memory (a view)."""
-    B, C, N, _ = t.shape
-    return t.permute(0, 2, 3, 1).reshape(B * N, C)
-
-
-def _conv1x1_rows_fwd(x: torch.Tensor, cw: torch.Tensor) -> torch.Tensor:
-    B, _, N, _ = x.shape
-    Cout = cw.shape[0]
-    with _conv_tf32_policy():
-        h2 = _rows2d(x) @ cw.reshape(Cout, -1).t()
-    return h2.view(B, N, 1, Cout).permute(0, 3, 1, 2)        # logical (B, Cout, N, 1), rows in memory
-
-
-def _conv1x1_rows_bwd(dh: torch.Tensor, x: torch.Tensor, cw: torch.Tensor, need_dx: bool, need_dw: bool):
-    B, Cin, N, _ = x.shape
-    Cout = cw.shape[0]
-    dx = dcw = None
-    with _conv_tf32_policy():
-        d2 = _rows2d(dh)
-        if need_dx:
-            dx = (d2 @ cw.reshape(Cout, Cin)).view(B, N, 1, Cin).permute(0, 3, 1, 2)
-        if need_dw:
-            dcw = (d2.t() @ _rows2d(x)).reshape(cw.shape)
-    return dx, dcw
+def match_grad_strides(module: torch.nn.Module) -> None:
+    """Register :func:`grad_with_param_strides` on every convolution weight of ``module``."""
+    for m in module.modules():
+        if isinstance(m, torch.nn.Conv2d) and m.weight.requires_grad:
+            m.weight.register_hook(lambda g, p=m.weight: grad_with_param_strides(g, p))
 
 
 class _ConvBatchNormTrain(torch.autograd.Function):
     """Conv2d(1x1, bias) -> train-mode BatchNorm [-> ReLU | + residual] as one autograd node: the convolution stays
     cuDNN, the BatchNorm is the fused kernel pair, and the convolution's bias gradient - the per-channel sum of the
-    BatchNorm's input gradient - is accumulated while that gradient is written instead of by a separate reduction
-    pass over it (aten::convolution_backward is asked for the input and weight gradients only).
+    BatchNorm's input gradient - comes out of the BatchNorm backward instead of a separate reduction pass over that
+    gradient (aten::convolution_backward is asked for the input and weight gradients only).
 
     The convolution itself runs WITHOUT its bias: a per-channel constant in front of a train-mode BatchNorm cancels in
     (h - mean(h)), so adding it is a full read + write pass over the activations (cuDNN does not fuse it: ~105
     broadcast-add launches, ~10 ms of the 120 ms step in the ncu launch list) that changes nothing but rounding.  The
-    statistics are taken of the bias-free output and the bias is added back where it is visible: the running mean."""
+    statistics are taken of the bias-free output and the bias is added back where it is visible: the running mean.
+
+    ``x`` may be bf16 (torch.autocast) with fp32 parameters: the convolution then runs on a bf16 copy of the weight
+    (what autocast itself does) and the weight gradient is returned in the parameter's dtype."""
 
     @staticmethod
     def forward(ctx, x, residual, cw, cb, weight, bias, running_mean, running_var, eps, momentum, relu, conv_args):
         lib = _native.load()
         stride, padding, dilation, groups = conv_args
-        if _gemm_form(conv_args, cw) and _is_rows(x):
-            h = _conv1x1_rows_fwd(x, cw)
-        else:
-            h = torch.nn.functional.conv2d(x, cw, None, stride, padding, dilation, groups)   # bias: see the class docstring
+        with torch.autocast("cuda", enabled=False):
+            cw_x = cw if cw.dtype == x.dtype else cw.to(x.dtype)
+            h = torch.nn.functional.conv2d(x, cw_x, None, stride, padding, dilation, groups)   # bias: see the class docstring
         if not _is_rows(h):
             h = as_rows(h)
-        B, C, N, _ = h.shape
-        out = _new_rows(B, C, N, h)
-        save_mean = torch.empty(C, dtype=torch.float32, device=h.device)
-        save_invstd = torch.empty(C, dtype=torch.float32, device=h.device)
-        ws_bytes = lib.grafp_bn_workspace_bytes(C)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=h.device)
-        _call("bn_train_fwd", 3, dict(B=B, N=N, C=C, relu=int(relu), res=int(residual is not None)),
-              lib.grafp_bn_train_fwd, h.data_ptr(), residual.data_ptr() if residual is not None else None,
-              weight.data_ptr(), bias.data_ptr(),
-              running_mean.data_ptr() if running_mean is not None else None,
-              running_var.data_ptr() if running_var is not None else None,
-              out.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(), B * N, C, float(eps), float(momentum),
-              int(relu), ws.data_ptr(), ws_bytes, _stream())
-        if running_mean is not None:
+        if residual is not None and residual.shape != h.shape:
+            raise RuntimeError(f"grafp_b200.conv_batch_norm_act: residual {tuple(residual.shape)} does not match the "
+                               f"convolution output {tuple(h.shape)}")
+        out, save_mean, save_invstd = _bn_fwd_call(lib, h, residual, weight, bias, running_mean, running_var, eps,
+                                                   momentum, relu)
+        if running_mean is not None and cb is not None:
             # running_mean <- (1 - m) running_mean + m (mean(h) + cb): the kernel did the first two terms
             running_mean.add_(cb.detach().to(running_mean.dtype), alpha=float(momentum))
         ctx.save_for_backward(x, cw, h, weight, bias, save_mean, save_invstd)
         ctx.relu = bool(relu)
         ctx.has_res = residual is not None
+        ctx.has_cb = cb is not None
         ctx.conv_args = conv_args
         return out
 
@@ -579,29 +627,22 @@ class _ConvBatchNormTrain(torch.autograd.Function):
         lib = _native.load()
         x, cw, h, weight, bias, save_mean, save_invstd = ctx.saved_tensors
         stride, padding, dilation, groups = ctx.conv_args
-        B, C, N, _ = h.shape
-        g = as_rows(grad_out)
-        dh = _new_rows(B, C, N, h)
-        dweight = torch.empty_like(weight)
-        dbias = torch.empty_like(bias)
-        dcb = torch.empty(C, dtype=torch.float32, device=h.device)
-        ws_bytes = lib.grafp_bn_workspace_bytes(C)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=h.device)
-        _call("bn_train_bwd", 4, dict(B=B, N=N, C=C, relu=int(ctx.relu)), lib.grafp_bn_train_bwd,
-              g.data_ptr(), h.data_ptr(), weight.data_ptr(), bias.data_ptr(), save_mean.data_ptr(),
-              save_invstd.data_ptr(), dh.data_ptr(), dweight.data_ptr(), dbias.data_ptr(), dcb.data_ptr(), B * N, C,
-              int(ctx.relu), ws.data_ptr(), ws_bytes, _stream())
-        if _gemm_form(ctx.conv_args, cw) and _is_rows(x):
-            dx, dcw = _conv1x1_rows_bwd(dh, x, cw, ctx.needs_input_grad[0], ctx.needs_input_grad[2])
-        else:
-            dx, dcw, _ = torch.ops.aten.convolution_backward(
-                dh, x, cw, None, list(stride), list(padding), list(dilation), False, [0, 0], groups,
-                [ctx.needs_input_grad[0], ctx.needs_input_grad[2], False])
-        return (dx, (grad_out if ctx.has_res else None), dcw, dcb, dweight, dbias, None, None, None, None, None, None)
+        g = as_rows(grad_out.to(h.dtype))
+        dh, dweight, dbias, dcb = _bn_bwd_call(lib, g, h, weight, bias, save_mean, save_invstd, ctx.relu, ctx.has_cb)
+        cw_x = cw if cw.dtype == x.dtype else cw.to(x.dtype)
+        dx, dcw, _ = torch.ops.aten.convolution_backward(
+            dh, x, cw_x, None, list(stride), list(padding), list(dilation), False, [0, 0], groups,
+            [ctx.needs_input_grad[0], ctx.needs_input_grad[2], False])
+        if dcw is not None and dcw.dtype != cw.dtype:
+            dcw = dcw.to(cw.dtype)
+        if dcw is not None:
+            dcw = grad_with_param_strides(dcw, cw)
+        return (dx, (grad_out if ctx.has_res else None), dcw, dcb, dweight.to(weight.dtype), dbias.to(bias.dtype),
+                None, None, None, None, None, None)
 
 
 def _fold_eval_ok(x: torch.Tensor, bn: torch.nn.BatchNorm2d) -> bool:
-    return (os.environ.get("GRAFP_FOLD_BN", "1") != "0" and not bn.training and not torch.is_grad_enabled()
+    return (_FOLD_BN != "0" and not bn.training and not torch.is_grad_enabled()
             and x.is_cuda and x.dtype == torch.float32 and bn.track_running_stats and bn.running_var is not None
             and bn.affine)
 
@@ -615,7 +656,7 @@ def _folded_conv_bn_eval(x, cw, cb, bn, relu, residual, conv_args):
     scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
     w = cw * scale.view(-1, 1, 1, 1)
     b = bn.bias - bn.running_mean * scale if cb is None else (cb - bn.running_mean) * scale + bn.bias
-    if relu and residual is None and os.environ.get("GRAFP_FOLD_BN", "1") != "2":
+    if relu and residual is None and _FOLD_BN != "2":
         try:
             y = torch.cudnn_convolution_relu(x, w, b, list(stride), list(padding), list(dilation), groups)
             return y if _is_rows(y) else as_rows(y)
@@ -631,7 +672,7 @@ def conv_batch_norm_act(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.nn.Bat
                         residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``relu(bn(conv(x)))`` / ``bn(conv(x)) + residual`` / ``bn(conv(x))`` for node rows (B, C, N, 1).
 
-    With a biased 1x1 convolution in training mode (CUDA, fp32, channels-last) the three layers are one autograd
+    With a 1x1 convolution in training mode (CUDA, fp32 / bf16, channels-last) the three layers are one autograd
     node (see _ConvBatchNormTrain); otherwise the convolution runs as the module and the rest goes through
     :func:`batch_norm_act`, which applies its own envelope checks.
     """
@@ -639,7 +680,7 @@ def conv_batch_norm_act(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.nn.Bat
             and conv.weight.dtype == torch.float32):
         return _folded_conv_bn_eval(x, conv.weight, conv.bias, bn, relu, residual,
                                     (conv.stride, conv.padding, conv.dilation, conv.groups))
-    ok = (conv.bias is not None and conv.kernel_size == (1, 1) and conv.padding_mode == "zeros"
+    ok = (conv.kernel_size == (1, 1) and conv.padding_mode == "zeros"
           and isinstance(conv.padding, tuple) and not conv.transposed)
     if not ok:
         return batch_norm_act(conv(x), bn, relu=relu, residual=residual)
@@ -652,15 +693,17 @@ def pointwise_conv_batch_norm_act(x, cw, cb, bn, relu=False, residual=None, conv
     C = cw.shape[0]
     if _fold_eval_ok(x, bn) and cw.dtype == torch.float32:
         return _folded_conv_bn_eval(x, cw, cb, bn, relu, residual, conv_args)
-    fused = (os.environ.get("GRAFP_FUSED_BN", "1") != "0" and bn.training and x.is_cuda and x.dtype == torch.float32
-             and _is_rows(x) and cb is not None
+    stride, padding, dilation, groups = conv_args
+    unit = tuple(stride) == (1, 1) and tuple(padding) == (0, 0) and tuple(cw.shape[2:]) == (1, 1)
+    fused = (_FUSED_BN and bn.training and x.is_cuda and _is_rows(x)
              and bn.affine and bn.momentum is not None and not (relu and residual is not None)
-             and C % 4 == 0 and ((C // 4) & (C // 4 - 1)) == 0 and x.shape[0] * x.shape[2] > 1
-             and (residual is None or (residual.dtype == x.dtype and _is_rows(residual) and residual.shape[1] == C))
+             and _bn_kernel_ok(x, C) and x.shape[0] * x.shape[2] > 1
+             # the residual must have the convolution's output shape (B, C, N, 1); known up front for stride-1 1x1 convs
+             and (residual is None or (unit and residual.dtype == x.dtype and _is_rows(residual)
+                                       and tuple(residual.shape) == (x.shape[0], C, x.shape[2], 1)))
              and cw.dtype == torch.float32 and bn.weight.dtype == torch.float32
              and torch.is_grad_enabled())
     if not fused:
-        stride, padding, dilation, groups = conv_args
         return batch_norm_act(torch.nn.functional.conv2d(x, cw, cb, stride, padding, dilation, groups), bn, relu=relu,
                               residual=residual)
     if bn.track_running_stats and bn.num_batches_tracked is not None:
@@ -685,7 +728,7 @@ def downsample_rows(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.nn.BatchNo
     if not (x.dim() == 4 and x.shape[3] == 1 and x.shape[2] % 2 == 0 and x.shape[2] >= 2 and _is_rows(x)
             and conv.kernel_size == (3, 3) and conv.stride == (2, 2) and conv.padding == (1, 1)
             and conv.dilation == (1, 1) and conv.groups == 1 and conv.padding_mode == "zeros"
-            and os.environ.get("GRAFP_FUSED_BN", "1") != "0"):
+            and _FUSED_BN):
         return None
     B, C, N, _ = x.shape
     rows = x.permute(0, 2, 3, 1).reshape(B, N // 2, 2 * C)           # [x[2n'], x[2n'+1]] per output row: a view

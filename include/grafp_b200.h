@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GRAFP_ABI_VERSION 4
+#define GRAFP_ABI_VERSION 5
 
 #define GRAFP_OK 0
 #define GRAFP_EINVAL (-1)       /* null / misaligned pointer, non-positive size, k > M ... */
@@ -50,6 +50,30 @@ extern "C" {
 
 int grafp_abi_version(void);
 const char* grafp_last_error(void);
+
+/*
+ * Kernel-selection / diagnostic options (process-wide, atomically readable from any thread).  Defaults are read
+ * ONCE, when the first option is consulted, from the environment variable GRAFP_<NAME IN CAPITALS>; after that only
+ * grafp_set_option changes them (tests and benchmarks use this for A/B runs).  Names and values:
+ *   "mr_fwd_form"  K2: 0 generic, 1 register-prefetch kernel, 2 cp.async-pipelined persistent kernel (default)
+ *   "mr_bwd_form"  K3: 0 dense + scatter pair, 1 cluster kernel with a device-scope fence, 2 cluster kernel (default),
+ *                  3 deterministic gather over the reverse graph (fp32, k == 3, needs the workspace)
+ *   "knn_epilogue" K1 selection: 0 auto (default), 1 vote-gated scan, 2 candidate queues, 3 group maxima (K <= 4)
+ *   "edge_bwd_row" / "gather_row" / "edge_row" / "maxk_row": 1 = row-form kernels (default), 0 = per-edge forms
+ *   "bn_reverse"   K5: 1 = the second pass walks the rows back to front to start on L2 hits (default)
+ *   "check_index"  1 = grafp_check_index is run on user-supplied graphs by the Python layer (default 0)
+ * grafp_set_option returns GRAFP_EINVAL for an unknown name; grafp_get_option returns the value, or GRAFP_EINVAL.
+ */
+int grafp_set_option(const char* name, int value);
+int grafp_get_option(const char* name);
+
+/*
+ * Range check of an index tensor (the reference's advanced indexing raises IndexError for ids outside [0, M),
+ * torch_nn.py:92-96; the aggregation kernels address rows with them unchecked).  Counts the entries of
+ * idx[0 .. count) (int64 when idx_is_i64 != 0, else int32) outside [0, limit) into *bad_count (device int32, zeroed
+ * by the call).  The caller synchronises and reads it.
+ */
+int grafp_check_index(const void* idx, int idx_is_i64, long long count, int limit, int* bad_count, void* stream);
 
 /* Diagnostic: name of the k-NN kernel the last grafp_knn_fwd call on this thread launched
  * ("simt", "tcgen05"). */
@@ -156,8 +180,9 @@ int grafp_max_over_k_bwd(const void* grad_out, const uint8_t* argmax, void* grad
  * (SURVEY 8f row 2).  Replaces nn.BatchNorm2d (training) + nn.ReLU of BasicConv
  * (encoder/gcn_lib/torch_nn.py:52-64) and of FFN.fc1 + act (encoder/graph_encoder.py:56-66), and
  * nn.BatchNorm2d + the residual add of Grapher.fc2 / FFN.fc2 (torch_vertex.py:158-162,194;
- * graph_encoder.py:60-66).  fp32 only; x, residual, out, dy, dx are (R, C) rows, R = B * N,
- * C % 4 == 0 and C / 4 a power of two (else GRAFP_EUNSUPPORTED).
+ * graph_encoder.py:60-66).  x, residual, out, dy, dx are (R, C) rows of `dtype` (GRAFP_F32 / GRAFP_BF16),
+ * R = B * N; statistics, weight, bias and their gradients are always float32.  A thread owns 16 bytes of channels:
+ * C % V == 0 and C / V a power of two with V = 4 (fp32) / 8 (bf16), else GRAFP_EUNSUPPORTED.
  *
  *  forward : mean / biased variance over the R rows per channel (saved as save_mean, save_invstd =
  *            1 / sqrt(var + eps)); running_mean / running_var (may be NULL) are updated with `momentum`
@@ -167,18 +192,20 @@ int grafp_max_over_k_bwd(const void* grad_out, const uint8_t* argmax, void* grad
  *  backward: dz = dy masked by the ReLU (recomputed from x, no output is kept); dbias = sum dz,
  *            dweight = sum dz * xhat, dx = weight * invstd * (dz - dbias / R - xhat * dweight / R).
  *            The gradient of the residual input is dy itself and is not written here.
- *            dx_colsum (C floats, may be NULL): per-channel sum of dx over the rows, accumulated while dx is
- *            written - the bias gradient of the 1x1 convolution that produced x (Conv2d(bias=True) + BatchNorm2d
- *            in Grapher.fc1 / fc2 and BasicConv), so its backward needs no separate reduction pass over dx.
- *  workspace: grafp_bn_workspace_bytes(C) bytes of caller-owned scratch (block partials).
+ *            dx_colsum (C floats, may be NULL): per-channel sum of dx over the rows - the bias gradient of the 1x1
+ *            convolution that produced x (Conv2d(bias=True) + BatchNorm2d in Grapher.fc1 / fc2 and BasicConv), so
+ *            its backward needs no separate reduction pass over dx.  (Zero in real arithmetic; what is returned is
+ *            the rounding residue of the mean and of dbias / R, evaluated in double from the reduction sums.)
+ *  Two launches each way (no finalize kernels: block partials are folded with red.f64 into the workspace).
+ *  workspace: grafp_bn_workspace_bytes(C) bytes of caller-owned scratch, zeroed by the call itself.
  */
 size_t grafp_bn_workspace_bytes(int C);
-int grafp_bn_train_fwd(const float* x, const float* residual, const float* weight, const float* bias, float* running_mean,
-                       float* running_var, float* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
-                       float momentum, int relu, void* workspace, size_t workspace_bytes, void* stream);
-int grafp_bn_train_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* save_mean,
-                       const float* save_invstd, float* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
-                       int relu, void* workspace, size_t workspace_bytes, void* stream);
+int grafp_bn_train_fwd(const void* x, const void* residual, const float* weight, const float* bias, float* running_mean,
+                       float* running_var, void* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
+                       float momentum, int relu, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+int grafp_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,
+                       const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
+                       int relu, int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

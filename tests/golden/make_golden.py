@@ -179,6 +179,36 @@ def make_gconv(ref):
     save("gconv", **arrays)
 
 
+def make_gconv_r2(ref):
+    """DyGraphConv2d with r = 2 on an H x W feature map: the keys are the 2 x 2 average-pooled map
+    (torch_vertex.py:130-132), N = H * W queries against M = N / 4 keys."""
+    arrays = {}
+    B, C, H, W, k = 2, 16, 8, 8, 4
+    g = torch.Generator().manual_seed(23)
+    x0 = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(33))
+    for conv in ("mr", "edge", "sage", "gin"):
+        for d in (1, 2):
+            tag = f"{conv}_d{d}"
+            mod = ref.torch_vertex.DyGraphConv2d(C, 2 * C, kernel_size=k, dilation=d, conv=conv, act="relu",
+                                                 norm="batch", bias=True, stochastic=False, epsilon=0.0, r=2)
+            load_synth(mod, 50 + d)
+            mod.train()
+            x = x0.clone().requires_grad_(True)
+            out = mod(x)
+            up = torch.randn(out.shape, generator=g)
+            out.backward(up)
+            arrays[f"{tag}.out"] = out
+            arrays[f"{tag}.upstream"] = up
+            arrays[f"{tag}.grad_x"] = x.grad
+            for name, p in mod.named_parameters():
+                arrays[f"{tag}.grad.{name}"] = p.grad
+            for name, b in mod.named_buffers():
+                arrays[f"{tag}.buf.{name}"] = b
+    arrays["x"] = x0
+    arrays["cfg"] = np.array([B, C, H, W, k])
+    save("gconv_r2", **arrays)
+
+
 def make_grapher(ref):
     arrays = {}
     B, C, N, k, d = 2, 32, 64, 4, 2
@@ -274,7 +304,7 @@ def main():
     ref = _reference_import.load()
     torch.manual_seed(0)
     only = set(sys.argv[1:])
-    for name, fn in (("knn", make_knn), ("aggregate", make_aggregate), ("gconv", make_gconv),
+    for name, fn in (("knn", make_knn), ("aggregate", make_aggregate), ("gconv", make_gconv), ("gconv_r2", make_gconv_r2),
                      ("grapher", make_grapher), ("encoder", make_encoder), ("simclr", make_simclr)):
         if not only or name in only:
             fn(ref)

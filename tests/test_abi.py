@@ -40,7 +40,7 @@ def test_library_links_without_the_cuda_driver(lib_path):
 
 def test_abi_version_and_sizes(lib_path):
     lib = _native.load()
-    assert lib.grafp_abi_version() == _native.ABI_VERSION == 4
+    assert lib.grafp_abi_version() == _native.ABI_VERSION == 5
     assert lib.grafp_knn_workspace_bytes(0, 1, 1, 1, 1, 0) == 0
     need = lib.grafp_knn_workspace_bytes(4, 256, 256, 64, 3, 0)
     assert need >= 4 * 4 * 256 * 64 * 4  # hi + lo for queries and keys
@@ -63,3 +63,15 @@ def test_missing_library_is_an_error(monkeypatch, tmp_path):
     monkeypatch.setattr(_native, "_lib", None)
     with pytest.raises(RuntimeError, match="no PyTorch/CPU fallback"):
         _native.load()
+
+
+def test_options_are_settable_and_default_from_the_header(lib_path):
+    """grafp_set_option / grafp_get_option work without a device (they select kernels, they launch nothing)."""
+    lib = _native.load()
+    assert lib.grafp_get_option(b"mr_bwd_form") == 2 and lib.grafp_get_option(b"mr_fwd_form") == 2
+    assert lib.grafp_get_option(b"knn_epilogue") == 0 and lib.grafp_get_option(b"check_index") == 0
+    assert lib.grafp_set_option(b"mr_bwd_form", 3) == 0 and lib.grafp_get_option(b"mr_bwd_form") == 3
+    assert lib.grafp_set_option(b"mr_bwd_form", 2) == 0
+    assert lib.grafp_set_option(b"no_such_option", 1) == -1
+    assert b"unknown option" in lib.grafp_last_error()
+    assert lib.grafp_get_option(b"no_such_option") == -1

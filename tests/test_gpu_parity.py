@@ -34,6 +34,20 @@ def _exact_fp32_library_math():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
+_OPTION_DEFAULTS = {"mr_fwd_form": 2, "mr_bwd_form": 2, "knn_epilogue": 0, "edge_bwd_row": 1, "gather_row": 1, "edge_row": 1,
+                    "maxk_row": 1, "bn_reverse": 1, "check_index": 0}
+
+
+@pytest.fixture(autouse=True)
+def _default_kernel_options():
+    """Kernel-selection options are process-wide: every test starts from, and leaves, the defaults."""
+    for name, value in _OPTION_DEFAULTS.items():
+        ops.set_option(name, value)
+    yield
+    for name, value in _OPTION_DEFAULTS.items():
+        ops.set_option(name, value)
+
+
 def load_synth(module, seed):
     sd = module.state_dict()
     keep = {k: v for k, v in sd.items() if k.endswith("relative_pos")}
@@ -139,11 +153,12 @@ TC_CASES = [
 
 
 @pytest.mark.parametrize("B,C,N,M,k,d", TC_CASES)
-@pytest.mark.parametrize("algo", [_native.KNN_TC, _native.KNN_TC_TF32, "queue"])
-def test_knn_tensor_core_path_vs_oracle(B, C, N, M, k, d, algo, monkeypatch):
-    """("queue": the f16x3 kernels with the candidate-queue selection forced for K <= 8 too; K > 8 always uses it.)"""
-    if algo == "queue":
-        monkeypatch.setenv("GRAFP_KNN_EPI", "queue")
+@pytest.mark.parametrize("algo", [_native.KNN_TC, _native.KNN_TC_TF32, "queue", "vote"])
+def test_knn_tensor_core_path_vs_oracle(B, C, N, M, k, d, algo):
+    """("queue" / "vote": the f16x3 kernels with the candidate-queue / vote-gated selection forced for K <= 8;
+    K > 8 always uses the queues.  The default for K <= 4 is the group-maxima selection.)"""
+    if algo in ("queue", "vote"):
+        ops.set_option("knn_epilogue", 2 if algo == "queue" else 1)
         algo = _native.KNN_TC
     x = synth.synth_point_cloud(B, C, N, 3000 + N + C)
     y = synth.synth_point_cloud(B, C, M, 4000 + M) if M else None
@@ -325,10 +340,10 @@ def test_mr_aggregate_full_batch_properties():
 
 
 @pytest.mark.parametrize("N,C", STAGES)
-def test_mr_aggregate_kernel_variants_agree(N, C, monkeypatch):
-    """The pipelined forward / TMA-staged cluster backward (defaults) against the register-prefetch forward, the
-    earlier cluster-fused, the two-kernel atomic, the deterministic gather-form and the deterministic shared-memory
-    slice backwards on the same inputs, incl. a hub node with a huge in-degree."""
+def test_mr_aggregate_kernel_variants_agree(N, C):
+    """The pipelined forward / bulk-staged cluster backward (defaults) against the register-prefetch and generic
+    forwards and the fenced-cluster, two-kernel atomic and deterministic gather-form backwards on the same inputs,
+    incl. a hub node with a huge in-degree."""
     B, k = 5, 3
     x = synth.synth_point_cloud(B, C, N, 900 + N, relu=True)
     x[0, :, 5] = 0          # a zero node is everybody's near neighbour after ReLU: in-degree ~ N
@@ -338,14 +353,10 @@ def test_mr_aggregate_kernel_variants_agree(N, C, monkeypatch):
     up = torch.randn(B, 2 * C, N, 1, device=DEV, generator=torch.Generator(device=DEV).manual_seed(7))
     up = up.contiguous(memory_format=torch.channels_last)
     results = {}
-    for name, fv, bv in [("default", None, None), ("regs+cluster", "4", "2"), ("regs1+two-kernel", "1", "0"),
-                         ("generic+cluster4", "0", "4"), ("regs2+gather", "2", "8"), ("pipe+slice", "8", "32"),
-                         ("pipe+cluster-tma-e-order", "8", "16"), ("pipe+cluster16-j-order", "8", "18")]:
-        for var, val in (("GRAFP_MR_FWD_VARIANT", fv), ("GRAFP_MR_BWD_VARIANT", bv)):
-            if val is None:
-                monkeypatch.delenv(var, raising=False)
-            else:
-                monkeypatch.setenv(var, val)
+    for name, fv, bv in [("default", 2, 2), ("regs+fenced-cluster", 1, 1), ("generic+two-kernel", 0, 0),
+                         ("pipe+gather", 2, 3)]:
+        ops.set_option("mr_fwd_form", fv)
+        ops.set_option("mr_bwd_form", bv)
         xg = xd.clone().requires_grad_(True)
         out = ops.mr_aggregate(xg, nbr32)
         (gx,) = torch.autograd.grad(out, xg, up)
@@ -360,26 +371,22 @@ def test_mr_aggregate_kernel_variants_agree(N, C, monkeypatch):
         assert torch.equal(out, ref_out), name
         assert gio.rel_err(gx, ref_gx) < 1e-5, name
     # the gather-form backward has a fixed summation order: bit-reproducible
-    monkeypatch.delenv("GRAFP_MR_FWD_VARIANT", raising=False)
-    monkeypatch.setenv("GRAFP_MR_BWD_VARIANT", "8")
+    ops.set_option("mr_fwd_form", 2)
+    ops.set_option("mr_bwd_form", 3)
     xg = xd.clone().requires_grad_(True)
     (gx2,) = torch.autograd.grad(ops.mr_aggregate(xg, nbr32), xg, up)
-    assert torch.equal(gx2, results["regs2+gather"][1])
-    # so has the slice form (sorted in-edge lists in shared memory)
-    monkeypatch.setenv("GRAFP_MR_BWD_VARIANT", "32")
-    xg = xd.clone().requires_grad_(True)
-    (gx3,) = torch.autograd.grad(ops.mr_aggregate(xg, nbr32), xg, up)
-    assert torch.equal(gx3, results["pipe+slice"][1])
+    assert torch.equal(gx2, results["pipe+gather"][1])
 
 
 @pytest.mark.parametrize("shape", [(3, 64, 1024, 16), (2, 72, 300, 5), (4, 8, 50, 2), (2, 512, 128, 3), (1, 64, 2048, 3),
                                    (2, 48, 1000, 32)])
-@pytest.mark.parametrize("variant", ["16", "17", "18", "32"])
-def test_mr_aggregate_bwd_slice_shapes(shape, variant, monkeypatch):
-    """The cluster (default) and slice backwards over their whole envelope (wide k, ragged N, tiny and odd channel counts, N too large for
-    shared memory -> cluster fallback), arbitrary graphs with duplicate ids and self edges, int64 ids."""
+@pytest.mark.parametrize("form", [2, 1, 0])
+def test_mr_aggregate_bwd_envelope(shape, form):
+    """The cluster backward (default, and with the device-scope fence) and the two-kernel pair over the whole envelope
+    (wide k, ragged N, tiny and odd channel counts, shares too large for shared memory -> pair fallback), arbitrary
+    graphs with duplicate ids and self edges, int64 ids."""
     B, C, N, k = shape
-    monkeypatch.setenv("GRAFP_MR_BWD_VARIANT", variant)
+    ops.set_option("mr_bwd_form", form)
     g = torch.Generator().manual_seed(N * 7 + k)
     x = torch.randn(B, C, N, 1, generator=g)
     nbr = torch.randint(0, N, (B, N, k), generator=g)
@@ -399,13 +406,13 @@ def test_mr_aggregate_bwd_slice_shapes(shape, variant, monkeypatch):
         assert gio.rel_err(xg.grad.cpu(), xo.grad) < REL_TOL
 
 
-@pytest.mark.parametrize("edge_bwd_row", ["0", "1"])
+@pytest.mark.parametrize("edge_bwd_row", [0, 1])
 @pytest.mark.parametrize("shape", [(2, 16, 64, 4), (3, 128, 100, 9), (2, 6, 33, 5), (3, 64, 301, 3), (1, 32, 50, 2),
                                    (2, 256, 256, 3)])
-def test_gather_edge_maxk_vs_oracle(shape, edge_bwd_row, monkeypatch):
-    """(k = 2..4 with C % 4 == 0 take the row-form kernels, the rest the edge-form ones; GRAFP_EDGE_BWD_ROW switches
+def test_gather_edge_maxk_vs_oracle(shape, edge_bwd_row):
+    """(k = 2..4 with C % 4 == 0 take the row-form kernels, the rest the edge-form ones; option edge_bwd_row switches
     the EdgeConv backward between the dense + scatter pair and the one-pass form.)"""
-    monkeypatch.setenv("GRAFP_EDGE_BWD_ROW", edge_bwd_row)
+    ops.set_option("edge_bwd_row", edge_bwd_row)
     B, C, N, k = shape
     x = synth.synth_point_cloud(B, C, N, 400 + N)
     edge = O.dilated_knn_graph(x, k)
@@ -490,6 +497,28 @@ def test_dygraphconv_modules_match_reference_golden(conv, d):
     for name, b in mod.named_buffers():
         if b.dtype.is_floating_point:
             assert gio.rel_err(b.cpu(), gio.t(gold[f"{tag}.buf.{name}"])) < REL_TOL, name
+
+
+@pytest.mark.parametrize("conv", ["mr", "edge", "sage", "gin"])
+@pytest.mark.parametrize("d", [1, 2])
+def test_dygraphconv_r2_matches_reference_golden(conv, d):
+    """The r > 1 module path (torch_vertex.py:130-132): an H x W feature map queried against its 2 x 2 average-pooled
+    key set - a separate key tensor y through the k-NN, the aggregation and every backward."""
+    gold = gio.load("gconv_r2")
+    B, C, H, W, k = (int(v) for v in gold["cfg"])
+    tag = f"{conv}_d{d}"
+    mod = torch_vertex.DyGraphConv2d(C, 2 * C, kernel_size=k, dilation=d, conv=conv, act="relu", norm="batch",
+                                     bias=True, stochastic=False, epsilon=0.0, r=2)
+    load_synth(mod, 50 + d).to(DEV).train()
+    x = gio.t(gold["x"]).to(DEV).requires_grad_(True)
+    out = mod(x)
+    assert out.shape == (B, 2 * C, H, W)
+    assert gio.rel_err(out.cpu(), gio.t(gold[f"{tag}.out"])) < REL_TOL
+    out.backward(gio.t(gold[f"{tag}.upstream"]).to(DEV))
+    assert gio.rel_err(x.grad.cpu(), gio.t(gold[f"{tag}.grad_x"])) < REL_TOL
+    scale = max(float(np.linalg.norm(gold[key])) for key in gold if key.startswith(f"{tag}.grad."))
+    for name, p in mod.named_parameters():
+        assert gio.close(p.grad.cpu(), gio.t(gold[f"{tag}.grad.{name}"]), REL_TOL, scale), name
 
 
 def test_grapher_block_matches_reference_golden():
@@ -857,3 +886,203 @@ def test_fingerprint_writer_streams_from_the_device(tmp_path):
             w.append(runner(pts[lo:lo + 8]))      # the last chunk is ragged: eager path
     data, shape = load_fingerprint_db(str(tmp_path), "db")
     assert shape == want.shape and np.array_equal(np.asarray(data), want)
+
+
+# ------------------------------------------------------------------------------------------
+# bf16 (BASELINE configs[2]: torch.autocast(bfloat16) activations, fp32 parameters)
+# ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shape", [(4, 64, 1024), (3, 128, 300), (2, 2048, 128), (2, 256, 256)])
+@pytest.mark.parametrize("mode", ["plain", "relu", "residual"])
+def test_fused_batch_norm_bf16(shape, mode):
+    """bf16 rows, fp32 statistics / parameters: against nn.BatchNorm2d evaluated in fp64 on the same bf16-rounded
+    input.  Bounds: output within bf16 rounding (2^-8 relative per element -> 4e-3 in norm), input gradient 1e-2
+    (ReLU mask on rounded values), parameter gradients 1e-3 (they are fp32 sums of bf16 data)."""
+    B, C, N = shape
+    g = torch.Generator().manual_seed(B * 17 + C + N)
+    x = (torch.randn(B, C, N, 1, generator=g) * 2 + 3.0 * torch.randn(1, C, 1, 1, generator=g)).bfloat16()
+    res = torch.randn(B, C, N, 1, generator=g).bfloat16()
+    up = torch.randn(B, C, N, 1, generator=g).bfloat16()
+    bn_ref = torch.nn.BatchNorm2d(C).double()
+    with torch.no_grad():
+        bn_ref.weight.copy_(1 + 0.2 * torch.randn(C, generator=g).double())
+        bn_ref.bias.copy_(torch.randn(C, generator=g).double())
+    bn = torch.nn.BatchNorm2d(C)
+    bn.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in bn_ref.state_dict().items()})
+    bn.to(DEV).train(); bn_ref.train()
+
+    def cl(t):
+        return t.to(DEV).contiguous(memory_format=torch.channels_last)
+
+    xg, rg = cl(x).requires_grad_(True), cl(res).requires_grad_(True)
+    xr, rr = x.double().requires_grad_(True), res.double().requires_grad_(True)
+    if mode == "plain":
+        got, ref = ops.batch_norm_act(xg, bn), bn_ref(xr)
+    elif mode == "relu":
+        got, ref = ops.batch_norm_act(xg, bn, relu=True), torch.relu(bn_ref(xr))
+    else:
+        got, ref = ops.batch_norm_act(xg, bn, residual=rg), bn_ref(xr) + rr
+    assert got.dtype == torch.bfloat16 and ops._is_rows(got)
+    assert gio.rel_err(got.detach().cpu().double(), ref.detach()) < 4e-3
+    assert gio.rel_err(bn.running_mean.cpu().double(), bn_ref.running_mean) < 1e-5
+    assert gio.rel_err(bn.running_var.cpu().double(), bn_ref.running_var) < 1e-5
+    got.backward(cl(up)); ref.backward(up.double())
+    assert xg.grad.dtype == torch.bfloat16
+    assert gio.rel_err(xg.grad.float().cpu().double(), xr.grad) < 1e-2
+    assert gio.rel_err(bn.weight.grad.cpu().double(), bn_ref.weight.grad) < 2e-3
+    assert gio.rel_err(bn.bias.grad.cpu().double(), bn_ref.bias.grad) < 2e-3
+
+
+@pytest.mark.parametrize("N,C", STAGES)
+def test_bf16_hot_ops_take_the_fast_kernels(N, C):
+    """bf16 rows through K1 (tcgen05 f16x3 planes built from the bf16 input), K2 (pipelined) and K3 (cluster):
+    k-NN ids against the oracle on the same bf16-rounded features (identical except proven ties), K2 exact up to the
+    final bf16 rounding, K3 within 2e-2 (bf16 reductions)."""
+    B, k = 4, 3
+    x = synth.synth_point_cloud(B, C, N, 700 + N, relu=False).bfloat16()
+    xd = x.to(DEV)
+    nn_idx, nn32 = ops.knn_graph(xd, k)
+    assert (ops.knn_last_algo(), ops.knn_last_variant()) == ("tcgen05", "f16x3")
+    assert_knn_ok(x.float(), nn_idx, k, 1, what=f"bf16 knn N={N} C={C}")
+    edge = torch.stack([nn_idx.cpu(), torch.arange(N)[None, :, None].expand(B, N, k)])
+    xg = xd.clone().requires_grad_(True)
+    out = ops.mr_aggregate(xg, nn32)
+    xo = x.float().requires_grad_(True)
+    ref = O.max_relative_features(xo, edge)
+    assert torch.equal(out.float().cpu(), ref.detach().bfloat16().float())
+    up = torch.randn(ref.shape, generator=torch.Generator().manual_seed(4)).bfloat16()
+    ref.backward(up.float())
+    out.backward(up.to(DEV).contiguous(memory_format=torch.channels_last))
+    assert gio.rel_err(xg.grad.float().cpu(), xo.grad) < 2e-2
+    # the same through the generic kernels
+    ops.set_option("mr_fwd_form", 0); ops.set_option("mr_bwd_form", 0)
+    xg2 = xd.clone().requires_grad_(True)
+    out2 = ops.mr_aggregate(xg2, nn32)
+    assert torch.equal(out2, out)
+    out2.backward(up.to(DEV).contiguous(memory_format=torch.channels_last))
+    assert gio.rel_err(xg2.grad.float(), xg.grad.float()) < 2e-2
+
+
+def test_graph_encoder_bf16_autocast_vs_oracle():
+    """configs[2] arithmetic at model level: the encoder under torch.autocast(bfloat16) (fp32 parameters) against the
+    fp32 oracle on the graphs the device built.  Stated bf16 bounds (12 blocks of bf16 activations, 8 mantissa bits):
+    embeddings <= 5e-2, parameter gradients <= 0.25 in relative norm (measured values are printed)."""
+    cfg = dict(synth.DEFAULT_CFG)
+    enc = GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3)
+    load_synth(enc, 91)
+    base = {k: v.clone() for k, v in enc.state_dict().items() if not k.endswith("relative_pos")}
+    trainable = [n for n, q in enc.named_parameters() if q.requires_grad]
+    enc.to(DEV).train()
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(4, 8, 1024, generator=g)
+    up = torch.randn(4, 1024, generator=g)
+    rec, handles = record_graphs(enc)
+    timer = ops.KernelTimer(timing=False)
+    ops.set_timer(timer)
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = enc(x.to(DEV))
+        (out.float() * up.to(DEV)).sum().backward()
+    finally:
+        ops.set_timer(None)
+    for h in handles:
+        h.remove()
+    assert out.dtype == torch.bfloat16 and len(rec) == 12
+    assert ops.knn_last_algo() == "tcgen05", "bf16 features must stay on the tensor-core k-NN"
+    assert timer.launches >= 12 * 2 + 12 * 2 + 100, "the fused BatchNorm / aggregation kernels must run in bf16 too"
+    p = _to(base, torch.float32)
+    for n in trainable:
+        p[n].requires_grad_(True)
+    ref = O.graph_encoder(p, x, True, k=3, graph_fn=O.GraphReplay(rec, classify=False))
+    (ref * up).sum().backward()
+    e_out = gio.rel_err(out.float().cpu(), ref)
+    scale = max(float(p[n].grad.norm()) for n in trainable)
+    worst = max(float((dict(enc.named_parameters())[n].grad.cpu() - p[n].grad).norm()) / max(float(p[n].grad.norm()), 0.1 * scale)
+                for n in trainable)
+    print(f"bf16 encoder: embedding rel err {e_out:.3e}, worst parameter-gradient rel err {worst:.3e}")
+    assert e_out < 5e-2 and worst < 0.25
+
+
+def test_check_index_option_raises_like_the_reference():
+    """User-supplied graphs with ids outside [0, M) raise IndexError (as the reference's advanced indexing does) when
+    option check_index is on; graphs from the k-NN op are never checked."""
+    x = torch.randn(2, 16, 40, 1, device=DEV)
+    idx = torch.randint(0, 40, (2, 40, 3), device=DEV)
+    ctr = torch.arange(40, device=DEV).view(1, 40, 1).expand(2, 40, 3).contiguous()
+    ops.set_option("check_index", 1)
+    ops.mr_aggregate(x, idx, None, ctr)
+    ops.gather_neighbors(x, idx)
+    bad = idx.clone(); bad[1, 7, 2] = 40
+    with pytest.raises(IndexError, match="outside"):
+        ops.mr_aggregate(x, bad, None, ctr)
+    with pytest.raises(IndexError, match="outside"):
+        ops.gather_neighbors(x, bad)
+    with pytest.raises(IndexError, match="outside"):
+        ops.edge_features(x, idx, None, ctr - 1)
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE configs[4] at its stated size: 10 000 segments, 1 000 queries, top-1 retrieval
+# ------------------------------------------------------------------------------------------
+
+def test_fingerprint_generation_at_size_matches_the_reference_on_the_same_gpu():
+    """generate.py:34-57 at configs[4] size.  Fingerprints of 10 000 synthetic segments (eval mode, chunks of 128 like
+    generate.py:41, CUDA-graph replay) and of 1 000 queries (second views of a fixed subset); top-1 by exact inner
+    product (== IndexFlatL2 on unit vectors, eval.py:54-60).  Checked against the UNMODIFIED reference modules
+    (baseline/_ref, staged by __graft_entry__.build()) run eager on the same GPU with the same weights:
+      * fingerprints within 1e-3 relative per segment for all but documented graph ties (a random-weight encoder
+        amplifies one differently resolved near-tie; the bound on the affected fraction is stated below);
+      * identical top-1 ids, except queries whose best two candidates are closer than the embedding noise;
+      * size-independent properties: unit-norm rows, determinism, chunk-size independence of eval-mode outputs."""
+    from oracle import reference_arm as RA
+    from grafp_b200.inference import generate_fingerprints
+    if not RA.available():
+        pytest.skip("baseline/_ref not staged (run __graft_entry__.build() in the build container)")
+    ref = RA.load()
+    cfg = dict(synth.DEFAULT_CFG)
+    n_db, n_q, chunk = 10_000, 1_000, 128
+    torch.manual_seed(0)
+    ours = SimCLR(cfg, GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3))
+    load_synth(ours, 303)
+    theirs = ref.SimCLR(cfg, ref.GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3))
+    theirs.load_state_dict(ours.state_dict(), strict=True)
+    ours.to(DEV).eval(); theirs.to(DEV).eval()
+    db_specs, q_all = synth.synth_spec(n_db, 7)
+    pick = torch.randperm(n_db, generator=torch.Generator().manual_seed(8))[:n_q]
+    q_specs = q_all[pick]
+
+    def fingerprints(model, specs, graphed):
+        outs = []
+        with torch.no_grad():
+            if graphed:
+                pts = model.peak_extractor(specs.to(DEV))
+                h = generate_fingerprints(model.encoder, pts, chunk=chunk)
+                return torch.nn.functional.normalize(model.projector(h), p=2)
+            for lo in range(0, specs.shape[0], chunk):
+                s = specs[lo:lo + chunk].to(DEV)
+                outs.append(model(s, s)[2])
+        return torch.cat(outs)
+
+    db, q = fingerprints(ours, db_specs, True), fingerprints(ours, q_specs, True)
+    db_ref, q_ref = fingerprints(theirs, db_specs, False), fingerprints(theirs, q_specs, False)
+    assert db.shape == (n_db, cfg["d"]) and q.shape == (n_q, cfg["d"])
+    assert float((db.norm(dim=1) - 1).abs().max()) < 1e-5
+    assert torch.equal(db[:256], fingerprints(ours, db_specs[:256], True)), "deterministic"
+    with torch.no_grad():
+        s = db_specs[:64].to(DEV)
+        assert gio.rel_err(ours(s, s)[2], db[:64]) < 1e-5, "eval-mode outputs do not depend on the chunk size"
+    per_seg = (db - db_ref).norm(dim=1) / db_ref.norm(dim=1)
+    frac_off = float((per_seg > 1e-3).float().mean())
+    top1, top1_ref = (q @ db.T).argmax(1), (q_ref @ db_ref.T).argmax(1)
+    sims = q_ref @ db_ref.T
+    best2 = sims.topk(2, dim=1).values
+    margin = best2[:, 0] - best2[:, 1]
+    differs = top1 != top1_ref
+    hit = float((top1.cpu() == pick).float().mean())
+    hit_ref = float((top1_ref.cpu() == pick).float().mean())
+    print(f"configs[4] at size: median per-segment err {float(per_seg.median()):.2e}, fraction > 1e-3: {frac_off:.4f}, "
+          f"top-1 differing {int(differs.sum())} / {n_q}, hit rate ours {hit:.4f} reference {hit_ref:.4f}")
+    assert float(per_seg.median()) < 1e-4
+    assert frac_off < 0.05, "only segments with a differently resolved k-NN near-tie may move"
+    assert int(differs.sum()) <= n_q // 100 and bool((margin[differs] < 0.02).all()), "identical top-1 hits up to near-ties"
+    assert abs(hit - hit_ref) <= 0.01

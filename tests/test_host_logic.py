@@ -199,22 +199,3 @@ def test_fingerprint_writer_matches_the_reference_memmap_format(tmp_path):
     with pytest.raises(ValueError):
         with FingerprintWriter(str(tmp_path), "short", 10, 128) as w:
             w.append(torch.zeros(4, 128))
-
-
-def test_conv1x1_gemm_form_matches_conv2d():
-    """The experimental GEMM form of a dense 1x1 convolution on node rows (GRAFP_CONV_AS_GEMM=1, off by default) is the
-    same map as conv2d / its gradients (fp64, CPU), and returns node-row (channels-last) tensors."""
-    g = torch.Generator().manual_seed(2)
-    x = torch.randn(3, 16, 50, 1, generator=g, dtype=torch.float64).contiguous(memory_format=torch.channels_last)
-    w = torch.randn(24, 16, 1, 1, generator=g, dtype=torch.float64)
-    up = torch.randn(3, 24, 50, 1, generator=g, dtype=torch.float64).contiguous(memory_format=torch.channels_last)
-    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
-    ref = torch.nn.functional.conv2d(xr, wr)
-    ref.backward(up)
-    h = ops._conv1x1_rows_fwd(x, w)
-    assert h.shape == ref.shape and ops._is_rows(h)
-    assert float((h - ref.detach()).abs().max()) < 1e-12
-    dx, dw = ops._conv1x1_rows_bwd(up, x, w, True, True)
-    assert ops._is_rows(dx) and dw.shape == w.shape
-    assert float((dx - xr.grad).abs().max()) < 1e-12 and float((dw - wr.grad).abs().max()) < 1e-10
-    assert not ops._gemm_form(((1, 1), (0, 0), (1, 1), 1), w)            # off unless GRAFP_CONV_AS_GEMM=1

@@ -84,6 +84,29 @@ def test_graph_conv_modules_match_reference(conv, d):
             assert gio.rel_err(v, gio.t(gold[f"{tag}.buf.{name}"])) < 1e-6, name
 
 
+@pytest.mark.parametrize("conv", ["mr", "edge", "sage", "gin"])
+@pytest.mark.parametrize("d", [1, 2])
+def test_graph_conv_modules_r2_match_reference(conv, d):
+    """DyGraphConv2d(r=2) on an H x W map: queries against the average-pooled key set (torch_vertex.py:130-132)."""
+    gold = gio.load("gconv_r2")
+    B, C, H, W, k = (int(v) for v in gold["cfg"])
+    tag = f"{conv}_d{d}"
+    shapes = _params_for(gold, tag)
+    p = synth.synth_state_dict(shapes, 50 + d)
+    for name in list(p):
+        if f"{tag}.grad.{name}" in gold:
+            p[name].requires_grad_(True)
+    x = gio.t(gold["x"]).requires_grad_(True)
+    out = O.dy_graph_conv(p, "", x, True, k, d, conv, r=2)
+    assert out.shape == (B, 2 * C, H, W)
+    assert gio.rel_err(out, gio.t(gold[f"{tag}.out"])) < 1e-6
+    out.backward(gio.t(gold[f"{tag}.upstream"]))
+    assert gio.rel_err(x.grad, gio.t(gold[f"{tag}.grad_x"])) < 1e-5
+    for name, v in p.items():
+        if v.requires_grad:
+            assert gio.rel_err(v.grad, gio.t(gold[f"{tag}.grad.{name}"])) < 1e-5, name
+
+
 def test_grapher_block_matches_reference():
     gold = gio.load("grapher")
     B, C, N, k, d = (int(v) for v in gold["cfg"])
