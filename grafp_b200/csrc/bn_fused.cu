@@ -354,6 +354,266 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const flo
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Single-launch forms: both passes in one cooperative kernel (every block resident), separated by a grid barrier.
+// A block keeps its (row block, channel tile) assignment in both passes, so the second pass re-reads exactly the rows
+// the block streamed in the first - in reverse order, starting with what is still in L2 - and the launch gap and the
+// ramp-down / ramp-up between two kernels disappear (the 134 MB tensors, where cuDNN's single persistent BatchNorm
+// kernel beat the two-kernel form).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int expected) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // cumulative: the block's reductions (ordered before this by the barrier above) become visible
+    atomicAdd(counter, 1u);
+    while (ld_acquire_u32(counter) < expected) __nanosleep(40);
+  }
+  __syncthreads();
+}
+
+template <typename T, bool RELU, bool RES>
+__global__ void __launch_bounds__(kBnThreads)
+bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ weight,
+                         const float* __restrict__ bias, double* __restrict__ sums, unsigned int* __restrict__ counter,
+                         T* __restrict__ out, float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                         float* running_mean, float* running_var, long long R, int C, int tpr_shift, float eps,
+                         float momentum) {
+  constexpr int V = Vec16<T>::V;
+  __shared__ float sm[2 * V * kBnThreads];
+  const int tpr = 1 << tpr_shift;
+  const int rpp = kBnThreads >> tpr_shift;
+  const int tc = threadIdx.x & (tpr - 1);
+  const int rl = threadIdx.x >> tpr_shift;
+  const int c = (blockIdx.y * tpr + tc) * V;
+  const T* xp = x + c;
+  const long long step = (long long)gridDim.x * rpp;
+  const long long r0 = (long long)blockIdx.x * rpp + rl;
+  float sh[V], acc[2 * V];
+  Vec16<T>::load(xp, sh);
+#pragma unroll
+  for (int e = 0; e < 2 * V; ++e) acc[e] = 0.f;
+  auto add = [&](const float (&v)[V]) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float d = v[e] - sh[e];
+      acc[e] += d;
+      acc[V + e] = fmaf(d, d, acc[V + e]);
+    }
+  };
+  long long r = r0;
+  for (; r + 3 * step < R; r += 4 * step) {
+    float v[4][V];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Vec16<T>::load(xp + (r + u * step) * C, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) add(v[u]);
+  }
+  for (; r < R; r += step) {
+    float v[V];
+    Vec16<T>::load(xp + r * C, v);
+    add(v);
+  }
+  reduce_row_lanes<2 * V>(acc, sm, tpr_shift);
+  if (rl == 0) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      red_add_f64(sums + c + e, (double)acc[e]);
+      red_add_f64(sums + C + c + e, (double)acc[V + e]);
+    }
+  }
+  grid_barrier(counter, gridDim.x * gridDim.y);
+
+  float mu[V], is[V], a[V], bb[V];
+  double var_b[V];
+  bn_finish_stats<T, V>(x, sums, C, c, 1.0 / (double)R, eps, mu, is, var_b);
+#pragma unroll
+  for (int e = 0; e < V; ++e) { a[e] = __ldg(weight + c + e) * is[e]; bb[e] = __ldg(bias + c + e); }
+  if (blockIdx.x == 0 && rl == 0) {  // one thread per channel pack: the saved and the running statistics
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      save_mean[c + e] = mu[e];
+      save_invstd[c + e] = is[e];
+      if (running_mean != nullptr) running_mean[c + e] = (1.f - momentum) * running_mean[c + e] + momentum * mu[e];
+      if (running_var != nullptr) {
+        const double unbiased = var_b[e] * ((double)R / (double)(R - 1));
+        running_var[c + e] = (1.f - momentum) * running_var[c + e] + momentum * (float)unbiased;
+      }
+    }
+  }
+  if (r0 >= R) return;
+  auto one = [&](const float (&v)[V], const float (&rv)[V], T* o) {
+    float y[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      y[e] = fmaf(v[e] - mu[e], a[e], bb[e]);
+      if (RES) y[e] += rv[e];
+      if (RELU) y[e] = fmaxf(y[e], 0.f);
+    }
+    Vec16<T>::store(o, y);
+  };
+  const long long n = (R - r0 + step - 1) / step;  // this thread's rows: r0 + j * step; walked back to front
+  long long j = n - 1;
+  for (; j >= 3; j -= 4) {
+    float v[4][V], rv[4][V];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long off = (r0 + (j - u) * step) * C + c;
+      Vec16<T>::load(x + off, v[u]);
+      if (RES) Vec16<T>::load(res + off, rv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(v[u], rv[u], out + (r0 + (j - u) * step) * C + c);
+  }
+  for (; j >= 0; --j) {
+    float v[V], rv[V];
+    const long long off = (r0 + j * step) * C + c;
+    Vec16<T>::load(x + off, v);
+    if (RES) Vec16<T>::load(res + off, rv);
+    one(v, rv, out + off);
+  }
+}
+
+template <typename T, bool RELU>
+__global__ void __launch_bounds__(kBnThreads)
+bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ weight,
+                         const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ invstd,
+                         double* __restrict__ sums, unsigned int* __restrict__ counter, T* __restrict__ dx,
+                         float* __restrict__ dweight, float* __restrict__ dbias, float* __restrict__ colsum, long long R,
+                         int C, int tpr_shift) {
+  constexpr int V = Vec16<T>::V;
+  __shared__ float sm[3 * V * kBnThreads];
+  const int tpr = 1 << tpr_shift;
+  const int rpp = kBnThreads >> tpr_shift;
+  const int tc = threadIdx.x & (tpr - 1);
+  const int rl = threadIdx.x >> tpr_shift;
+  const int c = (blockIdx.y * tpr + tc) * V;
+  float mu[V], is[V], a[V], b[V], acc[3 * V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    mu[e] = __ldg(mean + c + e);
+    is[e] = __ldg(invstd + c + e);
+    a[e] = __ldg(weight + c + e) * is[e];
+    b[e] = RELU ? __ldg(bias + c + e) : 0.f;
+    acc[e] = 0.f; acc[V + e] = 0.f; acc[2 * V + e] = 0.f;
+  }
+  const T* xp = x + c;
+  const T* gp = dy + c;
+  const long long step = (long long)gridDim.x * rpp;
+  const long long r0 = (long long)blockIdx.x * rpp + rl;
+  auto add = [&](const float (&v)[V], const float (&g)[V]) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float d = v[e] - mu[e];
+      float gz = g[e];
+      if (RELU) gz = fmaf(d, a[e], b[e]) > 0.f ? gz : 0.f;
+      acc[e] += gz;
+      acc[V + e] = fmaf(gz, d * is[e], acc[V + e]);
+      acc[2 * V + e] += d;
+    }
+  };
+  long long r = r0;
+  for (; r + 3 * step < R; r += 4 * step) {
+    float v[4][V], g[4][V];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { Vec16<T>::load(xp + (r + u * step) * C, v[u]); Vec16<T>::load(gp + (r + u * step) * C, g[u]); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) add(v[u], g[u]);
+  }
+  for (; r < R; r += step) {
+    float v[V], g[V];
+    Vec16<T>::load(xp + r * C, v);
+    Vec16<T>::load(gp + r * C, g);
+    add(v, g);
+  }
+  reduce_row_lanes<3 * V>(acc, sm, tpr_shift);
+  if (rl == 0) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      red_add_f64(sums + c + e, (double)acc[e]);
+      red_add_f64(sums + C + c + e, (double)acc[V + e]);
+      red_add_f64(sums + 2 * C + c + e, (double)acc[2 * V + e]);
+    }
+  }
+  grid_barrier(counter, gridDim.x * gridDim.y);
+
+  const double inv_rows = 1.0 / (double)R;
+  float c1[V], c2[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    const double s1 = ld_f64_cg(sums + c + e), s2 = ld_f64_cg(sums + C + c + e);
+    c1[e] = (float)(s1 * inv_rows);
+    c2[e] = (float)(s2 * inv_rows);
+    if (blockIdx.x == 0 && rl == 0) {
+      dbias[c + e] = (float)s1;
+      dweight[c + e] = (float)s2;
+      if (colsum != nullptr) {
+        const double s3 = ld_f64_cg(sums + 2 * C + c + e);
+        colsum[c + e] = (float)((double)a[e] * ((s1 - (double)R * (double)c1[e]) - (double)is[e] * (double)c2[e] * s3));
+      }
+    }
+  }
+  if (r0 >= R) return;
+  auto one = [&](const float (&v)[V], const float (&g)[V], T* o) {
+    float rr[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float d = v[e] - mu[e];
+      float gz = g[e];
+      if (RELU) gz = fmaf(d, a[e], b[e]) > 0.f ? gz : 0.f;
+      rr[e] = a[e] * (gz - c1[e] - d * is[e] * c2[e]);
+    }
+    Vec16<T>::store(o, rr);
+  };
+  const long long n = (R - r0 + step - 1) / step;
+  long long j = n - 1;
+  for (; j >= 3; j -= 4) {
+    float v[4][V], g[4][V];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long off = (r0 + (j - u) * step) * C + c;
+      Vec16<T>::load(x + off, v[u]);
+      Vec16<T>::load(dy + off, g[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(v[u], g[u], dx + (r0 + (j - u) * step) * C + c);
+  }
+  for (; j >= 0; --j) {
+    float v[V], g[V];
+    const long long off = (r0 + j * step) * C + c;
+    Vec16<T>::load(x + off, v);
+    Vec16<T>::load(dy + off, g);
+    one(v, g, dx + off);
+  }
+}
+
+// Cooperative launch of one of the single-launch kernels on grid (gx, ctiles); returns false when all blocks cannot be
+// resident (the caller then takes the two-kernel form).  Blocks per SM from the occupancy calculator, cached per
+// kernel and device.
+struct CoopInfo {
+  int blocks_per_sm[64] = {};
+};
+template <typename Kernel>
+bool coop_capacity(Kernel kernel, CoopInfo& info, int* capacity) {
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64) return false;
+  if (info.blocks_per_sm[dev] == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kBnThreads, 0) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = -1;
+    }
+    info.blocks_per_sm[dev] = n;
+  }
+  if (info.blocks_per_sm[dev] < 0) return false;
+  *capacity = info.blocks_per_sm[dev] * num_sms();
+  return true;
+}
+
 int apply_grid(long long total, int cv) {
   // whole waves of 8 CTAs per SM, rounded so that grid * 256 is a multiple of cv
   long long need = (total + kBnThreads - 1) / kBnThreads;
@@ -378,8 +638,31 @@ int bn_fwd_t(const void* x_, const void* res_, const float* weight, const float*
   const T* res = static_cast<const T*>(res_);
   T* out = static_cast<T*>(out_);
   double* sums = reinterpret_cast<double*>(((uintptr_t)workspace + 255) / 256 * 256);
-  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), s);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(sums + (size_t)3 * C);
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)3 * C * sizeof(double) + 16, s);
   if (e != cudaSuccess) { set_error("bn_train_fwd: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+  if (option(OPT_BN_PERSISTENT) != 0) {
+    int tsh = shift_of(g.tpr);
+    void* args[] = {(void*)&x, (void*)&res, (void*)&weight, (void*)&bias, (void*)&sums, (void*)&counter, (void*)&out,
+                    (void*)&save_mean, (void*)&save_invstd, (void*)&running_mean, (void*)&running_var, (void*)&R, (void*)&C,
+                    (void*)&tsh, (void*)&eps, (void*)&momentum};
+    auto try_launch = [&](auto kernel, CoopInfo& info) -> int {
+      int cap = 0;
+      if (!coop_capacity(kernel, info, &cap)) return -1;
+      int gx = g.gx;
+      if ((long long)gx * g.ctiles > cap) gx = cap / g.ctiles;
+      if (gx < 1) return -1;
+      const cudaError_t le = cudaLaunchCooperativeKernel((const void*)kernel, dim3(gx, g.ctiles), dim3(kBnThreads), args, 0, s);
+      if (le != cudaSuccess) { cudaGetLastError(); return -1; }
+      return 0;
+    };
+    static CoopInfo i_relu, i_res, i_plain;
+    int rc;
+    if (relu) rc = try_launch(bn_fwd_persistent_kernel<T, true, false>, i_relu);
+    else if (res) rc = try_launch(bn_fwd_persistent_kernel<T, false, true>, i_res);
+    else rc = try_launch(bn_fwd_persistent_kernel<T, false, false>, i_plain);
+    if (rc == 0) return check_launch("bn_train_fwd (single launch)");
+  }
   bn_stats_kernel<T><<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(x, sums, R, C, shift_of(g.tpr));
   const long long total = R * g.cv;
   const int grid = apply_grid(total, g.cv);
@@ -405,9 +688,28 @@ int bn_bwd_t(const void* dy_, const void* x_, const float* weight, const float* 
   const T* x = static_cast<const T*>(x_);
   T* dx = static_cast<T*>(dx_);
   double* sums = reinterpret_cast<double*>(((uintptr_t)workspace + 255) / 256 * 256);
-  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)3 * C * sizeof(double), s);
+  unsigned int* counter = reinterpret_cast<unsigned int*>(sums + (size_t)3 * C);
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)3 * C * sizeof(double) + 16, s);
   if (e != cudaSuccess) { set_error("bn_train_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
-  const int tsh = shift_of(g.tpr);
+  int tsh = shift_of(g.tpr);
+  if (option(OPT_BN_PERSISTENT) != 0) {
+    void* args[] = {(void*)&dy, (void*)&x, (void*)&weight, (void*)&bias, (void*)&save_mean, (void*)&save_invstd, (void*)&sums,
+                    (void*)&counter, (void*)&dx, (void*)&dweight, (void*)&dbias, (void*)&dx_colsum, (void*)&R, (void*)&C,
+                    (void*)&tsh};
+    auto try_launch = [&](auto kernel, CoopInfo& info) -> int {
+      int cap = 0;
+      if (!coop_capacity(kernel, info, &cap)) return -1;
+      int gx = g.gx;
+      if ((long long)gx * g.ctiles > cap) gx = cap / g.ctiles;
+      if (gx < 1) return -1;
+      const cudaError_t le = cudaLaunchCooperativeKernel((const void*)kernel, dim3(gx, g.ctiles), dim3(kBnThreads), args, 0, s);
+      if (le != cudaSuccess) { cudaGetLastError(); return -1; }
+      return 0;
+    };
+    static CoopInfo i_relu, i_plain;
+    const int rc = relu ? try_launch(bn_bwd_persistent_kernel<T, true>, i_relu) : try_launch(bn_bwd_persistent_kernel<T, false>, i_plain);
+    if (rc == 0) return check_launch("bn_train_bwd (single launch)");
+  }
   if (relu) bn_bwd_reduce_kernel<T, true><<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, sums, R, C, tsh);
   else bn_bwd_reduce_kernel<T, false><<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(dy, x, weight, bias, save_mean, save_invstd, sums, R, C, tsh);
   const long long total = R * g.cv;
@@ -420,7 +722,7 @@ int bn_bwd_t(const void* dy_, const void* x_, const float* weight, const float* 
 
 }  // namespace
 
-size_t bn_workspace_bytes(int C) { return (size_t)3 * C * sizeof(double) + 256; }
+size_t bn_workspace_bytes(int C) { return (size_t)3 * C * sizeof(double) + 16 + 256; }
 
 bool bn_supported(long long R, int C, int dtype) {
   BnGeom g;

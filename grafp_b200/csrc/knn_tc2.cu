@@ -223,6 +223,118 @@ struct TopK {
   }
 };
 
+// ---- group-maxima selection (K <= 3, unit-norm keys) ------------------------------------------------------
+// The two forms above pay for SIMT divergence: a row's list changes ~K ln(M/K) times over M keys, at different
+// columns for each of the 32 rows of a warp, so either the whole warp walks the insertion path for most columns
+// (vote) or the lanes queue their candidates and drain them at the pace of the fullest lane (queues): 13 / 9.6
+// issued instructions per accumulator entry, against ~10 that a tensor-bound kernel could afford at C = 64.
+// Here the scan is branch-free and identical for every lane.  Keys are handled in groups of 8 consecutive columns;
+// per group: its maximum raw accumulator (3 FMNMX3 + 1 FMNMX), a K-entry insertion of (maximum, group id) into the
+// row's list of the K best GROUP maxima, and - predicated on the group entering that list - a 32-byte spill of the
+// group's 8 accumulators into one of K per-row slots in shared memory (the slot of the entry that drops out).
+// After the last tile the K best keys of a row lie inside its K listed groups: if key e is among the K best, its
+// group's maximum is >= acc_e, so fewer than K groups can precede it.  The 8 K spilled accumulators are then ranked
+// exactly - D = (|x_i|^2 + (-2 s)) + |y_j|^2 in the reference's association order, ties to the lower key id - in
+// ascending key order.  Ranking groups by the raw accumulator is ranking by distance only while all |y_j|^2 are
+// equal, i.e. for unit-norm keys (what DenseDilatedKnnGraph's F.normalize gives); the kernel checks the segment's
+// min / max |y|^2 and takes the vote-gated scan for segments with all-zero (or un-normalised) nodes.  Among
+// near-ties, picks can differ from the fp32 reference by the spread of the computed |y|^2 around 1 (2.4e-7), well
+// inside the documented tie band.  A warp skips a chunk of 32 columns when none of its rows has a group entering
+// its list (neighbouring spectrogram peaks find their candidates in the same few columns).
+template <int KG>
+struct GroupTop {
+  static constexpr int kInvalid = 0x00ffffff;
+  float gv[KG];    // the KG largest group maxima, descending; ties keep the earlier (lower-id) group in front
+  int gm[KG];      // (group id << 3) | spill slot
+  uint32_t spill;  // shared address of this thread's slot 0: warp base + 16 * lane; slot s at +1024 s, second half +512
+  __device__ __forceinline__ void init(uint32_t warp_spill, int lane) {
+#pragma unroll
+    for (int p = 0; p < KG; ++p) { gv[p] = -INFINITY; gm[p] = (kInvalid << 3) | p; }
+    spill = warp_spill + 16u * lane;
+  }
+  __device__ __forceinline__ static float max8(const uint32_t* v) {
+    float a, b;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(a) : "f"(__uint_as_float(v[0])), "f"(__uint_as_float(v[1])), "f"(__uint_as_float(v[2])));
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(b) : "f"(__uint_as_float(v[3])), "f"(__uint_as_float(v[4])), "f"(__uint_as_float(v[5])));
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(a) : "f"(a), "f"(__uint_as_float(v[6])), "f"(__uint_as_float(v[7])));
+    return fmaxf(a, b);
+  }
+  // group `gid` with maximum m and accumulators v[0..7]
+  __device__ __forceinline__ void offer(float m, int gid, const uint32_t* v) {
+    bool c[KG];
+#pragma unroll
+    for (int p = 0; p < KG; ++p) c[p] = m > gv[p];
+    const int slot = gm[KG - 1] & 7;
+    if (c[KG - 1]) {
+      const uint32_t a = spill + (uint32_t)slot * 1024u;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + 512u), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+    }
+    const int meta = (gid << 3) | slot;
+#pragma unroll
+    for (int p = KG - 1; p > 0; --p) {
+      gv[p] = c[p - 1] ? gv[p - 1] : (c[p] ? m : gv[p]);
+      gm[p] = c[p - 1] ? gm[p - 1] : (c[p] ? meta : gm[p]);
+    }
+    gv[0] = c[0] ? m : gv[0];
+    gm[0] = c[0] ? meta : gm[0];
+  }
+  // one 32-column chunk of this thread's accumulator row; key0 = key id of column 0 (a multiple of 8)
+  __device__ __forceinline__ void scan32(const uint32_t (&v)[32], int key0) {
+    float m[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) m[g] = max8(&v[8 * g]);
+    float mm;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(mm) : "f"(m[0]), "f"(m[1]), "f"(m[2]));
+    mm = fmaxf(mm, m[3]);
+    if (__any_sync(0xffffffffu, mm > gv[KG - 1])) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) offer(m[g], (key0 >> 3) + g, &v[8 * g]);
+    }
+  }
+  // exact ranking of the listed groups' keys into `top` (ascending key order, so ties keep the lower id)
+  template <int KREG, bool YS_SHARED>
+  __device__ __forceinline__ void finish(TopK<KREG>& top, uint32_t ys_addr, const float* ys_glob) {
+#pragma unroll
+    for (int i = 0; i < KG - 1; ++i) {  // sort by group id (the slot bits cannot reorder distinct ids)
+#pragma unroll
+      for (int p = 0; p < KG - 1 - i; ++p) {
+        const int lo = min(gm[p], gm[p + 1]), hi = max(gm[p], gm[p + 1]);
+        gm[p] = lo; gm[p + 1] = hi;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < KG; ++p) {
+      const int gid = gm[p] >> 3;
+      if (gid == kInvalid) continue;
+      const uint32_t a = spill + (uint32_t)(gm[p] & 7) * 1024u;
+      float acc[8], y[8];
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[0]), "=f"(acc[1]), "=f"(acc[2]), "=f"(acc[3]) : "r"(a));
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc[4]), "=f"(acc[5]), "=f"(acc[6]), "=f"(acc[7]) : "r"(a + 512u));
+      if constexpr (YS_SHARED) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y[0]), "=f"(y[1]), "=f"(y[2]), "=f"(y[3]) : "r"(ys_addr + 32u * gid));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y[4]), "=f"(y[5]), "=f"(y[6]), "=f"(y[7]) : "r"(ys_addr + 32u * gid + 16u));
+      } else {
+        const float4 y0 = __ldg(reinterpret_cast<const float4*>(ys_glob + 8 * gid));
+        const float4 y1 = __ldg(reinterpret_cast<const float4*>(ys_glob + 8 * gid) + 1);
+        y[0] = y0.x; y[1] = y0.y; y[2] = y0.z; y[3] = y0.w; y[4] = y1.x; y[5] = y1.y; y[6] = y1.z; y[7] = y1.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float dist = __fadd_rn(fmaf(TopK<KREG>::kM2, acc[e], top.sq_i), y[e]);
+        top.insert(dist, 8 * gid + e);
+      }
+    }
+  }
+};
+
+// bytes of per-warp epilogue scratch: candidate queues (QS > 0), group spill slots (QS < 0), none (vote-gated scan)
+template <int QS, int KREG>
+__host__ __device__ constexpr uint32_t epi_warp_bytes() {
+  return QS > 0 ? (uint32_t)QS * 512u : (QS < 0 ? (uint32_t)KREG * 1024u : 0u);
+}
+constexpr float kUnitNormTol = 1e-4f;  // group-maxima selection needs | |y|^2 - 1 | below this for every key of the segment
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -331,8 +443,8 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
   const int num_tiles = (M + BN - 1) / BN;
   unsigned char* q_base = smem;                                    // [NH][num_kc] blocks
   unsigned char* ring = q_base + (size_t)NH * num_kc * kBlockBytes; // [stages] blocks
-  unsigned char* queue = ring + (size_t)stages * kKeyBlockBytes;      // [4 NH warps][QS slots][32 lanes] x 16 B
-  uint64_t* bars = reinterpret_cast<uint64_t*>(queue + (size_t)(4 * NH) * QS * 512);
+  unsigned char* queue = ring + (size_t)stages * kKeyBlockBytes;      // per-warp epilogue scratch (queues / spill slots)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(queue + (size_t)(4 * NH) * epi_warp_bytes<QS, KREG>());
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;
   const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;
@@ -420,13 +532,20 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
     top.init(sq_i);
     if (q < N) load_bound<KREG>(top, bounds, (long long)b * N + q, rank0);
     if constexpr (QS > 0) top.queue_init(smem_u32(queue) + (uint32_t)warp * (QS * 512), lane, QS);
+    GroupTop<(QS < 0) ? KREG : 1> gt;
+    if constexpr (QS < 0) gt.init(smem_u32(queue) + (uint32_t)warp * epi_warp_bytes<QS, KREG>(), lane);
     // one threshold base per segment: min over all keys of |y|^2 (1 for normalised rows, 0 for all-zero rows)
+    bool unit_keys = false;
     {
-      float mn = INFINITY;
-      for (int i = lane; i < M; i += 32) mn = fminf(mn, __ldg(ysq_b + i));
+      float mn = INFINITY, mx = -INFINITY;
+      for (int i = lane; i < M; i += 32) { const float yv = __ldg(ysq_b + i); mn = fminf(mn, yv); mx = fmaxf(mx, yv); }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
       top.set_tile(mn);
+      unit_keys = mn >= 1.f - kUnitNormTol && mx <= 1.f + kUnitNormTol;  // warp- and CTA-uniform (same keys for all)
     }
     for (int t = 0; t < num_tiles; ++t) {
       const int as = t & 1;
@@ -439,17 +558,30 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
         if (ys_vec) scan_tile_queued<KREG, false, true>(top, trow, t * BN, ncols, 0u, ysq_b, M);
         else scan_tile_queued<KREG, false, false>(top, trow, t * BN, ncols, 0u, ysq_b, M);
       } else {
+        if (QS < 0 && unit_keys) {  // group maxima (the host guarantees M % 32 == 0 for this form)
 #pragma unroll 1
-        for (int cc = 0; cc * 8 < ncols; ++cc) {
-          uint32_t v[8];
-          tmem_ld8(trow + cc * 8, v);
-          tmem_ld_wait();
-          top.template scan8<false>(v, 0u, ysq_b + t * BN + cc * 8, ncols - cc * 8, t * BN + cc * 8);
+          for (int c0 = 0; c0 < ncols; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(trow + c0, v);
+            tmem_ld_wait();
+            gt.scan32(v, t * BN + c0);
+          }
+        } else {
+#pragma unroll 1
+          for (int cc = 0; cc * 8 < ncols; ++cc) {
+            uint32_t v[8];
+            tmem_ld8(trow + cc * 8, v);
+            tmem_ld_wait();
+            top.template scan8<false>(v, 0u, ysq_b + t * BN + cc * 8, ncols - cc * 8, t * BN + cc * 8);
+          }
         }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+    }
+    if constexpr (QS < 0) {
+      if (unit_keys) gt.template finish<KREG, false>(top, 0u, ysq_b);
     }
     if (q < N) {
       emit<KREG>(top, nn_idx, nn_idx32, ((long long)b * N + q) * k_out, k_out, stride, rank0);
@@ -481,10 +613,10 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int num_kc = (C + BK - 1) / BK;
   unsigned char* ring = smem;
-  unsigned char* queue = ring + (size_t)stages * kStageBytes;                     // [4 NH warps][QS][32] x 16 B
-  float* ysq_s = reinterpret_cast<float*>(queue + (size_t)(4 * NH) * QS * 512);  // [NH * BM]
-  float* ymin_s = ysq_s + NH * BM;                                               // [4 * NH]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ymin_s + 8);
+  unsigned char* queue = ring + (size_t)stages * kStageBytes;                     // per-warp epilogue scratch
+  float* ysq_s = reinterpret_cast<float*>(queue + (size_t)(4 * NH) * epi_warp_bytes<QS, KREG>());  // [NH * BM]
+  float* ymin_s = ysq_s + NH * BM;                                               // [4 * NH] minima, [4 * NH] maxima
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ymin_s + 16);
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;
   const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;
@@ -550,22 +682,28 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
     const float* xsq_b = xsq + (long long)b * N;
     const float sq_i = (q < N) ? xsq_b[q] : 0.f;
     {  // kEpilogueThreads == NH * BM: one key norm per thread, per-warp minima for the candidate threshold
-      const float yv = (threadIdx.x < N) ? xsq_b[threadIdx.x] : INFINITY;
+      const bool real = threadIdx.x < N;
+      const float yv = real ? xsq_b[threadIdx.x] : INFINITY;
       ysq_s[threadIdx.x] = yv;
-      float mn = yv;
+      float mn = yv, mx = real ? yv : -INFINITY;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      if (lane == 0) ymin_s[warp] = mn;
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      if (lane == 0) { ymin_s[warp] = mn; ymin_s[8 + warp] = mx; }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
     TopK<KREG> top;
     top.init(sq_i);
     if (q < N) load_bound<KREG>(top, bounds, (long long)b * N + q, rank0);
+    bool unit_keys = false;
     {
-      float mn = ymin_s[0];
+      float mn = ymin_s[0], mx = ymin_s[8];
 #pragma unroll
-      for (int w = 1; w < 4 * NH; ++w) mn = fminf(mn, ymin_s[w]);
+      for (int w = 1; w < 4 * NH; ++w) { mn = fminf(mn, ymin_s[w]); mx = fmaxf(mx, ymin_s[8 + w]); }
       top.set_tile(mn);
+      unit_keys = mn >= 1.f - kUnitNormTol && mx <= 1.f + kUnitNormTol;
     }
     mbar_wait(bar_tfull, 0);
     tcgen05_fence_after();
@@ -578,6 +716,17 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
         const int ncols = min(BM, N - t * BM);
         if (ncols > 0) scan_tile_queued<KREG, true, false>(top, trow + t * BM, t * BM, ncols, ys_addr, nullptr, N);
       }
+    } else if (QS < 0 && unit_keys) {  // group maxima (the host guarantees N % 32 == 0 for this form)
+      GroupTop<(QS < 0) ? KREG : 1> gt;
+      gt.init(smem_u32(queue) + (uint32_t)warp * epi_warp_bytes<QS, KREG>(), lane);
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + c0, v);
+        tmem_ld_wait();
+        gt.scan32(v, c0);
+      }
+      gt.template finish<KREG, true>(top, ys_addr, nullptr);
     } else {
 #pragma unroll 1
       for (int cc = 0; cc < NH * BM / 8; ++cc) {
@@ -618,7 +767,7 @@ static bool make_map_f16(CUtensorMap* map, const void* base, int B, int rows, in
   return r == CUDA_SUCCESS;
 }
 
-constexpr uint32_t kMiscBytes = 2 * BM * 4 + 32 + (2 * kMaxStages + 8) * 8 + 1024;  // ysq, barriers + TMEM slot, alignment slack
+constexpr uint32_t kMiscBytes = 2 * BM * 4 + 64 + (2 * kMaxStages + 8) * 8 + 1024;  // ysq, barriers + TMEM slot, alignment slack
 
 template <typename Kernel>
 static int set_smem(Kernel kernel, DeviceOnce* once, const char* what) {
@@ -630,6 +779,7 @@ static int set_smem(Kernel kernel, DeviceOnce* once, const char* what) {
 }
 
 constexpr int kQueueSlots = 6;  // candidate-queue depth per epilogue thread (16-byte quads); 0 selects the vote-gated scan
+constexpr bool kGroupMaxDefault = true;  // option knn_epilogue = 0 (auto): take the group-maxima selection where it applies
 
 struct Round {
   float2* bounds;
@@ -643,7 +793,8 @@ static int launch_stream(const CUtensorMap& xh, const CUtensorMap& xl, const CUt
   static DeviceOnce once;
   if (int rc = set_smem(knn_stream_kernel<NH, BN, KREG, QS>, &once, "knn_stream")) return rc;
   const int num_kc = (C + BK - 1) / BK;
-  const size_t smem = (size_t)(NH * num_kc) * kBlockBytes + (size_t)stages * (2 * BN * BK * 2) + (size_t)(4 * NH) * QS * 512 + kMiscBytes;
+  const size_t smem = (size_t)(NH * num_kc) * kBlockBytes + (size_t)stages * (2 * BN * BK * 2) +
+                      (size_t)(4 * NH) * epi_warp_bytes<QS, KREG>() + kMiscBytes;
   dim3 grid((N + BM * NH - 1) / (BM * NH), B);
   knn_stream_kernel<NH, BN, KREG, QS><<<grid, (4 * NH + 2) * 32, smem, s>>>(xh, xl, yh, yl, xsq, ysq, nn_idx, nn_idx32, N, M,
                                                                        C, k_out, stride, stages, r.bounds, r.rank0, r.more);
@@ -655,7 +806,7 @@ static int launch_self(const CUtensorMap& xh, const CUtensorMap& xl, const float
                        int B, int N, int C, int k_out, int stride, int stages, Round r, cudaStream_t s) {
   static DeviceOnce once;
   if (int rc = set_smem(knn_self_kernel<NH, KREG, QS>, &once, "knn_self")) return rc;
-  const size_t smem = (size_t)stages * NH * kBlockBytes + (size_t)(4 * NH) * QS * 512 + kMiscBytes;
+  const size_t smem = (size_t)stages * NH * kBlockBytes + (size_t)(4 * NH) * epi_warp_bytes<QS, KREG>() + kMiscBytes;
   knn_self_kernel<NH, KREG, QS><<<B, (4 * NH + 2) * 32, smem, s>>>(xh, xl, xsq, nn_idx, nn_idx32, N, C, k_out, stride, stages,
                                                                r.bounds, r.rank0, r.more);
   return check_launch("knn_self");
@@ -666,7 +817,17 @@ struct Plan {
   int kind = 0, nh = 0, bn = 0, stages = 0, qs = 0;
 };
 
+static Plan plan_with(int N, int M, int C, int K, int dtype, bool self, bool allow_group_max);
+
 static Plan plan(int N, int M, int C, int K, int dtype, bool self) {
+  // the group-maxima selection needs 3 KB of spill slots per epilogue warp next to the resident queries; where that does
+  // not fit (wide separate key sets) the vote-gated form of the same kernels is used
+  Plan p = plan_with(N, M, C, K, dtype, self, true);
+  if (p.kind == 0) p = plan_with(N, M, C, K, dtype, self, false);
+  return p;
+}
+
+static Plan plan_with(int N, int M, int C, int K, int dtype, bool self, bool allow_group_max) {
   Plan p;
   // (dtype: the planes are fp16 whatever the input was - the normalise kernel reads fp32 or bf16 rows)
   if ((dtype != GRAFP_F32 && dtype != GRAFP_BF16) || C % 8 != 0 || C < BK || N < BM || M < BM || K < 1 || K > 64) return p;
@@ -677,12 +838,15 @@ static Plan plan(int N, int M, int C, int K, int dtype, bool self) {
   // training step - where, as far as we can tell, the 32 consecutive rows of a warp are neighbouring spectrogram peaks
   // whose candidates sit in the SAME few key columns, so the vote-gated form skips almost everything - it wins (k-NN 5.1-5.5 vs 5.6-5.9 ms per
   // step, A/B on the same box).  The default follows the headline workload; option OPT_KNN_EPILOGUE = 2 forces the queues.
-  const bool force_queue = option(OPT_KNN_EPILOGUE) == 2;
+  // K <= 3 with a key count that is a multiple of 32 (every encoder stage): the group-maxima selection (qs = -1).
+  const int epi = option(OPT_KNN_EPILOGUE);
+  const bool force_queue = epi == 2;
+  const bool group_max = allow_group_max && K <= 3 && M % 32 == 0 && (epi == 3 || (epi == 0 && kGroupMaxDefault));
   const bool no_nh4 = false, bn128 = false;
-  p.qs = (K <= 8 && !force_queue) ? 0 : kQueueSlots;
+  p.qs = group_max ? -1 : ((K <= 8 && !force_queue) ? 0 : kQueueSlots);
   const int num_kc = (C + BK - 1) / BK;
   const uint32_t budget = kSmemLimit - kMiscBytes;
-  auto queue_bytes = [&](int nh) { return (uint32_t)(4 * nh) * p.qs * 512u; };
+  auto queue_bytes = [&](int nh) { return (uint32_t)(4 * nh) * (p.qs > 0 ? (uint32_t)p.qs * 512u : (p.qs < 0 ? 3u * 1024u : 0u)); };
   if (self && N <= 2 * BM) {
     const int nh = (N > BM) ? 2 : 1;
     // NH = 1: two CTAs per SM (<= 113 KB each); NH = 2: one CTA owns the SM
@@ -769,7 +933,10 @@ int launch_knn_tc2(const void* xhi, const void* xlo, const float* xsq, const voi
   }
   const Args a = {&xh, &xl, &yh, &yl, xsq, ysq, nn_idx, nn_idx32, B, N, M, C, k_out, stride, s};
   const Round one = {nullptr, 0, 0};
-  if (K <= 3) return p.qs > 0 ? launch_planned<3, kQueueSlots>(p, a, one) : launch_planned<3, 0>(p, a, one);
+  if (K <= 3) {
+    if (p.qs < 0) return launch_planned<3, -1>(p, a, one);
+    return p.qs > 0 ? launch_planned<3, kQueueSlots>(p, a, one) : launch_planned<3, 0>(p, a, one);
+  }
   if (K <= 8) return p.qs > 0 ? launch_planned<8, kQueueSlots>(p, a, one) : launch_planned<8, 0>(p, a, one);
   // 16-entry register lists; K = 17..64 takes ceil(K / 16) passes over the keys (the Gram tiles are recomputed: the
   // tensor pipe is far from busy, the selection is what costs), each pass bounded below by the previous one's last entry

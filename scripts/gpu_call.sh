@@ -1,0 +1,27 @@
+#!/bin/bash
+# One GPU lease: tests, bench lines, per-kernel timings.  Usage: gpurun -- bash scripts/gpu_call.sh <tag> [steps...]
+tag=${1:-r02}
+shift
+out=gpurun_out
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > $out/${tag}_gpu.txt 2>&1
+for step in "$@"; do
+  case $step in
+    tests) timeout 1500 python -m pytest tests -m gpu -q --timeout 600 -x > $out/${tag}_pytest_gpu.log 2>&1; tail -5 $out/${tag}_pytest_gpu.log ;;
+    tests_all) timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > $out/${tag}_pytest_gpu.log 2>&1; tail -15 $out/${tag}_pytest_gpu.log ;;
+    bench) timeout 900 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err; tail -c 600 $out/${tag}_bench_n1.err; cut -c1-400 $out/${tag}_bench_n1.json ;;
+    bench_quick) timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_quick.json 2> $out/${tag}_bench_n1_quick.err; tail -c 600 $out/${tag}_bench_n1_quick.err; cut -c1-400 $out/${tag}_bench_n1_quick.json ;;
+    bench_bf16) timeout 600 python bench.py --dtype bf16 --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_bf16.json 2> $out/${tag}_bench_n1_bf16.err; tail -c 600 $out/${tag}_bench_n1_bf16.err; cut -c1-400 $out/${tag}_bench_n1_bf16.json ;;
+    bench_ref) timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_reference_arm.json 2> $out/${tag}_bench_reference_arm.err; cut -c1-300 $out/${tag}_bench_reference_arm.json ;;
+    kernels) timeout 900 python scripts/bench_kernels.py > $out/${tag}_bench_kernels.log 2>&1; tail -60 $out/${tag}_bench_kernels.log ;;
+    k1) timeout 600 python scripts/bench_kernels.py k1 > $out/${tag}_bench_k1.log 2>&1; cat $out/${tag}_bench_k1.log ;;
+    k23) timeout 600 python scripts/bench_kernels.py k23 > $out/${tag}_bench_k23.log 2>&1; cat $out/${tag}_bench_k23.log ;;
+    k5) timeout 600 python scripts/bench_kernels.py k5 > $out/${tag}_bench_k5.log 2>&1; cat $out/${tag}_bench_k5.log ;;
+    prof_bf16) timeout 600 python scripts/profile_step.py 512 --bf16 > $out/${tag}_profile_step_bf16.log 2>&1; head -50 $out/${tag}_profile_step_bf16.log | cut -c1-200 ;;
+    prof) timeout 600 python scripts/profile_step.py 512 > $out/${tag}_profile_step.log 2>&1; head -50 $out/${tag}_profile_step.log | cut -c1-200 ;;
+    ncu_ops) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"knn_|mr_aggregate|bn_" -c 60 -f -o $out/${tag}_ncu_ops python scripts/ncu_ops.py 512 1 > $out/${tag}_ncu_ops.log 2>&1; tail -3 $out/${tag}_ncu_ops.log
+             python scripts/ncu_summary.py $out/${tag}_ncu_ops.ncu-rep > $out/${tag}_ncu_ops_summary.txt 2>&1; python scripts/ncu_stalls.py $out/${tag}_ncu_ops.ncu-rep > $out/${tag}_ncu_ops_stalls.txt 2>&1; cat $out/${tag}_ncu_ops_summary.txt ;;
+    smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
+    *) echo "unknown step $step" ;;
+  esac
+done

@@ -9,6 +9,7 @@ from grafp_b200.simclr.simclr import SimCLR
 from grafp_b200.simclr.ntxent import ntxent_loss
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+BF16 = "--bf16" in sys.argv
 cfg = dict(synth.DEFAULT_CFG)
 dev = torch.device("cuda")
 model = SimCLR(cfg, GraphEncoder(cfg=cfg, in_channels=8, k=3)).to(dev).train()
@@ -17,8 +18,9 @@ s_i, s_j = (t.to(dev) for t in synth.synth_spec(B, 1))
 
 def step():
     opt.zero_grad(set_to_none=True)
-    _, _, z_i, z_j = model(s_i, s_j)
-    loss = ntxent_loss(z_i, z_j, cfg)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=BF16):
+        _, _, z_i, z_j = model(s_i, s_j)
+    loss = ntxent_loss(z_i.float(), z_j.float(), cfg)
     loss.backward()
     opt.step()
 

@@ -300,12 +300,46 @@ def make_simclr(ref):
     save("simclr", **arrays)
 
 
+def make_retrieval(ref):
+    """Top-1 retrieval on a synthetic fingerprint DB whose margins are far above the embedding noise (the check of
+    the north star: "identical top-1 retrieval hits on a synthetic fingerprint DB").  Eval-mode model (running
+    statistics), 64 DB segments, 32 queries = DB segments + 0.02 dB of white noise (a random-weight encoder is chaotic in its graphs: 0.1 dB already flips hits); the generator asserts that every
+    query's best candidate leads the runner-up by > 0.05 in inner product, so no k-NN tie can flip a hit."""
+    cfg = dict(synth.DEFAULT_CFG)
+    cfg["bsz_train"] = 32
+    model = ref.simclr.SimCLR(cfg, encoder=ref.graph_encoder.GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3))
+    load_synth(model, 101)
+    db_specs, _ = synth.synth_spec(64, 131)
+    # calibrate the BatchNorm running statistics on the DB itself (one train-mode pass with momentum 1), as a trained
+    # checkpoint's would be; the calibrated buffers are stored so the device model evaluates the same function
+    bns = [m for m in model.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    for m in bns:
+        m.momentum = 1.0
+    model.train()
+    with torch.no_grad():
+        model(db_specs, db_specs)
+    model.eval()
+    buffers = {f"buf.{k}": v for k, v in model.state_dict().items() if k.endswith("running_mean") or k.endswith("running_var")}
+    pick = torch.randperm(64, generator=torch.Generator().manual_seed(132))[:32]
+    q_specs = db_specs[pick] + 0.02 * torch.randn(32, 64, 32, generator=torch.Generator().manual_seed(133))
+    with torch.no_grad():
+        db = torch.cat([model(db_specs[i:i + 32], db_specs[i:i + 32])[2] for i in (0, 32)])
+        q = model(q_specs, q_specs)[2]
+    sims = q @ db.T
+    best2 = torch.topk(sims, 2, dim=1).values
+    margin = best2[:, 0] - best2[:, 1]
+    top1 = sims.argmax(1)
+    print("retrieval: hits", int((top1 == pick).sum()), "/ 32, min margin", float(margin.min()))
+    assert float(margin.min()) > 0.05
+    save("retrieval", q_specs=q_specs, pick=pick, db=db, queries=q, top1=top1, margin=margin, **buffers)
+
+
 def main():
     ref = _reference_import.load()
     torch.manual_seed(0)
     only = set(sys.argv[1:])
     for name, fn in (("knn", make_knn), ("aggregate", make_aggregate), ("gconv", make_gconv), ("gconv_r2", make_gconv_r2),
-                     ("grapher", make_grapher), ("encoder", make_encoder), ("simclr", make_simclr)):
+                     ("grapher", make_grapher), ("encoder", make_encoder), ("simclr", make_simclr), ("retrieval", make_retrieval)):
         if not only or name in only:
             fn(ref)
 

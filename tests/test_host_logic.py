@@ -199,3 +199,21 @@ def test_fingerprint_writer_matches_the_reference_memmap_format(tmp_path):
     with pytest.raises(ValueError):
         with FingerprintWriter(str(tmp_path), "short", 10, 128) as w:
             w.append(torch.zeros(4, 128))
+
+
+def test_block_diagonal_form_of_a_grouped_pointwise_convolution():
+    """bf16 training runs BasicConv's grouped (4) 1x1 convolution as a dense one with a block-diagonal weight
+    (ops._dense_form_of_grouped): same outputs, input gradient and - on the diagonal blocks - weight gradient (fp64)."""
+    g = torch.Generator().manual_seed(0)
+    cw = torch.randn(32, 4, 1, 1, generator=g, dtype=torch.float64, requires_grad=True)
+    x = torch.randn(2, 16, 10, 1, generator=g, dtype=torch.float64, requires_grad=True)
+    ref = torch.nn.functional.conv2d(x, cw, None, groups=4)
+    up = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    ref.backward(up)
+    w = ops._block_diag_weight(cw.detach(), 4).requires_grad_(True)
+    x2 = x.detach().clone().requires_grad_(True)
+    out = torch.nn.functional.conv2d(x2, w)
+    out.backward(up)
+    assert torch.equal(out, ref) and torch.equal(x2.grad, x.grad)
+    assert torch.equal(ops._block_diag_grad(w.grad, 4), cw.grad)
+    assert ops._dense_form_of_grouped(x.bfloat16(), cw, 4) and not ops._dense_form_of_grouped(x, cw, 4)
