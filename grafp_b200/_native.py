@@ -25,7 +25,7 @@ SIGNATURES = {
     "grafp_knn_last_algo": (_c.c_char_p, []),
     "grafp_knn_last_variant": (_c.c_char_p, []),
     "grafp_knn_workspace_bytes": (_sz, [_i] * 6),
-    "grafp_knn_fwd": (_i, [_vp] * 5 + [_i] * 10 + [_vp, _sz, _vp]),
+    "grafp_knn_fwd": (_i, [_vp] * 5 + [_i] * 11 + [_vp, _sz, _vp]),
     "grafp_mr_aggregate_fwd": (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 6 + [_vp]),
     "grafp_mr_aggregate_bwd_workspace_bytes": (_sz, [_i] * 3),
     "grafp_mr_aggregate_bwd": (_i, [_vp] * 4 + [_i] + [_vp] * 2 + [_i] * 6 + [_vp, _sz, _vp]),
@@ -37,6 +37,8 @@ SIGNATURES = {
     "grafp_edge_gather_bwd": (_i, [_vp] * 3 + [_i] + [_vp] * 2 + [_i] * 6 + [_vp]),
     "grafp_max_over_k_fwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
     "grafp_max_over_k_bwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
+    "grafp_ntxent_fwd": (_i, [_vp] * 4 + [_i, _i, _c.c_float, _vp]),
+    "grafp_ntxent_bwd": (_i, [_vp] * 4 + [_i, _i, _c.c_float, _vp]),
     "grafp_bn_workspace_bytes": (_sz, [_i]),
     "grafp_bn_train_fwd": (_i, [_vp] * 9 + [_c.c_longlong, _i, _c.c_float, _c.c_float, _i, _i, _vp, _sz, _vp]),
     "grafp_bn_train_bwd": (_i, [_vp] * 10 + [_c.c_longlong, _i, _i, _i, _vp, _sz, _vp]),
@@ -45,6 +47,7 @@ SIGNATURES = {
 ABI_VERSION = 5
 KNN_AUTO, KNN_SIMT, KNN_TC, KNN_TC_TF32 = 0, 1, 2, 3
 KNN_MAX_K = 64
+METRIC_L2, METRIC_COSINE = 0, 1
 
 _lib = None
 _lock = threading.Lock()

@@ -173,9 +173,10 @@ size_t grafp_knn_workspace_bytes(int B, int N, int M, int C, int K, int dtype) {
 }
 
 int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn_idx, int32_t* nn_idx32, int B, int N,
-                  int M, int C, int k, int dilation, int emit_all, int normalize, int dtype, int algo, void* workspace,
-                  size_t workspace_bytes, void* stream) {
+                  int M, int C, int k, int dilation, int emit_all, int normalize, int dtype, int algo, int metric,
+                  void* workspace, size_t workspace_bytes, void* stream) {
   COMMON_SHAPE_CHECKS("grafp_knn_fwd");
+  GRAFP_REQUIRE(metric == GRAFP_METRIC_L2 || metric == GRAFP_METRIC_COSINE, GRAFP_EINVAL, "grafp_knn_fwd: unknown metric %d", metric);
   GRAFP_REQUIRE(x && nn_idx && workspace, GRAFP_EINVAL, "grafp_knn_fwd: x, nn_idx and workspace must be non-null");
   GRAFP_REQUIRE(dilation > 0, GRAFP_EINVAL, "grafp_knn_fwd: dilation must be positive");
   GRAFP_REQUIRE(y != nullptr || M == N, GRAFP_EINVAL, "grafp_knn_fwd: M (%d) must equal N (%d) when y is null", M, N);
@@ -224,6 +225,11 @@ int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn
     if (rc == GRAFP_OK && y) rc = launch_knn_normalize<__nv_bfloat16>(y, y_hi, y_lo, y_sq, (long long)B * M, C, mode, normalize != 0, s);
   }
   if (rc != GRAFP_OK) return rc;
+  if (metric == GRAFP_METRIC_COSINE) {  // 2 (1 - x.y) = (1 - 2 x.y) + 1: the L2 epilogue with unit squared norms
+    rc = launch_fill_f32(x_sq, (long long)B * N, 1.f, s);
+    if (rc == GRAFP_OK && y) rc = launch_fill_f32(y_sq, (long long)B * M, 1.f, s);
+    if (rc != GRAFP_OK) return rc;
+  }
   if (!y) { y_hi = x_hi; y_lo = x_lo; y_sq = x_sq; }
 
   const int k_out = emit_all ? (int)K : k;
@@ -398,6 +404,27 @@ int grafp_bn_train_bwd(const void* dy, const void* x, const float* weight, const
   { int rc = require_device_ptr("grafp_bn_train_bwd", "dy", dy); if (rc) return rc; }
   return launch_bn_train_bwd(dy, x, weight, bias, save_mean, save_invstd, dx, dweight, dbias, dx_colsum, R, C, relu, dtype,
                              workspace, static_cast<cudaStream_t>(stream));
+}
+
+int grafp_ntxent_fwd(const float* z, float* lse, float* row_loss, float* loss, int n2, int d, float inv_tau, void* stream) {
+  clear_error();
+  GRAFP_REQUIRE(z && lse && row_loss && loss, GRAFP_EINVAL, "grafp_ntxent_fwd: z, lse, row_loss and loss must be non-null");
+  GRAFP_REQUIRE(ntxent_supported(n2, d), GRAFP_EUNSUPPORTED, "grafp_ntxent_fwd: needs an even n2 >= 2 and d %% 4 == 0, d <= 256 (got %d, %d)", n2, d);
+  GRAFP_REQUIRE(aligned16(z), GRAFP_EINVAL, "grafp_ntxent_fwd: z must be 16-byte aligned");
+  { int rc = require_device("grafp_ntxent_fwd"); if (rc != GRAFP_OK) return rc; }
+  { int rc = require_device_ptr("grafp_ntxent_fwd", "z", z); if (rc) return rc; }
+  return launch_ntxent_fwd(z, lse, row_loss, loss, n2, d, inv_tau, static_cast<cudaStream_t>(stream));
+}
+
+int grafp_ntxent_bwd(const float* z, const float* lse, const float* grad_loss, float* dz, int n2, int d, float inv_tau,
+                     void* stream) {
+  clear_error();
+  GRAFP_REQUIRE(z && lse && grad_loss && dz, GRAFP_EINVAL, "grafp_ntxent_bwd: z, lse, grad_loss and dz must be non-null");
+  GRAFP_REQUIRE(ntxent_supported(n2, d), GRAFP_EUNSUPPORTED, "grafp_ntxent_bwd: needs an even n2 >= 2 and d %% 4 == 0, d <= 256 (got %d, %d)", n2, d);
+  GRAFP_REQUIRE(aligned16(z) && aligned16(dz), GRAFP_EINVAL, "grafp_ntxent_bwd: z and dz must be 16-byte aligned");
+  { int rc = require_device("grafp_ntxent_bwd"); if (rc != GRAFP_OK) return rc; }
+  { int rc = require_device_ptr("grafp_ntxent_bwd", "z", z); if (rc) return rc; }
+  return launch_ntxent_bwd(z, lse, grad_loss, dz, n2, d, inv_tau, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

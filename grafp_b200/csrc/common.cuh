@@ -232,4 +232,10 @@ int launch_bn_train_bwd(const void* dy, const void* x, const float* weight, cons
                         const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
                         int relu, int dtype, void* workspace, cudaStream_t s);
 
+// ---- ntxent.cu ----
+bool ntxent_supported(int n2, int d);
+int launch_ntxent_fwd(const float* z, float* lse, float* row_loss, float* loss, int n2, int d, float inv_tau, cudaStream_t s);
+int launch_ntxent_bwd(const float* z, const float* lse, const float* grad_loss, float* dz, int n2, int d, float inv_tau,
+                      cudaStream_t s);
+
 }  // namespace grafp

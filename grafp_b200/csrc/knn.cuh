@@ -13,6 +13,8 @@ template <typename T>
 int launch_knn_normalize(const void* x, float* xhat, float* lo, float* sq, long long rows, int C, int mode,
                          bool normalize, cudaStream_t s);
 
+int launch_fill_f32(float* p, long long n, float v, cudaStream_t s);
+
 int launch_knn_simt(const float* xh, const float* xsq, const float* yh, const float* ysq, const float* relpos,
                     long long* nn_idx, int* nn_idx32, int B, int N, int M, int C, int K, int k_out, int stride,
                     cudaStream_t s);

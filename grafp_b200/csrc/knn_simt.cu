@@ -270,6 +270,14 @@ int launch_knn_normalize(const void* x, float* xhat, float* lo, float* sq, long 
   else knn_normalize_kernel<T, 2><<<(int)blocks, threads, 0, s>>>(xs, xhat, lo, sq, rows, C, normalize);
   return check_launch("knn_normalize");
 }
+__global__ void __launch_bounds__(256) fill_f32_kernel(float* __restrict__ p, long long n, float v) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) p[i] = v;
+}
+int launch_fill_f32(float* p, long long n, float v, cudaStream_t s) {
+  fill_f32_kernel<<<grid_for(n, 256, 4), 256, 0, s>>>(p, n, v);
+  return check_launch("fill_f32");
+}
+
 template int launch_knn_normalize<float>(const void*, float*, float*, float*, long long, int, int, bool, cudaStream_t);
 template int launch_knn_normalize<__nv_bfloat16>(const void*, float*, float*, float*, long long, int, int, bool, cudaStream_t);
 

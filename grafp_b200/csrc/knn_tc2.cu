@@ -400,16 +400,40 @@ __device__ __forceinline__ void store_bound(const TopK<KREG>& top, float2* bound
   if (bounds != nullptr && more_rounds) bounds[row] = make_float2(top.d[KREG - 1], __int_as_float(top.id[KREG - 1]));
 }
 
-// three MMAs per 16-channel step over one 64-channel block pair (A block: 128 rows, B block: BN rows)
+// One thread of the warp, chosen by elect.sync.  Unlike `lane == 0`, ptxas knows the branch it guards holds a single
+// thread, so the uniform-datapath instructions inside (UTCHMMA, UTMALDG) need no per-instruction "which threads are
+// active" loop: the MMA-issuing thread went from ~12 to ~4 issued instructions per tcgen05.mma - it was pacing the
+// tensor pipe (48 MMAs of 32 cycles per key tile against ~580 dependent single-thread instructions).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Shared-memory matrix descriptors differ only in their 14-bit start-address field (low word, 16-byte units): the
+// loops carry the low word and add offsets to it instead of rebuilding the 64-bit descriptor per MMA.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_of(uint32_t lo) {
+  // high word: stride byte offset 1024 >> 4 (bits 32-45), descriptor version 1 (bit 46), SWIZZLE_128B (bits 61-63)
+  return (static_cast<uint64_t>((1024u >> 4) | (1u << 14) | (2u << 29)) << 32) | lo;
+}
+
+// three MMAs per 16-channel step over one 64-channel block pair (A block: 128 rows, B block: BN rows);
+// a_lo0 / b_lo0: descriptor low words of the blocks' hi planes
 template <int BN>
-__device__ __forceinline__ void mma_block(uint32_t acc, uint32_t a_blk, uint32_t b_blk, bool first) {
+__device__ __forceinline__ void mma_block(uint32_t acc, uint32_t a_lo0, uint32_t b_lo0, bool first) {
   constexpr uint32_t idesc = make_idesc_f16<BN>();
-  constexpr uint32_t kBPlane = BN * BK * 2;
+  constexpr uint32_t kAPlane16 = kPlaneBytes >> 4, kBPlane16 = (BN * BK * 2) >> 4, kStep16 = (UMMA_K * 2) >> 4;
 #pragma unroll
   for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-    const uint32_t off = kk * UMMA_K * 2;
-    const uint64_t a_hi = make_smem_desc(a_blk + off), a_lo = make_smem_desc(a_blk + kPlaneBytes + off);
-    const uint64_t b_hi = make_smem_desc(b_blk + off), b_lo = make_smem_desc(b_blk + kBPlane + off);
+    const uint64_t a_hi = desc_of(a_lo0 + kk * kStep16), a_lo = desc_of(a_lo0 + kAPlane16 + kk * kStep16);
+    const uint64_t b_hi = desc_of(b_lo0 + kk * kStep16), b_lo = desc_of(b_lo0 + kBPlane16 + kk * kStep16);
     umma_f16(acc, a_lo, b_hi, idesc, (first && kk == 0) ? 0u : 1u);
     umma_f16(acc, a_hi, b_lo, idesc, 1u);
     umma_f16(acc, a_hi, b_hi, idesc, 1u);
@@ -470,7 +494,7 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kProducerWarp) {
-    if (lane == 0) {
+    if (elect_one()) {
       // resident query blocks: one barrier, NH * num_kc * 2 boxes
       mbar_arrive_expect_tx(bar_q, (uint32_t)(NH * num_kc) * kBlockBytes);
       for (int h = 0; h < NH; ++h) {
@@ -495,11 +519,12 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_wait(bar_q, 0);
       tcgen05_fence_after();
       int s = 0;
       uint32_t ph = 0;
+      const uint32_t q_lo0 = desc_lo(smem_u32(q_base)), ring_lo0 = desc_lo(smem_u32(ring));
       for (int t = 0; t < num_tiles; ++t) {
         const int as = t & 1;
         mbar_wait(bar_tempty + 8 * as, ((t >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator set
@@ -507,11 +532,11 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
         for (int c = 0; c < num_kc; ++c) {
           mbar_wait(bar_full + 8 * s, ph);
           tcgen05_fence_after();
-          const uint32_t b_blk = smem_u32(ring + (size_t)s * kKeyBlockBytes);
+          const uint32_t b_lo0 = ring_lo0 + (uint32_t)s * (kKeyBlockBytes >> 4);
 #pragma unroll
           for (int h = 0; h < NH; ++h) {
-            const uint32_t a_blk = smem_u32(q_base + (size_t)(h * num_kc + c) * kBlockBytes);
-            mma_block<BN>(tmem_base + (as * NH + h) * BN, a_blk, b_blk, c == 0);
+            const uint32_t a_lo0 = q_lo0 + (uint32_t)(h * num_kc + c) * (kBlockBytes >> 4);
+            mma_block<BN>(tmem_base + (as * NH + h) * BN, a_lo0, b_lo0, c == 0);
           }
           tcgen05_commit(bar_empty + 8 * s);  // frees the ring slot when these MMAs retire
           if (++s == stages) { s = 0; ph ^= 1; }
@@ -638,7 +663,7 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kProducerWarp) {
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       for (int c = 0; c < num_kc; ++c) {
@@ -655,18 +680,19 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
+      const uint32_t ring_lo0 = desc_lo(smem_u32(ring));
       for (int c = 0; c < num_kc; ++c) {
         mbar_wait(bar_full + 8 * s, ph);
         tcgen05_fence_after();
-        const uint32_t stage = smem_u32(ring + (size_t)s * kStageBytes);
+        const uint32_t stage = ring_lo0 + (uint32_t)s * (kStageBytes >> 4);
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
 #pragma unroll
           for (int t = 0; t < NH; ++t) {
-            mma_block<BM>(tmem_base + (h * NH + t) * BM, stage + h * kBlockBytes, stage + t * kBlockBytes, c == 0);
+            mma_block<BM>(tmem_base + (h * NH + t) * BM, stage + h * (kBlockBytes >> 4), stage + t * (kBlockBytes >> 4), c == 0);
           }
         }
         tcgen05_commit(bar_empty + 8 * s);

@@ -21,12 +21,12 @@ class KnnTag:
         self.nbr32 = nbr32
 
 
-def _edge_index_from_knn(x, k, dilation=1, y=None, relative_pos=None, emit_all=False, normalize=True):
+def _edge_index_from_knn(x, k, dilation=1, y=None, relative_pos=None, emit_all=False, normalize=True, metric="l2"):
     B, _, N, _ = x.shape
     k_out = k * dilation if emit_all else k
     edge_index = torch.empty((2, B, N, k_out), dtype=torch.int64, device=x.device)
     _, nbr32 = ops.knn_graph(x, k, dilation, y, relative_pos, emit_all=emit_all, normalize=normalize,
-                             out=edge_index[0])
+                             out=edge_index[0], metric=metric)
     edge_index[1] = torch.arange(N, device=x.device).view(1, N, 1)
     edge_index._grafp_knn = KnnTag(nbr32)
     return edge_index
@@ -69,6 +69,41 @@ def xy_dense_knn_matrix(x, y, k=16, relative_pos=None):
     return _edge_index_from_knn(x, k, 1, y, relative_pos, normalize=False)
 
 
+# ---- cosine variants (reference: torch_edge.py:55-68, 106-141, 166-231; unused by GraphEncoder) ----
+
+def xy_pairwise_distance_cos(x, y):
+    """The reference computes x y^T and returns an EMPTY LIST (torch_edge.py:55-68: `cos_sim = []` is what it returns);
+    kept bug-compatible for callers that import it."""
+    return []
+
+
+def pair_cos_sim(x, y):
+    """(B, N, C), (B, M, C) -> (B, N, M) inner products (reference: torch_edge.py:221-227)."""
+    return torch.matmul(x, y.transpose(-2, -1))
+
+
+def cos_sim_x(x):
+    """(B, N, C) -> (B, N, N) inner products (reference: torch_edge.py:229-231)."""
+    return torch.matmul(x, x.transpose(-2, -1))
+
+
+def dense_knn_matrix_plg(x, k=16, relative_pos=None):
+    """k nearest neighbours by 1 - x x^T (+ relative_pos), features used as given (reference: torch_edge.py:106-141).
+    Like the reference, point clouds of more than 10 000 nodes switch to the squared Euclidean distance (:119-131)."""
+    metric = "cosine" if x.shape[2] <= 10000 else "l2"
+    return _edge_index_from_knn(x, k, 1, None, relative_pos, normalize=False, metric=metric)
+
+
+def xy_dense_knn_matrix_plg(x, y, k=16, relative_pos=None):
+    """k nearest key nodes by 1 - x y^T (+ relative_pos) (reference: torch_edge.py:166-192)."""
+    return _edge_index_from_knn(x, k, 1, y, relative_pos, normalize=False, metric="cosine")
+
+
+def xy_dense_knn_matrix_plg_new(x, y, k=16, relative_pos=None):
+    """Same map as :func:`xy_dense_knn_matrix_plg` (reference: torch_edge.py:194-219)."""
+    return _edge_index_from_knn(x, k, 1, y, relative_pos, normalize=False, metric="cosine")
+
+
 class DenseDilated(nn.Module):
     """Pick the dilated neighbours out of a (2, B, N, k*d) list (reference: torch_edge.py:233-255)."""
 
@@ -109,3 +144,42 @@ class DenseDilatedKnnGraph(nn.Module):
             return self._dilated(full)
         # deterministic: the kernel emits ranks 0, d, 2d, ... directly (== full[..., ::d])
         return _edge_index_from_knn(x, self.k, self.dilation, y, relative_pos)
+
+
+class _CosineKnnGraph(nn.Module):
+    """Shared body of the two cosine graph builders: L2-normalise, rank by 1 - x_hat . y_hat (+ relative_pos), dilate.
+    ``sim_alpha`` / ``sim_beta`` are parameters of the reference modules that their forward never uses
+    (torch_edge.py:297-298, 333-334); they are kept for state_dict compatibility."""
+
+    def __init__(self, k=9, dilation=1, stochastic=False, epsilon=0.0):
+        super().__init__()
+        self.dilation = dilation
+        self.stochastic = stochastic
+        self.epsilon = epsilon
+        self.k = k
+        self._dilated = DenseDilated(k, dilation, stochastic, epsilon)
+        self.sim_alpha = nn.Parameter(torch.ones(1))
+        self.sim_beta = nn.Parameter(torch.zeros(1))
+
+    def _graph(self, x, y, relative_pos):
+        if self.stochastic:
+            full = _edge_index_from_knn(x, self.k, self.dilation, y, relative_pos, emit_all=True, metric="cosine")
+            return self._dilated(full)
+        return _edge_index_from_knn(x, self.k, self.dilation, y, relative_pos, metric="cosine")
+
+
+class DenseDilatedKnnGraph_plg(_CosineKnnGraph):
+    """Dilated k-NN graph by cosine distance (reference: torch_edge.py:323-361)."""
+
+    def forward(self, x, y=None, relative_pos=None):
+        return self._graph(x, y, relative_pos)
+
+
+class DenseDilatedKnnGraph_new(_CosineKnnGraph):
+    """Cosine k-NN graph of queries x against keys y (reference: torch_edge.py:286-321; its forward normalises y
+    unconditionally, so y is required there too)."""
+
+    def forward(self, x, y=None, relative_pos=None):
+        if y is None:
+            raise TypeError("DenseDilatedKnnGraph_new needs the key set y (the reference normalises it unconditionally)")
+        return self._graph(x, y, relative_pos)

@@ -171,7 +171,7 @@ def _index_arg(idx: torch.Tensor) -> Tuple[torch.Tensor, int]:
 def knn_graph(x: torch.Tensor, k: int, dilation: int = 1, y: Optional[torch.Tensor] = None,
               relative_pos: Optional[torch.Tensor] = None, emit_all: bool = False, normalize: bool = True,
               want_i32: bool = True, algo: int = _native.KNN_AUTO,
-              out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+              out: Optional[torch.Tensor] = None, metric: str = "l2") -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Neighbour ids of the dilated k-NN graph (reference: torch_edge.py:270-284).
 
     x: (B, C, N, 1) queries, y: (B, C, M, 1) keys or None, relative_pos: (1, N, M) or None.
@@ -195,6 +195,8 @@ def knn_graph(x: torch.Tensor, k: int, dilation: int = 1, y: Optional[torch.Tens
         rp = None
         if relative_pos is not None:
             rp = relative_pos.detach().to(torch.float32).reshape(-1, relative_pos.shape[-1]).contiguous()
+            if metric == "cosine":
+                rp = rp * 2  # the kernels rank 2 (1 - x.y) + relpos' (see include/grafp_b200.h)
             if rp.shape != (N, M):
                 raise RuntimeError(f"grafp_b200.knn_graph: relative_pos must be (1, {N}, {M}), got {tuple(relative_pos.shape)}")
         K = int(k) * int(dilation)
@@ -212,7 +214,7 @@ def knn_graph(x: torch.Tensor, k: int, dilation: int = 1, y: Optional[torch.Tens
               rp.data_ptr() if rp is not None else None, out.data_ptr(),
               out32.data_ptr() if out32 is not None else None,
               B, N, M, C, int(k), int(dilation), int(emit_all), int(normalize), dt, int(algo),
-              ws.data_ptr(), ws_bytes, _stream(xr))
+              _native.METRIC_COSINE if metric == "cosine" else _native.METRIC_L2, ws.data_ptr(), ws_bytes, _stream(xr))
     return out, out32
 
 
@@ -453,6 +455,48 @@ def max_over_k(h: torch.Tensor) -> torch.Tensor:
     if h.dim() != 4:
         raise RuntimeError("grafp_b200.max_over_k: expected a (B, C, N, k) tensor")
     return _MaxOverK.apply(h)
+
+
+# --------------------------------------------------------------------------------------
+# NT-Xent loss
+# --------------------------------------------------------------------------------------
+
+class _NTXent(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, inv_tau):
+        lib = _native.load()
+        n2, d = z.shape
+        lse = torch.empty(n2, dtype=torch.float32, device=z.device)
+        row_loss = torch.empty(n2, dtype=torch.float32, device=z.device)
+        loss = torch.empty((), dtype=torch.float32, device=z.device)
+        _call("ntxent_fwd", 2, dict(B=1, N=n2, C=d), lib.grafp_ntxent_fwd, z.device, z.data_ptr(), lse.data_ptr(),
+              row_loss.data_ptr(), loss.data_ptr(), n2, d, float(inv_tau), _stream(z))
+        ctx.save_for_backward(z, lse)
+        ctx.inv_tau = float(inv_tau)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        lib = _native.load()
+        z, lse = ctx.saved_tensors
+        n2, d = z.shape
+        g = grad_loss.to(torch.float32).contiguous()
+        dz = torch.empty_like(z)
+        _call("ntxent_bwd", 1, dict(B=1, N=n2, C=d), lib.grafp_ntxent_bwd, z.device, z.data_ptr(), lse.data_ptr(),
+              g.data_ptr(), dz.data_ptr(), n2, d, ctx.inv_tau, _stream(z))
+        return dz, None
+
+
+def ntxent_supported(z: torch.Tensor) -> bool:
+    return z.is_cuda and z.dtype == torch.float32 and z.dim() == 2 and z.shape[0] % 2 == 0 and z.shape[1] % 4 == 0 \
+        and z.shape[1] <= 256
+
+
+def ntxent(z: torch.Tensor, tau: float) -> torch.Tensor:
+    """NT-Xent loss of (2B, d) embeddings whose rows 2m / 2m + 1 are partners (reference: simclr/ntxent.py:17-29),
+    forward and backward as fused kernels that never build the (2B, 2B) similarity matrix."""
+    _require_cuda(z)
+    return _NTXent.apply(z.contiguous(), 1.0 / float(tau))
 
 
 # --------------------------------------------------------------------------------------

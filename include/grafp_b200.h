@@ -100,11 +100,18 @@ const char* grafp_knn_last_variant(void);
  *           (the caller then applies DenseDilated's stochastic branch, :246-250).
  *  nn_idx32 optional int32 copy of nn_idx (same shape) or NULL.
  *  The centre ids (edge_index[1], :102) are arange(N) and are not produced here.
+ *  metric   GRAFP_METRIC_L2: squared Euclidean distance |x|^2 - 2 x.y + |y|^2 (pairwise_distance).
+ *           GRAFP_METRIC_COSINE: 1 - x.y (+ relpos), the distance of the cosine variants dense_knn_matrix_plg /
+ *           xy_dense_knn_matrix_plg(_new) (:106-141, :166-219).  Evaluated as 2 (1 - x.y) through the
+ *           same kernels with both squared norms forced to 1 - a power-of-two rescaling, so the order is the
+ *           reference's up to ties; the caller passes relpos already doubled.
  */
+#define GRAFP_METRIC_L2 0
+#define GRAFP_METRIC_COSINE 1
 size_t grafp_knn_workspace_bytes(int B, int N, int M, int C, int K, int dtype);
 int grafp_knn_fwd(const void* x, const void* y, const float* relpos, int64_t* nn_idx, int32_t* nn_idx32,
                   int B, int N, int M, int C, int k, int dilation, int emit_all, int normalize, int dtype,
-                  int algo, void* workspace, size_t workspace_bytes, void* stream);
+                  int algo, int metric, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Max-relative aggregation.  Replaces the body of MRConv2d.forward before self.nn
@@ -207,6 +214,20 @@ int grafp_bn_train_fwd(const void* x, const void* residual, const float* weight,
 int grafp_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,
                        const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
                        int relu, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * NT-Xent contrastive loss.  Replaces simclr/ntxent.py:17-29 - a Python loop over the 2B rows of
+ * z z^T / tau (log-softmax of each row without its diagonal entry, partner's entry picked) - and its autograd, without
+ * materialising the (2B, 2B) similarity matrix.
+ *   z        (n2, d) float32, the two views interleaved: rows 2m and 2m + 1 are partners (ntxent.py:18)
+ *   lse      (n2) out: log sum_{j != i} exp(z_i . z_j / tau), kept for the backward
+ *   row_loss (n2) scratch, loss (1) out: mean_i [lse_i - z_i . z_{i^1} / tau]
+ *   backward: dz (n2, d) = grad_loss * dloss/dz, grad_loss a DEVICE scalar (the upstream gradient)
+ * n2 even, d % 4 == 0, d <= 256 (else GRAFP_EUNSUPPORTED).
+ */
+int grafp_ntxent_fwd(const float* z, float* lse, float* row_loss, float* loss, int n2, int d, float inv_tau, void* stream);
+int grafp_ntxent_bwd(const float* z, const float* lse, const float* grad_loss, float* dz, int n2, int d, float inv_tau,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,34 @@ def knn_edge_index(x: Tensor, K: int, y: Optional[Tensor] = None,
     return torch.stack((nn_idx, centre), dim=0)
 
 
+def cosine_knn_edge_index(x: Tensor, K: int, y: Optional[Tensor] = None,
+                          relative_pos: Optional[Tensor] = None) -> Tensor:
+    """Top-K key nodes by the cosine distance 1 - x y^T (+ relative_pos), features as given.
+
+    dense_knn_matrix_plg (torch_edge.py:106-141, its N <= 10000 branch: cos_sim_x :229-231) and
+    xy_dense_knn_matrix_plg / _new (:166-219: pair_cos_sim :221-227).
+    """
+    with torch.no_grad():
+        xr = x.detach().transpose(2, 1).squeeze(-1)
+        yr = xr if y is None else y.detach().transpose(2, 1).squeeze(-1)
+        B, N, _ = xr.shape
+        dist = 1.0 - torch.matmul(xr, yr.transpose(-2, -1))
+        if relative_pos is not None:
+            dist = dist + relative_pos
+        nn_idx = torch.topk(-dist, k=K).indices
+        centre = torch.arange(N, device=x.device).view(1, N, 1).expand(B, N, K)
+    return torch.stack((nn_idx, centre), dim=0)
+
+
+def cosine_dilated_knn_graph(x: Tensor, k: int, dilation: int = 1, y: Optional[Tensor] = None,
+                             relative_pos: Optional[Tensor] = None) -> Tensor:
+    """DenseDilatedKnnGraph_plg.forward / DenseDilatedKnnGraph_new.forward with stochastic=False
+    (torch_edge.py:335-361, 299-321): normalise, cosine k-NN, dilate."""
+    xn = l2_normalize_channels(x)
+    yn = None if y is None else l2_normalize_channels(y)
+    return dilate_edge_index(cosine_knn_edge_index(xn, k * dilation, yn, relative_pos), dilation)
+
+
 def dilate_edge_index(edge_index: Tensor, dilation: int) -> Tensor:
     """Deterministic branch of DenseDilated.forward (torch_edge.py:252,254)."""
     return edge_index[:, :, :, ::dilation]
@@ -382,7 +410,7 @@ class GraphReplay:
 
 def knn_mismatch_report(x: Tensor, ours: Tensor, K: int, y: Optional[Tensor] = None,
                         relative_pos: Optional[Tensor] = None, ordered: bool = True,
-                        dilation: int = 1, tol_scale: float = 1.0) -> dict:
+                        dilation: int = 1, tol_scale: float = 1.0, metric: str = "l2") -> dict:
     """Compare neighbour ids against the oracle and classify every difference.
 
     ``x`` / ``y`` are the *un-normalised* (B, C, N, 1) inputs; ``ours`` is (B, N, k)
@@ -397,8 +425,12 @@ def knn_mismatch_report(x: Tensor, ours: Tensor, K: int, y: Optional[Tensor] = N
     yn = xn if y is None else l2_normalize_channels(y)
     xr = xn.transpose(2, 1).squeeze(-1)
     yr = yn.transpose(2, 1).squeeze(-1)
-    dist = sq_distance_matrix(xr, yr if y is not None else None)
-    d64 = sq_distance_matrix(xr.double(), yr.double())
+    if metric == "cosine":  # the *_plg variants: 1 - x_hat . y_hat
+        dist = 1.0 - torch.matmul(xr, yr.transpose(-2, -1))
+        d64 = 1.0 - torch.matmul(xr.double(), yr.double().transpose(-2, -1))
+    else:
+        dist = sq_distance_matrix(xr, yr if y is not None else None)
+        d64 = sq_distance_matrix(xr.double(), yr.double())
     if relative_pos is not None:
         dist = dist + relative_pos
         d64 = d64 + relative_pos.double()

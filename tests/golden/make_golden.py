@@ -83,6 +83,40 @@ def make_knn(ref):
     save("knn", **arrays)
 
 
+COS_CASES = [
+    # name,          cls,   B, C,  N,   k, d, M (0: y=None), relpos
+    ("plg_self",     "plg", 2, 16, 96,  3, 1, 0,  False),
+    ("plg_self_d2",  "plg", 2, 32, 128, 4, 2, 0,  False),
+    ("plg_relpos",   "plg", 1, 16, 64,  4, 1, 0,  True),
+    ("plg_xy",       "plg", 2, 16, 64,  4, 2, 16, True),
+    ("new_xy",       "new", 2, 16, 64,  4, 1, 16, False),
+    ("plg_stage2",   "plg", 1, 64, 256, 3, 1, 0,  False),
+]
+
+
+def make_knn_cos(ref):
+    """The cosine graph builders DenseDilatedKnnGraph_plg / _new (torch_edge.py:286-361)."""
+    arrays = {"names": np.array([c[0] for c in COS_CASES])}
+    for i, (name, cls, B, C, N, k, d, M, relpos) in enumerate(COS_CASES):
+        x = knn_input("randn", B, C, N, 300 + i)
+        y = knn_input("randn", B, C, M, 400 + i) if M else None
+        rp = None
+        if relpos:
+            rp = 0.1 * torch.randn(1, N, M if M else N, generator=torch.Generator().manual_seed(500 + i))
+        mod = (ref.torch_edge.DenseDilatedKnnGraph_plg if cls == "plg" else ref.torch_edge.DenseDilatedKnnGraph_new)(k=k, dilation=d)
+        with torch.no_grad():
+            edge = mod(x, y, rp)
+        arrays[f"{name}.x"] = x
+        if y is not None:
+            arrays[f"{name}.y"] = y
+        if rp is not None:
+            arrays[f"{name}.relative_pos"] = rp
+        arrays[f"{name}.kd"] = np.array([k, d])
+        arrays[f"{name}.cls"] = np.array(cls)
+        arrays[f"{name}.edge_index"] = edge.contiguous()
+    save("knn_cos", **arrays)
+
+
 def make_aggregate(ref):
     arrays = {}
     g = torch.Generator().manual_seed(7)
@@ -338,7 +372,7 @@ def main():
     ref = _reference_import.load()
     torch.manual_seed(0)
     only = set(sys.argv[1:])
-    for name, fn in (("knn", make_knn), ("aggregate", make_aggregate), ("gconv", make_gconv), ("gconv_r2", make_gconv_r2),
+    for name, fn in (("knn", make_knn), ("knn_cos", make_knn_cos), ("aggregate", make_aggregate), ("gconv", make_gconv), ("gconv_r2", make_gconv_r2),
                      ("grapher", make_grapher), ("encoder", make_encoder), ("simclr", make_simclr), ("retrieval", make_retrieval)):
         if not only or name in only:
             fn(ref)

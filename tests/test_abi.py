@@ -54,7 +54,7 @@ def test_calls_fail_loudly_without_a_device(lib_path):
     rc = lib.grafp_max_over_k_fwd(None, None, None, 1, 1, 4, 1, 0, None)
     assert rc == -4  # GRAFP_ENODEVICE: no CPU path
     assert b"no CPU path" in lib.grafp_last_error()
-    rc = lib.grafp_knn_fwd(None, None, None, None, None, 1, 8, 8, 4, 9, 1, 0, 1, 0, 0, None, 0, None)
+    rc = lib.grafp_knn_fwd(None, None, None, None, None, 1, 8, 8, 4, 9, 1, 0, 1, 0, 0, 0, None, 0, None)
     assert rc != 0
 
 

@@ -61,6 +61,17 @@ def _params_for(gold, tag, prefix_strip=""):
     return p
 
 
+@pytest.mark.parametrize("name", [str(n) for n in gio.load("knn_cos")["names"]])
+def test_cosine_knn_graphs_match_reference(name):
+    """DenseDilatedKnnGraph_plg / _new (torch_edge.py:286-361): the oracle's cosine graph is the reference's, bit for bit."""
+    gold = gio.load("knn_cos")
+    x = gio.t(gold[f"{name}.x"])
+    y = gio.t(gold[f"{name}.y"]) if f"{name}.y" in gold else None
+    rp = gio.t(gold[f"{name}.relative_pos"]) if f"{name}.relative_pos" in gold else None
+    k, d = (int(v) for v in gold[f"{name}.kd"])
+    assert torch.equal(O.cosine_dilated_knn_graph(x, k, d, y, rp), gio.t(gold[f"{name}.edge_index"]))
+
+
 @pytest.mark.parametrize("conv", ["mr", "edge", "sage", "gin"])
 @pytest.mark.parametrize("d", [1, 2])
 def test_graph_conv_modules_match_reference(conv, d):
