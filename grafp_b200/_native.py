@@ -37,6 +37,9 @@ SIGNATURES = {
     "grafp_edge_gather_bwd": (_i, [_vp] * 3 + [_i] + [_vp] * 2 + [_i] * 6 + [_vp]),
     "grafp_max_over_k_fwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
     "grafp_max_over_k_bwd": (_i, [_vp] * 3 + [_i] * 5 + [_vp]),
+    "grafp_peak_extract_workspace_bytes": (_sz, [_i] * 3),
+    "grafp_peak_extract_fwd": (_i, [_vp] * 4 + [_i] * 7 + [_vp]),
+    "grafp_peak_extract_bwd": (_i, [_vp] * 4 + [_sz] + [_vp] * 2 + [_i] * 7 + [_vp]),
     "grafp_ntxent_fwd": (_i, [_vp] * 4 + [_i, _i, _c.c_float, _vp]),
     "grafp_ntxent_bwd": (_i, [_vp] * 4 + [_i, _i, _c.c_float, _vp]),
     "grafp_bn_workspace_bytes": (_sz, [_i]),

@@ -427,4 +427,33 @@ int grafp_ntxent_bwd(const float* z, const float* lse, const float* grad_loss, f
   return launch_ntxent_bwd(z, lse, grad_loss, dz, n2, d, inv_tau, static_cast<cudaStream_t>(stream));
 }
 
+size_t grafp_peak_extract_workspace_bytes(int B, int kh, int kw) {
+  return (B > 0 && kh > 0 && kw > 0) ? peak_extract_workspace_bytes(B, kh, kw) : 0;
+}
+
+int grafp_peak_extract_fwd(const float* spec, const float* weight, const float* bias, float* out, int B, int H, int W, int F,
+                           int kh, int kw, int stride_h, void* stream) {
+  clear_error();
+  GRAFP_REQUIRE(spec && weight && bias && out && B > 0, GRAFP_EINVAL, "grafp_peak_extract_fwd: spec, weight, bias, out must be non-null, B positive");
+  GRAFP_REQUIRE(peak_extract_supported(H, W, F, kh, kw, stride_h), GRAFP_EUNSUPPORTED,
+                "grafp_peak_extract_fwd: needs F == 8, odd kh / kw and planes that fit shared memory (H=%d W=%d F=%d kh=%d kw=%d)", H, W, F, kh, kw);
+  GRAFP_REQUIRE(aligned16(out), GRAFP_EINVAL, "grafp_peak_extract_fwd: out must be 16-byte aligned");
+  { int rc = require_device("grafp_peak_extract_fwd"); if (rc != GRAFP_OK) return rc; }
+  { int rc = require_device_ptr("grafp_peak_extract_fwd", "spec", spec); if (rc) return rc; }
+  return launch_peak_extract_fwd(spec, weight, bias, out, B, H, W, kh, kw, stride_h, static_cast<cudaStream_t>(stream));
+}
+
+int grafp_peak_extract_bwd(const float* spec, const float* out, const float* grad_out, void* partial, size_t partial_bytes,
+                           float* dweight, float* dbias, int B, int H, int W, int F, int kh, int kw, int stride_h, void* stream) {
+  clear_error();
+  GRAFP_REQUIRE(spec && out && grad_out && partial && dweight && dbias && B > 0, GRAFP_EINVAL, "grafp_peak_extract_bwd: all pointers must be non-null, B positive");
+  GRAFP_REQUIRE(peak_extract_supported(H, W, F, kh, kw, stride_h), GRAFP_EUNSUPPORTED, "grafp_peak_extract_bwd: unsupported shape");
+  GRAFP_REQUIRE(partial_bytes >= peak_extract_workspace_bytes(B, kh, kw), GRAFP_EWORKSPACE, "grafp_peak_extract_bwd: workspace too small");
+  GRAFP_REQUIRE(aligned16(out) && aligned16(grad_out) && aligned16(partial), GRAFP_EINVAL, "grafp_peak_extract_bwd: out, grad_out and partial must be 16-byte aligned");
+  { int rc = require_device("grafp_peak_extract_bwd"); if (rc != GRAFP_OK) return rc; }
+  { int rc = require_device_ptr("grafp_peak_extract_bwd", "spec", spec); if (rc) return rc; }
+  return launch_peak_extract_bwd(spec, out, grad_out, static_cast<float*>(partial), dweight, dbias, B, H, W, kh, kw, stride_h,
+                                 static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -232,6 +232,14 @@ int launch_bn_train_bwd(const void* dy, const void* x, const float* weight, cons
                         const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
                         int relu, int dtype, void* workspace, cudaStream_t s);
 
+// ---- peak_extract.cu ----
+bool peak_extract_supported(int H, int W, int F, int kh, int kw, int sh);
+size_t peak_extract_workspace_bytes(int B, int kh, int kw);
+int launch_peak_extract_fwd(const float* spec, const float* weight, const float* bias, float* out, int B, int H, int W, int kh,
+                            int kw, int sh, cudaStream_t s);
+int launch_peak_extract_bwd(const float* spec, const float* out, const float* grad_out, float* partial, float* dweight,
+                            float* dbias, int B, int H, int W, int kh, int kw, int sh, cudaStream_t s);
+
 // ---- ntxent.cu ----
 bool ntxent_supported(int n2, int d);
 int launch_ntxent_fwd(const float* z, float* lse, float* row_loss, float* loss, int n2, int d, float inv_tau, cudaStream_t s);

@@ -628,8 +628,13 @@ knn_stream_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_cons
 template <int NH, int KREG, int QS>
 __global__ void __launch_bounds__((4 * NH + 2) * 32, (NH == 1) ? 2 : 1)
 knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_constant__ CUtensorMap tm_x_lo,
-                const float* __restrict__ xsq, long long* __restrict__ nn_idx, int* __restrict__ nn_idx32, int N, int C,
+                const float* __restrict__ xsq, long long* __restrict__ nn_idx, int* __restrict__ nn_idx32, int B, int N, int C,
                 int k_out, int stride, int stages, float2* bounds, int rank0, int more_rounds) {
+  // PERSISTENT over segments b = blockIdx.x, blockIdx.x + gridDim.x, ...: the producer keeps the TMA ring full across
+  // segment boundaries, so the 256 KB load of segment i + 1 overlaps the MMAs and the selection of segment i (with one
+  // CTA per segment the load, the MMAs and the selection of a segment ran back to back and nothing overlapped them:
+  // 512 TMEM columns at NH = 2 allow one CTA per SM).  The accumulators are single-buffered: the MMA thread waits for
+  // the epilogue's "TMEM drained" arrival before the first MMA of the next segment.
   constexpr int kEpilogueThreads = 128 * NH;
   constexpr int kProducerWarp = 4 * NH, kMmaWarp = 4 * NH + 1;
   constexpr uint32_t kTmemCols = NH * NH * BM;
@@ -645,15 +650,16 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;
   const uint32_t bar_tfull = bar_empty + 8 * kMaxStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+  const uint32_t bar_tempty = bar_tfull + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, 4 * NH);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
@@ -666,105 +672,124 @@ knn_self_kernel(const __grid_constant__ CUtensorMap tm_x_hi, const __grid_consta
     if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
-      for (int c = 0; c < num_kc; ++c) {
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        const uint32_t full = bar_full + 8 * s;
-        mbar_arrive_expect_tx(full, kStageBytes);
+      for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        for (int c = 0; c < num_kc; ++c) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t full = bar_full + 8 * s;
+          mbar_arrive_expect_tx(full, kStageBytes);
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
-          const uint32_t dst = smem_u32(ring + (size_t)s * kStageBytes + h * kBlockBytes);
-          tma_load_3d(dst, &tm_x_hi, full, c * BK, h * BM, b);
-          tma_load_3d(dst + kPlaneBytes, &tm_x_lo, full, c * BK, h * BM, b);
+          for (int h = 0; h < NH; ++h) {
+            const uint32_t dst = smem_u32(ring + (size_t)s * kStageBytes + h * kBlockBytes);
+            tma_load_3d(dst, &tm_x_hi, full, c * BK, h * BM, b);
+            tma_load_3d(dst + kPlaneBytes, &tm_x_lo, full, c * BK, h * BM, b);
+          }
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
-        if (++s == stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == kMmaWarp) {
     if (elect_one()) {
       int s = 0;
-      uint32_t ph = 0;
+      uint32_t ph = 0, it = 0;
       const uint32_t ring_lo0 = desc_lo(smem_u32(ring));
-      for (int c = 0; c < num_kc; ++c) {
-        mbar_wait(bar_full + 8 * s, ph);
+      for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+        mbar_wait(bar_tempty, (it & 1) ^ 1);  // the previous segment's accumulators are drained (first trip: passes)
         tcgen05_fence_after();
-        const uint32_t stage = ring_lo0 + (uint32_t)s * (kStageBytes >> 4);
+        for (int c = 0; c < num_kc; ++c) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tcgen05_fence_after();
+          const uint32_t stage = ring_lo0 + (uint32_t)s * (kStageBytes >> 4);
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
+          for (int h = 0; h < NH; ++h) {
 #pragma unroll
-          for (int t = 0; t < NH; ++t) {
-            mma_block<BM>(tmem_base + (h * NH + t) * BM, stage + h * (kBlockBytes >> 4), stage + t * (kBlockBytes >> 4), c == 0);
+            for (int t = 0; t < NH; ++t) {
+              mma_block<BM>(tmem_base + (h * NH + t) * BM, stage + h * (kBlockBytes >> 4), stage + t * (kBlockBytes >> 4), c == 0);
+            }
           }
+          tcgen05_commit(bar_empty + 8 * s);
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
-        tcgen05_commit(bar_empty + 8 * s);
-        if (++s == stages) { s = 0; ph ^= 1; }
+        tcgen05_commit(bar_tfull);
       }
-      tcgen05_commit(bar_tfull);
     }
   } else {
     const int h = warp >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const int q = h * BM + r;
-    const float* xsq_b = xsq + (long long)b * N;
-    const float sq_i = (q < N) ? xsq_b[q] : 0.f;
-    {  // kEpilogueThreads == NH * BM: one key norm per thread, per-warp minima for the candidate threshold
-      const bool real = threadIdx.x < N;
-      const float yv = real ? xsq_b[threadIdx.x] : INFINITY;
-      ysq_s[threadIdx.x] = yv;
-      float mn = yv, mx = real ? yv : -INFINITY;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      }
-      if (lane == 0) { ymin_s[warp] = mn; ymin_s[8 + warp] = mx; }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
-    TopK<KREG> top;
-    top.init(sq_i);
-    if (q < N) load_bound<KREG>(top, bounds, (long long)b * N + q, rank0);
-    bool unit_keys = false;
-    {
-      float mn = ymin_s[0], mx = ymin_s[8];
-#pragma unroll
-      for (int w = 1; w < 4 * NH; ++w) { mn = fminf(mn, ymin_s[w]); mx = fmaxf(mx, ymin_s[8 + w]); }
-      top.set_tile(mn);
-      unit_keys = mn >= 1.f - kUnitNormTol && mx <= 1.f + kUnitNormTol;
-    }
-    mbar_wait(bar_tfull, 0);
-    tcgen05_fence_after();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (h * NH) * BM;
     const uint32_t ys_addr = smem_u32(ysq_s);
-    if constexpr (QS > 0) {
-      top.queue_init(smem_u32(queue) + (uint32_t)warp * (QS * 512), lane, QS);
-#pragma unroll 1
-      for (int t = 0; t < NH; ++t) {
-        const int ncols = min(BM, N - t * BM);
-        if (ncols > 0) scan_tile_queued<KREG, true, false>(top, trow + t * BM, t * BM, ncols, ys_addr, nullptr, N);
+    uint32_t it = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x, ++it) {
+      const float* xsq_b = xsq + (long long)b * N;
+      const float sq_i = (q < N) ? xsq_b[q] : 0.f;
+      {  // kEpilogueThreads == NH * BM: one key norm per thread, per-warp minima / maxima for the candidate threshold
+        const bool real = threadIdx.x < N;
+        const float yv = real ? xsq_b[threadIdx.x] : INFINITY;
+        float mn = yv, mx = real ? yv : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");  // the previous segment's readers are done
+        ysq_s[threadIdx.x] = yv;
+        if (lane == 0) { ymin_s[warp] = mn; ymin_s[8 + warp] = mx; }
       }
-    } else if (QS < 0 && unit_keys) {  // group maxima (the host guarantees N % 32 == 0 for this form)
-      GroupTop<(QS < 0) ? KREG : 1> gt;
-      gt.init(smem_u32(queue) + (uint32_t)warp * epi_warp_bytes<QS, KREG>(), lane);
-#pragma unroll 1
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(trow + c0, v);
-        tmem_ld_wait();
-        gt.scan32(v, c0);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory");
+      TopK<KREG> top;
+      top.init(sq_i);
+      if (q < N) load_bound<KREG>(top, bounds, (long long)b * N + q, rank0);
+      bool unit_keys = false;
+      {
+        float mn = ymin_s[0], mx = ymin_s[8];
+#pragma unroll
+        for (int w = 1; w < 4 * NH; ++w) { mn = fminf(mn, ymin_s[w]); mx = fmaxf(mx, ymin_s[8 + w]); }
+        top.set_tile(mn);
+        unit_keys = mn >= 1.f - kUnitNormTol && mx <= 1.f + kUnitNormTol;
       }
-      gt.template finish<KREG, true>(top, ys_addr, nullptr);
-    } else {
+      mbar_wait(bar_tfull, it & 1);
+      tcgen05_fence_after();
+      if constexpr (QS > 0) {
+        top.queue_init(smem_u32(queue) + (uint32_t)warp * (QS * 512), lane, QS);
 #pragma unroll 1
-      for (int cc = 0; cc < NH * BM / 8; ++cc) {
-        uint32_t v[8];
-        tmem_ld8(trow + cc * 8, v);
-        tmem_ld_wait();
-        top.template scan8<true>(v, ys_addr + cc * 32, nullptr, 8, cc * 8);
+        for (int t = 0; t < NH; ++t) {
+          const int ncols = min(BM, N - t * BM);
+          if (ncols > 0) scan_tile_queued<KREG, true, false>(top, trow + t * BM, t * BM, ncols, ys_addr, nullptr, N);
+        }
+      } else if (QS < 0 && unit_keys) {  // group maxima (the host guarantees N % 32 == 0 for this form)
+        GroupTop<(QS < 0) ? KREG : 1> gt;
+        gt.init(smem_u32(queue) + (uint32_t)warp * epi_warp_bytes<QS, KREG>(), lane);
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(trow + c0, v);
+          tmem_ld_wait();
+          gt.scan32(v, c0);
+        }
+        // every accumulator this thread needs is in registers / its spill slots: release TMEM before the exact ranking
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty);
+        gt.template finish<KREG, true>(top, ys_addr, nullptr);
+      } else {
+#pragma unroll 1
+        for (int cc = 0; cc < NH * BM / 8; ++cc) {
+          uint32_t v[8];
+          tmem_ld8(trow + cc * 8, v);
+          tmem_ld_wait();
+          top.template scan8<true>(v, ys_addr + cc * 32, nullptr, 8, cc * 8);
+        }
       }
-    }
-    if (q < N) {
-      emit<KREG>(top, nn_idx, nn_idx32, ((long long)b * N + q) * k_out, k_out, stride, rank0);
-      store_bound<KREG>(top, bounds, (long long)b * N + q, more_rounds);
+      if (!(QS < 0 && unit_keys)) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty);
+      }
+      if (q < N) {
+        emit<KREG>(top, nn_idx, nn_idx32, ((long long)b * N + q) * k_out, k_out, stride, rank0);
+        store_bound<KREG>(top, bounds, (long long)b * N + q, more_rounds);
+      }
     }
   }
 
@@ -833,8 +858,11 @@ static int launch_self(const CUtensorMap& xh, const CUtensorMap& xl, const float
   static DeviceOnce once;
   if (int rc = set_smem(knn_self_kernel<NH, KREG, QS>, &once, "knn_self")) return rc;
   const size_t smem = (size_t)stages * NH * kBlockBytes + (size_t)(4 * NH) * epi_warp_bytes<QS, KREG>() + kMiscBytes;
-  knn_self_kernel<NH, KREG, QS><<<B, (4 * NH + 2) * 32, smem, s>>>(xh, xl, xsq, nn_idx, nn_idx32, N, C, k_out, stride, stages,
-                                                               r.bounds, r.rank0, r.more);
+  // persistent: one CTA (NH = 2; 512 TMEM columns) or two (NH = 1) per SM, each walking segments blockIdx.x, + gridDim.x, ...
+  int grid = num_sms() * (NH == 1 ? 2 : 1);
+  if (grid > B) grid = B;
+  knn_self_kernel<NH, KREG, QS><<<grid, (4 * NH + 2) * 32, smem, s>>>(xh, xl, xsq, nn_idx, nn_idx32, B, N, C, k_out, stride, stages,
+                                                                  r.bounds, r.rank0, r.more);
   return check_launch("knn_self");
 }
 

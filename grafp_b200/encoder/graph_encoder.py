@@ -138,7 +138,8 @@ class GraphEncoder(nn.Module):
         """x: (B, C, num_points) -> (B, 1024)."""
         # (B, C, N) -> logical (B, C, N, 1) stored as node rows (B, N, C) (canonical channels-last strides):
         # one transposing copy of the 8-channel input, after which every layer keeps that layout
-        x = x.unsqueeze(-1).contiguous(memory_format=torch.channels_last)
+        # (no copy at all when the fused peak extractor produced the point cloud: it writes node rows directly)
+        x = ops.canonical_rows(x.unsqueeze(-1)) if x.is_cuda else x.unsqueeze(-1).contiguous(memory_format=torch.channels_last)
         x = self.stem(x)
         for block in self.backbone:
             x = block(x)

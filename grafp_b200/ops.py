@@ -137,6 +137,16 @@ def as_rows(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def canonical_rows(x: torch.Tensor) -> torch.Tensor:
+    """``x`` (B, C, N, 1) as node rows with the CANONICAL channels-last strides (N*C, 1, C, C).  A view whose size-1 last
+    dimension carries another stride (e.g. ``t.unsqueeze(-1)``) is the same memory, but PyTorch / cuDNN only recognise
+    the canonical form as NHWC; anything else makes the next convolution fall back to an NCHW copy."""
+    x = as_rows(x)
+    B, C, N, _ = x.shape
+    want = (N * C, 1, C, C)
+    return x if x.stride() == want else x.as_strided(x.shape, want)
+
+
 def as_edge_rows(h: torch.Tensor) -> torch.Tensor:
     """Return ``h`` (B, C, N, k) backed by (B, N, k, C) memory."""
     B, C, N, k = h.shape
@@ -455,6 +465,58 @@ def max_over_k(h: torch.Tensor) -> torch.Tensor:
     if h.dim() != 4:
         raise RuntimeError("grafp_b200.max_over_k: expected a (B, C, N, k) tensor")
     return _MaxOverK.apply(h)
+
+
+# --------------------------------------------------------------------------------------
+# peak point-cloud front end
+# --------------------------------------------------------------------------------------
+
+class _PeakExtract(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, weight, bias, stride_h):
+        lib = _native.load()
+        B, H, W = spec.shape
+        F_, _, kh, kw = weight.shape
+        Ho = (H + 2 * (kh // 2) - kh) // stride_h + 1
+        # logical (B, F, N, 1) with node rows (B, N, F) in memory: what GraphEncoder.forward would otherwise copy into
+        out = torch.empty((B, F_, Ho * W, 1), dtype=torch.float32, device=spec.device, memory_format=torch.channels_last)
+        w, b = weight.detach().contiguous(), bias.detach().contiguous()
+        _call("peak_extract_fwd", 1, dict(B=B, N=Ho * W, C=F_), lib.grafp_peak_extract_fwd, spec.device, spec.data_ptr(),
+              w.data_ptr(), b.data_ptr(), out.data_ptr(), B, H, W, F_, kh, kw, int(stride_h), _stream(spec))
+        ctx.save_for_backward(spec, out)
+        ctx.geom = (B, H, W, F_, kh, kw, int(stride_h))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _native.load()
+        spec, out = ctx.saved_tensors
+        B, H, W, F_, kh, kw, sh = ctx.geom
+        g = as_rows(grad_out.to(torch.float32))
+        ws_bytes = lib.grafp_peak_extract_workspace_bytes(B, kh, kw)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=spec.device)
+        dweight = torch.empty((F_, 3, kh, kw), dtype=torch.float32, device=spec.device)
+        dbias = torch.empty(F_, dtype=torch.float32, device=spec.device)
+        _call("peak_extract_bwd", 2, dict(B=B, N=out.shape[2], C=F_), lib.grafp_peak_extract_bwd, spec.device, spec.data_ptr(),
+              out.data_ptr(), g.data_ptr(), ws.data_ptr(), ws_bytes, dweight.data_ptr(), dbias.data_ptr(), B, H, W, F_, kh, kw, sh,
+              _stream(spec))
+        return None, dweight, dbias, None
+
+
+def peak_extract_supported(spec: torch.Tensor, conv: torch.nn.Conv2d) -> bool:
+    kh, kw = conv.kernel_size
+    return (spec.is_cuda and spec.dtype == torch.float32 and spec.dim() == 3 and conv.weight.dtype == torch.float32
+            and conv.in_channels == 3 and conv.out_channels == 8 and kh % 2 == 1 and kw % 2 == 1 and conv.bias is not None
+            and conv.stride[1] == 1 and tuple(conv.padding) == (kh // 2, kw // 2) and tuple(conv.dilation) == (1, 1)
+            and conv.groups == 1 and conv.padding_mode == "zeros" and not spec.requires_grad
+            and 3 * (spec.shape[1] + kh) * (spec.shape[2] + kw) * 4 + spec.shape[1] * spec.shape[2] * 16 < 190 * 1024)
+
+
+def peak_extract(spec: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
+    """(B, H, W) log-mel segments -> (B, F, Ho * W, 1) peak point cloud stored as node rows: min-max normalisation,
+    position ramps, convolution and ReLU of GPUPeakExtractorv2.forward (peak_extractor.py:56-82) as one kernel."""
+    _require_cuda(spec)
+    return _PeakExtract.apply(spec.contiguous(), conv.weight, conv.bias, int(conv.stride[0]))
 
 
 # --------------------------------------------------------------------------------------

@@ -1,10 +1,13 @@
 """Peak point-cloud front end (reference: peak_extractor.py), the caller feeding GraphEncoder.
 
-Plain PyTorch (one strided convolution); not part of the kernel hot path, provided so the
-benchmark workloads and the reference's SimCLR wrapper run unchanged on this package.
+On CUDA fp32 spectrograms the whole forward (min-max normalisation, position ramps, strided convolution, ReLU,
+flattening) is one kernel that writes the point cloud as node rows - the layout the encoder's stem consumes - and its
+backward one kernel + a reduction; anything else runs the PyTorch ops of the reference.
 """
 import torch
 import torch.nn as nn
+
+from . import ops
 
 
 class GPUPeakExtractorv2(nn.Module):
@@ -43,6 +46,10 @@ class GPUPeakExtractorv2(nn.Module):
         return self._ramps[key]
 
     def forward(self, spec_tensor):
+        conv = self.convs[0]
+        if ops.peak_extract_supported(spec_tensor, conv) and not torch.is_autocast_enabled():
+            # (B, F, N, 1) channels-last -> the reference's (B, F, N) view of the same memory (node rows)
+            return ops.peak_extract(spec_tensor, conv).squeeze(-1)
         lo = torch.amin(spec_tensor, dim=(1, 2), keepdim=True)
         hi = torch.amax(spec_tensor, dim=(1, 2), keepdim=True)
         peaks = ((spec_tensor - lo) / (hi - lo)).unsqueeze(1)

@@ -229,6 +229,22 @@ int grafp_ntxent_fwd(const float* z, float* lse, float* row_loss, float* loss, i
 int grafp_ntxent_bwd(const float* z, const float* lse, const float* grad_loss, float* dz, int n2, int d, float inv_tau,
                      void* stream);
 
+/*
+ * Peak point-cloud front end.  Replaces GPUPeakExtractorv2.forward (peak_extractor.py:56-82): min-max
+ * normalisation of the (H, W) log-mel segment, the time / frequency position ramps (torch.linspace(0, 1, W / H)),
+ * Conv2d(3 -> F, kh x kw, stride (stride_h, 1), padding (kh / 2, kw / 2)) + ReLU and the reshape to a point cloud,
+ * written directly as node rows out[b][n][f], n = oh * W + ow - the layout the encoder's stem consumes.
+ *   spec (B, H, W) float32, weight (F, 3, kh, kw), bias (F), out (B, Ho * W, F), Ho = (H + 2 (kh / 2) - kh) / stride_h + 1.
+ *   backward: gradients of weight and bias only (the spectrogram has none): `partial` is
+ *   grafp_peak_extract_workspace_bytes(B, kh, kw) bytes of scratch (per-segment sums, reduced in a fixed order).
+ * F must be 8 (config n_filters), kh and kw odd; else GRAFP_EUNSUPPORTED (the caller then runs the PyTorch modules).
+ */
+size_t grafp_peak_extract_workspace_bytes(int B, int kh, int kw);
+int grafp_peak_extract_fwd(const float* spec, const float* weight, const float* bias, float* out, int B, int H, int W, int F,
+                           int kh, int kw, int stride_h, void* stream);
+int grafp_peak_extract_bwd(const float* spec, const float* out, const float* grad_out, void* partial, size_t partial_bytes,
+                           float* dweight, float* dbias, int B, int H, int W, int F, int kh, int kw, int stride_h, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

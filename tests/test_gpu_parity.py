@@ -1231,3 +1231,40 @@ def test_ntxent_kernels_match_the_reference_loop(B, d):
     assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
     assert gio.rel_err(x.grad.cpu().double(), 3.0 * a.grad) < 1e-4
     assert gio.rel_err(y.grad.cpu().double(), 3.0 * b.grad) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------
+# fused peak point-cloud front end
+# ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("B", [3, 130])
+def test_fused_peak_extractor_matches_the_reference_ops(B):
+    """ops.peak_extract (normalise + ramps + 7x7 strided conv + ReLU + flatten, one kernel; backward: weight / bias
+    gradients) against the oracle's restatement of GPUPeakExtractorv2.forward (peak_extractor.py:56-82) in fp64, and
+    the module against its own PyTorch path; the output is node rows the encoder consumes without a copy."""
+    from grafp_b200.peak_extractor import GPUPeakExtractorv2
+    cfg = dict(synth.DEFAULT_CFG)
+    torch.manual_seed(2)
+    mod = GPUPeakExtractorv2(cfg)
+    with torch.no_grad():
+        mod.convs[0].bias.copy_(0.1 * torch.randn(8))
+    spec, _ = synth.synth_spec(B, 40 + B)
+    p = {"peak_extractor.convs.0.weight": mod.convs[0].weight.detach().double().requires_grad_(True),
+         "peak_extractor.convs.0.bias": mod.convs[0].bias.detach().double().requires_grad_(True)}
+    ref = O.peak_extractor(p, spec.double())
+    up = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5))
+    ref.backward(up.double())
+    mod.to(DEV)
+    timer = ops.KernelTimer(timing=False)
+    ops.set_timer(timer)
+    try:
+        out = mod(spec.to(DEV))
+        out.backward(up.to(DEV))
+    finally:
+        ops.set_timer(None)
+    assert timer.launches == 3, "one forward kernel, backward kernel + reduction"
+    assert out.shape == ref.shape == (B, 8, 1024)
+    assert ops._is_rows(out.unsqueeze(-1)) and ops.canonical_rows(out.unsqueeze(-1)).data_ptr() == out.data_ptr()
+    assert gio.rel_err(out.detach().cpu().double(), ref.detach()) < 1e-5
+    assert gio.rel_err(mod.convs[0].weight.grad.cpu().double(), p["peak_extractor.convs.0.weight"].grad) < 1e-4
+    assert gio.rel_err(mod.convs[0].bias.grad.cpu().double(), p["peak_extractor.convs.0.bias"].grad) < 1e-4
