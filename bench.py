@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--dtype", choices=["fp32", "bf16"], default="fp32",
                     help="fp32 = configs[1]; bf16 = torch.autocast(bfloat16) activations with fp32 parameters (configs[2])")
     ap.add_argument("--knn-algo", choices=["auto", "simt", "tc"], default="auto")
+    ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",
+                    help="run the step as one CUDA graph (grafp_b200.training.GraphedTrainStep); auto = on at 1 GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-eager-on-this-GPU baseline")
     return ap.parse_args()
@@ -348,7 +350,8 @@ def run_ours(args):
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=True,
                                                         gradient_as_bucket_view=True)
-    opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"])
+    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"], capturable=use_graph)
     algo = {"auto": _native.KNN_AUTO, "simt": _native.KNN_SIMT, "tc": _native.KNN_TC}[args.knn_algo]
     if algo != _native.KNN_AUTO:
         _orig = ops.knn_graph
@@ -360,15 +363,25 @@ def run_ours(args):
     dev_i, dev_j = host_i.to(dev), host_j.to(dev)
     h2d_bytes = host_i.numel() * 4 + host_j.numel() * 4
 
-    def step(x_i, x_j):
+    def loss_of(h_i, h_j, z_i, z_j):
+        # global-batch negatives like the reference's DataParallel gather (train.py:69-71); the loss runs in fp32
+        return global_ntxent_loss(z_i.float(), z_j.float(), cfg)
+
+    def eager_step(x_i, x_j):
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
-            _, _, z_i, z_j = net(x_i, x_j)
-        # global-batch negatives like the reference's DataParallel gather (train.py:69-71); the loss runs in fp32
-        loss = global_ntxent_loss(z_i.float(), z_j.float(), cfg)
+            out = net(x_i, x_j)
+        loss = loss_of(*out)
         loss.backward()
         opt.step()
         return loss
+
+    step = eager_step
+    if use_graph:
+        # the whole step - both views forward, loss, backward, Adam - as ONE CUDA graph; new inputs are copied into
+        # its static buffers (from pinned host memory in the e2e region)
+        from grafp_b200.training import GraphedTrainStep
+        step = GraphedTrainStep(net, opt, loss_of, [dev_i, dev_j], autocast_dtype=torch.bfloat16 if bf16 else None)
 
     def barrier():
         if world > 1:
@@ -380,8 +393,9 @@ def run_ours(args):
     barrier()
 
     # ---- timed region 1: inputs resident in HBM (the `value`) ----
-    timer = ops.KernelTimer(timing=True)
-    ops.set_timer(timer)
+    timer = ops.KernelTimer(timing=not use_graph)   # (events cannot be recorded inside a replayed graph: see below)
+    if not use_graph:
+        ops.set_timer(timer)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -395,7 +409,7 @@ def run_ours(args):
     ms_resident = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
     ops.set_timer(None)
-    ksum = timer.summary()
+    n_instr = args.steps
 
     # ---- timed region 2: end to end through the public API with host buffers (the `e2e`) ----
     losses = []
@@ -403,12 +417,32 @@ def run_ours(args):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(args.steps):
-        x_i = host_i.to(dev, non_blocking=True)
-        x_j = host_j.to(dev, non_blocking=True)
-        losses.append(step(x_i, x_j).item())  # .item(): device -> host read of the step's result
+        if use_graph:   # H2D straight into the graph's static input buffers, replay, read the loss back
+            losses.append(step(host_i, host_j).item())
+        else:
+            x_i = host_i.to(dev, non_blocking=True)
+            x_j = host_j.to(dev, non_blocking=True)
+            losses.append(step(x_i, x_j).item())  # .item(): device -> host read of the step's result
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+
+    ms_instr = ms_resident
+    if use_graph:
+        # per-kernel breakdown: the same step run eagerly (same kernels, same order) with CUDA events around every C-ABI
+        # call; NOT part of `value` / `e2e`
+        n_instr = min(3, args.steps)
+        ops.set_timer(timer)
+        timer.timing = True
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        for _ in range(n_instr):
+            step._eager_step()
+        e5.record()
+        torch.cuda.synchronize()
+        ops.set_timer(None)
+        ms_instr = e4.elapsed_time(e5)
+    ksum = timer.summary()
 
     t = torch.tensor([ms_resident, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -429,9 +463,9 @@ def run_ours(args):
                 work["bytes"] += w.get("bytes", 0.0) * sh["calls"]
                 work["flops"] += w.get("flops", 0.0) * sh["calls"]
             sec = rec["ms_total"] / 1e3
-            kernels[name] = {"calls": rec["calls"], "ms_total": rec["ms_total"],
-                             "ms_per_step": rec["ms_total"] / args.steps,
-                             "share_of_step": rec["ms_total"] / ms_resident,
+            kernels[name] = {"calls_per_step": rec["calls"] / n_instr, "ms_total": rec["ms_total"],
+                             "ms_per_step": rec["ms_total"] / n_instr,
+                             "share_of_step": rec["ms_total"] / n_instr / (ms_resident / args.steps),
                              "gbs": work["bytes"] / sec / 1e9 if sec > 0 and work["bytes"] else None,
                              "tflops": work["flops"] / sec / 1e12 if sec > 0 and work["flops"] else None}
         # `roofline`: the costliest of our kernels (the contract's "dominant kernel"); `rooflines`: every hot-path kernel,
@@ -449,13 +483,17 @@ def run_ours(args):
             "dtype": "f32" if not bf16 else "bf16", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-            "gpu_launches": timer.launches, "knn_algo": ops.knn_last_algo(),
+            "gpu_launches": int(round(timer.launches / n_instr * args.steps)), "knn_algo": ops.knn_last_algo(),
+            "cuda_graph": bool(use_graph),
+            "kernel_timing": ("CUDA events around every C-ABI call of %d eagerly run steps (%.1f ms per step eager; the timed "
+                              "steps replay the same kernels as one CUDA graph)" % (n_instr, ms_instr / n_instr)) if use_graph
+                             else "CUDA events around every C-ABI call inside the timed region",
             "roofline": roofline, "rooflines": rooflines, "kernels": kernels, "clocks": clocks,
             "loss_last": losses[-1] if losses else None, "pairs_per_s": value / 2,
         }
         # ---- baselines (rank 0, one GPU only): the reference eager on this GPU, then on the host cores ----
         if world == 1:
-            del opt, net, model
+            del step, opt, net, model
             torch.cuda.empty_cache()
             if not args.no_gpu_eager:
                 try:

@@ -561,9 +561,10 @@ mr_aggregate_bwd_cluster_kernel(const T* __restrict__ g, const uint8_t* __restri
   __syncthreads();  // the barrier is initialised before anyone waits on it
   if (nrows > 0) k3_mbar_wait(bar, 0);
 
-  // phase 1: dense part of grad_x for this CTA's rows (everything it needs is in shared memory or registers).
-  // self_mask: bit j set when neighbour slot j of the row is the row itself (rank 0 of a k-NN graph always is):
-  // the centre and neighbour terms of such a winner cancel, no reduction is issued for it.
+  // phase 1: dense part of grad_x for this CTA's rows (everything it needs is in shared memory or registers)
+  // (Measured and dropped, round 2: a per-row bit mask of the self-edge slots instead of one id look-up per channel,
+  //  and skipping self slots before the select chain in phase 2 - fewer instructions, 120 -> 130 us: the extra
+  //  dependent shared-memory loads at the head of each item cost more than the selects they save.)
 #pragma unroll
   for (int u = 0; u < kItems; ++u) {
     const int it = threadIdx.x + u * kFusedThreads;
@@ -574,13 +575,11 @@ mr_aggregate_bwd_cluster_kernel(const T* __restrict__ g, const uint8_t* __restri
       const uint4* gp = reinterpret_cast<const uint4*>(gt + (size_t)rl * row_bytes + (size_t)2 * c * sizeof(T));
       float g0[V], g1[V];
       It::unpack_pairs(gp[0], gp[1], g0, g1);
-      unsigned self_mask = 0u;
-      for (int j = 0; j < k; ++j) self_mask |= (static_cast<int>(ids[rl * k + j]) == n ? 1u : 0u) << j;
       float r[V];
 #pragma unroll
       for (int e = 0; e < V; ++e) {
-        const unsigned a = (am[u][e >> 2] >> (8 * (e & 3))) & 0xff;
-        r[e] = ((self_mask >> a) & 1u) ? g0[e] : g0[e] - g1[e];
+        const int nb = static_cast<int>(ids[rl * k + ((am[u][e >> 2] >> (8 * (e & 3))) & 0xff)]);
+        r[e] = (nb == n) ? g0[e] : g0[e] - g1[e];
       }
       It::store(gxb + (long long)n * C + c, r);
     }
@@ -600,8 +599,6 @@ mr_aggregate_bwd_cluster_kernel(const T* __restrict__ g, const uint8_t* __restri
       float g0[V], g1[V];
       It::unpack_pairs(gp[0], gp[1], g0, g1);
       for (int j = 0; j < k; ++j) {
-        const int nb = static_cast<int>(ids[rl * k + j]);
-        if (nb == n) continue;  // self edge (rank 0 of every k-NN row): cancelled in phase 1
         float v[V];
         bool any = false;
 #pragma unroll
@@ -610,7 +607,8 @@ mr_aggregate_bwd_cluster_kernel(const T* __restrict__ g, const uint8_t* __restri
           v[f] = hit ? g1[f] : 0.f;
           any |= hit;
         }
-        if (any) It::red_add(gxb + (long long)nb * C + c, v);
+        const int nb = static_cast<int>(ids[rl * k + j]);
+        if (any && nb != n) It::red_add(gxb + (long long)nb * C + c, v);
       }
     }
   }
@@ -621,7 +619,7 @@ int launch_mr_bwd_cluster(const T* g, const uint8_t* argmax, const void* nbr, T*
                           bool fence, cudaStream_t s, bool* launched) {
   *launched = false;
   constexpr int V = Item16<T>::V;
-  if (C % V != 0 || k > 32) return GRAFP_OK;  // (k <= 32: the kernel keeps the row's self-edge slots in a 32-bit mask)
+  if (C % V != 0) return GRAFP_OK;
   const int cv = C / V;
   const size_t idsz = I64 ? 8 : 4;
   if ((cv & (cv - 1)) != 0 || !aligned16(g) || !aligned16(grad_x) || !aligned16(nbr) || (((uintptr_t)argmax) & 3) != 0 || N < 64)

@@ -1268,3 +1268,52 @@ def test_fused_peak_extractor_matches_the_reference_ops(B):
     assert gio.rel_err(out.detach().cpu().double(), ref.detach()) < 1e-5
     assert gio.rel_err(mod.convs[0].weight.grad.cpu().double(), p["peak_extractor.convs.0.weight"].grad) < 1e-4
     assert gio.rel_err(mod.convs[0].bias.grad.cpu().double(), p["peak_extractor.convs.0.bias"].grad) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------
+# whole training step as one CUDA graph
+# ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_graphed_train_step_replays_the_eager_step(bf16):
+    """grafp_b200.training.GraphedTrainStep (forward of both views, NT-Xent, backward, Adam as ONE CUDA graph) against
+    the same steps run eagerly from the same initial state: losses and parameters after 3 steps on fresh inputs
+    (nothing of the capture inputs may be baked in).  The graph launches the same kernels in the same order; the only
+    difference is the order of the fp32 reductions in the argmax-routed scatter, so: 1e-4 (fp32) / 2e-2 (bf16)."""
+    from grafp_b200.training import GraphedTrainStep
+    cfg = dict(synth.DEFAULT_CFG)
+    B = 6
+
+    def build():
+        torch.manual_seed(0)
+        m = SimCLR(cfg, GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3))
+        load_synth(m, 77)
+        m.to(DEV).train()
+        return m, torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True)
+
+    def loss_of(h_i, h_j, z_i, z_j):
+        return ntxent_loss(z_i.float(), z_j.float(), cfg)
+
+    batches = [tuple(t.to(DEV) for t in synth.synth_spec(B, 900 + i)) for i in range(4)]
+    dt = torch.bfloat16 if bf16 else None
+    m_e, opt_e = build()
+    m_g, opt_g = build()
+    gstep = GraphedTrainStep(m_g, opt_g, loss_of, list(batches[0]), autocast_dtype=dt, warmup=1)
+    # bring the eager twin to the same state: the graphed object ran warmup + capture steps on batches[0]
+    m_e.load_state_dict(m_g.state_dict())
+    opt_e.load_state_dict(opt_g.state_dict())
+    tol = 2e-2 if bf16 else 1e-4
+    for s_i, s_j in batches[1:]:
+        lg = float(gstep(s_i, s_j))
+        opt_e.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+            out = m_e(s_i, s_j)
+        le = loss_of(*out)
+        le.backward()
+        opt_e.step()
+        assert abs(lg - float(le)) < tol * abs(float(le)), (lg, float(le))
+    worst = 0.0
+    for (n, a), (_, b) in zip(m_g.named_parameters(), m_e.named_parameters()):
+        if a.requires_grad:
+            worst = max(worst, float((a - b).norm() / b.norm().clamp_min(1e-12)))
+    assert worst < 10 * tol, worst
