@@ -382,7 +382,7 @@ bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, con
                          const float* __restrict__ bias, double* __restrict__ sums, unsigned int* __restrict__ counter,
                          T* __restrict__ out, float* __restrict__ save_mean, float* __restrict__ save_invstd,
                          float* running_mean, float* running_var, long long R, int C, int tpr_shift, float eps,
-                         float momentum) {
+                         float momentum, int first_reverse) {
   constexpr int V = Vec16<T>::V;
   __shared__ float sm[2 * V * kBnThreads];
   const int tpr = 1 << tpr_shift;
@@ -405,17 +405,23 @@ bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, con
       acc[V + e] = fmaf(d, d, acc[V + e]);
     }
   };
-  long long r = r0;
-  for (; r + 3 * step < R; r += 4 * step) {
+  // this thread's rows: r0 + j * step, j < n.  first_reverse: the first pass walks them back to front (the producer of x
+  // wrote front to back, so the tail of x is what L2 still holds) and the second pass front to back; else the other
+  // way round.  Either way the second pass starts on the rows the first pass read last.
+  const long long n = r0 < R ? (R - r0 + step - 1) / step : 0;
+  auto row1 = [&](long long j) { return (r0 + (first_reverse ? (n - 1 - j) : j) * step) * C; };
+  auto row2 = [&](long long j) { return (r0 + (first_reverse ? j : (n - 1 - j)) * step) * C; };
+  long long j = 0;
+  for (; j + 3 < n; j += 4) {
     float v[4][V];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) Vec16<T>::load(xp + (r + u * step) * C, v[u]);
+    for (int u = 0; u < 4; ++u) Vec16<T>::load(xp + row1(j + u), v[u]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) add(v[u]);
   }
-  for (; r < R; r += step) {
+  for (; j < n; ++j) {
     float v[V];
-    Vec16<T>::load(xp + r * C, v);
+    Vec16<T>::load(xp + row1(j), v);
     add(v);
   }
   reduce_row_lanes<2 * V>(acc, sm, tpr_shift);
@@ -445,7 +451,6 @@ bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, con
       }
     }
   }
-  if (r0 >= R) return;
   auto one = [&](const float (&v)[V], const float (&rv)[V], T* o) {
     float y[V];
 #pragma unroll
@@ -456,22 +461,21 @@ bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, con
     }
     Vec16<T>::store(o, y);
   };
-  const long long n = (R - r0 + step - 1) / step;  // this thread's rows: r0 + j * step; walked back to front
-  long long j = n - 1;
-  for (; j >= 3; j -= 4) {
+  j = 0;
+  for (; j + 3 < n; j += 4) {
     float v[4][V], rv[4][V];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const long long off = (r0 + (j - u) * step) * C + c;
+      const long long off = row2(j + u) + c;
       Vec16<T>::load(x + off, v[u]);
       if (RES) Vec16<T>::load(res + off, rv[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) one(v[u], rv[u], out + (r0 + (j - u) * step) * C + c);
+    for (int u = 0; u < 4; ++u) one(v[u], rv[u], out + row2(j + u) + c);
   }
-  for (; j >= 0; --j) {
+  for (; j < n; ++j) {
     float v[V], rv[V];
-    const long long off = (r0 + j * step) * C + c;
+    const long long off = row2(j) + c;
     Vec16<T>::load(x + off, v);
     if (RES) Vec16<T>::load(res + off, rv);
     one(v, rv, out + off);
@@ -484,7 +488,7 @@ bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
                          const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ invstd,
                          double* __restrict__ sums, unsigned int* __restrict__ counter, T* __restrict__ dx,
                          float* __restrict__ dweight, float* __restrict__ dbias, float* __restrict__ colsum, long long R,
-                         int C, int tpr_shift) {
+                         int C, int tpr_shift, int first_reverse) {
   constexpr int V = Vec16<T>::V;
   __shared__ float sm[3 * V * kBnThreads];
   const int tpr = 1 << tpr_shift;
@@ -516,18 +520,21 @@ bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
       acc[2 * V + e] += d;
     }
   };
-  long long r = r0;
-  for (; r + 3 * step < R; r += 4 * step) {
+  const long long n = r0 < R ? (R - r0 + step - 1) / step : 0;   // (directions: see bn_fwd_persistent_kernel)
+  auto row1 = [&](long long j) { return (r0 + (first_reverse ? (n - 1 - j) : j) * step) * C; };
+  auto row2 = [&](long long j) { return (r0 + (first_reverse ? j : (n - 1 - j)) * step) * C; };
+  long long j = 0;
+  for (; j + 3 < n; j += 4) {
     float v[4][V], g[4][V];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { Vec16<T>::load(xp + (r + u * step) * C, v[u]); Vec16<T>::load(gp + (r + u * step) * C, g[u]); }
+    for (int u = 0; u < 4; ++u) { Vec16<T>::load(xp + row1(j + u), v[u]); Vec16<T>::load(gp + row1(j + u), g[u]); }
 #pragma unroll
     for (int u = 0; u < 4; ++u) add(v[u], g[u]);
   }
-  for (; r < R; r += step) {
+  for (; j < n; ++j) {
     float v[V], g[V];
-    Vec16<T>::load(xp + r * C, v);
-    Vec16<T>::load(gp + r * C, g);
+    Vec16<T>::load(xp + row1(j), v);
+    Vec16<T>::load(gp + row1(j), g);
     add(v, g);
   }
   reduce_row_lanes<3 * V>(acc, sm, tpr_shift);
@@ -557,7 +564,6 @@ bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
       }
     }
   }
-  if (r0 >= R) return;
   auto one = [&](const float (&v)[V], const float (&g)[V], T* o) {
     float rr[V];
 #pragma unroll
@@ -569,22 +575,21 @@ bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
     }
     Vec16<T>::store(o, rr);
   };
-  const long long n = (R - r0 + step - 1) / step;
-  long long j = n - 1;
-  for (; j >= 3; j -= 4) {
+  j = 0;
+  for (; j + 3 < n; j += 4) {
     float v[4][V], g[4][V];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const long long off = (r0 + (j - u) * step) * C + c;
+      const long long off = row2(j + u) + c;
       Vec16<T>::load(x + off, v[u]);
       Vec16<T>::load(dy + off, g[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) one(v[u], g[u], dx + (r0 + (j - u) * step) * C + c);
+    for (int u = 0; u < 4; ++u) one(v[u], g[u], dx + row2(j + u) + c);
   }
-  for (; j >= 0; --j) {
+  for (; j < n; ++j) {
     float v[V], g[V];
-    const long long off = (r0 + j * step) * C + c;
+    const long long off = row2(j) + c;
     Vec16<T>::load(x + off, v);
     Vec16<T>::load(dy + off, g);
     one(v, g, dx + off);
@@ -643,9 +648,10 @@ int bn_fwd_t(const void* x_, const void* res_, const float* weight, const float*
   if (e != cudaSuccess) { set_error("bn_train_fwd: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
   if (option(OPT_BN_PERSISTENT) != 0) {
     int tsh = shift_of(g.tpr);
+    int first_reverse = option(OPT_BN_REVERSE) != 0;
     void* args[] = {(void*)&x, (void*)&res, (void*)&weight, (void*)&bias, (void*)&sums, (void*)&counter, (void*)&out,
                     (void*)&save_mean, (void*)&save_invstd, (void*)&running_mean, (void*)&running_var, (void*)&R, (void*)&C,
-                    (void*)&tsh, (void*)&eps, (void*)&momentum};
+                    (void*)&tsh, (void*)&eps, (void*)&momentum, (void*)&first_reverse};
     auto try_launch = [&](auto kernel, CoopInfo& info) -> int {
       int cap = 0;
       if (!coop_capacity(kernel, info, &cap)) return -1;
@@ -693,9 +699,10 @@ int bn_bwd_t(const void* dy_, const void* x_, const float* weight, const float* 
   if (e != cudaSuccess) { set_error("bn_train_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
   int tsh = shift_of(g.tpr);
   if (option(OPT_BN_PERSISTENT) != 0) {
+    int first_reverse = option(OPT_BN_REVERSE) != 0;
     void* args[] = {(void*)&dy, (void*)&x, (void*)&weight, (void*)&bias, (void*)&save_mean, (void*)&save_invstd, (void*)&sums,
                     (void*)&counter, (void*)&dx, (void*)&dweight, (void*)&dbias, (void*)&dx_colsum, (void*)&R, (void*)&C,
-                    (void*)&tsh};
+                    (void*)&tsh, (void*)&first_reverse};
     auto try_launch = [&](auto kernel, CoopInfo& info) -> int {
       int cap = 0;
       if (!coop_capacity(kernel, info, &cap)) return -1;

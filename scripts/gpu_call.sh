@@ -21,6 +21,8 @@ for step in "$@"; do
     prof) timeout 600 python scripts/profile_step.py 512 > $out/${tag}_profile_step.log 2>&1; head -50 $out/${tag}_profile_step.log | cut -c1-200 ;;
     ncu_ops) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"knn_|mr_aggregate|bn_" -c 60 -f -o $out/${tag}_ncu_ops python scripts/ncu_ops.py 512 1 > $out/${tag}_ncu_ops.log 2>&1; tail -3 $out/${tag}_ncu_ops.log
              python scripts/ncu_summary.py $out/${tag}_ncu_ops.ncu-rep > $out/${tag}_ncu_ops_summary.txt 2>&1; python scripts/ncu_stalls.py $out/${tag}_ncu_ops.ncu-rep > $out/${tag}_ncu_ops_stalls.txt 2>&1; cat $out/${tag}_ncu_ops_summary.txt ;;
+    bench_rev) GRAFP_BN_REVERSE=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_bnrev.json 2> $out/${tag}_bench_n1_bnrev.err; tail -c 300 $out/${tag}_bench_n1_bnrev.err; cut -c1-300 $out/${tag}_bench_n1_bnrev.json ;;
+    bench_nograph) timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager --graph off > $out/${tag}_bench_n1_nograph.json 2> $out/${tag}_bench_n1_nograph.err; cut -c1-300 $out/${tag}_bench_n1_nograph.json ;;
     smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
     *) echo "unknown step $step" ;;
   esac

@@ -1277,9 +1277,12 @@ def test_fused_peak_extractor_matches_the_reference_ops(B):
 @pytest.mark.parametrize("bf16", [False, True])
 def test_graphed_train_step_replays_the_eager_step(bf16):
     """grafp_b200.training.GraphedTrainStep (forward of both views, NT-Xent, backward, Adam as ONE CUDA graph) against
-    the same steps run eagerly from the same initial state: losses and parameters after 3 steps on fresh inputs
-    (nothing of the capture inputs may be baked in).  The graph launches the same kernels in the same order; the only
-    difference is the order of the fp32 reductions in the argmax-routed scatter, so: 1e-4 (fp32) / 2e-2 (bf16)."""
+    the same step run eagerly from the same state, three times on fresh inputs (nothing of the capture inputs may be
+    baked in): the loss must agree to 1e-6 (the graph replays the same forward kernels: bit-identical in practice) and
+    every gradient to 1e-3 of the largest gradient norm.  The eager twin is re-synchronised after every step: about
+    half of the parameters (biases in front of a train-mode BatchNorm, Grapher.fc1's BatchNorm bias) have analytically
+    ZERO gradients, whose computed values are rounding noise that Adam normalises into +-lr steps - two eager runs
+    drift apart the same way (the scatter backward's fp32 reductions are not ordered)."""
     from grafp_b200.training import GraphedTrainStep
     cfg = dict(synth.DEFAULT_CFG)
     B = 6
@@ -1299,21 +1302,22 @@ def test_graphed_train_step_replays_the_eager_step(bf16):
     m_e, opt_e = build()
     m_g, opt_g = build()
     gstep = GraphedTrainStep(m_g, opt_g, loss_of, list(batches[0]), autocast_dtype=dt, warmup=1)
-    # bring the eager twin to the same state: the graphed object ran warmup + capture steps on batches[0]
-    m_e.load_state_dict(m_g.state_dict())
-    opt_e.load_state_dict(opt_g.state_dict())
-    tol = 2e-2 if bf16 else 1e-4
+    losses = []
     for s_i, s_j in batches[1:]:
+        m_e.load_state_dict(m_g.state_dict())          # same parameters, BatchNorm buffers and Adam state
+        opt_e.load_state_dict(opt_g.state_dict())
         lg = float(gstep(s_i, s_j))
         opt_e.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
             out = m_e(s_i, s_j)
         le = loss_of(*out)
         le.backward()
-        opt_e.step()
-        assert abs(lg - float(le)) < tol * abs(float(le)), (lg, float(le))
-    worst = 0.0
-    for (n, a), (_, b) in zip(m_g.named_parameters(), m_e.named_parameters()):
-        if a.requires_grad:
-            worst = max(worst, float((a - b).norm() / b.norm().clamp_min(1e-12)))
-    assert worst < 10 * tol, worst
+        assert abs(lg - float(le)) <= 1e-6 * abs(float(le)), (lg, float(le))
+        grads_e = {n: q.grad for n, q in m_e.named_parameters() if q.grad is not None}
+        grads_g = {n: q.grad for n, q in m_g.named_parameters() if q.grad is not None}
+        assert grads_e.keys() == grads_g.keys()
+        scale = max(float(g.norm()) for g in grads_e.values())
+        for n, g in grads_e.items():
+            assert gio.close(grads_g[n], g, 1e-3 if not bf16 else 2e-2, 10 * scale), n
+        losses.append(lg)
+    assert len(set(round(v, 6) for v in losses)) == len(losses), "every replay must see its own inputs"
