@@ -42,7 +42,7 @@ def parse_args():
                     help="fp32 = configs[1]; bf16 = torch.autocast(bfloat16) activations with fp32 parameters (configs[2])")
     ap.add_argument("--knn-algo", choices=["auto", "simt", "tc"], default="auto")
     ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",
-                    help="run the step as one CUDA graph (grafp_b200.training.GraphedTrainStep); auto = on at 1 GPU")
+                    help="run the step as one CUDA graph (grafp_b200.training.GraphedTrainStep); auto = on for bf16 at 1 GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-eager-on-this-GPU baseline")
     return ap.parse_args()
@@ -350,7 +350,9 @@ def run_ours(args):
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=True,
                                                         gradient_as_bucket_view=True)
-    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    # auto: the graph where the host's launch rate is the bound - one GPU, bf16 (70.8 vs 75.5 ms per step); the fp32 step
+    # is GPU-bound either way (109.7 vs 108.8 ms, profiles/r02f_*), and multi-GPU runs stay eager
+    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1 and args.dtype == "bf16")
     opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"], capturable=use_graph)
     algo = {"auto": _native.KNN_AUTO, "simt": _native.KNN_SIMT, "tc": _native.KNN_TC}[args.knn_algo]
     if algo != _native.KNN_AUTO:

@@ -41,7 +41,7 @@ enum Option {
   OPT_GATHER_ROW,        // plain gather: 1 row form (default)
   OPT_EDGE_ROW,          // EdgeConv features: 1 row form (default)
   OPT_MAXK_ROW,          // max over k: 1 row form (default)
-  OPT_BN_REVERSE,        // K5: 1 = the second pass walks the rows backwards so it starts in what L2 still holds (default 0)
+  OPT_BN_REVERSE,        // K5: 1 = first pass back to front, second pass front to back (default); 0 = the other way round
   OPT_BN_PERSISTENT,     // K5: 1 = both passes in one cooperative launch (default), 0 = two launches
   OPT_CHECK_INDEX,       // 1 = validate neighbour / centre ids against [0, M) before the aggregation kernels run
   OPT_COUNT

@@ -83,6 +83,17 @@ def get_option(name: str) -> int:
     return int(_native.load().grafp_get_option(name.encode()))
 
 
+_WARNED = set()
+
+
+def _warn_once(key: str, message: str) -> None:
+    """Performance cliffs are never silent: the first call that leaves a fast path says so (once per reason)."""
+    if key not in _WARNED:
+        _WARNED.add(key)
+        import warnings
+        warnings.warn("grafp_b200: " + message, RuntimeWarning, stacklevel=3)
+
+
 def _dtype_code(t: torch.Tensor) -> int:
     try:
         return _DTYPES[t.dtype]
@@ -225,6 +236,12 @@ def knn_graph(x: torch.Tensor, k: int, dilation: int = 1, y: Optional[torch.Tens
               out32.data_ptr() if out32 is not None else None,
               B, N, M, C, int(k), int(dilation), int(emit_all), int(normalize), dt, int(algo),
               _native.METRIC_COSINE if metric == "cosine" else _native.METRIC_L2, ws.data_ptr(), ws_bytes, _stream(xr))
+        if algo == _native.KNN_AUTO and N >= 128 and M >= 128 and C >= 32:
+            variant = lib.grafp_knn_last_variant().decode()
+            if variant != "f16x3":
+                _warn_once(f"knn-{variant}-{C % 8}-{int(normalize)}-{int(rp is not None)}",
+                           f"k-NN on (N={N}, M={M}, C={C}) took the {variant} kernel, not the fp16-plane tcgen05 path (needs "
+                           "normalised features, no relative_pos, C % 8 == 0, C >= 64, N, M >= 128): 2.7x (tf32x3) to 9x (SIMT) slower")
     return out, out32
 
 
@@ -662,6 +679,10 @@ def batch_norm_act(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = False
              and (residual is None or (residual.shape == x.shape and residual.dtype == x.dtype and _is_rows(residual)))
              and bn.weight.dtype == torch.float32)
     if not fused:
+        if _FUSED_BN and bn.training and x.is_cuda and x.numel() >= (1 << 20):
+            _warn_once(f"bn-fallback-{x.dtype}-{x.shape[1]}-{_is_rows(x)}",
+                       f"train-mode BatchNorm on a {tuple(x.shape)} {x.dtype} tensor runs the PyTorch modules (the fused kernels "
+                       "need fp32 / bf16 node rows with C / (16 bytes of channels) a power of two and an affine BatchNorm)")
         y = bn(x)
         if residual is not None:
             y = y + residual

@@ -60,7 +60,8 @@ const char* grafp_last_error(void);
  *                  3 deterministic gather over the reverse graph (fp32, k == 3, needs the workspace)
  *   "knn_epilogue" K1 selection: 0 auto (default), 1 vote-gated scan, 2 candidate queues, 3 group maxima (K <= 4)
  *   "edge_bwd_row" / "gather_row" / "edge_row" / "maxk_row": 1 = row-form kernels (default), 0 = per-edge forms
- *   "bn_reverse"   K5: 1 = the second pass walks the rows back to front to start on L2 hits (default 0: measured no gain)
+ *   "bn_reverse"   K5: 1 = first pass back to front (its input was just written front to back: the tail is in L2), second
+ *                  pass front to back (default); 0 = the other way round
  *   "bn_persistent" K5: 1 = statistics + apply in ONE cooperative launch with a grid barrier (default), 0 = two launches
  *   "check_index"  1 = grafp_check_index is run on user-supplied graphs by the Python layer (default 0)
  * grafp_set_option returns GRAFP_EINVAL for an unknown name; grafp_get_option returns the value, or GRAFP_EINVAL.
