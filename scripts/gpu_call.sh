@@ -23,6 +23,14 @@ for step in "$@"; do
              python scripts/ncu_summary.py $out/${tag}_ncu_ops.ncu-rep > $out/${tag}_ncu_ops_summary.txt 2>&1; python scripts/ncu_stalls.py $out/${tag}_ncu_ops.ncu-rep > $out/${tag}_ncu_ops_stalls.txt 2>&1; cat $out/${tag}_ncu_ops_summary.txt ;;
     bench_rev) GRAFP_BN_REVERSE=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_bnrev.json 2> $out/${tag}_bench_n1_bnrev.err; tail -c 300 $out/${tag}_bench_n1_bnrev.err; cut -c1-300 $out/${tag}_bench_n1_bnrev.json ;;
     bench_nograph) timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager --graph off > $out/${tag}_bench_n1_nograph.json 2> $out/${tag}_bench_n1_nograph.err; cut -c1-300 $out/${tag}_bench_n1_nograph.json ;;
+    launches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 1 --graph off --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_under_ncu.log 2>&1; wc -l $out/launches.csv ;;
+    ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"knn_|mr_aggregate|bn_|ntxent|peak_extract" -c 80 -f -o /tmp/prof_ops python scripts/ncu_ops.py 512 1 > $out/${tag}_ncu_ops.log 2>&1; tail -2 $out/${tag}_ncu_ops.log
+             python scripts/ncu_summary.py /tmp/prof_ops.ncu-rep > $out/${tag}_ncu_hot_kernels_summary.txt 2>&1
+             python scripts/ncu_stalls.py /tmp/prof_ops.ncu-rep > $out/${tag}_ncu_stalls.txt 2>&1
+             python scripts/dram_traffic.py /tmp/prof_ops.ncu-rep $out/${tag}_dram_traffic.json > /dev/null 2>&1
+             cp /tmp/prof_ops.ncu-rep $out/prof_ops.ncu-rep; python scripts/summarize_profiles.py ${tag} ncu_only $out > /dev/null 2>&1; rm -f $out/prof_ops.ncu-rep
+             cat $out/${tag}_ncu_hot_kernels_summary.txt ;;
+    bench_n2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > $out/${tag}_bench_n2.json 2> $out/${tag}_bench_n2.err; grep -c "Grad strides" $out/${tag}_bench_n2.err; tail -c 400 $out/${tag}_bench_n2.err; cut -c1-300 $out/${tag}_bench_n2.json ;;
     smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
     *) echo "unknown step $step" ;;
   esac

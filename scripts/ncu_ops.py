@@ -18,4 +18,15 @@ for (N, C) in [(1024, 64), (512, 128), (256, 256), (128, 512)]:
         g = torch.randn_like(y)
         (gx,) = torch.autograd.grad(y, x, g)
     torch.cuda.synchronize()
+# the 8f kernels at the bench shapes: NT-Xent on 1024 x 128 embeddings, the peak extractor on 512 segments
+from grafp_b200 import synth
+from grafp_b200.peak_extractor import GPUPeakExtractorv2
+z = torch.nn.functional.normalize(torch.randn(1024, 128, device=dev), dim=1).requires_grad_(True)
+loss = ops.ntxent(z, 0.05)
+loss.backward()
+pe = GPUPeakExtractorv2(dict(synth.DEFAULT_CFG)).to(dev)
+spec = synth.synth_spec(B, 3)[0].to(dev)
+pts = pe(spec)
+pts.sum().backward()
+torch.cuda.synchronize()
 print("done", ops.knn_last_algo())

@@ -13,6 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 SRC = os.path.join(ROOT, "gpurun_out")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+ncu_only = len(sys.argv) > 2 and sys.argv[2] == "ncu_only"   # on the GPU box: only the ncu report, written next to it
+if len(sys.argv) > 3:
+    OUT = sys.argv[3]
 os.makedirs(OUT, exist_ok=True)
 
 
@@ -37,11 +40,11 @@ def launches():
         tot[name][0] += 1
         tot[name][1] += us
         n += 1
-        if "grafp" in full or "knn_" in full or "mr_aggregate" in full:
+        if "grafp" in full or "knn_" in full or "mr_aggregate" in full or "bn_" in full or "ntxent" in full or "peak_extract" in full:
             ours.append((row["ID"], name, row.get("Grid Size", ""), row.get("Block Size", ""), f"{us:.2f}"))
     total = sum(v[1] for v in tot.values())
     with open(os.path.join(OUT, f"{tag}_launches_summary.csv"), "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 2 --warmup 1 --no-cpu-baseline\n")
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 2 --warmup 1 --graph off --no-cpu-baseline --no-gpu-eager\n")
         f.write(f"# {n} launches, {total/1e3:.1f} ms of kernel time (cold-cache, serialised: compare shares, not absolutes)\n")
         f.write("share_pct,total_ms,launches,kernel\n")
         for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
@@ -96,5 +99,6 @@ def ncu_report(rep, out_name):
     print("wrote", out_name, len(data), "launches")
 
 
-launches()
+if not ncu_only:
+    launches()
 ncu_report("prof_ops.ncu-rep", f"{tag}_ncu_hot_kernels.txt")
