@@ -43,13 +43,13 @@ SIGNATURES = {
     "grafp_ntxent_fwd": (_i, [_vp] * 4 + [_i, _i, _c.c_float, _vp]),
     "grafp_ntxent_bwd": (_i, [_vp] * 4 + [_i, _i, _c.c_float, _vp]),
     "grafp_bn_workspace_bytes": (_sz, [_i]),
-    "grafp_bn_train_fwd": (_i, [_vp] * 9 + [_c.c_longlong, _i, _c.c_float, _c.c_float, _i, _i, _vp, _sz, _vp]),
+    "grafp_bn_train_fwd": (_i, [_vp] * 11 + [_c.c_longlong, _i, _c.c_float, _c.c_float, _i, _i, _vp, _sz, _vp]),
     "grafp_bn_train_bwd": (_i, [_vp] * 10 + [_c.c_longlong, _i, _i, _i, _vp, _sz, _vp]),
 }
 
 ABI_VERSION = 5
 KNN_AUTO, KNN_SIMT, KNN_TC, KNN_TC_TF32 = 0, 1, 2, 3
-KNN_MAX_K = 64
+KNN_MAX_K = 128
 METRIC_L2, METRIC_COSINE = 0, 1
 
 _lib = None

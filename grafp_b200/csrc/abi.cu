@@ -45,7 +45,7 @@ namespace {
 struct OptionSpec { const char* name; int def; };
 const OptionSpec kOptionSpecs[OPT_COUNT] = {
     {"mr_fwd_form", 2}, {"mr_bwd_form", 2}, {"knn_epilogue", 0}, {"edge_bwd_row", 1}, {"gather_row", 1},
-    {"edge_row", 1},    {"maxk_row", 1},    {"bn_reverse", 1},   {"bn_persistent", 1}, {"check_index", 0},
+    {"edge_row", 1},    {"maxk_row", 1},    {"bn_reverse", 1},   {"bn_persistent", 1}, {"bn_l2_keep_mb", 0}, {"check_index", 0},
 };
 std::atomic<int> g_options[OPT_COUNT];
 std::once_flag g_options_once;
@@ -373,8 +373,9 @@ extern "C" {
 size_t grafp_bn_workspace_bytes(int C) { return C > 0 ? bn_workspace_bytes(C) : 0; }
 
 int grafp_bn_train_fwd(const void* x, const void* residual, const float* weight, const float* bias, float* running_mean,
-                       float* running_var, void* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
-                       float momentum, int relu, int dtype, void* workspace, size_t workspace_bytes, void* stream) {
+                       float* running_var, const float* conv_bias, long long* num_batches_tracked, void* out, float* save_mean,
+                       float* save_invstd, long long R, int C, float eps, float momentum, int relu, int dtype, void* workspace,
+                       size_t workspace_bytes, void* stream) {
   clear_error();
   GRAFP_REQUIRE(R > 1 && C > 0, GRAFP_EINVAL, "grafp_bn_train_fwd: needs at least two rows and C > 0");
   GRAFP_REQUIRE(dtype == GRAFP_F32 || dtype == GRAFP_BF16, GRAFP_EUNSUPPORTED, "grafp_bn_train_fwd: dtype %d not supported", dtype);
@@ -385,8 +386,8 @@ int grafp_bn_train_fwd(const void* x, const void* residual, const float* weight,
   GRAFP_REQUIRE(workspace_bytes >= bn_workspace_bytes(C), GRAFP_EWORKSPACE, "grafp_bn_train_fwd: workspace too small");
   { int rc = require_device("grafp_bn_train_fwd"); if (rc != GRAFP_OK) return rc; }
   { int rc = require_device_ptr("grafp_bn_train_fwd", "x", x); if (rc) return rc; }
-  return launch_bn_train_fwd(x, residual, weight, bias, running_mean, running_var, out, save_mean, save_invstd, R, C, eps,
-                             momentum, relu, dtype, workspace, static_cast<cudaStream_t>(stream));
+  return launch_bn_train_fwd(x, residual, weight, bias, running_mean, running_var, conv_bias, num_batches_tracked, out, save_mean,
+                             save_invstd, R, C, eps, momentum, relu, dtype, workspace, static_cast<cudaStream_t>(stream));
 }
 
 int grafp_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,

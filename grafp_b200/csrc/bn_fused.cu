@@ -26,11 +26,33 @@ constexpr int kBnThreads = 256;
 constexpr int kBnMaxTpr = 32;  // threads per row chunk: a block covers <= 32 * V channels, which bounds the number of
                                // red.f64 per block (blocks * channels-per-block * 2 per pass)
 
+// L2 eviction policies for the two-pass kernels: what pass 2 re-reads first is loaded "evict last" in pass 1, everything
+// that will not be touched again "evict first".
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ldg16_hint(const void* p, unsigned long long policy) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
+  return v;
+}
+
 template <typename T>
 struct Vec16;
 template <>
 struct Vec16<float> {
   static constexpr int V = 4;
+  static __device__ __forceinline__ void load_hint(const float* p, float (&v)[4], unsigned long long policy) {
+    const uint4 t = ldg16_hint(p, policy);
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+  }
   static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
     const float4 t = __ldg(reinterpret_cast<const float4*>(p));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -42,6 +64,12 @@ struct Vec16<float> {
 template <>
 struct Vec16<__nv_bfloat16> {
   static constexpr int V = 8;
+  static __device__ __forceinline__ void load_hint(const __nv_bfloat16* p, float (&v)[8], unsigned long long policy) {
+    const uint4 t = ldg16_hint(p, policy);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) { Pack8<__nv_bfloat16>::load(p, v); }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) { Pack8<__nv_bfloat16>::store(p, v); }
 };
@@ -171,6 +199,7 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ weight,
                 const float* __restrict__ bias, const double* __restrict__ sums, T* __restrict__ out,
                 float* __restrict__ save_mean, float* __restrict__ save_invstd, float* running_mean, float* running_var,
+                const float* __restrict__ conv_bias, long long* num_batches_tracked,
                 long long R, int C, int cv, float eps, float momentum, int reverse) {
   constexpr int V = Vec16<T>::V;
   const long long total = R * cv;                        // 16-byte items
@@ -182,12 +211,15 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float*
   bn_finish_stats<T, V>(x, sums, C, c, 1.0 / (double)R, eps, mu, is, var_b);
 #pragma unroll
   for (int e = 0; e < V; ++e) { a[e] = __ldg(weight + c + e) * is[e]; bb[e] = __ldg(bias + c + e); }
+  if (i0 == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
   if (i0 < cv) {  // one thread per channel pack: the saved and the running statistics
 #pragma unroll
     for (int e = 0; e < V; ++e) {
       save_mean[c + e] = mu[e];
       save_invstd[c + e] = is[e];
-      if (running_mean != nullptr) running_mean[c + e] = (1.f - momentum) * running_mean[c + e] + momentum * mu[e];
+      // conv_bias: the convolution in front ran without its bias (it cancels in x - mean); the running mean sees it
+      const float shift = conv_bias != nullptr ? __ldg(conv_bias + c + e) : 0.f;
+      if (running_mean != nullptr) running_mean[c + e] = (1.f - momentum) * running_mean[c + e] + momentum * (mu[e] + shift);
       if (running_var != nullptr) {
         const double unbiased = var_b[e] * ((double)R / (double)(R - 1));
         running_var[c + e] = (1.f - momentum) * running_var[c + e] + momentum * (float)unbiased;
@@ -381,8 +413,9 @@ __global__ void __launch_bounds__(kBnThreads)
 bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ weight,
                          const float* __restrict__ bias, double* __restrict__ sums, unsigned int* __restrict__ counter,
                          T* __restrict__ out, float* __restrict__ save_mean, float* __restrict__ save_invstd,
-                         float* running_mean, float* running_var, long long R, int C, int tpr_shift, float eps,
-                         float momentum, int first_reverse) {
+                         float* running_mean, float* running_var, const float* __restrict__ conv_bias,
+                         long long* num_batches_tracked, long long R, int C, int tpr_shift, float eps,
+                         float momentum, int first_reverse, int keep) {
   constexpr int V = Vec16<T>::V;
   __shared__ float sm[2 * V * kBnThreads];
   const int tpr = 1 << tpr_shift;
@@ -411,11 +444,18 @@ bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, con
   const long long n = r0 < R ? (R - r0 + step - 1) / step : 0;
   auto row1 = [&](long long j) { return (r0 + (first_reverse ? (n - 1 - j) : j) * step) * C; };
   auto row2 = [&](long long j) { return (r0 + (first_reverse ? j : (n - 1 - j)) * step) * C; };
+  // L2: the last `keep` rows of pass 1 are what pass 2 reads first - keep them; the rest streams through
+  const unsigned long long pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+  const long long keep_from = keep >= 0 ? (n > keep ? n - keep : 0) : n;  // keep < 0: no hints at all
   long long j = 0;
   for (; j + 3 < n; j += 4) {
     float v[4][V];
+    const unsigned long long pol = (j >= keep_from) ? pol_keep : pol_stream;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) Vec16<T>::load(xp + row1(j + u), v[u]);
+    for (int u = 0; u < 4; ++u) {
+      if (keep >= 0) Vec16<T>::load_hint(xp + row1(j + u), v[u], pol);
+      else Vec16<T>::load(xp + row1(j + u), v[u]);
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) add(v[u]);
   }
@@ -439,12 +479,14 @@ bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, con
   bn_finish_stats<T, V>(x, sums, C, c, 1.0 / (double)R, eps, mu, is, var_b);
 #pragma unroll
   for (int e = 0; e < V; ++e) { a[e] = __ldg(weight + c + e) * is[e]; bb[e] = __ldg(bias + c + e); }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
   if (blockIdx.x == 0 && rl == 0) {  // one thread per channel pack: the saved and the running statistics
 #pragma unroll
     for (int e = 0; e < V; ++e) {
       save_mean[c + e] = mu[e];
       save_invstd[c + e] = is[e];
-      if (running_mean != nullptr) running_mean[c + e] = (1.f - momentum) * running_mean[c + e] + momentum * mu[e];
+      const float shift = conv_bias != nullptr ? __ldg(conv_bias + c + e) : 0.f;
+      if (running_mean != nullptr) running_mean[c + e] = (1.f - momentum) * running_mean[c + e] + momentum * (mu[e] + shift);
       if (running_var != nullptr) {
         const double unbiased = var_b[e] * ((double)R / (double)(R - 1));
         running_var[c + e] = (1.f - momentum) * running_var[c + e] + momentum * (float)unbiased;
@@ -467,8 +509,13 @@ bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, con
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long off = row2(j + u) + c;
-      Vec16<T>::load(x + off, v[u]);
-      if (RES) Vec16<T>::load(res + off, rv[u]);
+      if (keep >= 0) {  // second and last use of x, only use of the residual: do not displace what is still to be re-read
+        Vec16<T>::load_hint(x + off, v[u], pol_stream);
+        if (RES) Vec16<T>::load_hint(res + off, rv[u], pol_stream);
+      } else {
+        Vec16<T>::load(x + off, v[u]);
+        if (RES) Vec16<T>::load(res + off, rv[u]);
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) one(v[u], rv[u], out + row2(j + u) + c);
@@ -488,7 +535,7 @@ bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
                          const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ invstd,
                          double* __restrict__ sums, unsigned int* __restrict__ counter, T* __restrict__ dx,
                          float* __restrict__ dweight, float* __restrict__ dbias, float* __restrict__ colsum, long long R,
-                         int C, int tpr_shift, int first_reverse) {
+                         int C, int tpr_shift, int first_reverse, int keep) {
   constexpr int V = Vec16<T>::V;
   __shared__ float sm[3 * V * kBnThreads];
   const int tpr = 1 << tpr_shift;
@@ -523,11 +570,17 @@ bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
   const long long n = r0 < R ? (R - r0 + step - 1) / step : 0;   // (directions: see bn_fwd_persistent_kernel)
   auto row1 = [&](long long j) { return (r0 + (first_reverse ? (n - 1 - j) : j) * step) * C; };
   auto row2 = [&](long long j) { return (r0 + (first_reverse ? j : (n - 1 - j)) * step) * C; };
+  const unsigned long long pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+  const long long keep_from = keep >= 0 ? (n > keep ? n - keep : 0) : n;
   long long j = 0;
   for (; j + 3 < n; j += 4) {
     float v[4][V], g[4][V];
+    const unsigned long long pol = (j >= keep_from) ? pol_keep : pol_stream;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { Vec16<T>::load(xp + row1(j + u), v[u]); Vec16<T>::load(gp + row1(j + u), g[u]); }
+    for (int u = 0; u < 4; ++u) {
+      if (keep >= 0) { Vec16<T>::load_hint(xp + row1(j + u), v[u], pol); Vec16<T>::load_hint(gp + row1(j + u), g[u], pol); }
+      else { Vec16<T>::load(xp + row1(j + u), v[u]); Vec16<T>::load(gp + row1(j + u), g[u]); }
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) add(v[u], g[u]);
   }
@@ -581,8 +634,8 @@ bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long off = row2(j + u) + c;
-      Vec16<T>::load(x + off, v[u]);
-      Vec16<T>::load(dy + off, g[u]);
+      if (keep >= 0) { Vec16<T>::load_hint(x + off, v[u], pol_stream); Vec16<T>::load_hint(dy + off, g[u], pol_stream); }
+      else { Vec16<T>::load(x + off, v[u]); Vec16<T>::load(dy + off, g[u]); }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) one(v[u], g[u], dx + row2(j + u) + c);
@@ -619,6 +672,18 @@ bool coop_capacity(Kernel kernel, CoopInfo& info, int* capacity) {
   return true;
 }
 
+// Rows per thread of pass 1 to load with the "evict last" policy: `mb` megabytes of L2 shared by `tensors` input tensors,
+// one row slice per (row, 16-byte pack) thread item, i.e. C * elem bytes per row.  mb <= 0: no cache hints (-1).
+int keep_rows_per_thread(int mb, int tensors, int C, size_t elem) {
+  if (mb <= 0) return -1;
+  const double rows_kept = (double)mb * 1048576.0 / ((double)tensors * C * elem);  // rows of the tensor that fit the budget
+  // a thread owns every (gx * rpp)-th row; gx * rpp is ~ (4 blocks per SM) * 256 / (C / V) rows per sweep of the grid
+  const int V = (int)(16 / elem);
+  const double rows_per_sweep = (double)num_sms() * 4 * kBnThreads / ((double)C / V);
+  const double k = rows_kept / rows_per_sweep;
+  return k < 1.0 ? 0 : (int)k;
+}
+
 int apply_grid(long long total, int cv) {
   // whole waves of 8 CTAs per SM, rounded so that grid * 256 is a multiple of cv
   long long need = (total + kBnThreads - 1) / kBnThreads;
@@ -633,8 +698,8 @@ int shift_of(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 
 template <typename T>
 int bn_fwd_t(const void* x_, const void* res_, const float* weight, const float* bias, float* running_mean, float* running_var,
-             void* out_, float* save_mean, float* save_invstd, long long R, int C, float eps, float momentum, int relu,
-             void* workspace, cudaStream_t s) {
+             const float* conv_bias, long long* nbt, void* out_, float* save_mean, float* save_invstd, long long R, int C,
+             float eps, float momentum, int relu, void* workspace, cudaStream_t s) {
   constexpr int V = Vec16<T>::V;
   BnGeom g;
   if (!bn_geometry(R, C, V, &g)) { set_error("bn_train_fwd: needs C %% %d == 0, C/%d a power of two and at least 2 rows", V, V); return GRAFP_EUNSUPPORTED; }
@@ -649,9 +714,11 @@ int bn_fwd_t(const void* x_, const void* res_, const float* weight, const float*
   if (option(OPT_BN_PERSISTENT) != 0) {
     int tsh = shift_of(g.tpr);
     int first_reverse = option(OPT_BN_REVERSE) != 0;
+    int keep = keep_rows_per_thread(option(OPT_BN_L2_KEEP_MB), 1, C, sizeof(T));
     void* args[] = {(void*)&x, (void*)&res, (void*)&weight, (void*)&bias, (void*)&sums, (void*)&counter, (void*)&out,
-                    (void*)&save_mean, (void*)&save_invstd, (void*)&running_mean, (void*)&running_var, (void*)&R, (void*)&C,
-                    (void*)&tsh, (void*)&eps, (void*)&momentum, (void*)&first_reverse};
+                    (void*)&save_mean, (void*)&save_invstd, (void*)&running_mean, (void*)&running_var, (void*)&conv_bias,
+                    (void*)&nbt, (void*)&R, (void*)&C, (void*)&tsh, (void*)&eps, (void*)&momentum, (void*)&first_reverse,
+                    (void*)&keep};
     auto try_launch = [&](auto kernel, CoopInfo& info) -> int {
       int cap = 0;
       if (!coop_capacity(kernel, info, &cap)) return -1;
@@ -675,7 +742,8 @@ int bn_fwd_t(const void* x_, const void* res_, const float* weight, const float*
   const int rev = option(OPT_BN_REVERSE) != 0;
 #define GRAFP_BN_APPLY(RELU_, RES_)                                                                                        \
   bn_apply_kernel<T, RELU_, RES_><<<grid, kBnThreads, 0, s>>>(x, res, weight, bias, sums, out, save_mean, save_invstd,      \
-                                                            running_mean, running_var, R, C, g.cv, eps, momentum, rev)
+                                                            running_mean, running_var, conv_bias, nbt, R, C, g.cv, eps,  \
+                                                            momentum, rev)
   if (relu) GRAFP_BN_APPLY(true, false);
   else if (res) GRAFP_BN_APPLY(false, true);
   else GRAFP_BN_APPLY(false, false);
@@ -700,9 +768,10 @@ int bn_bwd_t(const void* dy_, const void* x_, const float* weight, const float* 
   int tsh = shift_of(g.tpr);
   if (option(OPT_BN_PERSISTENT) != 0) {
     int first_reverse = option(OPT_BN_REVERSE) != 0;
+    int keep = keep_rows_per_thread(option(OPT_BN_L2_KEEP_MB), 2, C, sizeof(T));
     void* args[] = {(void*)&dy, (void*)&x, (void*)&weight, (void*)&bias, (void*)&save_mean, (void*)&save_invstd, (void*)&sums,
                     (void*)&counter, (void*)&dx, (void*)&dweight, (void*)&dbias, (void*)&dx_colsum, (void*)&R, (void*)&C,
-                    (void*)&tsh, (void*)&first_reverse};
+                    (void*)&tsh, (void*)&first_reverse, (void*)&keep};
     auto try_launch = [&](auto kernel, CoopInfo& info) -> int {
       int cap = 0;
       if (!coop_capacity(kernel, info, &cap)) return -1;
@@ -738,11 +807,14 @@ bool bn_supported(long long R, int C, int dtype) {
 }
 
 int launch_bn_train_fwd(const void* x, const void* res, const float* weight, const float* bias, float* running_mean,
-                        float* running_var, void* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
-                        float momentum, int relu, int dtype, void* workspace, cudaStream_t s) {
+                        float* running_var, const float* conv_bias, long long* num_batches_tracked, void* out, float* save_mean,
+                        float* save_invstd, long long R, int C, float eps, float momentum, int relu, int dtype, void* workspace,
+                        cudaStream_t s) {
   if (dtype == GRAFP_F32)
-    return bn_fwd_t<float>(x, res, weight, bias, running_mean, running_var, out, save_mean, save_invstd, R, C, eps, momentum, relu, workspace, s);
-  return bn_fwd_t<__nv_bfloat16>(x, res, weight, bias, running_mean, running_var, out, save_mean, save_invstd, R, C, eps, momentum, relu, workspace, s);
+    return bn_fwd_t<float>(x, res, weight, bias, running_mean, running_var, conv_bias, num_batches_tracked, out, save_mean,
+                           save_invstd, R, C, eps, momentum, relu, workspace, s);
+  return bn_fwd_t<__nv_bfloat16>(x, res, weight, bias, running_mean, running_var, conv_bias, num_batches_tracked, out, save_mean,
+                                 save_invstd, R, C, eps, momentum, relu, workspace, s);
 }
 
 int launch_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,

@@ -43,6 +43,7 @@ enum Option {
   OPT_MAXK_ROW,          // max over k: 1 row form (default)
   OPT_BN_REVERSE,        // K5: 1 = first pass back to front, second pass front to back (default); 0 = the other way round
   OPT_BN_PERSISTENT,     // K5: 1 = both passes in one cooperative launch (default), 0 = two launches
+  OPT_BN_L2_KEEP_MB,     // K5: megabytes of pass-1 input kept in L2 ("evict last") for pass 2; 0 = no cache hints
   OPT_CHECK_INDEX,       // 1 = validate neighbour / centre ids against [0, M) before the aggregation kernels run
   OPT_COUNT
 };
@@ -226,8 +227,9 @@ int launch_check_index(const void* idx, int idx_is_i64, long long count, int lim
 size_t bn_workspace_bytes(int C);
 bool bn_supported(long long R, int C, int dtype);
 int launch_bn_train_fwd(const void* x, const void* res, const float* weight, const float* bias, float* running_mean,
-                        float* running_var, void* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
-                        float momentum, int relu, int dtype, void* workspace, cudaStream_t s);
+                        float* running_var, const float* conv_bias, long long* num_batches_tracked, void* out, float* save_mean,
+                        float* save_invstd, long long R, int C, float eps, float momentum, int relu, int dtype, void* workspace,
+                        cudaStream_t s);
 int launch_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,
                         const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
                         int relu, int dtype, void* workspace, cudaStream_t s);

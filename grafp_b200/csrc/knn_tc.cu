@@ -25,7 +25,7 @@ constexpr int BK = 32;         // fp32 per k-chunk = one 128-byte swizzle-atom r
 constexpr int UMMA_K = 8;      // kind::tf32
 constexpr int kThreads = 192;
 constexpr int kEpilogueThreads = 128;
-constexpr int kMaxListK = GRAFP_KNN_MAX_K;
+constexpr int kMaxListK = 64;  // this first-generation kernel keeps whole K-entry lists in shared memory
 
 template <int BN, int KREG>
 struct Cfg {
@@ -330,7 +330,7 @@ EncodeTiledFn encode_tiled_fn() {
 
 bool knn_tc_supported(int N, int M, int C, int K, int dtype) {
   // (the tf32 planes live in fp32 containers whatever the input dtype: the normalise kernel reads fp32 or bf16 rows)
-  return (dtype == GRAFP_F32 || dtype == GRAFP_BF16) && C % 4 == 0 && C >= 32 && N >= 128 && M >= 128 && K >= 1 && K <= GRAFP_KNN_MAX_K;
+  return (dtype == GRAFP_F32 || dtype == GRAFP_BF16) && C % 4 == 0 && C >= 32 && N >= 128 && M >= 128 && K >= 1 && K <= tc::kMaxListK;
 }
 
 int launch_knn_tc(const void* xhi, const void* xlo, const float* xsq, const void* yhi, const void* ylo,

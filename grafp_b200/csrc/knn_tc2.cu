@@ -884,7 +884,7 @@ static Plan plan(int N, int M, int C, int K, int dtype, bool self) {
 static Plan plan_with(int N, int M, int C, int K, int dtype, bool self, bool allow_group_max) {
   Plan p;
   // (dtype: the planes are fp16 whatever the input was - the normalise kernel reads fp32 or bf16 rows)
-  if ((dtype != GRAFP_F32 && dtype != GRAFP_BF16) || C % 8 != 0 || C < BK || N < BM || M < BM || K < 1 || K > 64) return p;
+  if ((dtype != GRAFP_F32 && dtype != GRAFP_BF16) || C % 8 != 0 || C < BK || N < BM || M < BM || K < 1 || K > GRAFP_KNN_MAX_K) return p;
   // Which selection epilogue.  K > 8 (16-entry lists, rounds) exists in the candidate-queue form only.  For K <= 8 both
   // exist and neither dominates: on features with independent rows (random point clouds: scripts/bench_ops.py, the
   // configs[3] stress) the queue form is faster (stage 0: 385 vs 429 us) because some lane of a warp has a candidate

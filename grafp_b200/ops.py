@@ -609,7 +609,7 @@ def _bn_kernel_ok(t: torch.Tensor, C: int) -> bool:
     return C % v == 0 and ((C // v) & (C // v - 1)) == 0
 
 
-def _bn_fwd_call(lib, h, residual, weight, bias, running_mean, running_var, eps, momentum, relu):
+def _bn_fwd_call(lib, h, residual, weight, bias, running_mean, running_var, eps, momentum, relu, conv_bias=None, nbt=None):
     B, C, N, _ = h.shape
     out = _new_rows(B, C, N, h)
     save_mean = torch.empty(C, dtype=torch.float32, device=h.device)
@@ -621,6 +621,8 @@ def _bn_fwd_call(lib, h, residual, weight, bias, running_mean, running_var, eps,
           weight.data_ptr(), bias.data_ptr(),
           running_mean.data_ptr() if running_mean is not None else None,
           running_var.data_ptr() if running_var is not None else None,
+          conv_bias.data_ptr() if conv_bias is not None and running_mean is not None else None,
+          nbt.data_ptr() if nbt is not None else None,
           out.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(), B * N, C, float(eps), float(momentum),
           int(relu), _dtype_code(h), ws.data_ptr(), ws_bytes, _stream(h))
     return out, save_mean, save_invstd
@@ -644,10 +646,10 @@ def _bn_bwd_call(lib, g, h, weight, bias, save_mean, save_invstd, relu, want_col
 
 class _BatchNormTrain(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, running_mean, running_var, eps, momentum, relu):
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, eps, momentum, relu, nbt):
         lib = _native.load()
         out, save_mean, save_invstd = _bn_fwd_call(lib, x, residual, weight, bias, running_mean, running_var, eps,
-                                                   momentum, relu)
+                                                   momentum, relu, None, nbt)
         ctx.save_for_backward(x, weight, bias, save_mean, save_invstd)
         ctx.relu = bool(relu)
         ctx.has_res = residual is not None
@@ -660,7 +662,16 @@ class _BatchNormTrain(torch.autograd.Function):
         g = as_rows(grad_out.to(x.dtype))
         dx, dweight, dbias, _ = _bn_bwd_call(lib, g, x, weight, bias, save_mean, save_invstd, ctx.relu, False)
         return (dx, (grad_out if ctx.has_res else None), dweight.to(weight.dtype), dbias.to(bias.dtype), None, None, None,
-                None, None)
+                None, None, None)
+
+
+def _nbt(bn: torch.nn.BatchNorm2d) -> Optional[torch.Tensor]:
+    """The module's num_batches_tracked counter when the kernel can bump it in place (a CUDA int64 scalar)."""
+    t = bn.num_batches_tracked if bn.track_running_stats else None
+    if t is not None and not (t.is_cuda and t.dtype == torch.int64):
+        t.add_(1)
+        return None
+    return t
 
 
 def batch_norm_act(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = False,
@@ -687,11 +698,9 @@ def batch_norm_act(x: torch.Tensor, bn: torch.nn.BatchNorm2d, relu: bool = False
         if residual is not None:
             y = y + residual
         return torch.relu(y) if relu else y
-    if bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
-    return _BatchNormTrain.apply(x, residual, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, relu)
+    return _BatchNormTrain.apply(x, residual, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, relu, _nbt(bn))
 
 
 def grad_with_param_strides(grad: torch.Tensor, param: torch.Tensor) -> torch.Tensor:
@@ -749,7 +758,7 @@ class _ConvBatchNormTrain(torch.autograd.Function):
     (what autocast itself does) and the weight gradient is returned in the parameter's dtype."""
 
     @staticmethod
-    def forward(ctx, x, residual, cw, cb, weight, bias, running_mean, running_var, eps, momentum, relu, conv_args):
+    def forward(ctx, x, residual, cw, cb, weight, bias, running_mean, running_var, eps, momentum, relu, conv_args, nbt):
         lib = _native.load()
         stride, padding, dilation, groups = conv_args
         with torch.autocast("cuda", enabled=False):
@@ -763,11 +772,12 @@ class _ConvBatchNormTrain(torch.autograd.Function):
         if residual is not None and residual.shape != h.shape:
             raise RuntimeError(f"grafp_b200.conv_batch_norm_act: residual {tuple(residual.shape)} does not match the "
                                f"convolution output {tuple(h.shape)}")
+        # running_mean <- (1 - m) running_mean + m (mean(h) + cb): the kernel adds the bias the convolution skipped
+        cb32 = cb.detach() if cb is not None else None
+        if cb32 is not None and cb32.dtype != torch.float32:
+            cb32 = cb32.float()
         out, save_mean, save_invstd = _bn_fwd_call(lib, h, residual, weight, bias, running_mean, running_var, eps,
-                                                   momentum, relu)
-        if running_mean is not None and cb is not None:
-            # running_mean <- (1 - m) running_mean + m (mean(h) + cb): the kernel did the first two terms
-            running_mean.add_(cb.detach().to(running_mean.dtype), alpha=float(momentum))
+                                                   momentum, relu, cb32, nbt)
         ctx.save_for_backward(x, cw, h, weight, bias, save_mean, save_invstd)
         ctx.relu = bool(relu)
         ctx.has_res = residual is not None
@@ -798,7 +808,7 @@ class _ConvBatchNormTrain(torch.autograd.Function):
         if dcw is not None:
             dcw = grad_with_param_strides(dcw, cw)
         return (dx, (grad_out if ctx.has_res else None), dcw, dcb, dweight.to(weight.dtype), dbias.to(bias.dtype),
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None)
 
 
 def _fold_eval_ok(x: torch.Tensor, bn: torch.nn.BatchNorm2d) -> bool:
@@ -866,11 +876,10 @@ def pointwise_conv_batch_norm_act(x, cw, cb, bn, relu=False, residual=None, conv
     if not fused:
         return batch_norm_act(torch.nn.functional.conv2d(x, cw, cb, stride, padding, dilation, groups), bn, relu=relu,
                               residual=residual)
-    if bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
     rm = bn.running_mean if bn.track_running_stats else None
     rv = bn.running_var if bn.track_running_stats else None
-    return _ConvBatchNormTrain.apply(x, residual, cw, cb, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, relu, conv_args)
+    return _ConvBatchNormTrain.apply(x, residual, cw, cb, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, relu, conv_args,
+                                     _nbt(bn))
 
 
 def downsample_rows(x: torch.Tensor, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d) -> Optional[torch.Tensor]:

@@ -46,7 +46,7 @@ extern "C" {
 #define GRAFP_KNN_TC 2   /* TMA + tcgen05 + fused top-k: the f16x3 kernels when K <= 8, else the tf32x3 kernel */
 #define GRAFP_KNN_TC_TF32 3 /* force the first-generation tf32x3 tcgen05 kernel (cross-check)          */
 
-#define GRAFP_KNN_MAX_K 64 /* k * dilation */
+#define GRAFP_KNN_MAX_K 128 /* k * dilation: the reference caps dilation at 128 // k (graph_encoder.py:128) */
 
 int grafp_abi_version(void);
 const char* grafp_last_error(void);
@@ -63,6 +63,8 @@ const char* grafp_last_error(void);
  *   "bn_reverse"   K5: 1 = first pass back to front (its input was just written front to back: the tail is in L2), second
  *                  pass front to back (default); 0 = the other way round
  *   "bn_persistent" K5: 1 = statistics + apply in ONE cooperative launch with a grid barrier (default), 0 = two launches
+ *   "bn_l2_keep_mb" K5: megabytes of the first pass's input loaded "evict last" so the second pass finds them in L2
+ *                  (the rest of both passes is loaded "evict first"); 0 = no cache hints
  *   "check_index"  1 = grafp_check_index is run on user-supplied graphs by the Python layer (default 0)
  * grafp_set_option returns GRAFP_EINVAL for an unknown name; grafp_get_option returns the value, or GRAFP_EINVAL.
  */
@@ -198,6 +200,9 @@ int grafp_max_over_k_bwd(const void* grad_out, const uint8_t* argmax, void* grad
  *            and the unbiased variance, like torch.nn.functional.batch_norm(training=True);
  *            out = (x - mean) * invstd * weight + bias  [+ residual]  [ReLU when relu != 0]
  *            (relu together with a residual is not implemented).
+ *            conv_bias (C floats, may be NULL): bias of a convolution in front of the BatchNorm that was run WITHOUT it
+ *            (a per-channel constant cancels in x - mean): it is added to the mean that enters running_mean.
+ *            num_batches_tracked (device int64, may be NULL): incremented by one, like nn.BatchNorm2d does.
  *  backward: dz = dy masked by the ReLU (recomputed from x, no output is kept); dbias = sum dz,
  *            dweight = sum dz * xhat, dx = weight * invstd * (dz - dbias / R - xhat * dweight / R).
  *            The gradient of the residual input is dy itself and is not written here.
@@ -210,8 +215,9 @@ int grafp_max_over_k_bwd(const void* grad_out, const uint8_t* argmax, void* grad
  */
 size_t grafp_bn_workspace_bytes(int C);
 int grafp_bn_train_fwd(const void* x, const void* residual, const float* weight, const float* bias, float* running_mean,
-                       float* running_var, void* out, float* save_mean, float* save_invstd, long long R, int C, float eps,
-                       float momentum, int relu, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+                       float* running_var, const float* conv_bias, long long* num_batches_tracked, void* out, float* save_mean,
+                       float* save_invstd, long long R, int C, float eps, float momentum, int relu, int dtype, void* workspace,
+                       size_t workspace_bytes, void* stream);
 int grafp_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,
                        const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
                        int relu, int dtype, void* workspace, size_t workspace_bytes, void* stream);

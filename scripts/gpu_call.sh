@@ -22,6 +22,8 @@ for step in "$@"; do
     ncu_ops) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"knn_|mr_aggregate|bn_" -c 60 -f -o $out/${tag}_ncu_ops python scripts/ncu_ops.py 512 1 > $out/${tag}_ncu_ops.log 2>&1; tail -3 $out/${tag}_ncu_ops.log
              python scripts/ncu_summary.py $out/${tag}_ncu_ops.ncu-rep > $out/${tag}_ncu_ops_summary.txt 2>&1; python scripts/ncu_stalls.py $out/${tag}_ncu_ops.ncu-rep > $out/${tag}_ncu_ops_stalls.txt 2>&1; cat $out/${tag}_ncu_ops_summary.txt ;;
     bench_rev) GRAFP_BN_REVERSE=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_bnrev.json 2> $out/${tag}_bench_n1_bnrev.err; tail -c 300 $out/${tag}_bench_n1_bnrev.err; cut -c1-300 $out/${tag}_bench_n1_bnrev.json ;;
+    bench_l2) GRAFP_BN_L2_KEEP_MB=48 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_l2keep48.json 2> $out/${tag}_bench_n1_l2keep48.err; tail -c 300 $out/${tag}_bench_n1_l2keep48.err; cut -c1-300 $out/${tag}_bench_n1_l2keep48.json
+              GRAFP_BN_L2_KEEP_MB=80 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_l2keep80.json 2> $out/${tag}_bench_n1_l2keep80.err; cut -c1-300 $out/${tag}_bench_n1_l2keep80.json ;;
     bench_nograph) timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager --graph off > $out/${tag}_bench_n1_nograph.json 2> $out/${tag}_bench_n1_nograph.err; cut -c1-300 $out/${tag}_bench_n1_nograph.json ;;
     launches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 1 --graph off --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_under_ncu.log 2>&1; wc -l $out/launches.csv ;;
     ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"knn_|mr_aggregate|bn_|ntxent|peak_extract" -c 80 -f -o /tmp/prof_ops python scripts/ncu_ops.py 512 1 > $out/${tag}_ncu_ops.log 2>&1; tail -2 $out/${tag}_ncu_ops.log

@@ -35,7 +35,7 @@ def _exact_fp32_library_math():
 
 
 _OPTION_DEFAULTS = {"mr_fwd_form": 2, "mr_bwd_form": 2, "knn_epilogue": 0, "edge_bwd_row": 1, "gather_row": 1, "edge_row": 1,
-                    "maxk_row": 1, "bn_reverse": 1, "bn_persistent": 1, "check_index": 0}
+                    "maxk_row": 1, "bn_reverse": 1, "bn_persistent": 1, "bn_l2_keep_mb": 0, "check_index": 0}
 
 
 @pytest.fixture(autouse=True)
@@ -191,6 +191,8 @@ TC_CASES = [
     (2, 256, 256, 0, 16, 1),    # whole-segment self kernel (two halves) with 16-entry lists
     (2, 512, 128, 0, 12, 2),    # whole-segment self kernel (one half), K = 24
     (2, 256, 1024, 0, 16, 3),   # K = 48, one resident query block, 4 channel chunks
+    (2, 64, 512, 0, 32, 4),     # K = 128 (the reference's ceiling, dilation <= 128 // k): eight rounds of 16 ranks
+    (1, 128, 256, 0, 12, 8),    # K = 96 in the whole-segment self kernel
 ]
 
 
@@ -202,15 +204,26 @@ def test_knn_tensor_core_path_vs_oracle(B, C, N, M, k, d, algo):
     if algo in ("queue", "vote", "group-max"):
         ops.set_option("knn_epilogue", {"vote": 1, "queue": 2, "group-max": 3}[algo])
         algo = _native.KNN_TC
+    if algo == _native.KNN_TC_TF32 and k * d > 64:
+        pytest.skip("the first-generation tf32x3 kernel keeps K <= 64 lists in shared memory")
     x = synth.synth_point_cloud(B, C, N, 3000 + N + C)
     y = synth.synth_point_cloud(B, C, M, 4000 + M) if M else None
     nn_idx, _ = ops.knn_graph(x.to(DEV), k, d, None if y is None else y.to(DEV), algo=algo)
     assert ops.knn_last_algo() == "tcgen05"
     if algo == _native.KNN_TC_TF32:
         assert ops.knn_last_variant() == "tf32x3"
-    elif k * d <= 64 and C >= 64 and C % 8 == 0 and N >= 128 and (M == 0 or M >= 128):
+    elif k * d <= 128 and C >= 64 and C % 8 == 0 and N >= 128 and (M == 0 or M >= 128):
         assert ops.knn_last_variant() == "f16x3", (B, C, N, M, k, d)
     assert_knn_ok(x, nn_idx, k, d, y, what=f"tc N={N} M={M} C={C} k={k} d={d} {ops.knn_last_variant()}")
+
+
+def test_knn_k128_simt_and_with_relative_pos():
+    """K = k * dilation = 128 (the reference's ceiling) on the exact-fp32 SIMT kernel, with a relative_pos bias."""
+    B, C, N, k, d = 2, 24, 300, 16, 8
+    x = synth.synth_point_cloud(B, C, N, 8100)
+    rp = 0.05 * torch.randn(1, N, N, generator=torch.Generator().manual_seed(3))
+    nn_idx, _ = ops.knn_graph(x.to(DEV), k, d, relative_pos=rp.to(DEV), algo=_native.KNN_SIMT)
+    assert_knn_ok(x, nn_idx, k, d, rp=rp, what="K=128 simt relpos")
 
 
 @pytest.mark.parametrize("epilogue", [0, 1, 3])
@@ -281,8 +294,8 @@ def test_knn_errors():
     x = torch.randn(1, 8, 16, 1, device=DEV)
     with pytest.raises(RuntimeError, match="exceeds the number of key nodes"):
         ops.knn_graph(x, 17)
-    with pytest.raises(RuntimeError, match="exceeds 64"):
-        ops.knn_graph(torch.randn(1, 8, 256, 1, device=DEV), 33, 2)
+    with pytest.raises(RuntimeError, match="exceeds 128"):
+        ops.knn_graph(torch.randn(1, 8, 256, 1, device=DEV), 43, 3)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.knn_graph(x.cpu(), 3)
     with pytest.raises(RuntimeError, match="not supported"):
