@@ -45,7 +45,7 @@ namespace {
 struct OptionSpec { const char* name; int def; };
 const OptionSpec kOptionSpecs[OPT_COUNT] = {
     {"mr_fwd_form", 2}, {"mr_bwd_form", 2}, {"knn_epilogue", 0}, {"edge_bwd_row", 1}, {"gather_row", 1},
-    {"edge_row", 1},    {"maxk_row", 1},    {"bn_reverse", 1},   {"bn_persistent", 1}, {"bn_l2_keep_mb", 0}, {"check_index", 0},
+    {"edge_row", 1},    {"maxk_row", 1},    {"bn_reverse", 1},   {"bn_persistent", 1}, {"bn_l2_keep_mb", 80}, {"check_index", 0},
 };
 std::atomic<int> g_options[OPT_COUNT];
 std::once_flag g_options_once;

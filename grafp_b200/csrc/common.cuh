@@ -43,7 +43,7 @@ enum Option {
   OPT_MAXK_ROW,          // max over k: 1 row form (default)
   OPT_BN_REVERSE,        // K5: 1 = first pass back to front, second pass front to back (default); 0 = the other way round
   OPT_BN_PERSISTENT,     // K5: 1 = both passes in one cooperative launch (default), 0 = two launches
-  OPT_BN_L2_KEEP_MB,     // K5: megabytes of pass-1 input kept in L2 ("evict last") for pass 2; 0 = no cache hints
+  OPT_BN_L2_KEEP_MB,     // K5: megabytes of pass-1 input kept in L2 ("evict last") for pass 2 (default 80); 0 = no cache hints
   OPT_CHECK_INDEX,       // 1 = validate neighbour / centre ids against [0, M) before the aggregation kernels run
   OPT_COUNT
 };

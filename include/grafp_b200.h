@@ -64,7 +64,7 @@ const char* grafp_last_error(void);
  *                  pass front to back (default); 0 = the other way round
  *   "bn_persistent" K5: 1 = statistics + apply in ONE cooperative launch with a grid barrier (default), 0 = two launches
  *   "bn_l2_keep_mb" K5: megabytes of the first pass's input loaded "evict last" so the second pass finds them in L2
- *                  (the rest of both passes is loaded "evict first"); 0 = no cache hints
+ *                  (the rest of both passes is loaded "evict first"); default 80, 0 = no cache hints
  *   "check_index"  1 = grafp_check_index is run on user-supplied graphs by the Python layer (default 0)
  * grafp_set_option returns GRAFP_EINVAL for an unknown name; grafp_get_option returns the value, or GRAFP_EINVAL.
  */

@@ -35,7 +35,7 @@ def _exact_fp32_library_math():
 
 
 _OPTION_DEFAULTS = {"mr_fwd_form": 2, "mr_bwd_form": 2, "knn_epilogue": 0, "edge_bwd_row": 1, "gather_row": 1, "edge_row": 1,
-                    "maxk_row": 1, "bn_reverse": 1, "bn_persistent": 1, "bn_l2_keep_mb": 0, "check_index": 0}
+                    "maxk_row": 1, "bn_reverse": 1, "bn_persistent": 1, "bn_l2_keep_mb": 80, "check_index": 0}
 
 
 @pytest.fixture(autouse=True)
@@ -614,14 +614,20 @@ def assert_grads_as_accurate_as_reference(ours, ref32, ref64, names, slack=4.0):
     BatchNorm as well as with the fused one, and the worst parameter sits at 3.2 (PyTorch BN) / 4.2 (fused BN)
     x e_ref, i.e. 0.9 / 1.18 of a slack-3 bound: rounding noise of equally valid fp32 evaluations."""
     scale = max(float(ref64[n].double().norm()) for n in names)
-    worst = 0.0
+    worst, ratios = 0.0, []
     for n in names:
         g64 = ref64[n].double()
         denom = max(float(g64.norm()), 0.1 * scale)
         e_ours = float((ours[n].double().cpu() - g64).norm()) / denom
         e_ref = float((ref32[n].double() - g64).norm()) / denom
-        assert e_ours <= slack * e_ref + REL_TOL, (n, e_ours, e_ref)
+        ratios.append((e_ours / max(e_ref, 1e-12), n, e_ours, e_ref))
         worst = max(worst, e_ours)
+    ratios.sort(reverse=True)
+    med = ratios[len(ratios) // 2][0]
+    print(f"gradient accuracy vs the fp64 oracle: median e_ours / e_ref32 = {med:.2f}; worst three: "
+          + ", ".join(f"{n} {r:.2f}x (e_ours {eo:.2e}, e_ref32 {er:.2e})" for r, n, eo, er in ratios[:3]))
+    for r, n, e_ours, e_ref in ratios:
+        assert e_ours <= slack * e_ref + REL_TOL, (n, e_ours, e_ref)
     return worst
 
 
