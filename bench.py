@@ -352,7 +352,9 @@ def run_ours(args):
                                                         gradient_as_bucket_view=True)
     # auto: the graph where the host's launch rate is the bound - one GPU, bf16 (70.8 vs 75.5 ms per step); the fp32 step
     # is GPU-bound either way (109.7 vs 108.8 ms, profiles/r02f_*), and multi-GPU runs stay eager
-    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1 and args.dtype == "bf16")
+    # (DistributedDataParallel's reducer touches the legacy stream during a whole-step capture - measured: capture fails with
+    # cudaErrorStreamCaptureImplicit - so the graph is a one-GPU feature here)
+    use_graph = world == 1 and (args.graph == "on" or (args.graph == "auto" and args.dtype == "bf16"))
     opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"], capturable=use_graph)
     algo = {"auto": _native.KNN_AUTO, "simt": _native.KNN_SIMT, "tc": _native.KNN_TC}[args.knn_algo]
     if algo != _native.KNN_AUTO:
