@@ -49,6 +49,13 @@ struct Vec16;
 template <>
 struct Vec16<float> {
   static constexpr int V = 4;
+  // raw 16-byte loads: the unrolled loops keep the packed registers in flight and unpack at use (for bf16 the unpacked
+  // form is twice the registers: 174 per thread and one block per SM before this)
+  static __device__ __forceinline__ uint4 load_raw(const float* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ uint4 load_raw_hint(const float* p, unsigned long long policy) { return ldg16_hint(p, policy); }
+  static __device__ __forceinline__ void unpack(const uint4& t, float (&v)[4]) {
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+  }
   static __device__ __forceinline__ void load_hint(const float* p, float (&v)[4], unsigned long long policy) {
     const uint4 t = ldg16_hint(p, policy);
     v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
@@ -64,6 +71,13 @@ struct Vec16<float> {
 template <>
 struct Vec16<__nv_bfloat16> {
   static constexpr int V = 8;
+  static __device__ __forceinline__ uint4 load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  static __device__ __forceinline__ uint4 load_raw_hint(const __nv_bfloat16* p, unsigned long long policy) { return ldg16_hint(p, policy); }
+  static __device__ __forceinline__ void unpack(const uint4& t, float (&v)[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
   static __device__ __forceinline__ void load_hint(const __nv_bfloat16* p, float (&v)[8], unsigned long long policy) {
     const uint4 t = ldg16_hint(p, policy);
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
@@ -409,7 +423,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 }
 
 template <typename T, bool RELU, bool RES>
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, sizeof(T) == 4 ? 4 : 3)
 bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ weight,
                          const float* __restrict__ bias, double* __restrict__ sums, unsigned int* __restrict__ counter,
                          T* __restrict__ out, float* __restrict__ save_mean, float* __restrict__ save_invstd,
@@ -449,15 +463,17 @@ bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, con
   const long long keep_from = keep >= 0 ? (n > keep ? n - keep : 0) : n;  // keep < 0: no hints at all
   long long j = 0;
   for (; j + 3 < n; j += 4) {
-    float v[4][V];
+    uint4 raw[4];
     const unsigned long long pol = (j >= keep_from) ? pol_keep : pol_stream;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (keep >= 0) Vec16<T>::load_hint(xp + row1(j + u), v[u], pol);
-      else Vec16<T>::load(xp + row1(j + u), v[u]);
-    }
+    for (int u = 0; u < 4; ++u)
+      raw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(xp + row1(j + u), pol) : Vec16<T>::load_raw(xp + row1(j + u));
 #pragma unroll
-    for (int u = 0; u < 4; ++u) add(v[u]);
+    for (int u = 0; u < 4; ++u) {
+      float v[V];
+      Vec16<T>::unpack(raw[u], v);
+      add(v);
+    }
   }
   for (; j < n; ++j) {
     float v[V];
@@ -505,20 +521,21 @@ bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, con
   };
   j = 0;
   for (; j + 3 < n; j += 4) {
-    float v[4][V], rv[4][V];
+    uint4 raw[4], rraw[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long off = row2(j + u) + c;
-      if (keep >= 0) {  // second and last use of x, only use of the residual: do not displace what is still to be re-read
-        Vec16<T>::load_hint(x + off, v[u], pol_stream);
-        if (RES) Vec16<T>::load_hint(res + off, rv[u], pol_stream);
-      } else {
-        Vec16<T>::load(x + off, v[u]);
-        if (RES) Vec16<T>::load(res + off, rv[u]);
-      }
+      // second and last use of x, only use of the residual: do not displace what is still to be re-read
+      raw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(x + off, pol_stream) : Vec16<T>::load_raw(x + off);
+      if (RES) rraw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(res + off, pol_stream) : Vec16<T>::load_raw(res + off);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) one(v[u], rv[u], out + row2(j + u) + c);
+    for (int u = 0; u < 4; ++u) {
+      float v[V], rv[V];
+      Vec16<T>::unpack(raw[u], v);
+      if (RES) Vec16<T>::unpack(rraw[u], rv);
+      one(v, rv, out + row2(j + u) + c);
+    }
   }
   for (; j < n; ++j) {
     float v[V], rv[V];
@@ -530,7 +547,7 @@ bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, con
 }
 
 template <typename T, bool RELU>
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, sizeof(T) == 4 ? 3 : 2)
 bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ weight,
                          const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ invstd,
                          double* __restrict__ sums, unsigned int* __restrict__ counter, T* __restrict__ dx,
@@ -574,15 +591,20 @@ bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
   const long long keep_from = keep >= 0 ? (n > keep ? n - keep : 0) : n;
   long long j = 0;
   for (; j + 3 < n; j += 4) {
-    float v[4][V], g[4][V];
+    uint4 raw[4], graw[4];
     const unsigned long long pol = (j >= keep_from) ? pol_keep : pol_stream;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (keep >= 0) { Vec16<T>::load_hint(xp + row1(j + u), v[u], pol); Vec16<T>::load_hint(gp + row1(j + u), g[u], pol); }
-      else { Vec16<T>::load(xp + row1(j + u), v[u]); Vec16<T>::load(gp + row1(j + u), g[u]); }
+      raw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(xp + row1(j + u), pol) : Vec16<T>::load_raw(xp + row1(j + u));
+      graw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(gp + row1(j + u), pol) : Vec16<T>::load_raw(gp + row1(j + u));
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) add(v[u], g[u]);
+    for (int u = 0; u < 4; ++u) {
+      float v[V], g[V];
+      Vec16<T>::unpack(raw[u], v);
+      Vec16<T>::unpack(graw[u], g);
+      add(v, g);
+    }
   }
   for (; j < n; ++j) {
     float v[V], g[V];
@@ -630,15 +652,20 @@ bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
   };
   j = 0;
   for (; j + 3 < n; j += 4) {
-    float v[4][V], g[4][V];
+    uint4 raw[4], graw[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long off = row2(j + u) + c;
-      if (keep >= 0) { Vec16<T>::load_hint(x + off, v[u], pol_stream); Vec16<T>::load_hint(dy + off, g[u], pol_stream); }
-      else { Vec16<T>::load(x + off, v[u]); Vec16<T>::load(dy + off, g[u]); }
+      raw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(x + off, pol_stream) : Vec16<T>::load_raw(x + off);
+      graw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(dy + off, pol_stream) : Vec16<T>::load_raw(dy + off);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) one(v[u], g[u], dx + row2(j + u) + c);
+    for (int u = 0; u < 4; ++u) {
+      float v[V], g[V];
+      Vec16<T>::unpack(raw[u], v);
+      Vec16<T>::unpack(graw[u], g);
+      one(v, g, dx + row2(j + u) + c);
+    }
   }
   for (; j < n; ++j) {
     float v[V], g[V];

@@ -47,8 +47,10 @@ class GPUPeakExtractorv2(nn.Module):
 
     def forward(self, spec_tensor):
         conv = self.convs[0]
-        if ops.peak_extract_supported(spec_tensor, conv) and not torch.is_autocast_enabled():
-            # (B, F, N, 1) channels-last -> the reference's (B, F, N) view of the same memory (node rows)
+        if ops.peak_extract_supported(spec_tensor, conv):
+            # (B, F, N, 1) channels-last -> the reference's (B, F, N) view of the same memory (node rows).  Under
+            # torch.autocast the kernel still computes and returns fp32 (cuDNN would run this 3 -> 8 channel 7x7
+            # convolution through conv2d_grouped_direct_kernel at 0.5 ms per view); the stem's convolution casts it.
             return ops.peak_extract(spec_tensor, conv).squeeze(-1)
         lo = torch.amin(spec_tensor, dim=(1, 2), keepdim=True)
         hi = torch.amax(spec_tensor, dim=(1, 2), keepdim=True)

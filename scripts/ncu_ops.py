@@ -8,8 +8,9 @@ from grafp_b200 import ops
 dev = "cuda"
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+dtype = torch.bfloat16 if (len(sys.argv) > 3 and sys.argv[3] == "bf16") else torch.float32
 for (N, C) in [(1024, 64), (512, 128), (256, 256), (128, 512)]:
-    x = torch.relu(torch.randn(B, C, N, 1, device=dev)).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    x = torch.relu(torch.randn(B, C, N, 1, device=dev)).to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
     bn = torch.nn.BatchNorm2d(2 * C).to(dev).train()
     for _ in range(reps):
         nbr, nbr32 = ops.knn_graph(x, 3)
