@@ -17,6 +17,8 @@
 // catastrophically, in fp32 per thread and block, in double across blocks.
 // With OPT_BN_REVERSE the second pass walks the rows back to front: the first pass leaves the tail of the tensor in
 // the 126 MB L2, so the second pass starts on L2 hits instead of evicting them before it gets there.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace grafp {
@@ -461,25 +463,29 @@ bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, con
   // L2: the last `keep` rows of pass 1 are what pass 2 reads first - keep them; the rest streams through
   const unsigned long long pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   const long long keep_from = keep >= 0 ? (n > keep ? n - keep : 0) : n;  // keep < 0: no hints at all
-  long long j = 0;
-  for (; j + 3 < n; j += 4) {
-    uint4 raw[4];
-    const unsigned long long pol = (j >= keep_from) ? pol_keep : pol_stream;
+  // (two copies of each unrolled loop, with and without cache hints: a per-load select makes ptxas interleave both)
+  auto pass1 = [&](auto hinted) {
+    long long j = 0;
+    for (; j + 3 < n; j += 4) {
+      uint4 raw[4];
+      const unsigned long long pol = (j >= keep_from) ? pol_keep : pol_stream;
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      raw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(xp + row1(j + u), pol) : Vec16<T>::load_raw(xp + row1(j + u));
+      for (int u = 0; u < 4; ++u)
+        raw[u] = decltype(hinted)::value ? Vec16<T>::load_raw_hint(xp + row1(j + u), pol) : Vec16<T>::load_raw(xp + row1(j + u));
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 4; ++u) {
+        float v[V];
+        Vec16<T>::unpack(raw[u], v);
+        add(v);
+      }
+    }
+    for (; j < n; ++j) {
       float v[V];
-      Vec16<T>::unpack(raw[u], v);
+      Vec16<T>::load(xp + row1(j), v);
       add(v);
     }
-  }
-  for (; j < n; ++j) {
-    float v[V];
-    Vec16<T>::load(xp + row1(j), v);
-    add(v);
-  }
+  };
+  if (keep >= 0) pass1(std::true_type{}); else pass1(std::false_type{});
   reduce_row_lanes<2 * V>(acc, sm, tpr_shift);
   if (rl == 0) {
 #pragma unroll
@@ -519,35 +525,38 @@ bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, con
     }
     Vec16<T>::store(o, y);
   };
-  j = 0;
-  for (; j + 3 < n; j += 4) {
-    uint4 raw[4], rraw[4];
+  auto pass2 = [&](auto hinted) {
+    long long j = 0;
+    for (; j + 3 < n; j += 4) {
+      uint4 raw[4], rraw[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const long long off = row2(j + u) + c;
-      // second and last use of x, only use of the residual: do not displace what is still to be re-read
-      raw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(x + off, pol_stream) : Vec16<T>::load_raw(x + off);
-      if (RES) rraw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(res + off, pol_stream) : Vec16<T>::load_raw(res + off);
+      for (int u = 0; u < 4; ++u) {
+        const long long off = row2(j + u) + c;
+        // second and last use of x, only use of the residual: do not displace what is still to be re-read
+        raw[u] = decltype(hinted)::value ? Vec16<T>::load_raw_hint(x + off, pol_stream) : Vec16<T>::load_raw(x + off);
+        if (RES) rraw[u] = decltype(hinted)::value ? Vec16<T>::load_raw_hint(res + off, pol_stream) : Vec16<T>::load_raw(res + off);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[V], rv[V];
+        Vec16<T>::unpack(raw[u], v);
+        if (RES) Vec16<T>::unpack(rraw[u], rv);
+        one(v, rv, out + row2(j + u) + c);
+      }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (; j < n; ++j) {
       float v[V], rv[V];
-      Vec16<T>::unpack(raw[u], v);
-      if (RES) Vec16<T>::unpack(rraw[u], rv);
-      one(v, rv, out + row2(j + u) + c);
+      const long long off = row2(j) + c;
+      Vec16<T>::load(x + off, v);
+      if (RES) Vec16<T>::load(res + off, rv);
+      one(v, rv, out + off);
     }
-  }
-  for (; j < n; ++j) {
-    float v[V], rv[V];
-    const long long off = row2(j) + c;
-    Vec16<T>::load(x + off, v);
-    if (RES) Vec16<T>::load(res + off, rv);
-    one(v, rv, out + off);
-  }
+  };
+  if (keep >= 0) pass2(std::true_type{}); else pass2(std::false_type{});
 }
 
 template <typename T, bool RELU>
-__global__ void __launch_bounds__(kBnThreads, sizeof(T) == 4 ? 3 : 2)
+__global__ void __launch_bounds__(kBnThreads, 2)
 bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ weight,
                          const float* __restrict__ bias, const float* __restrict__ mean, const float* __restrict__ invstd,
                          double* __restrict__ sums, unsigned int* __restrict__ counter, T* __restrict__ dx,
@@ -589,29 +598,32 @@ bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
   auto row2 = [&](long long j) { return (r0 + (first_reverse ? j : (n - 1 - j)) * step) * C; };
   const unsigned long long pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   const long long keep_from = keep >= 0 ? (n > keep ? n - keep : 0) : n;
-  long long j = 0;
-  for (; j + 3 < n; j += 4) {
-    uint4 raw[4], graw[4];
-    const unsigned long long pol = (j >= keep_from) ? pol_keep : pol_stream;
+  auto pass1 = [&](auto hinted) {
+    long long j = 0;
+    for (; j + 3 < n; j += 4) {
+      uint4 raw[4], graw[4];
+      const unsigned long long pol = (j >= keep_from) ? pol_keep : pol_stream;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      raw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(xp + row1(j + u), pol) : Vec16<T>::load_raw(xp + row1(j + u));
-      graw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(gp + row1(j + u), pol) : Vec16<T>::load_raw(gp + row1(j + u));
+      for (int u = 0; u < 4; ++u) {
+        raw[u] = decltype(hinted)::value ? Vec16<T>::load_raw_hint(xp + row1(j + u), pol) : Vec16<T>::load_raw(xp + row1(j + u));
+        graw[u] = decltype(hinted)::value ? Vec16<T>::load_raw_hint(gp + row1(j + u), pol) : Vec16<T>::load_raw(gp + row1(j + u));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[V], g[V];
+        Vec16<T>::unpack(raw[u], v);
+        Vec16<T>::unpack(graw[u], g);
+        add(v, g);
+      }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (; j < n; ++j) {
       float v[V], g[V];
-      Vec16<T>::unpack(raw[u], v);
-      Vec16<T>::unpack(graw[u], g);
+      Vec16<T>::load(xp + row1(j), v);
+      Vec16<T>::load(gp + row1(j), g);
       add(v, g);
     }
-  }
-  for (; j < n; ++j) {
-    float v[V], g[V];
-    Vec16<T>::load(xp + row1(j), v);
-    Vec16<T>::load(gp + row1(j), g);
-    add(v, g);
-  }
+  };
+  if (keep >= 0) pass1(std::true_type{}); else pass1(std::false_type{});
   reduce_row_lanes<3 * V>(acc, sm, tpr_shift);
   if (rl == 0) {
 #pragma unroll
@@ -650,30 +662,33 @@ bn_bwd_persistent_kernel(const T* __restrict__ dy, const T* __restrict__ x, cons
     }
     Vec16<T>::store(o, rr);
   };
-  j = 0;
-  for (; j + 3 < n; j += 4) {
-    uint4 raw[4], graw[4];
+  auto pass2 = [&](auto hinted) {
+    long long j = 0;
+    for (; j + 3 < n; j += 4) {
+      uint4 raw[4], graw[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const long long off = row2(j + u) + c;
-      raw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(x + off, pol_stream) : Vec16<T>::load_raw(x + off);
-      graw[u] = keep >= 0 ? Vec16<T>::load_raw_hint(dy + off, pol_stream) : Vec16<T>::load_raw(dy + off);
+      for (int u = 0; u < 4; ++u) {
+        const long long off = row2(j + u) + c;
+        raw[u] = decltype(hinted)::value ? Vec16<T>::load_raw_hint(x + off, pol_stream) : Vec16<T>::load_raw(x + off);
+        graw[u] = decltype(hinted)::value ? Vec16<T>::load_raw_hint(dy + off, pol_stream) : Vec16<T>::load_raw(dy + off);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[V], g[V];
+        Vec16<T>::unpack(raw[u], v);
+        Vec16<T>::unpack(graw[u], g);
+        one(v, g, dx + row2(j + u) + c);
+      }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (; j < n; ++j) {
       float v[V], g[V];
-      Vec16<T>::unpack(raw[u], v);
-      Vec16<T>::unpack(graw[u], g);
-      one(v, g, dx + row2(j + u) + c);
+      const long long off = row2(j) + c;
+      Vec16<T>::load(x + off, v);
+      Vec16<T>::load(dy + off, g);
+      one(v, g, dx + off);
     }
-  }
-  for (; j < n; ++j) {
-    float v[V], g[V];
-    const long long off = row2(j) + c;
-    Vec16<T>::load(x + off, v);
-    Vec16<T>::load(dy + off, g);
-    one(v, g, dx + off);
-  }
+  };
+  if (keep >= 0) pass2(std::true_type{}); else pass2(std::false_type{});
 }
 
 // Cooperative launch of one of the single-launch kernels on grid (gx, ctiles); returns false when all blocks cannot be
