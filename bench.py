@@ -272,12 +272,17 @@ def workload_config(args, world):
 def algorithmic_work(name, m):
     """Algorithmic bytes / flops of one C-ABI call, fp32 (e = 4) or bf16 (e = 2)."""
     e = 4 if m.get("dtype", 0) == 0 else 2
+    if name == "conv1x1_bn_stats_fwd":  # read the input rows and the weight, write the output rows (moments: 16 bytes / channel)
+        B, N, Cin, Cout = m["B"], m["N"], m["Cin"], m["Cout"]
+        return {"flops": 2.0 * B * N * Cin * Cout, "bytes": B * N * (Cin + Cout) * e + Cin * Cout * e}
     B, N, C = m["B"], m["N"], m["C"]
     if name == "knn_fwd":
         M, K = m["M"], m["K"]
         return {"flops": 2.0 * B * N * M * C, "bytes": B * (N * C * e + (M * C * e if M != N else 0) + N * K * 12)}
     if name == "bn_train_fwd":  # statistics pass + apply pass (+ residual read)
         return {"bytes": B * N * C * e * (3 + m.get("res", 0))}
+    if name == "bn_apply_fwd":  # apply pass only: the moments came out of the convolution's epilogue
+        return {"bytes": B * N * C * e * (2 + m.get("res", 0))}
     if name == "bn_train_bwd":  # reduction pass (dy, x) + apply pass (dy, x -> dx)
         return {"bytes": B * N * C * e * 5}
     if name in ("ntxent_fwd", "ntxent_bwd"):
@@ -299,6 +304,8 @@ _ROOFLINE_NAMES = {
     "mr_aggregate_bwd": "K3 argmax-routed scatter backward",
     "bn_train_fwd": "K5 train-mode BatchNorm (+ReLU / +residual) forward",
     "bn_train_bwd": "K5 backward",
+    "bn_apply_fwd": "K5 forward, apply pass only (statistics from the convolution's epilogue)",
+    "conv1x1_bn_stats_fwd": "1x1 convolution as tcgen05 GEMM (TF32 / bf16) with BatchNorm statistics in the epilogue",
 }
 
 

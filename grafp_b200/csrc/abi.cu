@@ -46,6 +46,7 @@ struct OptionSpec { const char* name; int def; };
 const OptionSpec kOptionSpecs[OPT_COUNT] = {
     {"mr_fwd_form", 2}, {"mr_bwd_form", 2}, {"knn_epilogue", 0}, {"edge_bwd_row", 1}, {"gather_row", 1},
     {"edge_row", 1},    {"maxk_row", 1},    {"bn_reverse", 1},   {"bn_persistent", 1}, {"bn_l2_keep_mb", 80}, {"check_index", 0},
+    {"conv_gemm", 1},
 };
 std::atomic<int> g_options[OPT_COUNT];
 std::once_flag g_options_once;
@@ -387,7 +388,43 @@ int grafp_bn_train_fwd(const void* x, const void* residual, const float* weight,
   { int rc = require_device("grafp_bn_train_fwd"); if (rc != GRAFP_OK) return rc; }
   { int rc = require_device_ptr("grafp_bn_train_fwd", "x", x); if (rc) return rc; }
   return launch_bn_train_fwd(x, residual, weight, bias, running_mean, running_var, conv_bias, num_batches_tracked, out, save_mean,
-                             save_invstd, R, C, eps, momentum, relu, dtype, workspace, static_cast<cudaStream_t>(stream));
+                             save_invstd, R, C, eps, momentum, relu, dtype, workspace, false, static_cast<cudaStream_t>(stream));
+}
+
+int grafp_bn_train_fwd_from_moments(const void* x, const void* residual, const float* weight, const float* bias,
+                                    float* running_mean, float* running_var, const float* conv_bias,
+                                    long long* num_batches_tracked, void* out, float* save_mean, float* save_invstd, long long R,
+                                    int C, float eps, float momentum, int relu, int dtype, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  clear_error();
+  GRAFP_REQUIRE(R > 1 && C > 0, GRAFP_EINVAL, "grafp_bn_train_fwd_from_moments: needs at least two rows and C > 0");
+  GRAFP_REQUIRE(dtype == GRAFP_F32 || dtype == GRAFP_BF16, GRAFP_EUNSUPPORTED,
+                "grafp_bn_train_fwd_from_moments: dtype %d not supported", dtype);
+  GRAFP_REQUIRE(x && weight && bias && out && save_mean && save_invstd && workspace, GRAFP_EINVAL,
+                "grafp_bn_train_fwd_from_moments: x, weight, bias, out, save_mean, save_invstd and workspace must be non-null");
+  GRAFP_REQUIRE(aligned16(x) && aligned16(out) && (residual == nullptr || aligned16(residual)), GRAFP_EINVAL,
+                "grafp_bn_train_fwd_from_moments: x, out and residual must be 16-byte aligned");
+  GRAFP_REQUIRE(workspace_bytes >= bn_workspace_bytes(C), GRAFP_EWORKSPACE, "grafp_bn_train_fwd_from_moments: workspace too small");
+  { int rc = require_device("grafp_bn_train_fwd_from_moments"); if (rc != GRAFP_OK) return rc; }
+  { int rc = require_device_ptr("grafp_bn_train_fwd_from_moments", "x", x); if (rc) return rc; }
+  return launch_bn_train_fwd(x, residual, weight, bias, running_mean, running_var, conv_bias, num_batches_tracked, out, save_mean,
+                             save_invstd, R, C, eps, momentum, relu, dtype, workspace, true, static_cast<cudaStream_t>(stream));
+}
+
+int grafp_conv1x1_bn_stats_supported(long long R, int Cin, int Cout, int dtype) {
+  return conv1x1_stats_supported(R, Cin, Cout, dtype) ? 1 : 0;
+}
+
+int grafp_conv1x1_bn_stats_fwd(const void* x, const void* w, void* y, long long R, int Cin, int Cout, int dtype,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  clear_error();
+  GRAFP_REQUIRE(R > 0 && Cin > 0 && Cout > 0, GRAFP_EINVAL, "grafp_conv1x1_bn_stats_fwd: R, Cin and Cout must be positive");
+  GRAFP_REQUIRE(x && w && y && workspace, GRAFP_EINVAL, "grafp_conv1x1_bn_stats_fwd: x, w, y and workspace must be non-null");
+  GRAFP_REQUIRE(workspace_bytes >= bn_workspace_bytes(Cout), GRAFP_EWORKSPACE,
+                "grafp_conv1x1_bn_stats_fwd: workspace smaller than grafp_bn_workspace_bytes(Cout)");
+  { int rc = require_device("grafp_conv1x1_bn_stats_fwd"); if (rc != GRAFP_OK) return rc; }
+  { int rc = require_device_ptr("grafp_conv1x1_bn_stats_fwd", "x", x); if (rc) return rc; }
+  return launch_conv1x1_stats(x, w, y, bn_workspace_sums(workspace), R, Cin, Cout, dtype, static_cast<cudaStream_t>(stream));
 }
 
 int grafp_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,

@@ -28,6 +28,8 @@ constexpr int kBnThreads = 256;
 constexpr int kBnMaxTpr = 32;  // threads per row chunk: a block covers <= 32 * V channels, which bounds the number of
                                // red.f64 per block (blocks * channels-per-block * 2 per pass)
 
+inline double* bn_sums_of(void* workspace) { return reinterpret_cast<double*>(((uintptr_t)workspace + 255) / 256 * 256); }
+
 // L2 eviction policies for the two-pass kernels: what pass 2 re-reads first is loaded "evict last" in pass 1, everything
 // that will not be touched again "evict first".
 __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
@@ -51,6 +53,7 @@ struct Vec16;
 template <>
 struct Vec16<float> {
   static constexpr int V = 4;
+  static __device__ __forceinline__ float scalar(const float* p) { return __ldg(p); }
   // raw 16-byte loads: the unrolled loops keep the packed registers in flight and unpack at use (for bf16 the unpacked
   // form is twice the registers: 174 per thread and one block per SM before this)
   static __device__ __forceinline__ uint4 load_raw(const float* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
@@ -73,6 +76,7 @@ struct Vec16<float> {
 template <>
 struct Vec16<__nv_bfloat16> {
   static constexpr int V = 8;
+  static __device__ __forceinline__ float scalar(const __nv_bfloat16* p) { return __bfloat162float(*p); }
   static __device__ __forceinline__ uint4 load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
   static __device__ __forceinline__ uint4 load_raw_hint(const __nv_bfloat16* p, unsigned long long policy) { return ldg16_hint(p, policy); }
   static __device__ __forceinline__ void unpack(const uint4& t, float (&v)[8]) {
@@ -192,57 +196,53 @@ bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long R,
   }
 }
 
-// mean / invstd of this thread's V channels from the global sums (every thread of the second pass does this once)
-template <typename T, int V>
-__device__ __forceinline__ void bn_finish_stats(const T* x, const double* sums, int C, int c, double inv_rows, float eps,
-                                                float (&mean)[V], float (&invstd)[V], double (&var_b)[V]) {
-  float sh[V];
-  Vec16<T>::load(x + c, sh);
-#pragma unroll
-  for (int e = 0; e < V; ++e) {
-    const double s = ld_f64_cg(sums + c + e) * inv_rows;
-    const double q = ld_f64_cg(sums + C + c + e) * inv_rows;
-    const double var = fmax(q - s * s, 0.0);
-    mean[e] = (float)((double)sh[e] + s);
-    invstd[e] = (float)(1.0 / sqrt(var + (double)eps));
-    var_b[e] = var;
-  }
-}
-
 // ---- forward apply: y = (x - mean) * a + bias (+ residual) (ReLU), a = weight * invstd ----
+// The per-channel coefficients are finished once per block into shared memory (one channel per thread and round: the
+// double-precision variance, square root and division are ~100 instructions per channel - done per thread for its own
+// V channels they cost more than the ~14 items a thread then streams), the rows stream through packed registers.
 template <typename T, bool RELU, bool RES>
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, 4)
 bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ weight,
                 const float* __restrict__ bias, const double* __restrict__ sums, T* __restrict__ out,
                 float* __restrict__ save_mean, float* __restrict__ save_invstd, float* running_mean, float* running_var,
                 const float* __restrict__ conv_bias, long long* num_batches_tracked,
-                long long R, int C, int cv, float eps, float momentum, int reverse) {
+                long long R, int C, int cv, float eps, float momentum, int reverse, int raw_moments) {
   constexpr int V = Vec16<T>::V;
-  const long long total = R * cv;                        // 16-byte items
-  const long long T_ = (long long)gridDim.x * kBnThreads;  // a multiple of cv: a thread's channel pack never changes
-  const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
-  const int c = (int)(i0 % cv) * V;
-  float mu[V], is[V], a[V], bb[V];
-  double var_b[V];
-  bn_finish_stats<T, V>(x, sums, C, c, 1.0 / (double)R, eps, mu, is, var_b);
-#pragma unroll
-  for (int e = 0; e < V; ++e) { a[e] = __ldg(weight + c + e) * is[e]; bb[e] = __ldg(bias + c + e); }
-  if (i0 == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
-  if (i0 < cv) {  // one thread per channel pack: the saved and the running statistics
-#pragma unroll
-    for (int e = 0; e < V; ++e) {
-      save_mean[c + e] = mu[e];
-      save_invstd[c + e] = is[e];
+  extern __shared__ float coef[];  // [3][C]: mean, a, bias
+  const double inv_rows = 1.0 / (double)R;
+  for (int ch = threadIdx.x; ch < C; ch += kBnThreads) {
+    // raw_moments: the sums are sum x and sum x^2 (the convolution's epilogue, conv_gemm.cu); else about row 0 of x
+    const double sh = raw_moments ? 0.0 : (double)Vec16<T>::scalar(x + ch);
+    const double s1 = ld_f64_cg(sums + ch) * inv_rows;
+    const double q = ld_f64_cg(sums + C + ch) * inv_rows;
+    const double var = fmax(q - s1 * s1, 0.0);
+    const float mu = (float)(sh + s1);
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    coef[ch] = mu;
+    coef[C + ch] = __ldg(weight + ch) * is;
+    coef[2 * C + ch] = __ldg(bias + ch);
+    if (blockIdx.x == 0) {  // the saved and the running statistics
+      save_mean[ch] = mu;
+      save_invstd[ch] = is;
       // conv_bias: the convolution in front ran without its bias (it cancels in x - mean); the running mean sees it
-      const float shift = conv_bias != nullptr ? __ldg(conv_bias + c + e) : 0.f;
-      if (running_mean != nullptr) running_mean[c + e] = (1.f - momentum) * running_mean[c + e] + momentum * (mu[e] + shift);
+      const float shift = conv_bias != nullptr ? __ldg(conv_bias + ch) : 0.f;
+      if (running_mean != nullptr) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (mu + shift);
       if (running_var != nullptr) {
-        const double unbiased = var_b[e] * ((double)R / (double)(R - 1));
-        running_var[c + e] = (1.f - momentum) * running_var[c + e] + momentum * (float)unbiased;
+        const double unbiased = var * ((double)R / (double)(R - 1));
+        running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
       }
     }
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+  __syncthreads();
+  const long long total = R * cv;                          // 16-byte items
+  const long long T_ = (long long)gridDim.x * kBnThreads;  // a multiple of cv: a thread's channel pack never changes
+  const long long i0 = (long long)blockIdx.x * kBnThreads + threadIdx.x;
   if (i0 >= total) return;
+  const int c = (int)(i0 % cv) * V;
+  float mu[V], a[V], bb[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) { mu[e] = coef[c + e]; a[e] = coef[C + c + e]; bb[e] = coef[2 * C + c + e]; }
   // (x - mean) first: exact-ish difference, no cancellation against a pre-multiplied shift when |mean| >> std
   auto one = [&](const float (&v)[V], const float (&rv)[V], T* o) {
     float y[V];
@@ -258,14 +258,19 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, const float*
   auto at = [&](long long j) { return (i0 + (reverse ? (n - 1 - j) : j) * T_) * V; };
   long long j = 0;
   for (; j + 3 < n; j += 4) {
-    float v[4][V], rv[4][V];
+    uint4 raw[4], rraw[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      Vec16<T>::load(x + at(j + u), v[u]);
-      if (RES) Vec16<T>::load(res + at(j + u), rv[u]);
+      raw[u] = Vec16<T>::load_raw(x + at(j + u));
+      if (RES) rraw[u] = Vec16<T>::load_raw(res + at(j + u));
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) one(v[u], rv[u], out + at(j + u));
+    for (int u = 0; u < 4; ++u) {
+      float v[V], rv[V];
+      Vec16<T>::unpack(raw[u], v);
+      if (RES) Vec16<T>::unpack(rraw[u], rv);
+      one(v, rv, out + at(j + u));
+    }
   }
   for (; j < n; ++j) {
     float v[V], rv[V];
@@ -496,23 +501,41 @@ bn_fwd_persistent_kernel(const T* __restrict__ x, const T* __restrict__ res, con
   }
   grid_barrier(counter, gridDim.x * gridDim.y);
 
-  float mu[V], is[V], a[V], bb[V];
-  double var_b[V];
-  bn_finish_stats<T, V>(x, sums, C, c, 1.0 / (double)R, eps, mu, is, var_b);
-#pragma unroll
-  for (int e = 0; e < V; ++e) { a[e] = __ldg(weight + c + e) * is[e]; bb[e] = __ldg(bias + c + e); }
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
-  if (blockIdx.x == 0 && rl == 0) {  // one thread per channel pack: the saved and the running statistics
+  // The block's tpr * V channels are finished once, one channel per thread, into shared memory (the double-precision
+  // variance / square root / division are ~100 instructions per channel; every thread doing its own V channels made
+  // this prologue a visible share of the smaller launches).
+  float mu[V], a[V], bb[V];
+  {
+    const int nch = tpr * V;                      // <= 256 channels per block
+    const int ch0 = blockIdx.y * tpr * V;
+    if (threadIdx.x < nch) {
+      const int ch = ch0 + threadIdx.x;
+      const double inv_rows = 1.0 / (double)R;
+      const double s1 = ld_f64_cg(sums + ch) * inv_rows;
+      const double q = ld_f64_cg(sums + C + ch) * inv_rows;
+      const double var = fmax(q - s1 * s1, 0.0);
+      const float m = (float)((double)Vec16<T>::scalar(x + ch) + s1);
+      const float is = (float)(1.0 / sqrt(var + (double)eps));
+      sm[threadIdx.x] = m;
+      sm[kBnThreads + threadIdx.x] = __ldg(weight + ch) * is;
+      if (blockIdx.x == 0) {  // the saved and the running statistics
+        save_mean[ch] = m;
+        save_invstd[ch] = is;
+        const float shift = conv_bias != nullptr ? __ldg(conv_bias + ch) : 0.f;
+        if (running_mean != nullptr) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (m + shift);
+        if (running_var != nullptr) {
+          const double unbiased = var * ((double)R / (double)(R - 1));
+          running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+        }
+      }
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+    __syncthreads();
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      save_mean[c + e] = mu[e];
-      save_invstd[c + e] = is[e];
-      const float shift = conv_bias != nullptr ? __ldg(conv_bias + c + e) : 0.f;
-      if (running_mean != nullptr) running_mean[c + e] = (1.f - momentum) * running_mean[c + e] + momentum * (mu[e] + shift);
-      if (running_var != nullptr) {
-        const double unbiased = var_b[e] * ((double)R / (double)(R - 1));
-        running_var[c + e] = (1.f - momentum) * running_var[c + e] + momentum * (float)unbiased;
-      }
+      mu[e] = sm[tc * V + e];
+      a[e] = sm[kBnThreads + tc * V + e];
+      bb[e] = __ldg(bias + c + e);
     }
   }
   auto one = [&](const float (&v)[V], const float (&rv)[V], T* o) {
@@ -726,10 +749,10 @@ int keep_rows_per_thread(int mb, int tensors, int C, size_t elem) {
   return k < 1.0 ? 0 : (int)k;
 }
 
-int apply_grid(long long total, int cv) {
-  // whole waves of 8 CTAs per SM, rounded so that grid * 256 is a multiple of cv
+int apply_grid(long long total, int cv, int per_sm = 8) {
+  // whole waves of `per_sm` CTAs per SM, rounded so that grid * 256 is a multiple of cv
   long long need = (total + kBnThreads - 1) / kBnThreads;
-  long long g = (long long)num_sms() * 8;
+  long long g = (long long)num_sms() * per_sm;
   if (g > need) g = need;
   const int q = cv > kBnThreads ? cv / kBnThreads : 1;
   g = (g + q - 1) / q * q;
@@ -741,7 +764,7 @@ int shift_of(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 template <typename T>
 int bn_fwd_t(const void* x_, const void* res_, const float* weight, const float* bias, float* running_mean, float* running_var,
              const float* conv_bias, long long* nbt, void* out_, float* save_mean, float* save_invstd, long long R, int C,
-             float eps, float momentum, int relu, void* workspace, cudaStream_t s) {
+             float eps, float momentum, int relu, void* workspace, bool from_moments, cudaStream_t s) {
   constexpr int V = Vec16<T>::V;
   BnGeom g;
   if (!bn_geometry(R, C, V, &g)) { set_error("bn_train_fwd: needs C %% %d == 0, C/%d a power of two and at least 2 rows", V, V); return GRAFP_EUNSUPPORTED; }
@@ -749,11 +772,13 @@ int bn_fwd_t(const void* x_, const void* res_, const float* weight, const float*
   const T* x = static_cast<const T*>(x_);
   const T* res = static_cast<const T*>(res_);
   T* out = static_cast<T*>(out_);
-  double* sums = reinterpret_cast<double*>(((uintptr_t)workspace + 255) / 256 * 256);
+  double* sums = bn_sums_of(workspace);
   unsigned int* counter = reinterpret_cast<unsigned int*>(sums + (size_t)3 * C);
-  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)3 * C * sizeof(double) + 16, s);
-  if (e != cudaSuccess) { set_error("bn_train_fwd: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
-  if (option(OPT_BN_PERSISTENT) != 0) {
+  if (!from_moments) {
+    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)3 * C * sizeof(double) + 16, s);
+    if (e != cudaSuccess) { set_error("bn_train_fwd: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  if (!from_moments && option(OPT_BN_PERSISTENT) != 0) {
     int tsh = shift_of(g.tpr);
     int first_reverse = option(OPT_BN_REVERSE) != 0;
     int keep = keep_rows_per_thread(option(OPT_BN_L2_KEEP_MB), 1, C, sizeof(T));
@@ -778,14 +803,18 @@ int bn_fwd_t(const void* x_, const void* res_, const float* weight, const float*
     else rc = try_launch(bn_fwd_persistent_kernel<T, false, false>, i_plain);
     if (rc == 0) return check_launch("bn_train_fwd (single launch)");
   }
-  bn_stats_kernel<T><<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(x, sums, R, C, shift_of(g.tpr));
+  // from_moments: the workspace already holds sum x and sum x^2 per channel (grafp_conv1x1_bn_stats_fwd) - apply only
+  if (!from_moments) bn_stats_kernel<T><<<dim3(g.gx, g.ctiles), kBnThreads, 0, s>>>(x, sums, R, C, shift_of(g.tpr));
+  const int raw = from_moments ? 1 : 0;
   const long long total = R * g.cv;
-  const int grid = apply_grid(total, g.cv);
+  const int grid = apply_grid(total, g.cv, 4);
+  const size_t coef_bytes = (size_t)3 * C * sizeof(float);
+  if (coef_bytes > 48 * 1024) { set_error("bn_train_fwd: more than 4096 channels"); return GRAFP_EUNSUPPORTED; }
   const int rev = option(OPT_BN_REVERSE) != 0;
 #define GRAFP_BN_APPLY(RELU_, RES_)                                                                                        \
-  bn_apply_kernel<T, RELU_, RES_><<<grid, kBnThreads, 0, s>>>(x, res, weight, bias, sums, out, save_mean, save_invstd,      \
+  bn_apply_kernel<T, RELU_, RES_><<<grid, kBnThreads, coef_bytes, s>>>(x, res, weight, bias, sums, out, save_mean, save_invstd, \
                                                             running_mean, running_var, conv_bias, nbt, R, C, g.cv, eps,  \
-                                                            momentum, rev)
+                                                            momentum, rev, raw)
   if (relu) GRAFP_BN_APPLY(true, false);
   else if (res) GRAFP_BN_APPLY(false, true);
   else GRAFP_BN_APPLY(false, false);
@@ -851,13 +880,15 @@ bool bn_supported(long long R, int C, int dtype) {
 int launch_bn_train_fwd(const void* x, const void* res, const float* weight, const float* bias, float* running_mean,
                         float* running_var, const float* conv_bias, long long* num_batches_tracked, void* out, float* save_mean,
                         float* save_invstd, long long R, int C, float eps, float momentum, int relu, int dtype, void* workspace,
-                        cudaStream_t s) {
+                        bool from_moments, cudaStream_t s) {
   if (dtype == GRAFP_F32)
     return bn_fwd_t<float>(x, res, weight, bias, running_mean, running_var, conv_bias, num_batches_tracked, out, save_mean,
-                           save_invstd, R, C, eps, momentum, relu, workspace, s);
+                           save_invstd, R, C, eps, momentum, relu, workspace, from_moments, s);
   return bn_fwd_t<__nv_bfloat16>(x, res, weight, bias, running_mean, running_var, conv_bias, num_batches_tracked, out, save_mean,
-                                 save_invstd, R, C, eps, momentum, relu, workspace, s);
+                                 save_invstd, R, C, eps, momentum, relu, workspace, from_moments, s);
 }
+
+double* bn_workspace_sums(void* workspace) { return bn_sums_of(workspace); }
 
 int launch_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,
                         const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,

@@ -45,6 +45,8 @@ enum Option {
   OPT_BN_PERSISTENT,     // K5: 1 = both passes in one cooperative launch (default), 0 = two launches
   OPT_BN_L2_KEEP_MB,     // K5: megabytes of pass-1 input kept in L2 ("evict last") for pass 2 (default 80); 0 = no cache hints
   OPT_CHECK_INDEX,       // 1 = validate neighbour / centre ids against [0, M) before the aggregation kernels run
+  OPT_CONV_GEMM,         // 1 = dense 1x1 convolutions in front of a train-mode BatchNorm run as the tcgen05 GEMM with the
+                         //     statistics in its epilogue (host-side switch, read by ops.py); 0 = cuDNN + full BatchNorm
   OPT_COUNT
 };
 int option(Option o);
@@ -229,7 +231,12 @@ bool bn_supported(long long R, int C, int dtype);
 int launch_bn_train_fwd(const void* x, const void* res, const float* weight, const float* bias, float* running_mean,
                         float* running_var, const float* conv_bias, long long* num_batches_tracked, void* out, float* save_mean,
                         float* save_invstd, long long R, int C, float eps, float momentum, int relu, int dtype, void* workspace,
-                        cudaStream_t s);
+                        bool from_moments, cudaStream_t s);
+double* bn_workspace_sums(void* workspace);  // where the per-channel sums live inside a BatchNorm workspace
+// conv_gemm.cu: Y = X W^T on tcgen05 with sum y / sum y^2 per output channel (2 * Cout doubles, zeroed by the call)
+bool conv1x1_stats_supported(long long R, int Cin, int Cout, int dtype);
+int launch_conv1x1_stats(const void* x, const void* w, void* y, double* sums, long long R, int Cin, int Cout, int dtype,
+                         cudaStream_t s);
 int launch_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,
                         const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
                         int relu, int dtype, void* workspace, cudaStream_t s);

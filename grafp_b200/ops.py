@@ -609,15 +609,21 @@ def _bn_kernel_ok(t: torch.Tensor, C: int) -> bool:
     return C % v == 0 and ((C // v) & (C // v - 1)) == 0
 
 
-def _bn_fwd_call(lib, h, residual, weight, bias, running_mean, running_var, eps, momentum, relu, conv_bias=None, nbt=None):
+def _bn_fwd_call(lib, h, residual, weight, bias, running_mean, running_var, eps, momentum, relu, conv_bias=None, nbt=None,
+                 moments_ws=None):
+    """Train-mode BatchNorm forward on rows ``h``.  ``moments_ws``: a workspace that already holds the per-channel raw
+    moments of ``h`` (written by :func:`_conv1x1_stats_call`) - the statistics pass is skipped."""
     B, C, N, _ = h.shape
     out = _new_rows(B, C, N, h)
     save_mean = torch.empty(C, dtype=torch.float32, device=h.device)
     save_invstd = torch.empty(C, dtype=torch.float32, device=h.device)
     ws_bytes = lib.grafp_bn_workspace_bytes(C)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=h.device)
-    _call("bn_train_fwd", 2, dict(B=B, N=N, C=C, relu=int(relu), res=int(residual is not None), dtype=_dtype_code(h)),
-          lib.grafp_bn_train_fwd, h.device, h.data_ptr(), residual.data_ptr() if residual is not None else None,
+    ws = moments_ws if moments_ws is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=h.device)
+    name, fn = (("bn_train_fwd", lib.grafp_bn_train_fwd) if moments_ws is None
+                else ("bn_apply_fwd", lib.grafp_bn_train_fwd_from_moments))
+    _call(name, 2 if moments_ws is None else 1,
+          dict(B=B, N=N, C=C, relu=int(relu), res=int(residual is not None), dtype=_dtype_code(h)),
+          fn, h.device, h.data_ptr(), residual.data_ptr() if residual is not None else None,
           weight.data_ptr(), bias.data_ptr(),
           running_mean.data_ptr() if running_mean is not None else None,
           running_var.data_ptr() if running_var is not None else None,
@@ -642,6 +648,45 @@ def _bn_bwd_call(lib, g, h, weight, bias, save_mean, save_invstd, relu, want_col
           colsum.data_ptr() if colsum is not None else None, B * N, C, int(relu), _dtype_code(h),
           ws.data_ptr(), ws_bytes, _stream(h))
     return dh, dweight, dbias, colsum
+
+
+def conv1x1_stats_ok(x: torch.Tensor, cw: torch.Tensor, conv_args) -> bool:
+    """Whether the 1x1 convolution ``cw`` over rows ``x`` takes the tcgen05 GEMM with the BatchNorm statistics in its
+    epilogue (``grafp_conv1x1_bn_stats_fwd``): dense, unit stride, no padding, and - for fp32 - TF32 convolutions allowed
+    (``torch.backends.cudnn.allow_tf32``, PyTorch's default: the kernel computes what cuDNN computes then; with TF32
+    off the convolution stays cuDNN's fp32 and the BatchNorm takes its own statistics pass).  Option ``conv_gemm``
+    (``GRAFP_CONV_GEMM``): 1 = on where it wins (default), 2 = always, 0 = off (A/B)."""
+    stride, padding, dilation, groups = conv_args
+    if get_option("conv_gemm") == 0:
+        return False
+    if not (groups == 1 and tuple(stride) == (1, 1) and tuple(padding) == (0, 0) and tuple(cw.shape[2:]) == (1, 1)):
+        return False
+    if x.dtype == torch.float32 and not torch.backends.cudnn.allow_tf32:
+        return False
+    if x.dtype not in (torch.float32, torch.bfloat16) or not (x.is_cuda and _is_rows(x)):
+        return False
+    B, Cin, N, _ = x.shape
+    # measured (profiles/, scripts/bench_kernels.py gemm): with rows of more than 2 KB (Cin > 512 fp32 / 1024 bf16) the
+    # layer is tensor- / L2-bound, cuDNN's larger tiles win by more than the saved statistics pass; conv_gemm = 2 forces
+    if get_option("conv_gemm") != 2 and Cin * x.element_size() > 2048:
+        return False
+    return bool(_native.load().grafp_conv1x1_bn_stats_supported(B * N, Cin, cw.shape[0], _dtype_code(x)))
+
+
+def _conv1x1_stats_call(lib, x, cw_x):
+    """h = conv1x1(x, cw_x) as rows, plus the BatchNorm workspace holding sum h / sum h^2 per channel."""
+    B, Cin, N, _ = x.shape
+    Cout = cw_x.shape[0]
+    h = _new_rows(B, Cout, N, x)
+    w = cw_x.reshape(Cout, Cin)
+    if not w.is_contiguous():
+        w = w.contiguous()
+    ws_bytes = lib.grafp_bn_workspace_bytes(Cout)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    _call("conv1x1_bn_stats_fwd", 1, dict(B=B, N=N, Cin=Cin, Cout=Cout, dtype=_dtype_code(x)),
+          lib.grafp_conv1x1_bn_stats_fwd, x.device, x.data_ptr(), w.data_ptr(), h.data_ptr(), B * N, Cin, Cout,
+          _dtype_code(x), ws.data_ptr(), ws_bytes, _stream(x))
+    return h, ws
 
 
 class _BatchNormTrain(torch.autograd.Function):
@@ -725,6 +770,8 @@ def _dense_form_of_grouped(x: torch.Tensor, cw: torch.Tensor, groups: int) -> bo
     conv2d_grouped_direct_kernel at 29 ms per call (B = 512; torch.profiler, profiles/), 80 % of a bf16 training step.
     The same map as a DENSE 1x1 convolution with a block-diagonal weight is a plain tensor-core GEMM: 4x the flops on
     zeros, still HBM-bound at these channel counts, and exact (the added terms are products with 0)."""
+    # (fp32: cuDNN's grouped kernels are fine; taking the dense form there just to put the layer on the tcgen05 GEMM with
+    #  the statistics epilogue was measured - 106.3 vs 105.6 ms per step - and dropped)
     return groups > 1 and x.dtype == torch.bfloat16 and tuple(cw.shape[2:]) == (1, 1)
 
 
@@ -761,12 +808,17 @@ class _ConvBatchNormTrain(torch.autograd.Function):
     def forward(ctx, x, residual, cw, cb, weight, bias, running_mean, running_var, eps, momentum, relu, conv_args, nbt):
         lib = _native.load()
         stride, padding, dilation, groups = conv_args
+        moments_ws = None
         with torch.autocast("cuda", enabled=False):
             cw_x = cw if cw.dtype == x.dtype else cw.to(x.dtype)
-            if _dense_form_of_grouped(x, cw, groups):
-                h = torch.nn.functional.conv2d(x, _block_diag_weight(cw_x, groups), None, stride, padding, dilation, 1)
+            dense = _dense_form_of_grouped(x, cw, groups)
+            w_eff = _block_diag_weight(cw_x, groups) if dense else cw_x
+            eff_args = (stride, padding, dilation, 1 if dense else groups)
+            if conv1x1_stats_ok(x, w_eff, eff_args):
+                # own GEMM: the convolution output and its per-channel moments in one pass (conv_gemm.cu)
+                h, moments_ws = _conv1x1_stats_call(lib, x, w_eff)
             else:
-                h = torch.nn.functional.conv2d(x, cw_x, None, stride, padding, dilation, groups)   # bias: see the class docstring
+                h = torch.nn.functional.conv2d(x, w_eff, None, *eff_args)   # bias: see the class docstring
         if not _is_rows(h):
             h = as_rows(h)
         if residual is not None and residual.shape != h.shape:
@@ -777,7 +829,7 @@ class _ConvBatchNormTrain(torch.autograd.Function):
         if cb32 is not None and cb32.dtype != torch.float32:
             cb32 = cb32.float()
         out, save_mean, save_invstd = _bn_fwd_call(lib, h, residual, weight, bias, running_mean, running_var, eps,
-                                                   momentum, relu, cb32, nbt)
+                                                   momentum, relu, cb32, nbt, moments_ws)
         ctx.save_for_backward(x, cw, h, weight, bias, save_mean, save_invstd)
         ctx.relu = bool(relu)
         ctx.has_res = residual is not None

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GRAFP_ABI_VERSION 5
+#define GRAFP_ABI_VERSION 6
 
 #define GRAFP_OK 0
 #define GRAFP_EINVAL (-1)       /* null / misaligned pointer, non-positive size, k > M ... */
@@ -66,6 +66,9 @@ const char* grafp_last_error(void);
  *   "bn_l2_keep_mb" K5: megabytes of the first pass's input loaded "evict last" so the second pass finds them in L2
  *                  (the rest of both passes is loaded "evict first"); default 80, 0 = no cache hints
  *   "check_index"  1 = grafp_check_index is run on user-supplied graphs by the Python layer (default 0)
+ *   "conv_gemm"    1 = the Python layer runs dense 1x1 convolutions in front of a train-mode BatchNorm through
+ *                  grafp_conv1x1_bn_stats_fwd when TF32 convolutions are allowed and a row of x is at most 2 KB
+ *                  (default 1); 2 = whatever the row size; 0 = cuDNN + full BatchNorm
  * grafp_set_option returns GRAFP_EINVAL for an unknown name; grafp_get_option returns the value, or GRAFP_EINVAL.
  */
 int grafp_set_option(const char* name, int value);
@@ -221,6 +224,29 @@ int grafp_bn_train_fwd(const void* x, const void* residual, const float* weight,
 int grafp_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,
                        const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
                        int relu, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * 1x1 convolution with the BatchNorm statistics in its epilogue ("Conv2d(1x1) + BatchNorm [+ act]
+ * fusion").  Replaces the Conv2d(Cin, Cout, 1) of torch_nn.py:52-64 (BasicConv), torch_vertex.py:152-162,183-194
+ * (Grapher.fc1 / fc2) and graph_encoder.py:45-67 (FFN) together with the statistics pass of the train-mode BatchNorm2d
+ * behind it: y = x w^T as one tcgen05 GEMM over the node rows, and per output channel sum y and sum y^2 (taken of the
+ * values as stored, accumulated in double) left in the BatchNorm workspace.
+ *   x (R, Cin), w (Cout, Cin), y (R, Cout): rows of `dtype`; GRAFP_F32 runs as TF32 with fp32 accumulation (what cuDNN
+ *   does for this layer under torch.backends.cudnn.allow_tf32, PyTorch's default - callers that need full fp32 keep
+ *   cuDNN), GRAFP_BF16 as bf16 with fp32 accumulation.  No bias: a per-channel constant cancels in the BatchNorm
+ *   (conv_bias of grafp_bn_train_fwd* puts it back where it is visible, the running mean).
+ *   Cin and Cout must be multiples of 16 bytes of elements (GRAFP_EUNSUPPORTED otherwise; _supported() tells).
+ * grafp_bn_train_fwd_from_moments is grafp_bn_train_fwd without its statistics pass: `workspace` must be the one the
+ * convolution call wrote (same C = Cout); everything else - outputs, running statistics, saved mean / invstd - as there.
+ */
+int grafp_conv1x1_bn_stats_supported(long long R, int Cin, int Cout, int dtype);
+int grafp_conv1x1_bn_stats_fwd(const void* x, const void* w, void* y, long long R, int Cin, int Cout, int dtype, void* workspace,
+                               size_t workspace_bytes, void* stream);
+int grafp_bn_train_fwd_from_moments(const void* x, const void* residual, const float* weight, const float* bias,
+                                    float* running_mean, float* running_var, const float* conv_bias,
+                                    long long* num_batches_tracked, void* out, float* save_mean, float* save_invstd, long long R,
+                                    int C, float eps, float momentum, int relu, int dtype, void* workspace,
+                                    size_t workspace_bytes, void* stream);
 
 /*
  * NT-Xent contrastive loss.  Replaces simclr/ntxent.py:17-29 - a Python loop over the 2B rows of

@@ -1,7 +1,7 @@
 """Time the hot-path kernels alone at the benchmark batch (B = 512 segments): CUDA events on the launching stream,
 L2 flushed between launches, median of 10.  fp32 and bf16, with the A/B options of include/grafp_b200.h.
 
-    python scripts/bench_kernels.py [k1] [k23] [k5] [--dtype fp32|bf16|both]
+    python scripts/bench_kernels.py [k1] [k23] [k5] [gemm] [--dtype fp32|bf16|both]
 """
 import json
 import os
@@ -119,6 +119,34 @@ def bench_k5(dtype):
         print(line, flush=True)
 
 
+def bench_gemm(dtype):
+    """1x1 convolution + train-mode BatchNorm forward: tcgen05 GEMM with the statistics in its epilogue + apply pass
+    (conv_gemm = 1) against cuDNN convolution + the two-pass BatchNorm kernel (conv_gemm = 0), TF32 allowed in both."""
+    e = 4 if dtype == torch.float32 else 2
+    torch.backends.cudnn.allow_tf32 = True
+    print(f"=== 1x1 convolution (+ BatchNorm forward), dtype={dtype}, B={B}: GB/s over R (Cin + Cout) e")
+    lib = ops._native.load()
+    for (N, C) in STAGES:
+        for (cin, cout) in ((C, C), (2 * C, C), (C, 4 * C), (4 * C, C)):
+            x = rows(N, cin, dtype, relu=True)
+            conv = torch.nn.Conv2d(cin, cout, 1, bias=False).to(dev)
+            bn = torch.nn.BatchNorm2d(cout).to(dev).train()
+            w = conv.weight.detach().to(dtype)
+            bytes_conv = B * N * (cin + cout) * e
+            t_own = timed(lambda: ops._conv1x1_stats_call(lib, x, w))
+            t_lib = timed(lambda: torch.nn.functional.conv2d(x, w))
+            line = (f"N={N:5d} {cin:5d}->{cout:5d} | conv: ours {t_own*1e3:7.1f} us ({bytes_conv/t_own/1e6:5.0f} GB/s, "
+                    f"{bytes_conv/t_own/1e6/PEAK*100:3.0f}%)  cuDNN {t_lib*1e3:7.1f} us ({bytes_conv/t_lib/1e6:5.0f} GB/s)")
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+                for flag in (2, 0):
+                    ops.set_option("conv_gemm", flag)
+                    xg = x.detach().requires_grad_(True)
+                    t = timed(lambda: ops.conv_batch_norm_act(xg, conv, bn, relu=True))
+                    line += f" | conv+BN+ReLU conv_gemm={flag}: {t*1e3:7.1f} us"
+            ops.set_option("conv_gemm", 1)
+            print(line, flush=True)
+
+
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     which = set(args) or {"k1", "k23", "k5"}
@@ -134,3 +162,5 @@ if __name__ == "__main__":
             bench_k23(dtype)
         if "k5" in which:
             bench_k5(dtype)
+        if "gemm" in which:
+            bench_gemm(dtype)

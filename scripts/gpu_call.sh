@@ -11,11 +11,15 @@ for step in "$@"; do
     tests_all) timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > $out/${tag}_pytest_gpu.log 2>&1; tail -15 $out/${tag}_pytest_gpu.log ;;
     bench) timeout 900 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err; tail -c 600 $out/${tag}_bench_n1.err; cut -c1-400 $out/${tag}_bench_n1.json ;;
     bench_quick) timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_quick.json 2> $out/${tag}_bench_n1_quick.err; tail -c 600 $out/${tag}_bench_n1_quick.err; cut -c1-400 $out/${tag}_bench_n1_quick.json ;;
+    bench_g0) GRAFP_CONV_GEMM=0 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_gemm0.json 2> $out/${tag}_bench_n1_gemm0.err; tail -c 300 $out/${tag}_bench_n1_gemm0.err; cut -c1-300 $out/${tag}_bench_n1_gemm0.json ;;
+    bench_bf16_g0) GRAFP_CONV_GEMM=0 timeout 600 python bench.py --dtype bf16 --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_bf16_gemm0.json 2> $out/${tag}_bench_n1_bf16_gemm0.err; tail -c 300 $out/${tag}_bench_n1_bf16_gemm0.err; cut -c1-300 $out/${tag}_bench_n1_bf16_gemm0.json ;;
     bench_bf16) timeout 600 python bench.py --dtype bf16 --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_bf16.json 2> $out/${tag}_bench_n1_bf16.err; tail -c 600 $out/${tag}_bench_n1_bf16.err; cut -c1-400 $out/${tag}_bench_n1_bf16.json ;;
     bench_ref) timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_reference_arm.json 2> $out/${tag}_bench_reference_arm.err; cut -c1-300 $out/${tag}_bench_reference_arm.json ;;
     kernels) timeout 900 python scripts/bench_kernels.py > $out/${tag}_bench_kernels.log 2>&1; tail -60 $out/${tag}_bench_kernels.log ;;
     k1) timeout 600 python scripts/bench_kernels.py k1 > $out/${tag}_bench_k1.log 2>&1; cat $out/${tag}_bench_k1.log ;;
     k23) timeout 600 python scripts/bench_kernels.py k23 > $out/${tag}_bench_k23.log 2>&1; cat $out/${tag}_bench_k23.log ;;
+    gemm) timeout 600 python scripts/bench_kernels.py gemm > $out/${tag}_bench_gemm.log 2>&1; cat $out/${tag}_bench_gemm.log ;;
+    gemm_test) timeout 900 python -m pytest tests -m gpu -x -q -k "conv1x1 or gemm or conv_batch_norm" > $out/${tag}_pytest_gemm.log 2>&1; tail -25 $out/${tag}_pytest_gemm.log ;;
     k5) timeout 600 python scripts/bench_kernels.py k5 > $out/${tag}_bench_k5.log 2>&1; cat $out/${tag}_bench_k5.log ;;
     prof_bf16) timeout 600 python scripts/profile_step.py 512 --bf16 > $out/${tag}_profile_step_bf16.log 2>&1; head -50 $out/${tag}_profile_step_bf16.log | cut -c1-200 ;;
     prof) timeout 600 python scripts/profile_step.py 512 > $out/${tag}_profile_step.log 2>&1; head -50 $out/${tag}_profile_step.log | cut -c1-200 ;;

@@ -35,7 +35,7 @@ def _exact_fp32_library_math():
 
 
 _OPTION_DEFAULTS = {"mr_fwd_form": 2, "mr_bwd_form": 2, "knn_epilogue": 0, "edge_bwd_row": 1, "gather_row": 1, "edge_row": 1,
-                    "maxk_row": 1, "bn_reverse": 1, "bn_persistent": 1, "bn_l2_keep_mb": 80, "check_index": 0}
+                    "maxk_row": 1, "bn_reverse": 1, "bn_persistent": 1, "bn_l2_keep_mb": 80, "check_index": 0, "conv_gemm": 1}
 
 
 @pytest.fixture(autouse=True)
@@ -913,6 +913,168 @@ def test_fused_conv_batch_norm_matches_torch(shape, mode):
     assert gio.rel_err(bn.running_var.cpu().double(), bn_ref.running_var) < 1e-5
     if mode == "residual":
         assert gio.rel_err(rg.grad.cpu().double(), rr.grad) < 1e-6
+
+
+def _bn_moments(ws, C):
+    """The per-channel (sum, sum of squares) doubles inside a BatchNorm workspace (256-byte aligned, bn_fused.cu)."""
+    off = (-ws.data_ptr()) % 256
+    return ws[off:off + 16 * C].view(torch.float64).view(2, C)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(4, 256, 64, 64), (3, 500, 128, 256), (2, 129, 256, 320), (5, 77, 8, 24), (1, 1024, 2048, 512),
+                                   (2, 300, 96, 1024), (1, 2, 64, 128)])
+def test_conv1x1_stats_kernel(shape, dtype):
+    """grafp_conv1x1_bn_stats_fwd: y = x w^T against fp64 at the operand precision of the tensor-core mode (TF32 keeps
+    10 mantissa bits of x and w; bf16 operands are exact, the stored result is rounded once), ragged row / channel
+    tiles, and the epilogue's per-channel moments against double sums over the kernel's own output."""
+    B, N, Cin, Cout = shape
+    g = torch.Generator().manual_seed(B * 1000 + N + Cin + Cout)
+    x = (torch.randn(B, Cin, N, 1, generator=g) + 0.5).to(dtype).to(DEV).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).to(dtype).to(DEV)
+    lib = ops._native.load()
+    assert lib.grafp_conv1x1_bn_stats_supported(B * N, Cin, Cout, 0 if dtype == torch.float32 else 1) == 1
+    h, ws = ops._conv1x1_stats_call(lib, x, w)
+    torch.cuda.synchronize()
+    assert h.shape == (B, Cout, N, 1) and h.dtype == dtype and ops._is_rows(h)
+    ref = torch.nn.functional.conv2d(x.double(), w.double())
+    err = gio.rel_err(h.double().cpu(), ref.cpu())
+    assert err < (1.5e-3 if dtype == torch.float32 else 4e-3), err
+    m = _bn_moments(ws, Cout).cpu()
+    hd = h.double().permute(0, 2, 3, 1).reshape(B * N, Cout).cpu()
+    s1, s2 = hd.sum(0), (hd * hd).sum(0)
+    assert float((m[1] - s2).abs().max() / s2.abs().max()) < 3e-6    # fp32 partial sums per 64-row half tile
+    assert float((m[0] - s1).abs().max()) < 1e-6 * float(s2.sum().sqrt()) * (B * N) ** 0.5 / Cout ** 0.5 + 1e-9
+    # the mean / variance the BatchNorm derives from them
+    mean, var = m[0] / (B * N), m[1] / (B * N) - (m[0] / (B * N)) ** 2
+    assert torch.allclose(mean, hd.mean(0), atol=1e-6 * float(hd.abs().max()))
+    assert torch.allclose(var, hd.var(0, unbiased=False), rtol=1e-5, atol=1e-9)
+
+
+def test_conv1x1_stats_large_mean():
+    """|mean| >> std per channel: the moments are taken about each tile's first row, so the variance survives."""
+    g = torch.Generator().manual_seed(5)
+    B, N, Cin, Cout = 2, 640, 64, 128
+    x = torch.randn(B, Cin, N, 1, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    x[:, 0] = 1000.0                                   # a constant input channel: a large per-channel offset of y
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / 8).to(DEV)
+    h, ws = ops._conv1x1_stats_call(ops._native.load(), x, w)
+    m = _bn_moments(ws, Cout).cpu()
+    hd = h.double().permute(0, 2, 3, 1).reshape(B * N, Cout).cpu()
+    var = m[1] / (B * N) - (m[0] / (B * N)) ** 2
+    assert float(hd.mean(0).abs().median() / hd.std(0).max()) > 10.0     # the offset dominates in most channels
+    assert torch.allclose(var, hd.var(0, unbiased=False), rtol=2e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["plain", "relu", "residual"])
+def test_conv_batch_norm_gemm_path(mode, dtype):
+    """conv_gemm = 1 (tcgen05 GEMM + statistics epilogue + apply pass) against conv_gemm = 0 (cuDNN convolution +
+    two-pass BatchNorm kernel) with TF32 allowed in both, and against fp64: outputs, all gradients, running statistics."""
+    B, Cin, Cout, N = 3, 128, 256, 500
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, Cin, N, 1, generator=g)
+    res = torch.randn(B, Cout, N, 1, generator=g)
+    up = torch.randn(B, Cout, N, 1, generator=g)
+    conv0 = torch.nn.Conv2d(Cin, Cout, 1)
+    bn0 = torch.nn.BatchNorm2d(Cout)
+    with torch.no_grad():
+        bn0.weight.copy_(torch.randn(Cout, generator=g)); bn0.bias.copy_(torch.randn(Cout, generator=g))
+
+    def cl(t):
+        return t.to(DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+
+    def run(flag):
+        import copy
+        conv, bn = copy.deepcopy(conv0).to(DEV), copy.deepcopy(bn0).to(DEV).train()
+        ops.set_option("conv_gemm", flag)
+        xg, rg = cl(x).requires_grad_(True), cl(res).requires_grad_(True)
+        timer = ops.KernelTimer(timing=True)
+        ops.set_timer(timer)
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+                out = ops.conv_batch_norm_act(xg, conv, bn, relu=mode == "relu", residual=rg if mode == "residual" else None)
+        finally:
+            ops.set_timer(None)
+        names = [rec[0] for rec in timer.records]
+        assert ("conv1x1_bn_stats_fwd" in names) == bool(flag) and ("bn_apply_fwd" in names) == bool(flag), names
+        out.backward(cl(up))
+        return dict(out=out.detach(), dx=xg.grad, dw=conv.weight.grad, dg=bn.weight.grad, db=bn.bias.grad,
+                    rm=bn.running_mean.clone(), rv=bn.running_var.clone(), nbt=int(bn.num_batches_tracked)), names
+
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        a, _ = run(1)
+        b, _ = run(0)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    conv_ref, bn_ref = torch.nn.Conv2d(Cin, Cout, 1).double(), torch.nn.BatchNorm2d(Cout).double().train()
+    conv_ref.load_state_dict({k: v.double() for k, v in conv0.state_dict().items()})
+    bn_ref.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in bn0.state_dict().items()})
+    xr = x.to(dtype).double().requires_grad_(True)
+    ref = bn_ref(conv_ref(xr))
+    ref = torch.relu(ref) if mode == "relu" else (ref + res.to(dtype).double() if mode == "residual" else ref)
+    ref.backward(up.to(dtype).double())
+    tol = 3e-3 if dtype == torch.float32 else 2e-2
+    assert a["nbt"] == b["nbt"] == 1
+    for key, r in (("out", ref.detach()), ("dx", xr.grad), ("dw", conv_ref.weight.grad), ("dg", bn_ref.weight.grad),
+                   ("db", bn_ref.bias.grad), ("rv", bn_ref.running_var), ("rm", bn_ref.running_mean)):
+        ea, eb = gio.rel_err(a[key].double().cpu(), r), gio.rel_err(b[key].double().cpu(), r)
+        assert ea < max(tol, 2.0 * eb), (key, ea, eb)
+
+
+def test_ffn_and_downsample_tf32_gemm_path_agrees_with_cudnn_tf32():
+    """The smooth pieces of a block (FFN: conv-BN-ReLU-conv-BN + residual; Downsample: 3-tap convolution + BN) in the mode
+    bench.py measures (TF32 convolutions allowed): tcgen05 convolution path against the cuDNN TF32 path, outputs and
+    gradients at TF32 tolerance."""
+    from grafp_b200.encoder.graph_encoder import FFN, Downsample
+    torch.manual_seed(2)
+    mods = [(FFN(128, 512, 128).to(DEV).train(), (3, 128, 512, 1)), (Downsample(64, 128).to(DEV).train(), (3, 64, 512, 1))]
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        for mod, shape in mods:
+            x0 = torch.randn(*shape, device=DEV).contiguous(memory_format=torch.channels_last)
+            res = {}
+            for flag in (1, 0):
+                ops.set_option("conv_gemm", flag)
+                mod.zero_grad(set_to_none=True)
+                x = x0.clone().requires_grad_(True)
+                y = mod(x)
+                y.square().mean().backward()
+                res[flag] = [y.detach(), x.grad] + [p.grad for p in mod.parameters() if p.grad is not None and p.dim() > 1]
+            # (the gradients pass two BatchNorm backwards, each a difference of projections: TF32 noise is amplified)
+            for i, (got, ref) in enumerate(zip(res[1], res[0])):
+                assert gio.rel_err(got.double().cpu(), ref.double().cpu()) < (4e-3 if i == 0 else 3e-2)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def test_graph_encoder_tf32_gemm_path_is_as_close_to_fp32_as_cudnn_tf32():
+    """The whole encoder (train mode, k-NN graphs rebuilt from the features in every block): TF32 rounding flips near-tied
+    neighbours, so two TF32 implementations do not agree closely with each other - what can be asked is that the
+    tcgen05 convolution path is no further from the exact-fp32 run than cuDNN's TF32 path is."""
+    cfg = dict(synth.DEFAULT_CFG)
+    torch.manual_seed(9)
+    enc = load_synth(GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3), 21).to(DEV).train()
+    g = torch.Generator().manual_seed(4)
+    pts = torch.rand(4, cfg["n_filters"], 1024, generator=g).to(DEV)
+    old = torch.backends.cudnn.allow_tf32
+    outs = {}
+    try:
+        for name, tf32, flag in (("gemm", True, 1), ("cudnn_tf32", True, 0), ("fp32", False, 0)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            ops.set_option("conv_gemm", flag)
+            with torch.no_grad():
+                outs[name] = enc(pts).double().cpu()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    d_gemm = gio.rel_err(outs["gemm"], outs["fp32"])
+    d_lib = gio.rel_err(outs["cudnn_tf32"], outs["fp32"])
+    print(f"encoder, TF32 modes against fp32: tcgen05 convolutions {d_gemm:.3e}, cuDNN TF32 {d_lib:.3e}")
+    assert torch.isfinite(outs["gemm"]).all()
+    assert d_gemm < 2.5 * d_lib + 2e-2, (d_gemm, d_lib)
 
 
 def test_graphed_encoder_replays_the_eager_forward():
