@@ -465,6 +465,28 @@ int grafp_ntxent_bwd(const float* z, const float* lse, const float* grad_loss, f
   return launch_ntxent_bwd(z, lse, grad_loss, dz, n2, d, inv_tau, static_cast<cudaStream_t>(stream));
 }
 
+int grafp_downsample_taps_fwd(const void* x, void* taps, int B, int N, int C, int dtype, void* stream) {
+  clear_error();
+  GRAFP_REQUIRE(x && taps && B > 0, GRAFP_EINVAL, "grafp_downsample_taps_fwd: x and taps must be non-null, B positive");
+  GRAFP_REQUIRE(downsample_taps_supported(N, C, dtype), GRAFP_EUNSUPPORTED,
+                "grafp_downsample_taps_fwd: needs an even N >= 2 and fp32 / bf16 rows of a multiple of 16 bytes (N=%d C=%d)", N, C);
+  GRAFP_REQUIRE(aligned16(x) && aligned16(taps), GRAFP_EINVAL, "grafp_downsample_taps_fwd: x and taps must be 16-byte aligned");
+  { int rc = require_device("grafp_downsample_taps_fwd"); if (rc != GRAFP_OK) return rc; }
+  { int rc = require_device_ptr("grafp_downsample_taps_fwd", "x", x); if (rc) return rc; }
+  return launch_downsample_taps_fwd(x, taps, B, N, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int grafp_downsample_taps_bwd(const void* dtaps, void* dx, int B, int N, int C, int dtype, void* stream) {
+  clear_error();
+  GRAFP_REQUIRE(dtaps && dx && B > 0, GRAFP_EINVAL, "grafp_downsample_taps_bwd: dtaps and dx must be non-null, B positive");
+  GRAFP_REQUIRE(downsample_taps_supported(N, C, dtype), GRAFP_EUNSUPPORTED,
+                "grafp_downsample_taps_bwd: needs an even N >= 2 and fp32 / bf16 rows of a multiple of 16 bytes (N=%d C=%d)", N, C);
+  GRAFP_REQUIRE(aligned16(dtaps) && aligned16(dx), GRAFP_EINVAL, "grafp_downsample_taps_bwd: dtaps and dx must be 16-byte aligned");
+  { int rc = require_device("grafp_downsample_taps_bwd"); if (rc != GRAFP_OK) return rc; }
+  { int rc = require_device_ptr("grafp_downsample_taps_bwd", "dtaps", dtaps); if (rc) return rc; }
+  return launch_downsample_taps_bwd(dtaps, dx, B, N, C, dtype, static_cast<cudaStream_t>(stream));
+}
+
 size_t grafp_peak_extract_workspace_bytes(int B, int kh, int kw) {
   return (B > 0 && kh > 0 && kw > 0) ? peak_extract_workspace_bytes(B, kh, kw) : 0;
 }

@@ -241,6 +241,11 @@ int launch_bn_train_bwd(const void* dy, const void* x, const float* weight, cons
                         const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
                         int relu, int dtype, void* workspace, cudaStream_t s);
 
+// ---- downsample.cu ----
+bool downsample_taps_supported(int N, int C, int dtype);
+int launch_downsample_taps_fwd(const void* x, void* taps, int B, int N, int C, int dtype, cudaStream_t s);
+int launch_downsample_taps_bwd(const void* dtaps, void* dx, int B, int N, int C, int dtype, cudaStream_t s);
+
 // ---- peak_extract.cu ----
 bool peak_extract_supported(int H, int W, int F, int kh, int kw, int sh);
 size_t peak_extract_workspace_bytes(int B, int kh, int kw);

@@ -143,5 +143,10 @@ class GraphEncoder(nn.Module):
         x = self.stem(x)
         for block in self.backbone:
             x = block(x)
-        x = self.proj(x)
-        return torch.mean(x, dim=2).squeeze(-1).squeeze(-1)
+        # The reference projects every node and then averages (graph_encoder.py:186-187).  proj is a 1x1 convolution -
+        # linear - so the mean over the nodes commutes with it: averaging first is the same map (differences are fp32
+        # rounding of the mean, ~1e-7) and leaves a (B, C) x (C, 1024) product instead of a convolution over all B * N
+        # rows, its bias add, the layout copy and the reduction over the 4x larger projected tensor (and their backwards):
+        # ~3 ms of a 105 ms training step at batch 512.
+        x = self.proj(ops.mean_over_nodes(x))
+        return x.flatten(1)

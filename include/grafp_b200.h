@@ -249,6 +249,16 @@ int grafp_bn_train_fwd_from_moments(const void* x, const void* residual, const f
                                     size_t workspace_bytes, void* stream);
 
 /*
+ * Tap rows of the Downsample block (graph_encoder.py:16-28: Conv2d(3x3, stride 2, padding 1) over (B, C, N, 1): the image
+ * is one pixel wide, so only the middle kernel column meets data and the layer is a 3-tap stride-2 convolution along
+ * the node axis, i.e. a 1x1 convolution over taps[b][n'] = (x[b][2n'-1], x[b][2n'], x[b][2n'+1]), x[b][-1] = 0).
+ *   x (B, N, C) rows -> taps (B, N/2, 3C) rows; backward: dtaps (B, N/2, 3C) -> dx (B, N, C), the overlapping thirds
+ *   summed.  N even, C a multiple of 16 bytes of `dtype` elements (GRAFP_EUNSUPPORTED otherwise).
+ */
+int grafp_downsample_taps_fwd(const void* x, void* taps, int B, int N, int C, int dtype, void* stream);
+int grafp_downsample_taps_bwd(const void* dtaps, void* dx, int B, int N, int C, int dtype, void* stream);
+
+/*
  * NT-Xent contrastive loss.  Replaces simclr/ntxent.py:17-29 - a Python loop over the 2B rows of
  * z z^T / tau (log-softmax of each row without its diagonal entry, partner's entry picked) - and its autograd, without
  * materialising the (2B, 2B) similarity matrix.

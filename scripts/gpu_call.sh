@@ -18,8 +18,9 @@ for step in "$@"; do
     kernels) timeout 900 python scripts/bench_kernels.py > $out/${tag}_bench_kernels.log 2>&1; tail -60 $out/${tag}_bench_kernels.log ;;
     k1) timeout 600 python scripts/bench_kernels.py k1 > $out/${tag}_bench_k1.log 2>&1; cat $out/${tag}_bench_k1.log ;;
     k23) timeout 600 python scripts/bench_kernels.py k23 > $out/${tag}_bench_k23.log 2>&1; cat $out/${tag}_bench_k23.log ;;
+    copies) timeout 600 python scripts/profile_copies.py 512 > $out/${tag}_copies.log 2>&1; cut -c1-250 $out/${tag}_copies.log | head -60 ;;
     gemm) timeout 600 python scripts/bench_kernels.py gemm > $out/${tag}_bench_gemm.log 2>&1; cat $out/${tag}_bench_gemm.log ;;
-    gemm_test) timeout 900 python -m pytest tests -m gpu -x -q -k "conv1x1 or gemm or conv_batch_norm" > $out/${tag}_pytest_gemm.log 2>&1; tail -25 $out/${tag}_pytest_gemm.log ;;
+    gemm_test) timeout 900 python -m pytest tests -m gpu -x -q -k "conv1x1 or gemm or conv_batch_norm or downsample" > $out/${tag}_pytest_gemm.log 2>&1; tail -25 $out/${tag}_pytest_gemm.log ;;
     k5) timeout 600 python scripts/bench_kernels.py k5 > $out/${tag}_bench_k5.log 2>&1; cat $out/${tag}_bench_k5.log ;;
     prof_bf16) timeout 600 python scripts/profile_step.py 512 --bf16 > $out/${tag}_profile_step_bf16.log 2>&1; head -50 $out/${tag}_profile_step_bf16.log | cut -c1-200 ;;
     prof) timeout 600 python scripts/profile_step.py 512 > $out/${tag}_profile_step.log 2>&1; head -50 $out/${tag}_profile_step.log | cut -c1-200 ;;

@@ -915,6 +915,27 @@ def test_fused_conv_batch_norm_matches_torch(shape, mode):
         assert gio.rel_err(rg.grad.cpu().double(), rr.grad) < 1e-6
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(3, 64, 1024), (2, 8, 2), (5, 24, 6), (1, 512, 128)])
+def test_downsample_tap_rows(shape, dtype):
+    """grafp_downsample_taps_fwd / _bwd against the PyTorch construction of the same rows (pad + slice + cat) and its
+    autograd: bit-exact forward, backward exact up to the one addition of the overlapping thirds."""
+    B, C, N = shape
+    g = torch.Generator().manual_seed(C + N)
+    x0 = torch.randn(B, C, N, 1, generator=g).to(dtype).to(DEV).contiguous(memory_format=torch.channels_last)
+    up = torch.randn(B, 3 * C, N // 2, 1, generator=g).to(dtype).to(DEV).contiguous(memory_format=torch.channels_last)
+    x = x0.clone().requires_grad_(True)
+    taps = ops._DownsampleTaps.apply(x)
+    taps.backward(up)
+    xr = x0.clone().requires_grad_(True)
+    rows = xr.permute(0, 2, 3, 1).reshape(B, N // 2, 2 * C)
+    prev = torch.nn.functional.pad(rows[:, :-1, C:], (0, 0, 1, 0))
+    ref = torch.cat([prev, rows], dim=2).view(B, N // 2, 1, 3 * C).permute(0, 3, 1, 2)
+    ref.backward(up)
+    assert taps.shape == ref.shape and torch.equal(taps, ref)
+    assert torch.equal(x.grad, xr.grad)
+
+
 def _bn_moments(ws, C):
     """The per-channel (sum, sum of squares) doubles inside a BatchNorm workspace (256-byte aligned, bn_fused.cu)."""
     off = (-ws.data_ptr()) % 256
