@@ -42,7 +42,7 @@ def parse_args():
                     help="fp32 = configs[1]; bf16 = torch.autocast(bfloat16) activations with fp32 parameters (configs[2])")
     ap.add_argument("--knn-algo", choices=["auto", "simt", "tc"], default="auto")
     ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",
-                    help="run the step as one CUDA graph (grafp_b200.training.GraphedTrainStep); auto = on for bf16 at 1 GPU")
+                    help="run the step as one CUDA graph (grafp_b200.training.GraphedTrainStep); auto = on; off = eager (DistributedDataParallel at N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference-eager-on-this-GPU baseline")
     return ap.parse_args()
@@ -354,14 +354,17 @@ def run_ours(args):
     torch.manual_seed(0)
     model = SimCLR(cfg, GraphEncoder(cfg=cfg, in_channels=cfg["n_filters"], k=3)).to(dev).train()
     net = model
-    if world > 1:
+    # whole step incl. the gradient all-reduce as one CUDA graph per rank (GRAFP_BENCH_DP_GRAPH=0: DistributedDataParallel, eager)
+    graph_dp = world > 1 and (args.graph == "on" or (args.graph == "auto" and os.environ.get("GRAFP_BENCH_DP_GRAPH", "1") != "0"))
+    if world > 1 and not graph_dp:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=True,
                                                         gradient_as_bucket_view=True)
-    # auto: the graph where the host's launch rate is the bound - one GPU, bf16 (70.8 vs 75.5 ms per step); the fp32 step
-    # is GPU-bound either way (109.7 vs 108.8 ms, profiles/r02f_*), and multi-GPU runs stay eager
-    # (DistributedDataParallel's reducer touches the legacy stream during a whole-step capture - measured: capture fails with
-    # cudaErrorStreamCaptureImplicit - so the graph is a one-GPU feature here)
-    use_graph = world == 1 and (args.graph == "on" or (args.graph == "auto" and args.dtype == "bf16"))
+    # auto = graph.  The step is ~6 000 launches; with the kernels at ~97 ms the host's launch rate (~94 ms of CPU per step,
+    # more with 8 processes sharing the host) is the bound in eager mode: fp32 101.7 -> 99.1 ms at one GPU, 101.2 -> 97.2 ms
+    # at two (profiles/r03*), bf16 75.5 -> 70.8 ms.  DistributedDataParallel's reducer cannot be captured (it touches the
+    # legacy stream: cudaErrorStreamCaptureImplicit), so the multi-GPU graph replaces it by one captured all-reduce of a flat
+    # gradient buffer (grafp_b200.training.FlatGradients).
+    use_graph = graph_dp or (world == 1 and args.graph in ("on", "auto"))
     opt = torch.optim.Adam(model.parameters(), lr=cfg["lr"], capturable=use_graph)
     algo = {"auto": _native.KNN_AUTO, "simt": _native.KNN_SIMT, "tc": _native.KNN_TC}[args.knn_algo]
     if algo != _native.KNN_AUTO:
@@ -392,7 +395,8 @@ def run_ours(args):
         # the whole step - both views forward, loss, backward, Adam - as ONE CUDA graph; new inputs are copied into
         # its static buffers (from pinned host memory in the e2e region)
         from grafp_b200.training import GraphedTrainStep
-        step = GraphedTrainStep(net, opt, loss_of, [dev_i, dev_j], autocast_dtype=torch.bfloat16 if bf16 else None)
+        step = GraphedTrainStep(net, opt, loss_of, [dev_i, dev_j], autocast_dtype=torch.bfloat16 if bf16 else None,
+                                data_parallel=graph_dp)
 
     def barrier():
         if world > 1:
@@ -526,6 +530,15 @@ def run_ours(args):
         line.setdefault("cpu_baseline", None)
         print(json.dumps(line), flush=True)
     if world > 1:
+        if graph_dp:
+            # The CUDA graph holds captured NCCL kernels; tearing the communicator down under it hung the process at
+            # exit (measured: the JSON line printed, then torchrun's children never returned).  Everything is flushed
+            # and every rank is past the last collective: leave without the NCCL teardown.
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

@@ -19,6 +19,7 @@ for step in "$@"; do
     k1) timeout 600 python scripts/bench_kernels.py k1 > $out/${tag}_bench_k1.log 2>&1; cat $out/${tag}_bench_k1.log ;;
     k23) timeout 600 python scripts/bench_kernels.py k23 > $out/${tag}_bench_k23.log 2>&1; cat $out/${tag}_bench_k23.log ;;
     copies) timeout 600 python scripts/profile_copies.py 512 > $out/${tag}_copies.log 2>&1; cut -c1-250 $out/${tag}_copies.log | head -60 ;;
+    k3_test) timeout 900 python -m pytest tests -m gpu -x -q -k "mr_aggregate or aggregation or bf16_hot" > $out/${tag}_pytest_k3.log 2>&1; tail -8 $out/${tag}_pytest_k3.log ;;
     gemm) timeout 600 python scripts/bench_kernels.py gemm > $out/${tag}_bench_gemm.log 2>&1; cat $out/${tag}_bench_gemm.log ;;
     gemm_test) timeout 900 python -m pytest tests -m gpu -x -q -k "conv1x1 or gemm or conv_batch_norm or downsample" > $out/${tag}_pytest_gemm.log 2>&1; tail -25 $out/${tag}_pytest_gemm.log ;;
     k5) timeout 600 python scripts/bench_kernels.py k5 > $out/${tag}_bench_k5.log 2>&1; cat $out/${tag}_bench_k5.log ;;
@@ -40,7 +41,9 @@ for step in "$@"; do
     bench_n2) NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,COLL NCCL_DEBUG_FILE=$out/${tag}_nccl_n2_%p.log timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > $out/${tag}_bench_n2.json 2> $out/${tag}_bench_n2.err; for f in $out/${tag}_nccl_n2_*.log; do head -c 20000 $f > $f.head; rm -f $f; done; grep -c "Grad strides" $out/${tag}_bench_n2.err; tail -c 400 $out/${tag}_bench_n2.err; cut -c1-300 $out/${tag}_bench_n2.json ;;
     ncu_bf16) timeout 900 ncu --set full --clock-control none -k regex:"mr_aggregate|bn_" -c 40 -f -o /tmp/prof_bf16 python scripts/ncu_ops.py 512 1 bf16 > $out/${tag}_ncu_ops_bf16.log 2>&1; tail -2 $out/${tag}_ncu_ops_bf16.log
              python scripts/ncu_summary.py /tmp/prof_bf16.ncu-rep > $out/${tag}_ncu_bf16_summary.txt 2>&1; python scripts/ncu_stalls.py /tmp/prof_bf16.ncu-rep > $out/${tag}_ncu_bf16_stalls.txt 2>&1; cat $out/${tag}_ncu_bf16_summary.txt; cat $out/${tag}_ncu_bf16_stalls.txt | cut -c1-220 ;;
-    bench_n2_graph) timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --graph on > $out/${tag}_bench_n2_graph.json 2> $out/${tag}_bench_n2_graph.err; tail -c 1500 $out/${tag}_bench_n2_graph.err; cut -c1-300 $out/${tag}_bench_n2_graph.json ;;
+    bench_n2_graph) timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --graph on > $out/${tag}_bench_n2_graph.json 2> $out/${tag}_bench_n2_graph.err; tail -c 1500 $out/${tag}_bench_n2_graph.err; cut -c1-300 $out/${tag}_bench_n2_graph.json ;;
+    bench_graph) timeout 600 python bench.py --steps 10 --warmup 3 --graph on --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_graph.json 2> $out/${tag}_bench_n1_graph.err; tail -c 300 $out/${tag}_bench_n1_graph.err; cut -c1-300 $out/${tag}_bench_n1_graph.json ;;
+    bench_n8_graph) timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 8 --steps 8 --warmup 3 --graph on > $out/${tag}_bench_n8_graph.json 2> $out/${tag}_bench_n8_graph.err; tail -c 600 $out/${tag}_bench_n8_graph.err; cut -c1-300 $out/${tag}_bench_n8_graph.json ;;
     bench_n8) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 10 --warmup 3 > $out/${tag}_bench_n8.json 2> $out/${tag}_bench_n8.err; grep -c "Grad strides" $out/${tag}_bench_n8.err; tail -c 400 $out/${tag}_bench_n8.err; cut -c1-300 $out/${tag}_bench_n8.json ;;
     smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
     *) echo "unknown step $step" ;;
