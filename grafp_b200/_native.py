@@ -45,6 +45,8 @@ SIGNATURES = {
     "grafp_bn_workspace_bytes": (_sz, [_i]),
     "grafp_bn_train_fwd": (_i, [_vp] * 11 + [_c.c_longlong, _i, _c.c_float, _c.c_float, _i, _i, _vp, _sz, _vp]),
     "grafp_bn_train_bwd": (_i, [_vp] * 10 + [_c.c_longlong, _i, _i, _i, _vp, _sz, _vp]),
+    "grafp_ntxent_rows_fwd": (_i, [_vp] * 4 + [_i, _i, _i, _i, _c.c_float, _vp]),
+    "grafp_ntxent_rows_bwd": (_i, [_vp] * 4 + [_i, _i, _i, _i, _c.c_float, _c.c_float, _vp]),
     "grafp_downsample_taps_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "grafp_downsample_taps_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "grafp_conv1x1_bn_stats_supported": (_i, [_c.c_longlong, _i, _i, _i]),

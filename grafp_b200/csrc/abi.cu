@@ -451,7 +451,7 @@ int grafp_ntxent_fwd(const float* z, float* lse, float* row_loss, float* loss, i
   GRAFP_REQUIRE(aligned16(z), GRAFP_EINVAL, "grafp_ntxent_fwd: z must be 16-byte aligned");
   { int rc = require_device("grafp_ntxent_fwd"); if (rc != GRAFP_OK) return rc; }
   { int rc = require_device_ptr("grafp_ntxent_fwd", "z", z); if (rc) return rc; }
-  return launch_ntxent_fwd(z, lse, row_loss, loss, n2, d, inv_tau, static_cast<cudaStream_t>(stream));
+  return launch_ntxent_fwd(z, lse, row_loss, loss, n2, d, inv_tau, 0, n2, static_cast<cudaStream_t>(stream));
 }
 
 int grafp_ntxent_bwd(const float* z, const float* lse, const float* grad_loss, float* dz, int n2, int d, float inv_tau,
@@ -462,7 +462,33 @@ int grafp_ntxent_bwd(const float* z, const float* lse, const float* grad_loss, f
   GRAFP_REQUIRE(aligned16(z) && aligned16(dz), GRAFP_EINVAL, "grafp_ntxent_bwd: z and dz must be 16-byte aligned");
   { int rc = require_device("grafp_ntxent_bwd"); if (rc != GRAFP_OK) return rc; }
   { int rc = require_device_ptr("grafp_ntxent_bwd", "z", z); if (rc) return rc; }
-  return launch_ntxent_bwd(z, lse, grad_loss, dz, n2, d, inv_tau, static_cast<cudaStream_t>(stream));
+  return launch_ntxent_bwd(z, lse, grad_loss, dz, n2, d, inv_tau, 0, n2, 1.f, static_cast<cudaStream_t>(stream));
+}
+
+int grafp_ntxent_rows_fwd(const float* z, float* lse, float* row_loss, float* loss_part, int n2, int d, int row_lo, int row_hi,
+                          float inv_tau, void* stream) {
+  clear_error();
+  GRAFP_REQUIRE(z && lse && row_loss && loss_part, GRAFP_EINVAL, "grafp_ntxent_rows_fwd: z, lse, row_loss and loss_part must be non-null");
+  GRAFP_REQUIRE(ntxent_supported(n2, d), GRAFP_EUNSUPPORTED, "grafp_ntxent_rows_fwd: needs an even n2 >= 2 and d %% 4 == 0, d <= 256 (got %d, %d)", n2, d);
+  GRAFP_REQUIRE(row_lo >= 0 && row_lo < row_hi && row_hi <= n2 && row_lo % 2 == 0 && row_hi % 2 == 0, GRAFP_EINVAL,
+                "grafp_ntxent_rows_fwd: needs 0 <= row_lo < row_hi <= n2, both even (got %d, %d)", row_lo, row_hi);
+  GRAFP_REQUIRE(aligned16(z), GRAFP_EINVAL, "grafp_ntxent_rows_fwd: z must be 16-byte aligned");
+  { int rc = require_device("grafp_ntxent_rows_fwd"); if (rc != GRAFP_OK) return rc; }
+  { int rc = require_device_ptr("grafp_ntxent_rows_fwd", "z", z); if (rc) return rc; }
+  return launch_ntxent_fwd(z, lse, row_loss, loss_part, n2, d, inv_tau, row_lo, row_hi, static_cast<cudaStream_t>(stream));
+}
+
+int grafp_ntxent_rows_bwd(const float* z, const float* lse, const float* grad_loss, float* dz_rows, int n2, int d, int row_lo,
+                          int row_hi, float inv_tau, float grad_scale, void* stream) {
+  clear_error();
+  GRAFP_REQUIRE(z && lse && grad_loss && dz_rows, GRAFP_EINVAL, "grafp_ntxent_rows_bwd: z, lse, grad_loss and dz_rows must be non-null");
+  GRAFP_REQUIRE(ntxent_supported(n2, d), GRAFP_EUNSUPPORTED, "grafp_ntxent_rows_bwd: needs an even n2 >= 2 and d %% 4 == 0, d <= 256 (got %d, %d)", n2, d);
+  GRAFP_REQUIRE(row_lo >= 0 && row_lo < row_hi && row_hi <= n2 && row_lo % 2 == 0 && row_hi % 2 == 0, GRAFP_EINVAL,
+                "grafp_ntxent_rows_bwd: needs 0 <= row_lo < row_hi <= n2, both even (got %d, %d)", row_lo, row_hi);
+  GRAFP_REQUIRE(aligned16(z) && aligned16(dz_rows), GRAFP_EINVAL, "grafp_ntxent_rows_bwd: z and dz_rows must be 16-byte aligned");
+  { int rc = require_device("grafp_ntxent_rows_bwd"); if (rc != GRAFP_OK) return rc; }
+  { int rc = require_device_ptr("grafp_ntxent_rows_bwd", "z", z); if (rc) return rc; }
+  return launch_ntxent_bwd(z, lse, grad_loss, dz_rows, n2, d, inv_tau, row_lo, row_hi, grad_scale, static_cast<cudaStream_t>(stream));
 }
 
 int grafp_downsample_taps_fwd(const void* x, void* taps, int B, int N, int C, int dtype, void* stream) {

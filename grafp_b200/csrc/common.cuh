@@ -256,8 +256,9 @@ int launch_peak_extract_bwd(const float* spec, const float* out, const float* gr
 
 // ---- ntxent.cu ----
 bool ntxent_supported(int n2, int d);
-int launch_ntxent_fwd(const float* z, float* lse, float* row_loss, float* loss, int n2, int d, float inv_tau, cudaStream_t s);
+int launch_ntxent_fwd(const float* z, float* lse, float* row_loss, float* loss, int n2, int d, float inv_tau, int row_lo,
+                      int row_hi, cudaStream_t s);
 int launch_ntxent_bwd(const float* z, const float* lse, const float* grad_loss, float* dz, int n2, int d, float inv_tau,
-                      cudaStream_t s);
+                      int row_lo, int row_hi, float grad_scale, cudaStream_t s);
 
 }  // namespace grafp

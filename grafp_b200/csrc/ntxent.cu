@@ -51,12 +51,12 @@ __device__ __forceinline__ void logits_2x2(const float* zi, const float* zj, int
 
 __global__ void __launch_bounds__(kNtThreads)
 ntxent_fwd_kernel(const float* __restrict__ z, float* __restrict__ lse, float* __restrict__ row_loss, int n2, int d,
-                  float inv_tau) {
+                  float inv_tau, int row_lo, int row_hi) {
   extern __shared__ float nt_smem[];
   float* zi = nt_smem;
   float* zj = nt_smem + kNtTile * (d + 1);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int row0 = blockIdx.x * kNtTile;
+  const int row0 = row_lo + blockIdx.x * kNtTile;   // rows [row_lo, row_hi) of the (global) batch: a rank's own anchors
   load_tile(zi, z, row0, n2, d);
   float m[2] = {-INFINITY, -INFINITY}, s[2] = {0.f, 0.f}, pos[2] = {0.f, 0.f};
   for (int col0 = 0; col0 < n2; col0 += kNtTile) {
@@ -93,7 +93,7 @@ ntxent_fwd_kernel(const float* __restrict__ z, float* __restrict__ lse, float* _
       s[p] = sa + sb; m[p] = mn; pos[p] += po;  // exactly one lane holds the partner's logit, the others 0
     }
     const int i = row0 + 2 * ty + p;
-    if (tx == 0 && i < n2) {
+    if (tx == 0 && i < row_hi) {
       const float l = m[p] + __logf(s[p]);
       lse[i] = l;
       row_loss[i] = l - pos[p];
@@ -101,12 +101,12 @@ ntxent_fwd_kernel(const float* __restrict__ z, float* __restrict__ lse, float* _
   }
 }
 
-// loss = sum(row_loss) / n2 in a fixed order (one CTA)
+// loss = sum(row_loss[row_lo : row_hi]) / n2 in a fixed order (one CTA)
 __global__ void __launch_bounds__(256)
-ntxent_loss_reduce_kernel(const float* __restrict__ row_loss, float* __restrict__ loss, int n2) {
+ntxent_loss_reduce_kernel(const float* __restrict__ row_loss, float* __restrict__ loss, int n2, int row_lo, int row_hi) {
   __shared__ double sm[256];
   double acc = 0.0;
-  for (int i = threadIdx.x; i < n2; i += 256) acc += (double)row_loss[i];
+  for (int i = row_lo + threadIdx.x; i < row_hi; i += 256) acc += (double)row_loss[i];
   sm[threadIdx.x] = acc;
   __syncthreads();
   for (int h = 128; h > 0; h >>= 1) {
@@ -118,14 +118,14 @@ ntxent_loss_reduce_kernel(const float* __restrict__ row_loss, float* __restrict_
 
 __global__ void __launch_bounds__(kNtThreads)
 ntxent_bwd_kernel(const float* __restrict__ z, const float* __restrict__ lse, const float* __restrict__ grad_loss,
-                  float* __restrict__ dz, int n2, int d, float inv_tau) {
+                  float* __restrict__ dz, int n2, int d, float inv_tau, int row_lo, int row_hi, float grad_scale) {
   extern __shared__ float nt_smem[];
   float* zi = nt_smem;
   float* zj = zi + kNtTile * (d + 1);
   float* w = zj + kNtTile * (d + 1);   // [32][33] weights of the current tile
   float* lse_j = w + kNtTile * (kNtTile + 1);  // [32]
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int row0 = blockIdx.x * kNtTile;
+  const int row0 = row_lo + blockIdx.x * kNtTile;
   load_tile(zi, z, row0, n2, d);
   float lse_i[2];
 #pragma unroll
@@ -175,13 +175,13 @@ ntxent_bwd_kernel(const float* __restrict__ z, const float* __restrict__ lse, co
     }
   }
   const int i = row0 + ar;
-  if (i < n2) {
-    const float scale = __ldg(grad_loss) * inv_tau / (float)n2;
+  if (i < row_hi) {
+    const float scale = __ldg(grad_loss) * grad_scale * inv_tau / (float)n2;
 #pragma unroll
     for (int q = 0; q < kNtMaxD / 32; ++q) {
       const int c4 = ac + 8 * q;
       if (c4 < npk) {
-        reinterpret_cast<float4*>(dz + (size_t)i * d)[c4] =
+        reinterpret_cast<float4*>(dz + (size_t)(i - row_lo) * d)[c4] =   // dz holds the rows [row_lo, row_hi)
             make_float4(acc[q].x * scale, acc[q].y * scale, acc[q].z * scale, acc[q].w * scale);
       }
     }
@@ -192,7 +192,8 @@ ntxent_bwd_kernel(const float* __restrict__ z, const float* __restrict__ lse, co
 
 bool ntxent_supported(int n2, int d) { return n2 >= 2 && n2 % 2 == 0 && d >= 4 && d % 4 == 0 && d <= kNtMaxD; }
 
-int launch_ntxent_fwd(const float* z, float* lse, float* row_loss, float* loss, int n2, int d, float inv_tau, cudaStream_t s) {
+int launch_ntxent_fwd(const float* z, float* lse, float* row_loss, float* loss, int n2, int d, float inv_tau, int row_lo,
+                      int row_hi, cudaStream_t s) {
   const size_t smem = (size_t)2 * kNtTile * (d + 1) * sizeof(float);
   static DeviceOnce once;
   if (once.pending()) {
@@ -201,13 +202,13 @@ int launch_ntxent_fwd(const float* z, float* lse, float* row_loss, float* loss, 
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(ntxent): %s", cudaGetErrorString(e)); return (int)e; }
     once.mark();
   }
-  ntxent_fwd_kernel<<<(n2 + kNtTile - 1) / kNtTile, kNtThreads, smem, s>>>(z, lse, row_loss, n2, d, inv_tau);
-  ntxent_loss_reduce_kernel<<<1, 256, 0, s>>>(row_loss, loss, n2);
+  ntxent_fwd_kernel<<<(row_hi - row_lo + kNtTile - 1) / kNtTile, kNtThreads, smem, s>>>(z, lse, row_loss, n2, d, inv_tau, row_lo, row_hi);
+  ntxent_loss_reduce_kernel<<<1, 256, 0, s>>>(row_loss, loss, n2, row_lo, row_hi);
   return check_launch("ntxent_fwd");
 }
 
 int launch_ntxent_bwd(const float* z, const float* lse, const float* grad_loss, float* dz, int n2, int d, float inv_tau,
-                      cudaStream_t s) {
+                      int row_lo, int row_hi, float grad_scale, cudaStream_t s) {
   const size_t smem = ((size_t)2 * kNtTile * (d + 1) + kNtTile * (kNtTile + 1) + kNtTile) * sizeof(float);
   static DeviceOnce once;
   if (once.pending()) {
@@ -215,7 +216,8 @@ int launch_ntxent_bwd(const float* z, const float* lse, const float* grad_loss, 
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(ntxent_bwd): %s", cudaGetErrorString(e)); return (int)e; }
     once.mark();
   }
-  ntxent_bwd_kernel<<<(n2 + kNtTile - 1) / kNtTile, kNtThreads, smem, s>>>(z, lse, grad_loss, dz, n2, d, inv_tau);
+  ntxent_bwd_kernel<<<(row_hi - row_lo + kNtTile - 1) / kNtTile, kNtThreads, smem, s>>>(z, lse, grad_loss, dz, n2, d, inv_tau, row_lo,
+                                                                                       row_hi, grad_scale);
   return check_launch("ntxent_bwd");
 }
 

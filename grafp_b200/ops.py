@@ -566,6 +566,59 @@ class _NTXent(torch.autograd.Function):
         return dz, None
 
 
+class _NTXentSharded(torch.autograd.Function):
+    """NT-Xent over the global batch of a data-parallel run, each rank evaluating only its own anchor rows.
+
+    ``z_local`` (2 B_local, d): this rank's interleaved embeddings.  Forward: all-gather z (every rank holds the same number
+    of rows), the rank's rows of the loss against all rows, the scalar summed over the ranks.  Backward: all-gather of the
+    per-row log-sum-exps, then d loss / d z for the rank's own rows - complete (the other ranks' anchors enter through
+    P_ji), so there is no gradient exchange for z.  The result is scaled by the world size: the data-parallel reduction
+    that follows (DistributedDataParallel, training.FlatGradients) AVERAGES the parameter gradients over the ranks, and
+    the average of world x (each rank's share) is the exact gradient of the global-batch loss - the same contract as the
+    replicated form in simclr/distributed.py."""
+
+    @staticmethod
+    def forward(ctx, z_local, inv_tau, group):
+        import torch.distributed as dist
+        lib = _native.load()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        nl, d = z_local.shape
+        n2 = nl * world
+        z_all = torch.empty(n2, d, dtype=torch.float32, device=z_local.device)
+        dist.all_gather_into_tensor(z_all, z_local.contiguous(), group=group)
+        lo, hi = rank * nl, (rank + 1) * nl
+        lse = torch.empty(n2, dtype=torch.float32, device=z_local.device)
+        row_loss = torch.empty(n2, dtype=torch.float32, device=z_local.device)
+        loss = torch.empty((), dtype=torch.float32, device=z_local.device)
+        _call("ntxent_fwd", 2, dict(B=1, N=n2, C=d, rows=nl), lib.grafp_ntxent_rows_fwd, z_local.device, z_all.data_ptr(),
+              lse.data_ptr(), row_loss.data_ptr(), loss.data_ptr(), n2, d, lo, hi, float(inv_tau), _stream(z_local))
+        dist.all_reduce(loss, group=group)
+        lse_all = torch.empty(n2, dtype=torch.float32, device=z_local.device)
+        dist.all_gather_into_tensor(lse_all, lse[lo:hi].contiguous(), group=group)
+        ctx.save_for_backward(z_all, lse_all)
+        ctx.meta = (float(inv_tau), lo, hi, world)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        lib = _native.load()
+        z_all, lse_all = ctx.saved_tensors
+        inv_tau, lo, hi, world = ctx.meta
+        n2, d = z_all.shape
+        g = grad_loss.to(torch.float32).contiguous()
+        dz = torch.empty(hi - lo, d, dtype=torch.float32, device=z_all.device)
+        _call("ntxent_bwd", 1, dict(B=1, N=n2, C=d, rows=hi - lo), lib.grafp_ntxent_rows_bwd, z_all.device, z_all.data_ptr(),
+              lse_all.data_ptr(), g.data_ptr(), dz.data_ptr(), n2, d, lo, hi, inv_tau, float(world), _stream(z_all))
+        return dz, None, None
+
+
+def ntxent_sharded(z_local: torch.Tensor, tau: float, group=None) -> torch.Tensor:
+    """Global-batch NT-Xent of a data-parallel run from this rank's (2 B_local, d) interleaved embeddings (same B_local on
+    every rank); see :class:`_NTXentSharded`."""
+    _require_cuda(z_local)
+    return _NTXentSharded.apply(z_local.contiguous(), 1.0 / float(tau), group)
+
+
 def ntxent_supported(z: torch.Tensor) -> bool:
     return z.is_cuda and z.dtype == torch.float32 and z.dim() == 2 and z.shape[0] % 2 == 0 and z.shape[1] % 4 == 0 \
         and z.shape[1] <= 256

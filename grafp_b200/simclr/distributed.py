@@ -25,6 +25,12 @@ def global_ntxent_loss(z_i, z_j, cfg):
     """
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return ntxent_loss(z_i, z_j, cfg)
+    from .. import ops
+    z = torch.stack((z_i, z_j), dim=1).view(2 * z_i.shape[0], z_i.shape[1])
+    if ops.ntxent_supported(z):
+        # CUDA: every rank evaluates only its own anchor rows against the gathered embeddings (1 / world of the work;
+        # the replicated form below costs world^2 x the single-GPU loss per rank) - same value, same gradient contract
+        return ops.ntxent_sharded(z, cfg['tau'])
     import torch.distributed.nn.functional as dfn
     zi_all = torch.cat(dfn.all_gather(z_i), dim=0)
     zj_all = torch.cat(dfn.all_gather(z_j), dim=0)

@@ -273,6 +273,23 @@ int grafp_ntxent_bwd(const float* z, const float* lse, const float* grad_loss, f
                      void* stream);
 
 /*
+ * The same loss sharded by anchor rows, for data-parallel training (one process per GPU): z holds the embeddings of ALL
+ * ranks (all-gathered), a rank evaluates only its own anchors [row_lo, row_hi) against every row - 1 / world of the work
+ * instead of the whole (n2 x n2) problem on every rank.
+ *   forward:  lse[i], row_loss[i] for i in [row_lo, row_hi) (arrays indexed by the global row), loss_part =
+ *             sum of those row losses / n2; the loss is the sum of loss_part over the ranks.
+ *   backward: needs lse of ALL rows (all-gather the slices).  dz_rows (row_hi - row_lo, d) = grad_scale * grad_loss *
+ *             d loss / d z_i for the rank's own rows - complete, the P_ji terms of the other ranks' anchors included, so no
+ *             gradient exchange for z is needed.  grad_scale: e.g. the world size when the parameter gradients are averaged
+ *             over the ranks afterwards.
+ * row_lo, row_hi even (partners stay together).
+ */
+int grafp_ntxent_rows_fwd(const float* z, float* lse, float* row_loss, float* loss_part, int n2, int d, int row_lo, int row_hi,
+                          float inv_tau, void* stream);
+int grafp_ntxent_rows_bwd(const float* z, const float* lse, const float* grad_loss, float* dz_rows, int n2, int d, int row_lo,
+                          int row_hi, float inv_tau, float grad_scale, void* stream);
+
+/*
  * Peak point-cloud front end.  Replaces GPUPeakExtractorv2.forward (peak_extractor.py:56-82): min-max
  * normalisation of the (H, W) log-mel segment, the time / frequency position ramps (torch.linspace(0, 1, W / H)),
  * Conv2d(3 -> F, kh x kw, stride (stride_h, 1), padding (kh / 2, kw / 2)) + ReLU and the reshape to a point cloud,

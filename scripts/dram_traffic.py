@@ -13,7 +13,7 @@ kn, rd, wr = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("d
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 ops = {"knn_fwd": ("knn_normalize", "knn_stream_kernel"), "mr_aggregate_fwd": ("mr_aggregate_fwd",),
        "mr_aggregate_bwd": ("mr_aggregate_bwd",), "bn_train_fwd": ("bn_fwd", "bn_stats", "bn_apply"),
-       "bn_train_bwd": ("bn_bwd",)}
+       "bn_train_bwd": ("bn_bwd",), "conv1x1_bn_stats_fwd": ("conv1x1_stats_kernel",)}
 result = {}
 seen = {k: set() for k in ops}
 for row in rows[2:]:
@@ -27,6 +27,6 @@ for row in rows[2:]:
                 break
 result = {k: int(v) for k, v in result.items()}
 result["_note"] = ("per-launch DRAM bytes (read + write) from ncu --set full, first launch of each kernel in scripts/ncu_ops.py: "
-                   "B=512, N=1024, C=64 (K1 = normalise + Gram/top-k launches; K5 on the (B, N, 128) tensor)")
+                   "B=512, N=1024, C=64 (K1 = normalise + Gram/top-k launches; K5 on the (B, N, 128) tensor; convolution 64 -> 256)")
 json.dump(result, open(out_path, "w"), indent=1)
 print(json.dumps(result, indent=1))

@@ -15,7 +15,7 @@ for step in "$@"; do
     bench_bf16_g0) GRAFP_CONV_GEMM=0 timeout 600 python bench.py --dtype bf16 --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_bf16_gemm0.json 2> $out/${tag}_bench_n1_bf16_gemm0.err; tail -c 300 $out/${tag}_bench_n1_bf16_gemm0.err; cut -c1-300 $out/${tag}_bench_n1_bf16_gemm0.json ;;
     bench_bf16) timeout 600 python bench.py --dtype bf16 --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_bf16.json 2> $out/${tag}_bench_n1_bf16.err; tail -c 600 $out/${tag}_bench_n1_bf16.err; cut -c1-400 $out/${tag}_bench_n1_bf16.json ;;
     bench_ref) timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_reference_arm.json 2> $out/${tag}_bench_reference_arm.err; cut -c1-300 $out/${tag}_bench_reference_arm.json ;;
-    kernels) timeout 900 python scripts/bench_kernels.py > $out/${tag}_bench_kernels.log 2>&1; tail -60 $out/${tag}_bench_kernels.log ;;
+    kernels) timeout 900 python scripts/bench_kernels.py k1 k23 k5 gemm > $out/${tag}_bench_kernels.log 2>&1; tail -60 $out/${tag}_bench_kernels.log ;;
     k1) timeout 600 python scripts/bench_kernels.py k1 > $out/${tag}_bench_k1.log 2>&1; cat $out/${tag}_bench_k1.log ;;
     k23) timeout 600 python scripts/bench_kernels.py k23 > $out/${tag}_bench_k23.log 2>&1; cat $out/${tag}_bench_k23.log ;;
     copies) timeout 600 python scripts/profile_copies.py 512 > $out/${tag}_copies.log 2>&1; cut -c1-250 $out/${tag}_copies.log | head -60 ;;
@@ -32,7 +32,7 @@ for step in "$@"; do
               GRAFP_BN_L2_KEEP_MB=80 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_l2keep80.json 2> $out/${tag}_bench_n1_l2keep80.err; cut -c1-300 $out/${tag}_bench_n1_l2keep80.json ;;
     bench_nograph) timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager --graph off > $out/${tag}_bench_n1_nograph.json 2> $out/${tag}_bench_n1_nograph.err; cut -c1-300 $out/${tag}_bench_n1_nograph.json ;;
     launches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 1 --graph off --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_under_ncu.log 2>&1; wc -l $out/launches.csv ;;
-    ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"knn_|mr_aggregate|bn_|ntxent|peak_extract" -c 80 -f -o /tmp/prof_ops python scripts/ncu_ops.py 512 1 > $out/${tag}_ncu_ops.log 2>&1; tail -2 $out/${tag}_ncu_ops.log
+    ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"knn_|mr_aggregate|bn_|ntxent|peak_extract|conv1x1|taps_" -c 110 -f -o /tmp/prof_ops python scripts/ncu_ops.py 512 1 > $out/${tag}_ncu_ops.log 2>&1; tail -2 $out/${tag}_ncu_ops.log
              python scripts/ncu_summary.py /tmp/prof_ops.ncu-rep > $out/${tag}_ncu_hot_kernels_summary.txt 2>&1
              python scripts/ncu_stalls.py /tmp/prof_ops.ncu-rep > $out/${tag}_ncu_stalls.txt 2>&1
              python scripts/dram_traffic.py /tmp/prof_ops.ncu-rep $out/${tag}_dram_traffic.json > /dev/null 2>&1

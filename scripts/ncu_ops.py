@@ -18,6 +18,18 @@ for (N, C) in [(1024, 64), (512, 128), (256, 256), (128, 512)]:
         y = ops.batch_norm_act(out, bn, relu=True)           # fused train-mode BatchNorm + ReLU on the (B, N, 2C) rows
         g = torch.randn_like(y)
         (gx,) = torch.autograd.grad(y, x, g)
+    # FFN fc1 of the stage (C -> 4C) through the tcgen05 convolution with the statistics epilogue + the apply pass
+    torch.backends.cudnn.allow_tf32 = True
+    conv = torch.nn.Conv2d(C, 4 * C, 1, bias=False).to(dev)
+    bn4 = torch.nn.BatchNorm2d(4 * C).to(dev).train()
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        for _ in range(reps):
+            ops.set_option("conv_gemm", 2)
+            h = ops.conv_batch_norm_act(x, conv, bn4, relu=True)
+    ops.set_option("conv_gemm", 1)
+    if N >= 256:
+        taps = ops._DownsampleTaps.apply(x)
+        taps.backward(torch.ones_like(taps))
     torch.cuda.synchronize()
 # the 8f kernels at the bench shapes: NT-Xent on 1024 x 128 embeddings, the peak extractor on 512 segments
 from grafp_b200 import synth

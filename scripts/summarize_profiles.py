@@ -40,7 +40,8 @@ def launches():
         tot[name][0] += 1
         tot[name][1] += us
         n += 1
-        if "grafp" in full or "knn_" in full or "mr_aggregate" in full or "bn_" in full or "ntxent" in full or "peak_extract" in full:
+        if ("grafp" in full or "knn_" in full or "mr_aggregate" in full or "bn_" in full or "ntxent" in full or "peak_extract" in full
+                or "conv1x1" in full or "taps_" in full):
             ours.append((row["ID"], name, row.get("Grid Size", ""), row.get("Block Size", ""), f"{us:.2f}"))
     total = sum(v[1] for v in tot.values())
     with open(os.path.join(OUT, f"{tag}_launches_summary.csv"), "w") as f:

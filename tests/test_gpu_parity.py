@@ -936,6 +936,39 @@ def test_downsample_tap_rows(shape, dtype):
     assert torch.equal(x.grad, xr.grad)
 
 
+def test_ntxent_row_shards_equal_the_full_problem():
+    """grafp_ntxent_rows_fwd / _bwd (what a rank of a data-parallel run evaluates: its own anchor rows against the gathered
+    embeddings) over the four quarters of a batch against the full-problem kernels: the loss parts sum to the loss, the
+    per-row log-sum-exps and the gradient rows are the full problem's."""
+    lib = ops._native.load()
+    n2, d, tau, world = 1024, 128, 0.05, 4
+    g = torch.Generator().manual_seed(12)
+    z = torch.nn.functional.normalize(torch.randn(n2, d, generator=g), dim=1).to(DEV).requires_grad_(True)
+    full = ops.ntxent(z, tau)
+    full.backward()
+    stream = torch.cuda.current_stream().cuda_stream
+    zc = z.detach().contiguous()
+    lse = torch.zeros(n2, device=DEV)
+    row_loss = torch.zeros(n2, device=DEV)
+    parts = torch.zeros(world, device=DEV)
+    nl = n2 // world
+    for r in range(world):
+        rc = lib.grafp_ntxent_rows_fwd(zc.data_ptr(), lse.data_ptr(), row_loss.data_ptr(), parts[r:].data_ptr(), n2, d,
+                                       r * nl, (r + 1) * nl, 1.0 / tau, stream)
+        assert rc == 0
+    assert abs(float(parts.sum()) - float(full)) < 1e-5 * abs(float(full))
+    one = torch.ones((), device=DEV)
+    dz = torch.empty(n2, d, device=DEV)
+    for r in range(world):
+        rc = lib.grafp_ntxent_rows_bwd(zc.data_ptr(), lse.data_ptr(), one.data_ptr(), dz[r * nl:].data_ptr(), n2, d, r * nl,
+                                       (r + 1) * nl, 1.0 / tau, 1.0, stream)
+        assert rc == 0
+    torch.cuda.synchronize()
+    assert gio.rel_err(dz.double().cpu(), z.grad.double().cpu()) < 1e-6
+    assert lib.grafp_ntxent_rows_fwd(zc.data_ptr(), lse.data_ptr(), row_loss.data_ptr(), parts.data_ptr(), n2, d, 1, 33,
+                                     1.0 / tau, stream) == -1     # odd bounds would split a pair
+
+
 def _bn_moments(ws, C):
     """The per-channel (sum, sum of squares) doubles inside a BatchNorm workspace (256-byte aligned, bn_fused.cu)."""
     off = (-ws.data_ptr()) % 256
