@@ -614,93 +614,9 @@ mr_aggregate_bwd_cluster_kernel(const T* __restrict__ g, const uint8_t* __restri
   }
 }
 
-// Register-resident variant (option mr_bwd_form = 4): the CTA's share of grad_out goes straight from global memory
-// into registers (two coalesced 16-byte loads per item) and is used from there in both phases - no bulk copy, no
-// mbarrier, no shared-memory round trip of the 64 KB share; only the neighbour ids (rows * k) sit in shared memory.
-// Two CTAs per SM (the share is 64 + 8..16 registers per thread).
-template <typename T, bool I64>
-__global__ void __launch_bounds__(kFusedThreads, 2)
-mr_aggregate_bwd_cluster_reg_kernel(const T* __restrict__ g, const uint8_t* __restrict__ argmax,
-                                    const void* __restrict__ nbr, T* __restrict__ grad_x, int N, int C, int k,
-                                    int rows_per_cta, int cv_shift) {
-  using It = Item16<T>;
-  constexpr int V = It::V;
-  constexpr int kItems = 2048 / kFusedThreads;
-  extern __shared__ __align__(16) unsigned char reg_smem[];
-  int* ids = reinterpret_cast<int*>(reg_smem);  // [rows][k]
-  const int cv = 1 << cv_shift;
-  const unsigned csize = cluster_nctarank();
-  const long long b = blockIdx.x / csize;
-  const int row0 = static_cast<int>(cluster_ctarank()) * rows_per_cta;
-  const int nrows = max(0, min(rows_per_cta, N - row0));
-  const int items = nrows << cv_shift;
-  T* gxb = grad_x + b * (long long)N * C;
-  const T* gb = g + (b * N + row0) * 2LL * C;
-
-  uint4 ga[kItems], gc[kItems];
-  unsigned int am[kItems][V / 4];
-#pragma unroll
-  for (int u = 0; u < kItems; ++u) {
-    const int it = threadIdx.x + u * kFusedThreads;
-    const bool ok = it < items;
-    const uint4* gp = reinterpret_cast<const uint4*>(gb) + 2 * (long long)it;   // item `it` = 32 consecutive bytes of the share
-    ga[u] = ok ? __ldg(gp) : make_uint4(0u, 0u, 0u, 0u);
-    gc[u] = ok ? __ldg(gp + 1) : make_uint4(0u, 0u, 0u, 0u);
-    const uint8_t* ap = argmax + (b * N + row0 + (it >> cv_shift)) * (long long)C + (it & (cv - 1)) * V;
-#pragma unroll
-    for (int q = 0; q < V / 4; ++q) am[u][q] = ok ? __ldg(reinterpret_cast<const unsigned int*>(ap) + q) : 0u;
-  }
-  for (int i = threadIdx.x; i < nrows * k; i += kFusedThreads)
-    ids[i] = static_cast<int>(load_index<I64>(nbr, (b * N + row0) * (long long)k + i));
-  __syncthreads();
-
-  // phase 1: dense part of grad_x for this CTA's rows
-#pragma unroll
-  for (int u = 0; u < kItems; ++u) {
-    const int it = threadIdx.x + u * kFusedThreads;
-    if (it < items) {
-      const int rl = it >> cv_shift;
-      const int n = row0 + rl;
-      const int c = (it & (cv - 1)) * V;
-      float g0[V], g1[V];
-      It::unpack_pairs(ga[u], gc[u], g0, g1);
-      float r[V];
-#pragma unroll
-      for (int e = 0; e < V; ++e) {
-        const int nb = ids[rl * k + ((am[u][e >> 2] >> (8 * (e & 3))) & 0xff)];
-        r[e] = (nb == n) ? g0[e] : g0[e] - g1[e];
-      }
-      It::store(gxb + (long long)n * C + c, r);
-    }
-  }
-  cluster_sync_all();
-
-  // phase 2: route g[.., 2c+1] to the winning neighbour rows of this segment (L2-resident, just written)
-#pragma unroll
-  for (int u = 0; u < kItems; ++u) {
-    const int it = threadIdx.x + u * kFusedThreads;
-    if (it < items) {
-      const int rl = it >> cv_shift;
-      const int n = row0 + rl;
-      const int c = (it & (cv - 1)) * V;
-      float g0[V], g1[V];
-      It::unpack_pairs(ga[u], gc[u], g0, g1);
-      for (int j = 0; j < k; ++j) {
-        float v[V];
-        bool any = false;
-#pragma unroll
-        for (int f = 0; f < V; ++f) {
-          const bool hit = ((am[u][f >> 2] >> (8 * (f & 3))) & 0xff) == (unsigned)j;
-          v[f] = hit ? g1[f] : 0.f;
-          any |= hit;
-        }
-        const int nb = ids[rl * k + j];
-        if (any && nb != n) It::red_add(gxb + (long long)nb * C + c, v);
-      }
-    }
-  }
-}
-
+// (Measured and dropped, round 2: a variant that loads the CTA's share of grad_out straight into registers - no bulk
+//  copy, no mbarrier, no shared-memory round trip - runs in the same 120.8 us as this one (121.9 us): the kernel is bound
+//  by the reductions at L2, not by how its inputs arrive.  profiles/r03c_bench_k23.log.)
 template <typename T, bool I64>
 int launch_mr_bwd_cluster(const T* g, const uint8_t* argmax, const void* nbr, T* grad_x, int B, int N, int C, int k,
                           bool fence, cudaStream_t s, bool* launched) {
@@ -753,25 +669,6 @@ int launch_mr_bwd_cluster(const T* g, const uint8_t* argmax, const void* nbr, T*
     return check_launch("mr_aggregate_bwd_cluster");
   };
   static DeviceOnce once_fence, once_nofence;
-  if (option(OPT_MR_BWD_FORM) == 4) {  // register-resident share: only the ids in shared memory
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(B * cl));
-    cfg.blockDim = dim3(kFusedThreads);
-    cfg.dynamicSmemBytes = (size_t)rows_per_cta * k * sizeof(int);
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cl;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, mr_aggregate_bwd_cluster_reg_kernel<T, I64>, g, argmax, nbr, grad_x, N, C, k,
-                                       rows_per_cta, cv_shift);
-    if (e != cudaSuccess) { set_error("mr_aggregate_bwd_cluster_reg launch: %s", cudaGetErrorString(e)); return (int)e; }
-    *launched = true;
-    return check_launch("mr_aggregate_bwd_cluster_reg");
-  }
   if (fence) return launch(mr_aggregate_bwd_cluster_kernel<T, I64, true>, once_fence);
   return launch(mr_aggregate_bwd_cluster_kernel<T, I64, false>, once_nofence);
 }

@@ -69,7 +69,7 @@ def bench_k1(dtype):
 def bench_k23(dtype):
     e = 4 if dtype == torch.float32 else 2
     print(f"=== K2 / K3, dtype={dtype}, B={B}, k={k}")
-    for bwd_form, label in ((2, "cluster, bulk-staged"), (4, "cluster, registers"), (3, "gather (deterministic)"), (0, "dense + scatter pair")):
+    for bwd_form, label in ((2, "cluster, bulk-staged"), (1, "cluster + device fence"), (3, "gather (deterministic)"), (0, "dense + scatter pair")):
         ops.set_option("mr_bwd_form", bwd_form)
         for (N, C) in STAGES:
             x = rows(N, C, dtype, grad=True)
