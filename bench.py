@@ -395,8 +395,24 @@ def run_ours(args):
         # the whole step - both views forward, loss, backward, Adam - as ONE CUDA graph; new inputs are copied into
         # its static buffers (from pinned host memory in the e2e region)
         from grafp_b200.training import GraphedTrainStep
-        step = GraphedTrainStep(net, opt, loss_of, [dev_i, dev_j], autocast_dtype=torch.bfloat16 if bf16 else None,
-                                data_parallel=graph_dp)
+        try:
+            step = GraphedTrainStep(net, opt, loss_of, [dev_i, dev_j], autocast_dtype=torch.bfloat16 if bf16 else None,
+                                    data_parallel=graph_dp)
+            captured = 1
+        except Exception as exc:  # a capture that fails must not cost the bench line (nor hang the other ranks)
+            print(f"bench.py: CUDA-graph capture failed on rank {rank} ({type(exc).__name__}: {exc}); running eagerly",
+                  file=sys.stderr, flush=True)
+            captured = 0
+        if world > 1:   # nothing of a capture executes, so every rank gets here: agree on one form
+            flag = torch.tensor([captured], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            captured = int(flag.item())
+        if not captured:
+            use_graph = graph_dp = False
+            step = eager_step
+            if world > 1:
+                net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=True,
+                                                                gradient_as_bucket_view=True)
 
     def barrier():
         if world > 1:
