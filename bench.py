@@ -281,7 +281,8 @@ def algorithmic_work(name, m):
     e = 4 if m.get("dtype", 0) == 0 else 2
     if name == "conv1x1_bn_stats_fwd":  # read the input rows and the weight, write the output rows (moments: 16 bytes / channel)
         B, N, Cin, Cout = m["B"], m["N"], m["Cin"], m["Cout"]
-        return {"flops": 2.0 * B * N * Cin * Cout, "bytes": B * N * (Cin + Cout) * e + Cin * Cout * e}
+        G = m.get("groups", 1)
+        return {"flops": 2.0 * B * N * Cin * Cout / G, "bytes": B * N * (Cin + Cout) * e + Cin * Cout * e // G}
     B, N, C = m["B"], m["N"], m["C"]
     if name == "knn_fwd":
         M, K = m["M"], m["K"]

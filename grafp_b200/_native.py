@@ -49,12 +49,12 @@ SIGNATURES = {
     "grafp_ntxent_rows_bwd": (_i, [_vp] * 4 + [_i, _i, _i, _i, _c.c_float, _c.c_float, _vp]),
     "grafp_downsample_taps_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "grafp_downsample_taps_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "grafp_conv1x1_bn_stats_supported": (_i, [_c.c_longlong, _i, _i, _i]),
-    "grafp_conv1x1_bn_stats_fwd": (_i, [_vp] * 3 + [_c.c_longlong, _i, _i, _i, _vp, _sz, _vp]),
+    "grafp_conv1x1_bn_stats_supported": (_i, [_c.c_longlong, _i, _i, _i, _i]),
+    "grafp_conv1x1_bn_stats_fwd": (_i, [_vp] * 3 + [_c.c_longlong, _i, _i, _i, _i, _vp, _sz, _vp]),
     "grafp_bn_train_fwd_from_moments": (_i, [_vp] * 11 + [_c.c_longlong, _i, _c.c_float, _c.c_float, _i, _i, _vp, _sz, _vp]),
 }
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 KNN_AUTO, KNN_SIMT, KNN_TC, KNN_TC_TF32 = 0, 1, 2, 3
 KNN_MAX_K = 128
 METRIC_L2, METRIC_COSINE = 0, 1

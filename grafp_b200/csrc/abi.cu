@@ -411,20 +411,22 @@ int grafp_bn_train_fwd_from_moments(const void* x, const void* residual, const f
                              save_invstd, R, C, eps, momentum, relu, dtype, workspace, true, static_cast<cudaStream_t>(stream));
 }
 
-int grafp_conv1x1_bn_stats_supported(long long R, int Cin, int Cout, int dtype) {
-  return conv1x1_stats_supported(R, Cin, Cout, dtype) ? 1 : 0;
+int grafp_conv1x1_bn_stats_supported(long long R, int Cin, int Cout, int groups, int dtype) {
+  return conv1x1_stats_supported(R, Cin, Cout, groups, dtype) ? 1 : 0;
 }
 
-int grafp_conv1x1_bn_stats_fwd(const void* x, const void* w, void* y, long long R, int Cin, int Cout, int dtype,
+int grafp_conv1x1_bn_stats_fwd(const void* x, const void* w, void* y, long long R, int Cin, int Cout, int groups, int dtype,
                                void* workspace, size_t workspace_bytes, void* stream) {
   clear_error();
-  GRAFP_REQUIRE(R > 0 && Cin > 0 && Cout > 0, GRAFP_EINVAL, "grafp_conv1x1_bn_stats_fwd: R, Cin and Cout must be positive");
+  GRAFP_REQUIRE(R > 0 && Cin > 0 && Cout > 0 && groups > 0, GRAFP_EINVAL,
+                "grafp_conv1x1_bn_stats_fwd: R, Cin, Cout and groups must be positive");
   GRAFP_REQUIRE(x && w && y && workspace, GRAFP_EINVAL, "grafp_conv1x1_bn_stats_fwd: x, w, y and workspace must be non-null");
   GRAFP_REQUIRE(workspace_bytes >= bn_workspace_bytes(Cout), GRAFP_EWORKSPACE,
                 "grafp_conv1x1_bn_stats_fwd: workspace smaller than grafp_bn_workspace_bytes(Cout)");
   { int rc = require_device("grafp_conv1x1_bn_stats_fwd"); if (rc != GRAFP_OK) return rc; }
   { int rc = require_device_ptr("grafp_conv1x1_bn_stats_fwd", "x", x); if (rc) return rc; }
-  return launch_conv1x1_stats(x, w, y, bn_workspace_sums(workspace), R, Cin, Cout, dtype, static_cast<cudaStream_t>(stream));
+  return launch_conv1x1_stats(x, w, y, bn_workspace_sums(workspace), R, Cin, Cout, groups, dtype,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int grafp_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,

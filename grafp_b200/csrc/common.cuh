@@ -234,9 +234,9 @@ int launch_bn_train_fwd(const void* x, const void* res, const float* weight, con
                         bool from_moments, cudaStream_t s);
 double* bn_workspace_sums(void* workspace);  // where the per-channel sums live inside a BatchNorm workspace
 // conv_gemm.cu: Y = X W^T on tcgen05 with sum y / sum y^2 per output channel (2 * Cout doubles, zeroed by the call)
-bool conv1x1_stats_supported(long long R, int Cin, int Cout, int dtype);
-int launch_conv1x1_stats(const void* x, const void* w, void* y, double* sums, long long R, int Cin, int Cout, int dtype,
-                         cudaStream_t s);
+bool conv1x1_stats_supported(long long R, int Cin, int Cout, int groups, int dtype);
+int launch_conv1x1_stats(const void* x, const void* w, void* y, double* sums, long long R, int Cin, int Cout, int groups,
+                         int dtype, cudaStream_t s);
 int launch_bn_train_bwd(const void* dy, const void* x, const float* weight, const float* bias, const float* save_mean,
                         const float* save_invstd, void* dx, float* dweight, float* dbias, float* dx_colsum, long long R, int C,
                         int relu, int dtype, void* workspace, cudaStream_t s);

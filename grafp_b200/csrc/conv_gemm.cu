@@ -8,6 +8,9 @@
 // take its per-channel mean and variance.  Here the accumulator tile is already in registers on its way out, so
 // the moments are taken there and the BatchNorm is left with its apply pass: one read of Y instead of two.
 //
+// Grouped convolutions (BasicConv's groups = 4) keep the dense 128 x BN output tile and make the MMA schedule
+// block-diagonal: a group's columns of the tile are one MMA of N = Cout / groups over that group's k-range.
+//
 // fp32 rows run as TF32 (tcgen05.mma.kind::tf32, fp32 accumulate - the arithmetic cuDNN uses for the same layer when
 // torch.backends.cudnn.allow_tf32 is set, which is PyTorch's default; the host takes this path only then), bf16 rows as
 // kind::f16 with bf16 operands.  The layer is HBM-bound for every shape of the encoder but the last stage.
@@ -56,11 +59,11 @@ struct Cfg {
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;
 };
 
-// instruction descriptor: D = f32, A = B = tf32 (2) or bf16 (1), both K-major, M = 128, N = BN
+// instruction descriptor: D = f32, A = B = tf32 (2) or bf16 (1), both K-major, M = 128, N = n (a multiple of 16, <= BN)
 template <typename T, int BN>
-__device__ __forceinline__ constexpr uint32_t make_idesc() {
+__device__ __forceinline__ uint32_t make_idesc(int n) {
   constexpr uint32_t fmt = sizeof(T) == 4 ? 2u : 1u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
 }
 
 __device__ __forceinline__ bool elect_one() {
@@ -117,7 +120,8 @@ __device__ __forceinline__ void red_add_f64(double* p, double v) {
 template <typename T, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv1x1_stats_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                     const __grid_constant__ CUtensorMap tm_y, double* __restrict__ sums, long long R, int Cin, int Cout) {
+                     const __grid_constant__ CUtensorMap tm_y, double* __restrict__ sums, long long R, int Cin, int Cout,
+                     int Cg, int Og, int wN) {
   using cfg = Cfg<T, BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -135,7 +139,11 @@ conv1x1_stats_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   const int col_tiles = (Cout + BN - 1) / BN;
   const long long row_tiles = (R + BM - 1) / BM;
   const long long num_tiles = row_tiles * col_tiles;
-  const int num_kc = (Cin + cfg::BK - 1) / cfg::BK;
+  // Grouped convolution (Cg = Cin / groups input, Og = Cout / groups output channels per group; dense: Cg = Cin,
+  // Og = Cout): the output tile stays 128 x BN, the MMA schedule becomes block-diagonal - the tile's columns are filled
+  // in sub-blocks of wN = min(BN, Og) columns, each from the k-range [g Cg, (g + 1) Cg) of its own group g.
+  const int num_kc = (Cg + cfg::BK - 1) / cfg::BK;
+  const int sub_blocks = BN / wN;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < cfg::kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -161,42 +169,53 @@ conv1x1_stats_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int r0 = static_cast<int>(tile / col_tiles) * BM;
         const int n0 = static_cast<int>(tile % col_tiles) * BN;
-        for (int c = 0; c < num_kc; ++c, ++it) {
-          const int s = it % cfg::kStages;
-          const uint32_t ph = (it / cfg::kStages) & 1;
-          mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          const uint32_t full = bar_full + 8 * s;
-          mbar_arrive_expect_tx(full, cfg::kStageBytes);
-          const uint32_t sa = ring + s * cfg::kStageBytes;
-          tma_load_2d(sa, &tm_x, full, c * cfg::BK, r0);
-          tma_load_2d(sa + cfg::kABytes, &tm_w, full, c * cfg::BK, n0);
+        for (int sb = 0; sb < sub_blocks; ++sb) {
+          const int nc0 = n0 + sb * wN;
+          if (nc0 >= Cout) break;
+          const int kbase = (nc0 / Og) * Cg;
+          for (int c = 0; c < num_kc; ++c, ++it) {
+            const int s = it % cfg::kStages;
+            const uint32_t ph = (it / cfg::kStages) & 1;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1);
+            const uint32_t full = bar_full + 8 * s;
+            mbar_arrive_expect_tx(full, cfg::kABytes + static_cast<uint32_t>(wN) * 128u);
+            const uint32_t sa = ring + s * cfg::kStageBytes;
+            // (a chunk may run past the group's k-range into the next group's columns of x: the matching columns of the
+            //  W box lie beyond its Cg-wide rows and arrive as zeros)
+            tma_load_2d(sa, &tm_x, full, kbase + c * cfg::BK, r0);
+            tma_load_2d(sa + cfg::kABytes, &tm_w, full, c * cfg::BK, nc0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc<T, BN>();
+      const uint32_t idesc = make_idesc<T, BN>(wN);
       int it = 0, lt = 0;
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int as = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
+        const int n0 = static_cast<int>(tile % col_tiles) * BN;
         mbar_wait(bar_tempty + 8 * as, aph ^ 1);  // the epilogue has drained this accumulator buffer
         tcgen05_fence_after();
-        const uint32_t acc = tmem_base + as * BN;
-        for (int c = 0; c < num_kc; ++c, ++it) {
-          const int s = it % cfg::kStages;
-          const uint32_t ph = (it / cfg::kStages) & 1;
-          mbar_wait(bar_full + 8 * s, ph);
-          tcgen05_fence_after();
-          const uint32_t sa = ring + s * cfg::kStageBytes;
-          const uint32_t a_lo0 = desc_lo(sa), b_lo0 = desc_lo(sa + cfg::kABytes);
+        for (int sb = 0; sb < sub_blocks; ++sb) {
+          if (n0 + sb * wN >= Cout) break;
+          const uint32_t acc = tmem_base + as * BN + sb * wN;
+          for (int c = 0; c < num_kc; ++c, ++it) {
+            const int s = it % cfg::kStages;
+            const uint32_t ph = (it / cfg::kStages) & 1;
+            mbar_wait(bar_full + 8 * s, ph);
+            tcgen05_fence_after();
+            const uint32_t sa = ring + s * cfg::kStageBytes;
+            const uint32_t a_lo0 = desc_lo(sa), b_lo0 = desc_lo(sa + cfg::kABytes);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {  // four 32-byte k-steps per 128-byte chunk row
-            if constexpr (sizeof(T) == 4) umma_tf32(acc, desc_of(a_lo0 + kk * 2), desc_of(b_lo0 + kk * 2), idesc, (c | kk) != 0 ? 1u : 0u);
-            else umma_f16(acc, desc_of(a_lo0 + kk * 2), desc_of(b_lo0 + kk * 2), idesc, (c | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk) {  // four 32-byte k-steps per 128-byte chunk row
+              if constexpr (sizeof(T) == 4) umma_tf32(acc, desc_of(a_lo0 + kk * 2), desc_of(b_lo0 + kk * 2), idesc, (c | kk) != 0 ? 1u : 0u);
+              else umma_f16(acc, desc_of(a_lo0 + kk * 2), desc_of(b_lo0 + kk * 2), idesc, (c | kk) != 0 ? 1u : 0u);
+            }
+            tcgen05_commit(bar_empty + 8 * s);  // frees the stage when these MMAs retire
           }
-          tcgen05_commit(bar_empty + 8 * s);  // frees the stage when these MMAs retire
         }
         tcgen05_commit(bar_tfull + 8 * as);
       }
@@ -347,7 +366,7 @@ bool make_map(CUtensorMap* map, const void* base, long long rows, int cols, int 
 }
 
 template <typename T, int BN>
-int launch_variant(const void* x, const void* w, void* y, double* sums, long long R, int Cin, int Cout, int dtype,
+int launch_variant(const void* x, const void* w, void* y, double* sums, long long R, int Cin, int Cout, int groups, int dtype,
                    cudaStream_t s) {
   using cfg = Cfg<T, BN>;
   static DeviceOnce once;
@@ -357,30 +376,49 @@ int launch_variant(const void* x, const void* w, void* y, double* sums, long lon
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv1x1_stats): %s", cudaGetErrorString(e)); return (int)e; }
     once.mark();
   }
+  const int Cg = Cin / groups, Og = Cout / groups;
+  const int wN = (groups > 1 && Og < BN) ? Og : BN;   // columns one MMA fills: a whole tile, or one group's share of it
   CUtensorMap tx, tw, ty;
-  if (!make_map(&tx, x, R, Cin, BM, dtype) || !make_map(&tw, w, Cout, Cin, BN, dtype) || !make_map(&ty, y, R, Cout, BM, dtype)) {
+  if (!make_map(&tx, x, R, Cin, BM, dtype) || !make_map(&tw, w, Cout, Cg, wN, dtype) || !make_map(&ty, y, R, Cout, BM, dtype)) {
     set_error("conv1x1_bn_stats: cuTensorMapEncodeTiled failed (driver entry point unavailable or bad shape)");
     return GRAFP_EUNSUPPORTED;
   }
   const long long tiles = ((R + BM - 1) / BM) * ((Cout + BN - 1) / BN);
   const int sms = num_sms();
   const int grid = (int)(tiles < sms ? tiles : sms);
-  conv1x1_stats_kernel<T, BN><<<grid, kThreads, cfg::kSmemBytes, s>>>(tx, tw, ty, sums, R, Cin, Cout);
+  conv1x1_stats_kernel<T, BN><<<grid, kThreads, cfg::kSmemBytes, s>>>(tx, tw, ty, sums, R, Cin, Cout, Cg, Og, wN);
   return check_launch("conv1x1_bn_stats");
 }
 
 }  // namespace cg
 
-bool conv1x1_stats_supported(long long R, int Cin, int Cout, int dtype) {
-  if (dtype != GRAFP_F32 && dtype != GRAFP_BF16) return false;
-  const int es = dtype == GRAFP_F32 ? 4 : 2;
-  return R >= 1 && R < (1LL << 31) - 256 && Cin >= 1 && Cout >= 1 && (Cin * es) % 16 == 0 && (Cout * es) % 16 == 0;
+// tile width for Cout output channels in `groups` groups, or 0 when the shape cannot be tiled: a tile must not straddle
+// a group boundary unless it holds whole groups, and a group's share of a tile is one MMA (N a multiple of 16)
+static int tile_width(int Cout, int groups) {
+  const int bn = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
+  if (groups == 1) return bn;
+  const int Og = Cout / groups;
+  for (int cand : {bn, 128, 64}) {
+    if (cand > bn) continue;
+    if (Og >= cand ? (Og % cand == 0) : (cand % Og == 0 && Og % 16 == 0)) return cand;
+  }
+  return 0;
 }
 
-int launch_conv1x1_stats(const void* x, const void* w, void* y, double* sums, long long R, int Cin, int Cout, int dtype,
-                         cudaStream_t s) {
-  if (!conv1x1_stats_supported(R, Cin, Cout, dtype)) {
-    set_error("conv1x1_bn_stats: needs fp32 / bf16 rows with Cin and Cout multiples of 16 bytes");
+bool conv1x1_stats_supported(long long R, int Cin, int Cout, int groups, int dtype) {
+  if (dtype != GRAFP_F32 && dtype != GRAFP_BF16) return false;
+  const int es = dtype == GRAFP_F32 ? 4 : 2;
+  if (!(R >= 1 && R < (1LL << 31) - 256 && Cin >= 1 && Cout >= 1 && groups >= 1)) return false;
+  if (Cin % groups != 0 || Cout % groups != 0) return false;
+  if ((Cin * es) % 16 != 0 || (Cout * es) % 16 != 0 || ((Cin / groups) * es) % 16 != 0) return false;
+  return tile_width(Cout, groups) != 0;
+}
+
+int launch_conv1x1_stats(const void* x, const void* w, void* y, double* sums, long long R, int Cin, int Cout, int groups,
+                         int dtype, cudaStream_t s) {
+  if (!conv1x1_stats_supported(R, Cin, Cout, groups, dtype)) {
+    set_error("conv1x1_bn_stats: needs fp32 / bf16 rows, Cin, Cout and Cin / groups multiples of 16 bytes, and groups whose "
+              "output share is a multiple of 16 channels that tiles 64 / 128 / 256 columns");
     return GRAFP_EUNSUPPORTED;
   }
   if (!aligned16(x) || !aligned16(w) || !aligned16(y)) {
@@ -389,8 +427,8 @@ int launch_conv1x1_stats(const void* x, const void* w, void* y, double* sums, lo
   }
   cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)2 * Cout * sizeof(double), s);
   if (e != cudaSuccess) { set_error("conv1x1_bn_stats: cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
-  const int bn = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
-#define GRAFP_CG_LAUNCH(T_, BN_) cg::launch_variant<T_, BN_>(x, w, y, sums, R, Cin, Cout, dtype, s)
+  const int bn = tile_width(Cout, groups);
+#define GRAFP_CG_LAUNCH(T_, BN_) cg::launch_variant<T_, BN_>(x, w, y, sums, R, Cin, Cout, groups, dtype, s)
   if (dtype == GRAFP_F32) {
     if (bn == 256) return GRAFP_CG_LAUNCH(float, 256);
     if (bn == 128) return GRAFP_CG_LAUNCH(float, 128);

@@ -705,39 +705,40 @@ def _bn_bwd_call(lib, g, h, weight, bias, save_mean, save_invstd, relu, want_col
 
 def conv1x1_stats_ok(x: torch.Tensor, cw: torch.Tensor, conv_args) -> bool:
     """Whether the 1x1 convolution ``cw`` over rows ``x`` takes the tcgen05 GEMM with the BatchNorm statistics in its
-    epilogue (``grafp_conv1x1_bn_stats_fwd``): dense, unit stride, no padding, and - for fp32 - TF32 convolutions allowed
+    epilogue (``grafp_conv1x1_bn_stats_fwd``): dense or grouped, unit stride, no padding, and - for fp32 - TF32 convolutions allowed
     (``torch.backends.cudnn.allow_tf32``, PyTorch's default: the kernel computes what cuDNN computes then; with TF32
     off the convolution stays cuDNN's fp32 and the BatchNorm takes its own statistics pass).  Option ``conv_gemm``
     (``GRAFP_CONV_GEMM``): 1 = on where it wins (default), 2 = always, 0 = off (A/B)."""
     stride, padding, dilation, groups = conv_args
     if get_option("conv_gemm") == 0:
         return False
-    if not (groups == 1 and tuple(stride) == (1, 1) and tuple(padding) == (0, 0) and tuple(cw.shape[2:]) == (1, 1)):
+    if not (tuple(stride) == (1, 1) and tuple(padding) == (0, 0) and tuple(cw.shape[2:]) == (1, 1)):
         return False
     if x.dtype == torch.float32 and not torch.backends.cudnn.allow_tf32:
         return False
     if x.dtype not in (torch.float32, torch.bfloat16) or not (x.is_cuda and _is_rows(x)):
         return False
     B, Cin, N, _ = x.shape
-    # measured (profiles/, scripts/bench_kernels.py gemm): with rows of more than 2 KB (Cin > 512 fp32 / 1024 bf16) the
-    # layer is tensor- / L2-bound, cuDNN's larger tiles win by more than the saved statistics pass; conv_gemm = 2 forces
-    if get_option("conv_gemm") != 2 and Cin * x.element_size() > 2048:
+    # measured (profiles/, scripts/bench_kernels.py gemm): with a k-range of more than 2 KB per row (Cin / groups > 512
+    # fp32 / 1024 bf16) the layer is tensor- / L2-bound, cuDNN's larger tiles win by more than the saved statistics pass;
+    # conv_gemm = 2 forces
+    if get_option("conv_gemm") != 2 and (Cin // groups) * x.element_size() > 2048:
         return False
-    return bool(_native.load().grafp_conv1x1_bn_stats_supported(B * N, Cin, cw.shape[0], _dtype_code(x)))
+    return bool(_native.load().grafp_conv1x1_bn_stats_supported(B * N, Cin, cw.shape[0], groups, _dtype_code(x)))
 
 
-def _conv1x1_stats_call(lib, x, cw_x):
-    """h = conv1x1(x, cw_x) as rows, plus the BatchNorm workspace holding sum h / sum h^2 per channel."""
+def _conv1x1_stats_call(lib, x, cw_x, groups=1):
+    """h = conv1x1(x, cw_x, groups) as rows, plus the BatchNorm workspace holding sum h / sum h^2 per channel."""
     B, Cin, N, _ = x.shape
     Cout = cw_x.shape[0]
     h = _new_rows(B, Cout, N, x)
-    w = cw_x.reshape(Cout, Cin)
+    w = cw_x.reshape(Cout, Cin // groups)
     if not w.is_contiguous():
         w = w.contiguous()
     ws_bytes = lib.grafp_bn_workspace_bytes(Cout)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-    _call("conv1x1_bn_stats_fwd", 1, dict(B=B, N=N, Cin=Cin, Cout=Cout, dtype=_dtype_code(x)),
-          lib.grafp_conv1x1_bn_stats_fwd, x.device, x.data_ptr(), w.data_ptr(), h.data_ptr(), B * N, Cin, Cout,
+    _call("conv1x1_bn_stats_fwd", 1, dict(B=B, N=N, Cin=Cin, Cout=Cout, groups=groups, dtype=_dtype_code(x)),
+          lib.grafp_conv1x1_bn_stats_fwd, x.device, x.data_ptr(), w.data_ptr(), h.data_ptr(), B * N, Cin, Cout, groups,
           _dtype_code(x), ws.data_ptr(), ws_bytes, _stream(x))
     return h, ws
 
@@ -864,14 +865,14 @@ class _ConvBatchNormTrain(torch.autograd.Function):
         moments_ws = None
         with torch.autocast("cuda", enabled=False):
             cw_x = cw if cw.dtype == x.dtype else cw.to(x.dtype)
-            dense = _dense_form_of_grouped(x, cw, groups)
-            w_eff = _block_diag_weight(cw_x, groups) if dense else cw_x
-            eff_args = (stride, padding, dilation, 1 if dense else groups)
-            if conv1x1_stats_ok(x, w_eff, eff_args):
-                # own GEMM: the convolution output and its per-channel moments in one pass (conv_gemm.cu)
-                h, moments_ws = _conv1x1_stats_call(lib, x, w_eff)
+            if conv1x1_stats_ok(x, cw_x, conv_args):
+                # own GEMM (grouped: block-diagonal MMA schedule): the convolution output and its per-channel moments in
+                # one pass (conv_gemm.cu)
+                h, moments_ws = _conv1x1_stats_call(lib, x, cw_x, groups)
             else:
-                h = torch.nn.functional.conv2d(x, w_eff, None, *eff_args)   # bias: see the class docstring
+                dense = _dense_form_of_grouped(x, cw, groups)
+                w_eff = _block_diag_weight(cw_x, groups) if dense else cw_x
+                h = torch.nn.functional.conv2d(x, w_eff, None, stride, padding, dilation, 1 if dense else groups)   # bias: see the class docstring
         if not _is_rows(h):
             h = as_rows(h)
         if residual is not None and residual.shape != h.shape:

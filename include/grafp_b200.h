@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GRAFP_ABI_VERSION 6
+#define GRAFP_ABI_VERSION 7
 
 #define GRAFP_OK 0
 #define GRAFP_EINVAL (-1)       /* null / misaligned pointer, non-positive size, k > M ... */
@@ -231,17 +231,19 @@ int grafp_bn_train_bwd(const void* dy, const void* x, const float* weight, const
  * (Grapher.fc1 / fc2) and graph_encoder.py:45-67 (FFN) together with the statistics pass of the train-mode BatchNorm2d
  * behind it: y = x w^T as one tcgen05 GEMM over the node rows, and per output channel sum y and sum y^2 (taken of the
  * values as stored, accumulated in double) left in the BatchNorm workspace.
- *   x (R, Cin), w (Cout, Cin), y (R, Cout): rows of `dtype`; GRAFP_F32 runs as TF32 with fp32 accumulation (what cuDNN
+ *   x (R, Cin), w (Cout, Cin / groups), y (R, Cout): rows of `dtype`; groups > 1 is Conv2d(groups=...) - output channels
+ *   [g Cout/groups, (g+1) Cout/groups) see input channels [g Cin/groups, (g+1) Cin/groups) (BasicConv's groups = 4); GRAFP_F32 runs as TF32 with fp32 accumulation (what cuDNN
  *   does for this layer under torch.backends.cudnn.allow_tf32, PyTorch's default - callers that need full fp32 keep
  *   cuDNN), GRAFP_BF16 as bf16 with fp32 accumulation.  No bias: a per-channel constant cancels in the BatchNorm
  *   (conv_bias of grafp_bn_train_fwd* puts it back where it is visible, the running mean).
- *   Cin and Cout must be multiples of 16 bytes of elements (GRAFP_EUNSUPPORTED otherwise; _supported() tells).
+ *   Cin, Cout and Cin / groups must be multiples of 16 bytes of elements, Cout / groups a multiple of 16 channels that
+ *   tiles 64 / 128 / 256 columns (GRAFP_EUNSUPPORTED otherwise; _supported() tells).
  * grafp_bn_train_fwd_from_moments is grafp_bn_train_fwd without its statistics pass: `workspace` must be the one the
  * convolution call wrote (same C = Cout); everything else - outputs, running statistics, saved mean / invstd - as there.
  */
-int grafp_conv1x1_bn_stats_supported(long long R, int Cin, int Cout, int dtype);
-int grafp_conv1x1_bn_stats_fwd(const void* x, const void* w, void* y, long long R, int Cin, int Cout, int dtype, void* workspace,
-                               size_t workspace_bytes, void* stream);
+int grafp_conv1x1_bn_stats_supported(long long R, int Cin, int Cout, int groups, int dtype);
+int grafp_conv1x1_bn_stats_fwd(const void* x, const void* w, void* y, long long R, int Cin, int Cout, int groups, int dtype,
+                               void* workspace, size_t workspace_bytes, void* stream);
 int grafp_bn_train_fwd_from_moments(const void* x, const void* residual, const float* weight, const float* bias,
                                     float* running_mean, float* running_var, const float* conv_bias,
                                     long long* num_batches_tracked, void* out, float* save_mean, float* save_invstd, long long R,

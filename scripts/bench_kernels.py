@@ -127,15 +127,19 @@ def bench_gemm(dtype):
     print(f"=== 1x1 convolution (+ BatchNorm forward), dtype={dtype}, B={B}: GB/s over R (Cin + Cout) e")
     lib = ops._native.load()
     for (N, C) in STAGES:
-        for (cin, cout) in ((C, C), (2 * C, C), (C, 4 * C), (4 * C, C)):
+        for (cin, cout, G) in ((C, C, 1), (2 * C, 2 * C, 4), (2 * C, C, 1), (C, 4 * C, 1), (4 * C, C, 1)):
             x = rows(N, cin, dtype, relu=True)
-            conv = torch.nn.Conv2d(cin, cout, 1, bias=False).to(dev)
+            conv = torch.nn.Conv2d(cin, cout, 1, bias=False, groups=G).to(dev)
             bn = torch.nn.BatchNorm2d(cout).to(dev).train()
             w = conv.weight.detach().to(dtype)
             bytes_conv = B * N * (cin + cout) * e
-            t_own = timed(lambda: ops._conv1x1_stats_call(lib, x, w))
-            t_lib = timed(lambda: torch.nn.functional.conv2d(x, w))
-            line = (f"N={N:5d} {cin:5d}->{cout:5d} | conv: ours {t_own*1e3:7.1f} us ({bytes_conv/t_own/1e6:5.0f} GB/s, "
+            t_own = timed(lambda: ops._conv1x1_stats_call(lib, x, w, G))
+            if G > 1 and dtype == torch.bfloat16:   # (cuDNN's bf16 grouped kernel is the 29 ms one: its dense form instead)
+                wd = ops._block_diag_weight(w, G)
+                t_lib = timed(lambda: torch.nn.functional.conv2d(x, wd))
+            else:
+                t_lib = timed(lambda: torch.nn.functional.conv2d(x, w, groups=G))
+            line = (f"N={N:5d} {cin:5d}->{cout:5d}{' g4' if G > 1 else '   '} | conv: ours {t_own*1e3:7.1f} us ({bytes_conv/t_own/1e6:5.0f} GB/s, "
                     f"{bytes_conv/t_own/1e6/PEAK*100:3.0f}%)  cuDNN {t_lib*1e3:7.1f} us ({bytes_conv/t_lib/1e6:5.0f} GB/s)")
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
                 for flag in (2, 0):

@@ -40,7 +40,7 @@ def test_library_links_without_the_cuda_driver(lib_path):
 
 def test_abi_version_and_sizes(lib_path):
     lib = _native.load()
-    assert lib.grafp_abi_version() == _native.ABI_VERSION == 6
+    assert lib.grafp_abi_version() == _native.ABI_VERSION == 7
     assert lib.grafp_knn_workspace_bytes(0, 1, 1, 1, 1, 0) == 0
     need = lib.grafp_knn_workspace_bytes(4, 256, 256, 64, 3, 0)
     assert need >= 4 * 4 * 256 * 64 * 4  # hi + lo for queries and keys

@@ -987,7 +987,7 @@ def test_conv1x1_stats_kernel(shape, dtype):
     x = (torch.randn(B, Cin, N, 1, generator=g) + 0.5).to(dtype).to(DEV).contiguous(memory_format=torch.channels_last)
     w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).to(dtype).to(DEV)
     lib = ops._native.load()
-    assert lib.grafp_conv1x1_bn_stats_supported(B * N, Cin, Cout, 0 if dtype == torch.float32 else 1) == 1
+    assert lib.grafp_conv1x1_bn_stats_supported(B * N, Cin, Cout, 1, 0 if dtype == torch.float32 else 1) == 1
     h, ws = ops._conv1x1_stats_call(lib, x, w)
     torch.cuda.synchronize()
     assert h.shape == (B, Cout, N, 1) and h.dtype == dtype and ops._is_rows(h)
@@ -1003,6 +1003,33 @@ def test_conv1x1_stats_kernel(shape, dtype):
     mean, var = m[0] / (B * N), m[1] / (B * N) - (m[0] / (B * N)) ** 2
     assert torch.allclose(mean, hd.mean(0), atol=1e-6 * float(hd.abs().max()))
     assert torch.allclose(var, hd.var(0, unbiased=False), rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(3, 500, 128, 128, 4), (2, 256, 512, 512, 4), (2, 130, 1024, 1024, 4), (2, 100, 64, 32, 2),
+                                   (1, 300, 256, 512, 8), (2, 64, 2048, 2048, 4)])
+def test_conv1x1_stats_kernel_grouped(shape, dtype):
+    """The grouped form (block-diagonal MMA schedule: BasicConv's groups = 4 and other group counts, a group narrower
+    than / as wide as / wider than a tile) against the grouped convolution in fp64, moments as in the dense test."""
+    B, N, Cin, Cout, G = shape
+    g = torch.Generator().manual_seed(N + Cin + G)
+    x = (torch.randn(B, Cin, N, 1, generator=g) + 0.5).to(dtype).to(DEV).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin // G, 1, 1, generator=g) / (Cin // G) ** 0.5).to(dtype).to(DEV)
+    lib = ops._native.load()
+    assert lib.grafp_conv1x1_bn_stats_supported(B * N, Cin, Cout, G, 0 if dtype == torch.float32 else 1) == 1
+    h, ws = ops._conv1x1_stats_call(lib, x, w, G)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), groups=G)
+    err = gio.rel_err(h.double().cpu(), ref.cpu())
+    assert err < (1.5e-3 if dtype == torch.float32 else 4e-3), err
+    m = _bn_moments(ws, Cout).cpu()
+    hd = h.double().permute(0, 2, 3, 1).reshape(B * N, Cout).cpu()
+    s1, s2 = hd.sum(0), (hd * hd).sum(0)
+    assert float((m[1] - s2).abs().max() / s2.abs().max()) < 3e-6
+    assert torch.allclose(m[0] / (B * N), hd.mean(0), atol=1e-6 * float(hd.abs().max()))
+    # shapes the tiling cannot express are refused, not mis-computed
+    assert lib.grafp_conv1x1_bn_stats_supported(B * N, 96, 96, 4, 0) == 0      # 24 output channels per group
+    assert lib.grafp_conv1x1_bn_stats_supported(B * N, 100, 128, 3, 0) == 0
 
 
 def test_conv1x1_stats_large_mean():
@@ -1021,16 +1048,18 @@ def test_conv1x1_stats_large_mean():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("groups", [1, 4])
 @pytest.mark.parametrize("mode", ["plain", "relu", "residual"])
-def test_conv_batch_norm_gemm_path(mode, dtype):
+def test_conv_batch_norm_gemm_path(mode, groups, dtype):
     """conv_gemm = 1 (tcgen05 GEMM + statistics epilogue + apply pass) against conv_gemm = 0 (cuDNN convolution +
-    two-pass BatchNorm kernel) with TF32 allowed in both, and against fp64: outputs, all gradients, running statistics."""
+    two-pass BatchNorm kernel) with TF32 allowed in both, and against fp64: outputs, all gradients, running statistics.
+    groups = 4 is BasicConv's grouped convolution."""
     B, Cin, Cout, N = 3, 128, 256, 500
     g = torch.Generator().manual_seed(17)
     x = torch.randn(B, Cin, N, 1, generator=g)
     res = torch.randn(B, Cout, N, 1, generator=g)
     up = torch.randn(B, Cout, N, 1, generator=g)
-    conv0 = torch.nn.Conv2d(Cin, Cout, 1)
+    conv0 = torch.nn.Conv2d(Cin, Cout, 1, groups=groups)
     bn0 = torch.nn.BatchNorm2d(Cout)
     with torch.no_grad():
         bn0.weight.copy_(torch.randn(Cout, generator=g)); bn0.bias.copy_(torch.randn(Cout, generator=g))
@@ -1063,7 +1092,7 @@ def test_conv_batch_norm_gemm_path(mode, dtype):
         b, _ = run(0)
     finally:
         torch.backends.cudnn.allow_tf32 = old
-    conv_ref, bn_ref = torch.nn.Conv2d(Cin, Cout, 1).double(), torch.nn.BatchNorm2d(Cout).double().train()
+    conv_ref, bn_ref = torch.nn.Conv2d(Cin, Cout, 1, groups=groups).double(), torch.nn.BatchNorm2d(Cout).double().train()
     conv_ref.load_state_dict({k: v.double() for k, v in conv0.state_dict().items()})
     bn_ref.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in bn0.state_dict().items()})
     xr = x.to(dtype).double().requires_grad_(True)
