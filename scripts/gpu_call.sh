@@ -31,8 +31,8 @@ for step in "$@"; do
     bench_l2) GRAFP_BN_L2_KEEP_MB=48 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_l2keep48.json 2> $out/${tag}_bench_n1_l2keep48.err; tail -c 300 $out/${tag}_bench_n1_l2keep48.err; cut -c1-300 $out/${tag}_bench_n1_l2keep48.json
               GRAFP_BN_L2_KEEP_MB=80 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_l2keep80.json 2> $out/${tag}_bench_n1_l2keep80.err; cut -c1-300 $out/${tag}_bench_n1_l2keep80.json ;;
     bench_nograph) timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager --graph off > $out/${tag}_bench_n1_nograph.json 2> $out/${tag}_bench_n1_nograph.err; cut -c1-300 $out/${tag}_bench_n1_nograph.json ;;
-    launches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 1 --graph off --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_under_ncu.log 2>&1; wc -l $out/launches.csv ;;
-    ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"knn_|mr_aggregate|bn_|ntxent|peak_extract|conv1x1|taps_" -c 110 -f -o /tmp/prof_ops python scripts/ncu_ops.py 512 1 > $out/${tag}_ncu_ops.log 2>&1; tail -2 $out/${tag}_ncu_ops.log
+    launches) timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 1 --graph off --cudnn-benchmark off --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_under_ncu.log 2>&1; wc -l $out/launches.csv ;;
+    ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"knn_|mr_aggregate|bn_|ntxent|peak_extract|conv1x1|taps_" -c 130 -f -o /tmp/prof_ops python scripts/ncu_ops.py 512 1 > $out/${tag}_ncu_ops.log 2>&1; tail -2 $out/${tag}_ncu_ops.log
              python scripts/ncu_summary.py /tmp/prof_ops.ncu-rep > $out/${tag}_ncu_hot_kernels_summary.txt 2>&1
              python scripts/ncu_stalls.py /tmp/prof_ops.ncu-rep > $out/${tag}_ncu_stalls.txt 2>&1
              python scripts/dram_traffic.py /tmp/prof_ops.ncu-rep $out/${tag}_dram_traffic.json > /dev/null 2>&1
@@ -43,6 +43,7 @@ for step in "$@"; do
              python scripts/ncu_summary.py /tmp/prof_bf16.ncu-rep > $out/${tag}_ncu_bf16_summary.txt 2>&1; python scripts/ncu_stalls.py /tmp/prof_bf16.ncu-rep > $out/${tag}_ncu_bf16_stalls.txt 2>&1; cat $out/${tag}_ncu_bf16_summary.txt; cat $out/${tag}_ncu_bf16_stalls.txt | cut -c1-220 ;;
     bench_n2_graph) timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --graph on > $out/${tag}_bench_n2_graph.json 2> $out/${tag}_bench_n2_graph.err; tail -c 1500 $out/${tag}_bench_n2_graph.err; cut -c1-300 $out/${tag}_bench_n2_graph.json ;;
     bench_graph) timeout 600 python bench.py --steps 10 --warmup 3 --graph on --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_graph.json 2> $out/${tag}_bench_n1_graph.err; tail -c 300 $out/${tag}_bench_n1_graph.err; cut -c1-300 $out/${tag}_bench_n1_graph.json ;;
+    bench_n4_graph) timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus 4 --steps 8 --warmup 3 > $out/${tag}_bench_n4_graph.json 2> $out/${tag}_bench_n4_graph.err; tail -c 400 $out/${tag}_bench_n4_graph.err; cut -c1-300 $out/${tag}_bench_n4_graph.json ;;
     bench_n8_graph) timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 8 --steps 8 --warmup 3 --graph on > $out/${tag}_bench_n8_graph.json 2> $out/${tag}_bench_n8_graph.err; tail -c 600 $out/${tag}_bench_n8_graph.err; cut -c1-300 $out/${tag}_bench_n8_graph.json ;;
     bench_n8) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 10 --warmup 3 > $out/${tag}_bench_n8.json 2> $out/${tag}_bench_n8.err; grep -c "Grad strides" $out/${tag}_bench_n8.err; tail -c 400 $out/${tag}_bench_n8.err; cut -c1-300 $out/${tag}_bench_n8.json ;;
     smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;

@@ -22,10 +22,12 @@ for (N, C) in [(1024, 64), (512, 128), (256, 256), (128, 512)]:
     torch.backends.cudnn.allow_tf32 = True
     conv = torch.nn.Conv2d(C, 4 * C, 1, bias=False).to(dev)
     bn4 = torch.nn.BatchNorm2d(4 * C).to(dev).train()
+    gconv = torch.nn.Conv2d(2 * C, 2 * C, 1, groups=4).to(dev)   # BasicConv of the graph convolution on the K2 output
     with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
         for _ in range(reps):
             ops.set_option("conv_gemm", 2)
             h = ops.conv_batch_norm_act(x, conv, bn4, relu=True)
+            hg = ops.conv_batch_norm_act(out.detach(), gconv, bn, relu=True)
     ops.set_option("conv_gemm", 1)
     if N >= 256:
         taps = ops._DownsampleTaps.apply(x)

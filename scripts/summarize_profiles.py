@@ -45,7 +45,7 @@ def launches():
             ours.append((row["ID"], name, row.get("Grid Size", ""), row.get("Block Size", ""), f"{us:.2f}"))
     total = sum(v[1] for v in tot.values())
     with open(os.path.join(OUT, f"{tag}_launches_summary.csv"), "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 2 --warmup 1 --graph off --no-cpu-baseline --no-gpu-eager\n")
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 2 --warmup 1 --graph off --cudnn-benchmark off --no-cpu-baseline --no-gpu-eager\n")
         f.write(f"# {n} launches, {total/1e3:.1f} ms of kernel time (cold-cache, serialised: compare shares, not absolutes)\n")
         f.write("share_pct,total_ms,launches,kernel\n")
         for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1]):
