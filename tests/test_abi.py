@@ -75,3 +75,24 @@ def test_options_are_settable_and_default_from_the_header(lib_path):
     assert lib.grafp_set_option(b"no_such_option", 1) == -1
     assert b"unknown option" in lib.grafp_last_error()
     assert lib.grafp_get_option(b"no_such_option") == -1
+
+
+def test_conv1x1_envelope_is_answered_on_the_host(lib_path):
+    """grafp_conv1x1_bn_stats_supported is pure host logic: the shapes of the encoder (dense and BasicConv's 4 groups) are
+    in, shapes the 64 / 128 / 256-column tiling cannot express are refused before any launch."""
+    lib = _native.load()
+    ok = lib.grafp_conv1x1_bn_stats_supported
+    F32, BF16 = 0, 1
+    for C in (64, 128, 256, 512):
+        R = 512 * 65536 // C
+        for cin, cout, g in ((C, C, 1), (2 * C, 2 * C, 4), (2 * C, C, 1), (C, 4 * C, 1), (4 * C, C, 1), (3 * C // 2 * 2, 2 * C, 1)):
+            assert ok(R, cin, cout, g, F32) == 1 and ok(R, cin, cout, g, BF16) == 1, (cin, cout, g)
+    assert ok(1000, 8, 64, 1, F32) == 1 and ok(1000, 8, 64, 1, BF16) == 1      # the stem's 8 input channels: 32 / 16 bytes
+    assert ok(1000, 6, 64, 1, F32) == 0                                        # 24-byte rows
+    assert ok(1000, 4, 64, 1, BF16) == 0                                       # 8-byte rows
+    assert ok(1000, 96, 96, 4, F32) == 0                                       # 24 output channels per group
+    assert ok(1000, 128, 128, 3, F32) == 0                                     # channels not divisible by the groups
+    assert ok(1000, 128, 192, 2, F32) == 0                                     # 96 per group: neither fills nor divides a tile
+    assert ok(1000, 128, 128, 8, F32) == 1 and ok(1000, 64, 64, 4, F32) == 1   # 16 per group: four / four groups per tile
+    assert ok(0, 64, 64, 1, F32) == 0 and ok(1 << 31, 64, 64, 1, F32) == 0
+    assert ok(1000, 64, 64, 1, 7) == 0
