@@ -136,15 +136,15 @@ knn_normalize_vec_kernel(const T* __restrict__ x, float* __restrict__ xhat, floa
   }
 }
 
-// Lean fp32 -> fp16 hi/lo plane producer for the f16x3 tensor-core kernels (mode 3, C % 4 == 0, C <= 1024).
+// Lean fp32 / bf16 -> fp16 hi/lo plane producer for the f16x3 tensor-core kernels (mode 3, C % 4 == 0, C <= 1024).
 // Same row ownership as the vectorised kernel above, but the warp never diverges (rows past the end are
 // clamped and only their stores are guarded), the quotient x / denom is formed as one reciprocal per row
 // plus a Newton correction per element (q0 = x * r; q = fma(fma(-q0, denom, x), r, q0), which is the
 // correctly rounded quotient except in rare double-rounding cases), and the planes leave as packed
 // 8-byte stores.  ~4x fewer instructions than the generic kernel, which was issue-bound.
-template <int LPR, int PACKS>
+template <typename T, int LPR, int PACKS>
 __global__ void __launch_bounds__(256)
-knn_normalize_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
+knn_normalize_f16_kernel(const T* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo,
                          float* __restrict__ sq, long long rows, int C, bool normalize) {
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
@@ -161,7 +161,16 @@ knn_normalize_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, _
 #pragma unroll
     for (int p = 0; p < PACKS; ++p) {
       const int c4 = sub + p * LPR;
-      v[p] = (c4 < cv) ? __ldg(reinterpret_cast<const float4*>(x + row * C) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < cv) {
+        if constexpr (std::is_same<T, float>::value) {
+          v[p] = __ldg(reinterpret_cast<const float4*>(x + row * C) + c4);
+        } else {  // bf16 rows (the generic kernel these took before was issue-bound: 95 us against 45)
+          float t[4];
+          Pack<T, 4>::load(x + row * C + c4 * 4, t);
+          v[p] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+      }
       ss = fmaf(v[p].x, v[p].x, ss); ss = fmaf(v[p].y, v[p].y, ss);
       ss = fmaf(v[p].z, v[p].z, ss); ss = fmaf(v[p].w, v[p].w, ss);
     }
@@ -200,7 +209,8 @@ knn_normalize_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, _
   }
 }
 
-static bool launch_normalize_f16(const float* xs, float* hi, float* lo, float* sq, long long rows, int C, bool normalize,
+template <typename T>
+static bool launch_normalize_f16(const T* xs, float* hi, float* lo, float* sq, long long rows, int C, bool normalize,
                                  cudaStream_t s) {
   const int cv = C / 4;
   __half* h = reinterpret_cast<__half*>(hi);
@@ -210,7 +220,7 @@ static bool launch_normalize_f16(const float* xs, float* hi, float* lo, float* s
     const long long need = (rows + (256 / LPR_) - 1) / (256 / LPR_);                                 \
     const long long cap = (long long)num_sms() * 8;                                                  \
     const int blocks = (int)(need < cap ? (need < 1 ? 1 : need) : cap);                              \
-    knn_normalize_f16_kernel<LPR_, PACKS_><<<blocks, 256, 0, s>>>(xs, h, l, sq, rows, C, normalize); \
+    knn_normalize_f16_kernel<T, LPR_, PACKS_><<<blocks, 256, 0, s>>>(xs, h, l, sq, rows, C, normalize); \
     return true;                                                                                     \
   }
   if (cv <= 4) GRAFP_NORM16_CASE(4, 1)
@@ -252,9 +262,8 @@ int launch_knn_normalize(const void* x, float* xhat, float* lo, float* sq, long 
   if (blocks < 1) blocks = 1;
   const T* xs = static_cast<const T*>(x);
   const bool vec = (C % 4 == 0) && aligned16(x) && aligned16(xhat) && aligned16(lo);
-  if (vec && mode == 3 && std::is_same<T, float>::value) {
-    if (launch_normalize_f16(reinterpret_cast<const float*>(x), xhat, lo, sq, rows, C, normalize, s))
-      return check_launch("knn_normalize_f16");
+  if (vec && mode == 3) {
+    if (launch_normalize_f16<T>(xs, xhat, lo, sq, rows, C, normalize, s)) return check_launch("knn_normalize_f16");
   }
   if (vec) {
     bool done = false;

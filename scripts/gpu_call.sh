@@ -39,7 +39,7 @@ for step in "$@"; do
              cp /tmp/prof_ops.ncu-rep $out/prof_ops.ncu-rep; python scripts/summarize_profiles.py ${tag} ncu_only $out > /dev/null 2>&1; rm -f $out/prof_ops.ncu-rep
              cat $out/${tag}_ncu_hot_kernels_summary.txt ;;
     bench_n2) NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,COLL NCCL_DEBUG_FILE=$out/${tag}_nccl_n2_%p.log timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > $out/${tag}_bench_n2.json 2> $out/${tag}_bench_n2.err; for f in $out/${tag}_nccl_n2_*.log; do head -c 20000 $f > $f.head; rm -f $f; done; grep -c "Grad strides" $out/${tag}_bench_n2.err; tail -c 400 $out/${tag}_bench_n2.err; cut -c1-300 $out/${tag}_bench_n2.json ;;
-    ncu_bf16) timeout 900 ncu --set full --clock-control none -k regex:"mr_aggregate|bn_" -c 40 -f -o /tmp/prof_bf16 python scripts/ncu_ops.py 512 1 bf16 > $out/${tag}_ncu_ops_bf16.log 2>&1; tail -2 $out/${tag}_ncu_ops_bf16.log
+    ncu_bf16) timeout 900 ncu --set full --clock-control none -k regex:"mr_aggregate|bn_|conv1x1|knn_" -c 70 -f -o /tmp/prof_bf16 python scripts/ncu_ops.py 512 1 bf16 > $out/${tag}_ncu_ops_bf16.log 2>&1; tail -2 $out/${tag}_ncu_ops_bf16.log
              python scripts/ncu_summary.py /tmp/prof_bf16.ncu-rep > $out/${tag}_ncu_bf16_summary.txt 2>&1; python scripts/ncu_stalls.py /tmp/prof_bf16.ncu-rep > $out/${tag}_ncu_bf16_stalls.txt 2>&1; cat $out/${tag}_ncu_bf16_summary.txt; cat $out/${tag}_ncu_bf16_stalls.txt | cut -c1-220 ;;
     bench_n2_graph) timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --graph on > $out/${tag}_bench_n2_graph.json 2> $out/${tag}_bench_n2_graph.err; tail -c 1500 $out/${tag}_bench_n2_graph.err; cut -c1-300 $out/${tag}_bench_n2_graph.json ;;
     bench_graph) timeout 600 python bench.py --steps 10 --warmup 3 --graph on --no-cpu-baseline --no-gpu-eager > $out/${tag}_bench_n1_graph.json 2> $out/${tag}_bench_n1_graph.err; tail -c 300 $out/${tag}_bench_n1_graph.err; cut -c1-300 $out/${tag}_bench_n1_graph.json ;;
