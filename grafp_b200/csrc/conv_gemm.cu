@@ -13,7 +13,8 @@
 //
 // fp32 rows run as TF32 (tcgen05.mma.kind::tf32, fp32 accumulate - the arithmetic cuDNN uses for the same layer when
 // torch.backends.cudnn.allow_tf32 is set, which is PyTorch's default; the host takes this path only then), bf16 rows as
-// kind::f16 with bf16 operands.  The layer is HBM-bound for every shape of the encoder but the last stage.
+// kind::f16 with bf16 operands.  The layer is HBM-bound at the first two stages of the encoder; beyond, a 128 x 256
+// tile is bound by the operand traffic from L2 (the host keeps k-ranges above 2 KB per row on cuDNN: ops.py).
 //
 // Persistent CTAs (one per SM), tile = 128 rows x BN output channels, column tile fastest so the CTAs that share an X
 // row block run at the same time and it is read from HBM once.  Warp roles (320 threads): warp 0 = TMA producer
@@ -24,10 +25,10 @@
 // Epilogue (two teams of four warps, alternating 64-column units, one staging buffer each): tcgen05.ld (one accumulator
 // row per thread) -> round to the output type -> swizzled staging tile in shared memory -> TMA store (coalesced,
 // asynchronous, clipped at the matrix edge); while the store drains, thread (c, h) sums column c over row half h of the
-// staging tile.  Moments are taken of
-// the values as stored (the bf16 roundings included), about the first row of the half (no cancellation when
-// |mean| >> std), widened to double and shifted back to raw moments there; a thread keeps its double accumulators
-// across tiles of the same column block and issues its red.global.add.f64 only when the block changes.
+// staging tile.  Moments are taken of the values as stored (the bf16 roundings included), about the first row of the
+// half (no cancellation when |mean| >> std), widened to double and shifted back to raw moments there; a thread keeps
+// its double accumulators across tiles of the same column block and issues its red.global.add.f64 only when the
+// block changes.  (With the weights (Cout, Cin / groups) the first line reads W[Cout x Cin/groups] per group.)
 #include <cuda_bf16.h>
 
 #include "tc_ptx.cuh"
